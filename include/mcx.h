@@ -1,0 +1,138 @@
+/*
+ * mcx.h -- C ABI of libmcx.so, the B200 (sm_100a) replacement for the translated marker search of
+ * MicrobeCensus.  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * What each entry point replaces in the reference (/root/reference/microbe_census/microbe_census.py = mc.py):
+ *
+ *   mcx_create / mcx_destroy     loading of data/rapdb_2.15 by the RAPsearch2 child process
+ *                                (command line built at mc.py:375; DB made by prerapsearch,
+ *                                training/search_reads.py:50)
+ *   mcx_set_params               args['read_length'|'quality_offset'|'min_quality'|'mean_quality'|
+ *                                'max_unknown'|'filter_dups'] (mc.py:189-224) and the per-family cutoff
+ *                                rows find_opt_pars() returns (mc.py:61-72)
+ *   mcx_push_reads[_dev]         process_seqfile()'s per-read filter chain (mc.py:328-356) and
+ *                                quality_filter() (mc.py:265-279); the reads are what the reference
+ *                                writes to its FASTA tempfile (mc.py:352)
+ *   mcx_qc_counts                the too_short / low_qual / dups / read_id counters (mc.py:336, 363-367)
+ *   mcx_search                   search_seqs() (mc.py:369-389, the rapsearch child) + classify_reads()
+ *                                (mc.py:432-460) + aggregate_hits() (mc.py:462-472), with the `-n` cut
+ *                                (mc.py:356) applied as a quota of kept reads
+ *   mcx_result                   args['sampled_reads'] (mc.py:362), "reads hit marker proteins"
+ *                                (mc.py:386), "reads assigned" (mc.py:459) and agg_hits (mc.py:620)
+ *   mcx_get_hits                 the lines of the .m8 file RAPsearch2 writes (mc.py:391-398)
+ *   mcx_last_error               stderr of the child (mc.py:389)
+ *
+ * All functions return 0 on success or a negative MCX_E* code; nothing throws across the ABI.
+ * A context is bound to one CUDA device and is not re-entrant.  There is no CPU fallback: every
+ * entry point that computes fails with MCX_ECUDA when no usable device is present.
+ */
+#ifndef MCX_H
+#define MCX_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCX_OK        0
+#define MCX_EINVAL   -1   /* bad argument */
+#define MCX_ECUDA    -2   /* CUDA runtime error / no device */
+#define MCX_ESTATE   -3   /* call out of order */
+#define MCX_ENOMEM   -4   /* a device buffer overflowed; the message names it */
+
+#define MCX_N_FAM    30
+#define MCX_LEN_BINS 1280 /* subject lengths are < 1280 (max 1183) */
+
+typedef struct mcx_ctx mcx_ctx;
+
+/* marker database: caller-owned host arrays, copied by mcx_create */
+typedef struct {
+    int32_t        n_subj;
+    const int32_t *off;      /* n_subj + 1 residue offsets */
+    const uint8_t *res;      /* residue codes 0..19 (ARNDCQEGHILKMFPSTWYV), 20 = X */
+    const uint8_t *fam;      /* family index 0..29 per subject */
+} mcx_db;
+
+/* cutoffs of one family at the current read length (one pars.map row) */
+typedef struct {
+    double  min_cov;         /* aln_cov      */
+    double  max_aaid;        /* max_aaid     */
+    int32_t min_raw;         /* smallest raw score whose printed bit score reaches score_cutoff */
+    int32_t stat;            /* 0 hits, 1 cov, 2 aln */
+} mcx_cutoff;
+
+typedef struct {
+    int32_t read_length;     /* -l : one of the 20 lengths of read_len.map */
+    int32_t has_quality;     /* 1 for FASTQ input */
+    int32_t quality_offset;  /* 33 / 64 style offset (args['quality_offset']) */
+    int32_t min_quality;     /* -q */
+    int32_t mean_quality;    /* -m */
+    int32_t max_unknown;     /* -u */
+    int32_t filter_dups;     /* -d */
+    int32_t min_report_raw;  /* raw score floor of reported HSPs (RAPsearch2 -e 1 at this length) */
+    mcx_cutoff cut[MCX_N_FAM];
+} mcx_params;
+
+typedef struct {
+    int64_t n_reads;         /* reads pushed */
+    int64_t kept;            /* reads passing all filters (before the -n cut) */
+    int64_t too_short, low_qual, dups;
+} mcx_qc;
+
+typedef struct {
+    int64_t sampled_reads;   /* reads searched (kept reads up to the quota) */
+    int64_t too_short, low_qual, dups;   /* counted up to the read that filled the quota */
+    int64_t reads_with_hits; /* reads with at least one reported HSP */
+    int64_t reads_classified;
+    int64_t n_hsp;           /* reported HSPs ("m8 lines") */
+    int64_t n_seed_hits;     /* seeds whose ungapped extension reached the report floor */
+    int64_t n_gapped;        /* gapped X-drop extensions run */
+    int64_t gapped_cells;    /* DP cells evaluated by them */
+    int64_t fam_hits[MCX_N_FAM];          /* classified reads per family */
+    int64_t fam_aln[MCX_N_FAM];           /* sum of aln-len per family */
+    int64_t aln_by_len[MCX_N_FAM * MCX_LEN_BINS]; /* sum of aln-len per (family, subject length) */
+} mcx_result;
+
+/* one reported HSP, the fields of an m8 line before formatting */
+typedef struct {
+    int32_t read;            /* index among the pushed reads */
+    int32_t subject;
+    int32_t frame;           /* 0..2 forward, 3..5 reverse complement */
+    int32_t score;           /* raw */
+    int32_t aln, ident, mism, gapo;
+    int32_t q0, q1;          /* 0-based inclusive aa range on the frame */
+    int32_t t0, t1;          /* 0-based inclusive aa range on the subject */
+} mcx_hit;
+
+int  mcx_create(mcx_ctx **out, const mcx_db *db, int device);
+void mcx_destroy(mcx_ctx *ctx);
+int  mcx_set_params(mcx_ctx *ctx, const mcx_params *p);
+
+/* Reads as ASCII bytes, read i = bases[offsets[i] .. offsets[i+1]); quals may be NULL (FASTA) and
+ * otherwise shares the offsets.  Host pointers (pinned or pageable).  Replaces any reads pushed before. */
+int  mcx_push_reads(mcx_ctx *ctx, const uint8_t *bases, const uint8_t *quals,
+                    const int64_t *offsets, int64_t n);
+/* same with device-resident buffers (no host->device copy) */
+int  mcx_push_reads_dev(mcx_ctx *ctx, const uint8_t *d_bases, const uint8_t *d_quals,
+                        const int64_t *d_offsets, int64_t n, int64_t total_bytes);
+
+int  mcx_qc_counts(mcx_ctx *ctx, mcx_qc *out);
+/* search the first `quota` kept reads (quota < 0: all of them) */
+int  mcx_search(mcx_ctx *ctx, int64_t quota);
+int  mcx_result_get(mcx_ctx *ctx, mcx_result *out);
+/* reported HSPs of the last search, ordered by (read, subject, score desc); *n receives the total */
+int  mcx_get_hits(mcx_ctx *ctx, mcx_hit *out, int64_t cap, int64_t *n);
+/* per pushed read: subject of the best passing hit or -1 */
+int  mcx_get_classified(mcx_ctx *ctx, int32_t *best_subject, int64_t n);
+
+/* device time (ms, CUDA events on the context's stream) of the stages of the last push/search:
+ * [0] h2d copy, [1] qc, [2] seed+ungapped, [3] gapped, [4] sort, [5] classify, [6] d2h; and kernel launches */
+int  mcx_timings(mcx_ctx *ctx, float ms[8], int64_t *launches);
+
+const char *mcx_last_error(mcx_ctx *ctx);
+const char *mcx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

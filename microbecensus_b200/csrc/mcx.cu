@@ -1,0 +1,1222 @@
+// mcx.cu -- libmcx.so: translated marker-gene search of MicrobeCensus on one B200 (sm_100a).
+//
+// One context = one GPU.  The hot path is five hand-written kernels (no CPU fallback anywhere):
+//
+//   k_qc        read QC                      mc.py:265-279, 342-356      one warp per read, HBM-bound
+//   k_seed      6-frame translation + SEG + murphy10 seed lookup + ungapped X-drop extension
+//               (RAPsearch2 BuildQHash / Searching / ExtendSeq2Set / AlignFwd / AlignBwd)
+//               one thread per (read, frame), frames staged in shared memory, seed index in L2/HBM
+//   k_gapped    gapped X-drop extension with alignment statistics carried forward
+//               (RAPsearch2 AlignSeqs / AlignGapped / CalRes)   one thread per surviving HSP
+//   k_classify  HSP de-duplication per (read, subject), the three cutoffs, best hit per read and the
+//               per-family integer sums       mc.py:400-472              one thread per read segment
+// plus CUB scans/sorts for compaction and ordering.  mc.py = /root/reference/microbe_census/
+// microbe_census.py; RAPsearch2 = the v2.15 binary it runs at mc.py:375 (behaviour pinned in DESIGN.md
+// and restated independently by oracle/mc_oracle.c, against which tests/ check every stage bit for bit).
+#include "../../include/mcx.h"
+#include "mcx_tables.h"
+
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace mcx;
+
+// ------------------------------------------------------------------------------------------------
+// device-side constants
+// ------------------------------------------------------------------------------------------------
+__constant__ double c_lnfac[256];     // ln(i!)
+__constant__ double c_ln20[256];      // i * ln 20
+__constant__ double c_ent[13 * 13];   // [tot][c] = -(c/tot) log2(c/tot)
+__constant__ int8_t c_blosum[21 * 32];
+__constant__ uint8_t c_codon[64];
+__constant__ mcx_cutoff c_cut[MCX_N_FAM];
+
+// murphy10 letters of residues 0..15 / 16..20, one nibble each (built from MURPHY10 at compile time)
+constexpr unsigned long long pack_m10(int first, int last) {
+    unsigned long long v = 0;
+    for (int a = first; a <= last; ++a) v |= (unsigned long long)MURPHY10_CE[a] << (4 * (a - first));
+    return v;
+}
+constexpr unsigned long long M10_LO = pack_m10(0, 15);
+constexpr unsigned long long M10_HI = pack_m10(16, 20);
+
+__device__ __forceinline__ int red_of(int a) {
+    return a < 16 ? (int)((M10_LO >> (4 * a)) & 15) : (int)((M10_HI >> (4 * (a - 16))) & 15);
+}
+__device__ __forceinline__ bool red_eq(int a, int b) {
+    int x = red_of(a);
+    return x < 10 && x == red_of(b);
+}
+
+struct DevDB {
+    int n_subj;
+    const int32_t *off;
+    const uint8_t *res;
+    const uint8_t *fam;
+    const uint32_t *hkey[N_PAT];   // open-addressing tables, 0xffffffff = empty
+    const uint32_t *hval[N_PAT];   // first posting of the word
+    uint32_t hmask[N_PAT];
+    int hshift[N_PAT];
+    const uint32_t *post;          // (subject << 11 | position), bit 31 = last posting of the word
+};
+
+struct Surv {                      // ungapped HSP that reached the report floor (16 bytes)
+    int32_t read;
+    uint16_t subject;
+    uint8_t frame, q0;
+    uint8_t q1, ident;
+    uint16_t t0;
+    int16_t score;
+    uint16_t pad;
+};
+
+struct SortKey {                   // (read, subject, score desc, frame, q0 | q1, t0, t1, aln, ident)
+    unsigned long long k1, k2;
+};
+struct SortKeyLess {
+    __device__ __forceinline__ bool operator()(const SortKey &a, const SortKey &b) const {
+        return a.k1 < b.k1 || (a.k1 == b.k1 && a.k2 < b.k2);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// frame construction: translation + SEG hard mask.  Frames live in shared memory, k-major
+// (element k of thread t at k*NT + t) so that a warp touching "its" residue k hits 32 distinct bytes
+// of 8 consecutive words: conflict-free.
+// ------------------------------------------------------------------------------------------------
+#define FR(k) s_aa[(k) * NT + tid]
+
+__device__ __forceinline__ int base_code(uint8_t c) {  // T C A G -> 0..3, anything else 4
+    return c == 'T' ? 0 : c == 'C' ? 1 : c == 'A' ? 2 : c == 'G' ? 3 : 4;
+}
+
+struct Comp {                      // composition of a <=12-residue window, nibble-packed
+    unsigned long long lo, hi, nc; // counts of letters 0..15 / 16..19 / number of letters having count c
+    int tot;
+    __device__ __forceinline__ void clear() { lo = hi = nc = 0; tot = 0; }
+    __device__ __forceinline__ void add(int a) {
+        if (a >= 20) return;
+        int c;
+        if (a < 16) { c = (int)((lo >> (4 * a)) & 15); lo += 1ull << (4 * a); }
+        else { c = (int)((hi >> (4 * (a - 16))) & 15); hi += 1ull << (4 * (a - 16)); }
+        if (c) nc -= 1ull << (4 * c);
+        nc += 1ull << (4 * (c + 1));
+        ++tot;
+    }
+    __device__ __forceinline__ void sub(int a) {
+        if (a >= 20) return;
+        int c;
+        if (a < 16) { c = (int)((lo >> (4 * a)) & 15); lo -= 1ull << (4 * a); }
+        else { c = (int)((hi >> (4 * (a - 16))) & 15); hi -= 1ull << (4 * (a - 16)); }
+        nc -= 1ull << (4 * c);
+        if (c > 1) nc += 1ull << (4 * (c - 1));
+        --tot;
+    }
+    // seg.c entropy(): terms added in descending-count order (the oracle sums its sorted state vector)
+    __device__ __forceinline__ double entropy(const double *ent) const {
+        double e = 0.0;
+        if (tot == 0) return 0.0;
+        for (int c = SEG_WINDOW; c >= 1; --c) {
+            int n = (int)((nc >> (4 * c)) & 15);
+            for (int r = 0; r < n; ++r) e += ent[tot * 13 + c];
+        }
+        return e;
+    }
+};
+
+template <int NT>
+__device__ double seg_win_entropy(const uint8_t *s_aa, int tid, int start, const double *ent) {
+    Comp w; w.clear();
+    for (int k = 0; k < SEG_WINDOW; ++k) w.add(FR(start + k));
+    return w.entropy(ent);
+}
+
+// seg.c getprob() of residues [start, start+len): lnass + lnperm - len*ln20 on the sorted composition
+template <int NT>
+__device__ double seg_getprob(const uint8_t *s_aa, int tid, int start, int len) {
+    uint8_t sv[21];
+    for (int a = 0; a < 21; ++a) sv[a] = 0;
+    for (int k = 0; k < len; ++k) { int a = FR(start + k); if (a < 20) sv[a]++; }
+    for (int i = 1; i < 20; ++i) {                 // insertion sort, descending
+        uint8_t v = sv[i]; int j = i - 1;
+        while (j >= 0 && sv[j] < v) { sv[j + 1] = sv[j]; --j; }
+        sv[j + 1] = v;
+    }
+    double lnperm = c_lnfac[len];
+    for (int i = 0; sv[i] != 0; ++i) lnperm -= c_lnfac[sv[i]];
+    double lnass = c_lnfac[20];
+    if (sv[0] != 0) {
+        int total = 20, cls = 1, svim1 = sv[0], svi, i = 0;
+        for (;;) {
+            if (++i == 20) { lnass -= c_lnfac[cls]; break; }
+            svi = sv[i];
+            if (svi == svim1) { cls++; continue; }
+            total -= cls;
+            lnass -= c_lnfac[cls];
+            if (svi == 0) { lnass -= c_lnfac[total]; break; }
+            cls = 1; svim1 = svi;
+        }
+    }
+    return lnass + lnperm - c_ln20[len];
+}
+
+// Seg::segseq as it behaves inside RAPsearch2 (downset 0, upset 1): rare path, run only for frames
+// that hold a window with entropy <= 2.2.  The recursion of seg.c only adds segments, so the left
+// parts are queued on a small work list instead.
+template <int NT>
+__device__ void seg_full(const uint8_t *s_aa, int tid, int m, const double *ent, unsigned long long mask[3]) {
+    int wl_off[12], wl_len[12], nwl = 1;
+    wl_off[0] = 0; wl_len[0] = m;
+    while (nwl > 0) {
+        --nwl;
+        int off = wl_off[nwl], slen = wl_len[nwl];
+        if (SEG_WINDOW > slen) continue;
+        int last = slen - 1, lowlim = 0, wmax = slen - SEG_WINDOW;
+        for (int i = 0; i <= last; ++i) {
+            double Hi = seg_win_entropy<NT>(s_aa, tid, off + (i < wmax ? i : wmax), ent);
+            if (!(Hi <= SEG_LOCUT)) continue;
+            int j, loi, hii;
+            for (j = i; j >= lowlim; --j)
+                if (seg_win_entropy<NT>(s_aa, tid, off + (j < wmax ? j : wmax), ent) > SEG_HICUT) break;
+            loi = j + 1;
+            for (j = i; j <= last; ++j)
+                if (seg_win_entropy<NT>(s_aa, tid, off + (j < wmax ? j : wmax), ent) > SEG_HICUT) break;
+            hii = j - 1;
+            int leftend = loi, rightend = hii;
+            {   // Seg::trim
+                int tl = rightend - leftend + 1, lend = 0, rend = tl - 1, minlen = 1;
+                if (tl - SEG_MAXTRIM > minlen) minlen = tl - SEG_MAXTRIM;
+                double minprob = 1.0;
+                for (int len = tl; len > minlen; --len)
+                    for (int s = 0; s + len <= tl; ++s) {
+                        double prob = seg_getprob<NT>(s_aa, tid, off + leftend + s, len);
+                        if (prob < minprob) { minprob = prob; lend = s; rend = len + s - 1; }
+                    }
+                rightend -= (tl - rend - 1);
+                leftend += lend;
+            }
+            if (i < leftend && nwl < 12) { wl_off[nwl] = off + loi; wl_len[nwl] = leftend - loi; ++nwl; }
+            for (j = off + leftend; j <= off + rightend; ++j) mask[j >> 6] |= 1ull << (j & 63);
+            i = hii < rightend ? hii : rightend;
+            lowlim = i + 1;
+        }
+    }
+}
+
+// translate frame `frame` of the read trimmed to L into FR(0..m) and hard-mask it; returns m
+template <int NT>
+__device__ int build_frame(uint8_t *s_aa, int tid, const uint8_t *__restrict__ rd, int L, int frame,
+                           const double *ent) {
+    int o = frame % 3, m = (L - o) / 3;
+    if (frame < 3) {
+        for (int k = 0; k < m; ++k) {
+            int p = o + 3 * k;
+            int b0 = base_code(rd[p]), b1 = base_code(rd[p + 1]), b2 = base_code(rd[p + 2]);
+            FR(k) = ((b0 | b1 | b2) & 4) ? AA_STOP : c_codon[16 * b0 + 4 * b1 + b2];
+        }
+    } else {
+        for (int k = 0; k < m; ++k) {
+            int p = L - 1 - (o + 3 * k);
+            int b0 = base_code(rd[p]), b1 = base_code(rd[p - 1]), b2 = base_code(rd[p - 2]);
+            FR(k) = ((b0 | b1 | b2) & 4) ? AA_STOP : c_codon[16 * (b0 ^ 2) + 4 * (b1 ^ 2) + (b2 ^ 2)];
+        }
+    }
+    if (m >= SEG_WINDOW) {
+        // fast path: slide the 12-window once; almost every frame has no window at or below locut
+        Comp w; w.clear();
+        for (int k = 0; k < SEG_WINDOW; ++k) w.add(FR(k));
+        bool trig = w.entropy(ent) <= SEG_LOCUT;
+        for (int s = 1; s + SEG_WINDOW <= m && !trig; ++s) {
+            w.sub(FR(s - 1)); w.add(FR(s + SEG_WINDOW - 1));
+            trig = w.entropy(ent) <= SEG_LOCUT;
+        }
+        if (trig) {
+            unsigned long long mask[3] = {0, 0, 0};
+            seg_full<NT>(s_aa, tid, m, ent, mask);
+            for (int k = 0; k < m; ++k)
+                if ((mask[k >> 6] >> (k & 63)) & 1) FR(k) = AA_STOP;
+        }
+    }
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: read QC (mc.py:342 too short on the untrimmed length; mc.py:265-279 on seq[:L], qual[:L]).
+// One warp per read, byte loads strided by lane (each warp request = consecutive bytes).
+// The reference's float comparisons are exact in integers (see oracle oc_read_qc).
+// codes: 0 keep, 1 too short, 2 low quality
+// ------------------------------------------------------------------------------------------------
+__global__ void k_qc(const uint8_t *__restrict__ bases, const uint8_t *__restrict__ quals,
+                     const int64_t *__restrict__ offs, int64_t n, int L, int qoff, int minq, int meanq,
+                     int maxunk, uint8_t *__restrict__ code) {
+    int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    int64_t b = offs[r];
+    int len = (int)(offs[r + 1] - b);
+    if (len < L) { if (lane == 0) code[r] = 1; return; }
+    int nN = 0, sum = 0, mn = 1 << 30;
+    for (int i = lane; i < L; i += 32) {
+        nN += (bases[b + i] == 'N');
+        if (quals) { int q = (int)quals[b + i] - qoff; sum += q; mn = q < mn ? q : mn; }
+    }
+    for (int s = 16; s; s >>= 1) {
+        nN += __shfl_xor_sync(0xffffffffu, nN, s);
+        sum += __shfl_xor_sync(0xffffffffu, sum, s);
+        int o = __shfl_xor_sync(0xffffffffu, mn, s);
+        mn = o < mn ? o : mn;
+    }
+    if (lane == 0) {
+        int c = 0;
+        if (100 * nN > maxunk * L) c = 2;
+        else if (quals && (sum < meanq * L || mn < minq)) c = 2;
+        code[r] = (uint8_t)c;
+    }
+}
+
+__global__ void k_keep_flags(const uint8_t *__restrict__ code, int64_t n, int32_t *__restrict__ flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = code[i] == 0;
+}
+__global__ void k_scatter_kept(const uint8_t *__restrict__ code, const int32_t *__restrict__ pos, int64_t n,
+                               int32_t *__restrict__ kept) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && code[i] == 0) kept[pos[i]] = (int32_t)i;
+}
+// counts of codes 0..3 among reads [0, upto)
+__global__ void k_count_codes(const uint8_t *__restrict__ code, int64_t upto, unsigned long long *__restrict__ cnt) {
+    __shared__ unsigned int s[4];
+    if (threadIdx.x < 4) s[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < upto; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&s[code[i] & 3], 1u);
+    __syncthreads();
+    if (threadIdx.x < 4 && s[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], (unsigned long long)s[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: seeds + ungapped extension.  One thread per (kept read, frame).
+// ------------------------------------------------------------------------------------------------
+struct SeedArgs {
+    const uint8_t *bases;
+    const int64_t *offs;
+    const int32_t *kept;
+    int64_t n_search;
+    int L;
+    int thr_report;                // ungapped HSPs at or above this raw score survive
+    DevDB db;
+    Surv *surv;
+    unsigned long long *n_surv;
+    unsigned long long cap_surv;
+};
+
+template <int NT>
+__device__ __forceinline__ void try_seed(const SeedArgs &A, const uint8_t *s_aa, int tid, int m, int read,
+                                         int frame, int p, int i, uint32_t posting) {
+    const int s = (int)((posting & 0x7fffffffu) >> 11), j = (int)(posting & 0x7ff);
+    const int32_t o = A.db.off[s];
+    const int n = A.db.off[s + 1] - o;
+    const uint8_t *__restrict__ t = A.db.res + o;
+    if (p == 0) {                  // exact words: left-maximal only (ExtendSeq2Set 0x4140c0-0x414113)
+        if (i > 0 && j > 0 && red_eq(FR(i - 1), t[j - 1])) return;
+    } else {                       // one-substitution words: the replaced letter differs by construction;
+        int w = p + 2;             // keep one window per substituted position (all give the same seed)
+        if (red_of(FR(i + w)) == red_of(t[j + w])) return;
+        if (w >= 4 && i + 10 < m && j + 10 < n && red_eq(FR(i + 10), t[j + 10])) return;
+    }
+    // grow the word to the maximal murphy10-identical stretch (right, then left)
+    int qb = i, sb = j, len = p == 0 ? 9 : 10;
+    while (qb + len < m && sb + len < n && red_eq(FR(qb + len), t[sb + len])) ++len;
+    while (qb > 0 && sb > 0 && red_eq(FR(qb - 1), t[sb - 1])) { --qb; --sb; ++len; }
+    int score0 = 0, id0 = 0;
+    for (int k = 0; k < len; ++k) {
+        int a = FR(qb + k), b = t[sb + k];
+        score0 += c_blosum[a * 32 + b];
+        id0 += (a == b && a < 20);
+    }
+    if (score0 < SEED_MIN_SCORE || id0 < SEED_MIN_IDENT) return;
+    // AlignFwd / AlignBwd: both walks start from the seed score; stop after a residue that leaves the
+    // running score below -20 or at least 9 (> 8.94) under the best so far
+    int fe = 0, fid = 0, gf = 0, be = 0, bid = 0, gb = 0;
+    {
+        int nq = m - qb - len, nt = n - sb - len;
+        if (nq > 0 && nt > 0) {
+            int best = score0, cur = score0, k = 0, id = 0;
+            for (;;) {
+                int a = FR(qb + len + k), b = t[sb + len + k];
+                cur += c_blosum[a * 32 + b];
+                id += (a == b && a < 20);
+                ++k;
+                if (cur > best) { best = cur; fe = k; fid = id; }
+                if (k >= nt || k >= nq) break;
+                if (cur < UNGAP_FLOOR || cur <= best - 9) break;
+            }
+            gf = best - score0;
+        }
+    }
+    {
+        int nq = qb, nt = sb;
+        if (nq > 0 && nt > 0) {
+            int best = score0, cur = score0, k = 0, id = 0;
+            for (;;) {
+                int a = FR(qb - 1 - k), b = t[sb - 1 - k];
+                cur += c_blosum[a * 32 + b];
+                id += (a == b && a < 20);
+                ++k;
+                if (cur > best) { best = cur; be = k; bid = id; }
+                if (k >= nt || k >= nq) break;
+                if (cur < UNGAP_FLOOR || cur <= best - 9) break;
+            }
+            gb = best - score0;
+        }
+    }
+    int total = score0 + gf + gb;
+    if (total < A.thr_report) return;
+    unsigned long long idx = atomicAdd(A.n_surv, 1ull);
+    if (idx >= A.cap_surv) return;
+    Surv v;
+    v.read = read; v.subject = (uint16_t)s; v.frame = (uint8_t)frame;
+    v.q0 = (uint8_t)(qb - be); v.q1 = (uint8_t)(qb + len + fe - 1);
+    v.ident = (uint8_t)(id0 + fid + bid); v.t0 = (uint16_t)(sb - be);
+    v.score = (int16_t)total; v.pad = 0;
+    A.surv[idx] = v;
+}
+
+template <int NT>
+__device__ __forceinline__ void probe(const SeedArgs &A, const uint8_t *s_aa, int tid, int m, int read, int frame,
+                                      int p, int i, uint32_t code) {
+    const uint32_t *__restrict__ hk = A.db.hkey[p];
+    uint32_t slot = (code * 2654435761u) >> A.db.hshift[p];
+    for (;;) {
+        uint32_t k = __ldg(hk + slot);
+        if (k == 0xffffffffu) return;
+        if (k == code) break;
+        slot = (slot + 1) & A.db.hmask[p];
+    }
+    uint32_t pi = __ldg(A.db.hval[p] + slot);
+    for (;;) {
+        uint32_t posting = __ldg(A.db.post + pi);
+        try_seed<NT>(A, s_aa, tid, m, read, frame, p, i, posting);
+        if (posting & 0x80000000u) break;
+        ++pi;
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_seed(SeedArgs A) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    double *s_ent = reinterpret_cast<double *>(smem);
+    uint8_t *s_aa = smem + 13 * 13 * sizeof(double);
+    const int tid = threadIdx.x;
+    for (int k = tid; k < 13 * 13; k += NT) s_ent[k] = c_ent[k];
+    __syncthreads();
+    int64_t g = (int64_t)blockIdx.x * NT + tid;
+    int64_t ki = g / 6;
+    if (ki >= A.n_search) return;
+    const int frame = (int)(g - ki * 6);
+    const int read = A.kept[ki];
+    const uint8_t *rd = A.bases + A.offs[read];
+    const int m = build_frame<NT>(s_aa, tid, rd, A.L, frame, s_ent);
+    if (m < 9) return;
+    // reduced letters of the 10-window [i, i+10) as nibbles (letter k at bits 4k); 15 past the end
+    unsigned long long win = 0;
+    for (int k = 0; k < 10; ++k) win |= (unsigned long long)(k < m ? red_of(FR(k)) : 15) << (4 * k);
+    for (int i = 0; i + 9 <= m; ++i) {
+        // invalid letters are 10 (stop / mask) or 15 (past the end): bit 3 and bit 1 set, or 15
+        unsigned long long w = win;
+        int bad9 = 0, bad10;
+        uint32_t c9 = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { uint32_t r = (uint32_t)(w >> (4 * k)) & 15; bad9 |= (r >= 10); c9 = c9 * 10 + r; }
+        uint32_t r9 = (uint32_t)(w >> 36) & 15;
+        bad10 = bad9 | (r9 >= 10);
+        if (!bad9) probe<NT>(A, s_aa, tid, m, read, frame, 0, i, c9);
+        if (!bad10) {
+#pragma unroll
+            for (int p = 1; p < N_PAT; ++p) {
+                const int wl = p + 2;
+                uint32_t c = 0;
+#pragma unroll
+                for (int k = 0; k < 10; ++k) if (k != wl) c = c * 10 + ((uint32_t)(w >> (4 * k)) & 15);
+                probe<NT>(A, s_aa, tid, m, read, frame, p, i, c);
+            }
+        }
+        int nx = i + 10;
+        win = (win >> 4) | ((unsigned long long)(nx < m ? red_of(FR(nx)) : 15) << 36);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: gapped X-drop extension (AlignGapped 0x40a550) with the alignment statistics carried forward.
+// The binary stores three trace matrices and walks back from the best cell; every choice it makes is
+// local to a cell (diagonal unless E is strictly larger, then F only if strictly larger; a gap opens
+// rather than extends on ties), so carrying (identities, columns, gap columns, gap runs) along the same
+// choices gives the same numbers without storing a matrix.  The live column window [cs, ce] and its
+// pruning follow the binary exactly because they decide which cells exist.
+// stats word: ident bits 0-7, aln 8-16, gap columns 17-25, gap runs 26-31
+// ------------------------------------------------------------------------------------------------
+#define ST_ALN 0x100u
+#define ST_GAPCOL 0x20000u
+#define ST_GAPRUN 0x4000000u
+constexpr int GROW = MAX_FRAME + GAP_SLACK + 2;
+
+struct GExt { int gain, eq, et; uint32_t st; int cells; };
+
+template <int NT>
+__device__ void gapped_xdrop(const uint8_t *s_aa, int tid, int q_first, int qstep, const uint8_t *__restrict__ t,
+                             int tstep, int nQ, int nD, GExt &g) {
+    g.gain = 0; g.eq = 0; g.et = 0; g.st = 0; g.cells = 0;
+    const int GI = GAP_OPEN, GE = GAP_EXT, GIE = GAP_OPEN + GAP_EXT;
+    const int limit = 15;                      // (int)((26.98 - 11) / 1)
+    int H[GROW], F[GROW];
+    uint32_t HS[GROW], FS[GROW];
+    H[0] = 0; F[0] = -GI; HS[0] = 0; FS[0] = 0;
+    {
+        int r = -GI;
+        for (int j = 1; j <= limit && j <= nD; ++j) {
+            r -= GE; H[j] = r; F[j] = r - GI;
+            HS[j] = (uint32_t)j * (ST_ALN + ST_GAPCOL) + ST_GAPRUN; FS[j] = HS[j];
+        }
+    }
+    int cs = 1, ce = limit, best = 0, bcol = 0, brow = 0, cells = 0;
+    uint32_t bst = 0;
+    for (int i = 1; i <= nQ; ++i) {
+        int diag = H[cs - 1];
+        uint32_t dst = HS[cs - 1];
+        // boundary cell (i, cs-1): value max(H-12, F-1), always traced as a vertical gap column
+        uint32_t bs = (i == 1 ? HS[cs - 1] + ST_GAPRUN : FS[cs - 1]) + ST_ALN + ST_GAPCOL;
+        int v = H[cs - 1] - GIE, f1 = F[cs - 1] - GE;
+        if (v < f1) v = f1;
+        F[cs - 1] = v; H[cs - 1] = v; HS[cs - 1] = bs; FS[cs - 1] = bs;
+        int E = v - GI, hl = v, j = cs;
+        uint32_t ES = bs, hls = bs;
+        bool skip_tail = false;
+        const int qa = FR(q_first + (i - 1) * qstep);
+        if (!(cs > ce || cs > nD)) {
+            for (;;) {
+                ++cells;
+                int a = hl - GIE, b = E - GE;
+                if (a >= b) { E = a; ES = hls + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { E = b; ES += ST_ALN + ST_GAPCOL; }
+                int c = H[j] - GIE, d = F[j] - GE, Fv;
+                uint32_t FSv;
+                if (c >= d) { Fv = c; FSv = HS[j] + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { Fv = d; FSv = FS[j] + ST_ALN + ST_GAPCOL; }
+                const int tb = t[(j - 1) * tstep];
+                int h = diag + c_blosum[qa * 32 + tb];
+                uint32_t hs = dst + ST_ALN + (uint32_t)(qa == tb && qa < 20);
+                if (E > h) { h = E; hs = ES; }
+                if (h < Fv) { h = Fv; hs = FSv; }
+                diag = H[j]; dst = HS[j];
+                H[j] = h; HS[j] = hs; F[j] = Fv; FS[j] = FSv; hl = h; hls = hs;
+                if (h > best) { best = h; bcol = j; brow = i; bst = hs; }
+                else if (h <= best - 27 && j > bcol) {       // h < best - 26.98
+                    if (j >= ce) { ce = j; break; }
+                    ce = j; skip_tail = true; break;
+                }
+                ++j;
+                if (j > nD || j > ce) break;
+            }
+        }
+        if (!skip_tail) {
+            for (int jj = ce + 1; jj <= nD; ++jj) {          // run on along the row by horizontal gaps
+                ++cells;
+                int a = hl - GIE, b = E - GE;
+                if (a > b) { E = a; ES = hls + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { E = b; ES += ST_ALN + ST_GAPCOL; }
+                H[jj] = E; HS[jj] = ES; F[jj] = E - GI; FS[jj] = ES; hl = E; hls = ES;
+                if (E > best) { best = E; bcol = jj; brow = i; bst = ES; }
+                else if (E <= best - 27) { ce = jj; break; }
+            }
+            if (cs <= bcol) {                                // drop dead cells on the left
+                int thr = best - 27;
+                if (H[bcol] <= thr) cs = bcol;
+                else for (int c = bcol - 1; c >= cs; --c) if (H[c] <= thr) { cs = c; break; }
+            }
+        }
+        if (!(cs < ce)) break;
+    }
+    g.cells = cells;
+    if (best > 0) { g.gain = best; g.eq = brow; g.et = bcol; g.st = bst; }
+}
+
+struct GapArgs {
+    const uint8_t *bases;
+    const int64_t *offs;
+    int L;
+    DevDB db;
+    const Surv *surv;
+    int64_t n_surv;
+    mcx_hit *hsp;
+    SortKey *keys;
+    int32_t *idx;
+    unsigned long long *counters;  // [0] gapped extensions, [1] cells
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_gapped(GapArgs A) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    double *s_ent = reinterpret_cast<double *>(smem);
+    uint8_t *s_aa = smem + 13 * 13 * sizeof(double);
+    const int tid = threadIdx.x;
+    for (int k = tid; k < 13 * 13; k += NT) s_ent[k] = c_ent[k];
+    __syncthreads();
+    int64_t g = (int64_t)blockIdx.x * NT + tid;
+    if (g >= A.n_surv) return;
+    const Surv v = A.surv[g];
+    const uint8_t *rd = A.bases + A.offs[v.read];
+    const int m = build_frame<NT>(s_aa, tid, rd, A.L, v.frame, s_ent);
+    const int32_t o = A.db.off[v.subject];
+    const int n = A.db.off[v.subject + 1] - o;
+    const uint8_t *t = A.db.res + o;
+    int q0 = v.q0, q1 = v.q1, t0 = v.t0, t1 = v.t0 + (v.q1 - v.q0);
+    int score = v.score, ident = v.ident, aln = q1 - q0 + 1, gapcols = 0, gapo = 0;
+    if (score >= 49) {                                       // >= 48.17: gapped extension from both ends
+        unsigned long long ng = 0, nc = 0;
+        int ql = m - (q1 + 1), tl = n - (t1 + 1);
+        if (ql > 2 && tl > 2) {
+            if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
+            GExt e; gapped_xdrop<NT>(s_aa, tid, q1 + 1, 1, t + t1 + 1, 1, ql, tl, e);
+            ++ng; nc += e.cells;
+            if (e.gain > 0) {
+                score += e.gain; q1 += e.eq; t1 += e.et;
+                ident += e.st & 0xff; aln += (e.st >> 8) & 0x1ff; gapcols += (e.st >> 17) & 0x1ff; gapo += e.st >> 26;
+            }
+        }
+        ql = q0; tl = t0;
+        if (ql > 2 && tl > 2) {
+            if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
+            GExt e; gapped_xdrop<NT>(s_aa, tid, q0 - 1, -1, t + t0 - 1, -1, ql, tl, e);
+            ++ng; nc += e.cells;
+            if (e.gain > 0) {
+                score += e.gain; q0 -= e.eq; t0 -= e.et;
+                ident += e.st & 0xff; aln += (e.st >> 8) & 0x1ff; gapcols += (e.st >> 17) & 0x1ff; gapo += e.st >> 26;
+            }
+        }
+        if (ng) { atomicAdd(&A.counters[0], ng); atomicAdd(&A.counters[1], nc); }
+    }
+    mcx_hit h;
+    h.read = v.read; h.subject = v.subject; h.frame = v.frame; h.score = score;
+    h.aln = aln; h.ident = ident; h.mism = aln - ident - gapcols; h.gapo = gapo;
+    h.q0 = q0; h.q1 = q1; h.t0 = t0; h.t1 = t1;
+    A.hsp[g] = h;
+    SortKey k;
+    k.k1 = ((unsigned long long)(uint32_t)v.read << 37) | ((unsigned long long)v.subject << 22) |
+           ((unsigned long long)(2047 - score) << 11) | ((unsigned long long)v.frame << 8) | (unsigned long long)q0;
+    k.k2 = ((unsigned long long)q1 << 48) | ((unsigned long long)t0 << 37) | ((unsigned long long)t1 << 26) |
+           ((unsigned long long)aln << 17) | ((unsigned long long)ident << 8);
+    A.keys[g] = k;
+    A.idx[g] = (int32_t)g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: per read -- HSP de-duplication, cutoffs, best hit, per-family sums.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dna_coords(int L, int frame, int q0, int q1, int &qs, int &qe) {
+    int a0 = q0 + 1, a1 = q1 + 1;
+    if (frame < 3) { qs = 3 * (a0 - 1) + frame + 1; qe = 3 * a1 + frame; }
+    else { int o = frame - 3; qs = L - o - 3 * (a0 - 1); qe = L - o - 3 * a1 + 1; }
+}
+
+// mc.py:400-418 operation for operation in IEEE double (compiled with -fmad=false)
+__device__ double alignment_coverage(int L, int qs_, int qe_, int t0, int t1, int aln_, int tlen) {
+    double query_len = (double)L / 3;
+    double qs = (double)(qs_ < qe_ ? qs_ : qe_), qe = (double)(qs_ < qe_ ? qe_ : qs_);
+    int fmi = (qs_ < qe_ ? qs_ : qe_) % 3;
+    double frame = (fmi == 1 || fmi == 2) ? (double)fmi : 3.0;
+    double query_start = (qs + 3 - frame) / 3;
+    double query_stop = (qe + 1 - frame) / 3;
+    double a = (double)t0 + 1, b = (double)t1 + 1;
+    double target_start = a < b ? a : b, target_stop = a < b ? b : a;
+    double x = (query_start - 1 < target_start - 1) ? query_start - 1 : target_start - 1;
+    double y = (double)aln_;
+    double tl = (double)tlen;
+    double z = (query_len - query_stop < tl - target_stop) ? query_len - query_stop : tl - target_stop;
+    double maxaln = x + y + z;
+    return (double)aln_ / maxaln;
+}
+
+struct ClsArgs {
+    const mcx_hit *hsp;
+    const int32_t *idx;            // sorted order
+    int64_t n;
+    int L;
+    int min_report;
+    DevDB db;
+    uint8_t *keep;                 // per hsp: 1 = reported line
+    int32_t *best_subject;         // per pushed read
+    unsigned long long *acc;       // [0] reads_with_hits [1] classified [2] n_hsp, then fam_hits[30], fam_aln[30]
+    unsigned long long *aln_by_len;
+};
+
+__global__ void k_classify(ClsArgs A) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.n) return;
+    const int read = A.hsp[A.idx[p]].read;
+    if (p > 0 && A.hsp[A.idx[p - 1]].read == read) return;   // not the first HSP of its read
+    int cur_subj = -1, nk = 0, nrep = 0, best = -1, best_score = -1;
+    int kqs[8], kqe[8], kt0[8], kt1[8];
+    for (int64_t e = p; e < A.n; ++e) {
+        const int id = A.idx[e];
+        const mcx_hit h = A.hsp[id];
+        if (h.read != read) break;
+        if (h.subject != cur_subj) { cur_subj = h.subject; nk = 0; }
+        int qs, qe;
+        dna_coords(A.L, h.frame, h.q0, h.q1, qs, qe);
+        int lo = qs < qe ? qs : qe, hi = qs < qe ? qe : qs;
+        bool keep = h.score >= A.min_report;
+        for (int k = 0; k < nk && keep; ++k)
+            if (!(hi < kqs[k] || kqe[k] < lo) || !(h.t1 < kt0[k] || kt1[k] < h.t0)) keep = false;
+        A.keep[id] = keep;
+        if (!keep) continue;
+        if (nk < 8) { kqs[nk] = lo; kqe[nk] = hi; kt0[nk] = h.t0; kt1[nk] = h.t1; ++nk; }
+        ++nrep;
+        const int fam = A.db.fam[h.subject];
+        const int slen = A.db.off[h.subject + 1] - A.db.off[h.subject];
+        const mcx_cutoff c = c_cut[fam];
+        if (alignment_coverage(A.L, qs, qe, h.t0, h.t1, h.aln, slen) < c.min_cov) continue;
+        if (h.score < c.min_raw) continue;
+        if ((double)(100 * h.ident) > c.max_aaid * (double)h.aln) continue;
+        if (best < 0 || best_score < h.score) { best = id; best_score = h.score; }
+    }
+    if (nrep) { atomicAdd(&A.acc[0], 1ull); atomicAdd(&A.acc[2], (unsigned long long)nrep); }
+    if (best >= 0) {
+        const mcx_hit h = A.hsp[best];
+        const int fam = A.db.fam[h.subject];
+        const int slen = A.db.off[h.subject + 1] - A.db.off[h.subject];
+        atomicAdd(&A.acc[1], 1ull);
+        atomicAdd(&A.acc[3 + fam], 1ull);
+        atomicAdd(&A.acc[3 + MCX_N_FAM + fam], (unsigned long long)h.aln);
+        atomicAdd(&A.aln_by_len[fam * MCX_LEN_BINS + slen], (unsigned long long)h.aln);
+        A.best_subject[read] = h.subject;
+    }
+}
+
+__global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_gather_hits(const mcx_hit *__restrict__ hsp, const int32_t *__restrict__ idx,
+                              const uint8_t *__restrict__ keep, const int32_t *__restrict__ pos, int64_t n,
+                              mcx_hit *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && keep[idx[i]]) out[pos[i]] = hsp[idx[i]];
+}
+__global__ void k_keep_sorted(const int32_t *__restrict__ idx, const uint8_t *__restrict__ keep, int64_t n,
+                              int32_t *__restrict__ flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = keep[idx[i]];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct mcx_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    mcx_params par{};
+    bool have_par = false;
+    // database
+    DevDB db{};
+    std::vector<void *> db_allocs;
+    int n_subj = 0;
+    // reads
+    int64_t n_reads = 0, total_bytes = 0;
+    uint8_t *d_bases = nullptr, *d_quals = nullptr;
+    int64_t *d_offs = nullptr;
+    bool own_reads = false;
+    int64_t cap_bases = 0, cap_quals = 0, cap_offs = 0;
+    uint8_t *d_code = nullptr;
+    int32_t *d_flag = nullptr, *d_pos = nullptr, *d_kept = nullptr;
+    int64_t cap_reads = 0, cap_flag = 0, cap_pos = 0, cap_kept = 0;
+    int64_t kept = 0;
+    mcx_qc qc{};
+    bool pushed = false, searched = false;
+    // search buffers
+    Surv *d_surv = nullptr;
+    mcx_hit *d_hsp = nullptr, *d_hits_out = nullptr;
+    SortKey *d_keys = nullptr;
+    int32_t *d_idx = nullptr, *d_best = nullptr, *d_hflag = nullptr, *d_hpos = nullptr;
+    uint8_t *d_keep = nullptr;
+    int64_t cap_surv = 0, cap_best = 0;
+    unsigned long long *d_cnt = nullptr;     // 16 scalar counters
+    unsigned long long *d_acc = nullptr;     // 3 + 60
+    unsigned long long *d_abl = nullptr;     // 30 * 1280
+    void *d_temp = nullptr;
+    size_t temp_bytes = 0;
+    int64_t n_hsp_sorted = 0;
+    mcx_result res{};
+    float ms[8] = {0};
+    int64_t launches = 0;
+    cudaEvent_t ev[10] = {nullptr};
+};
+
+static thread_local std::string g_err;
+
+static int fail(mcx_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, MCX_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+    } while (0)
+
+template <typename T>
+static cudaError_t dev_alloc(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T) ? n * sizeof(T) : 1); }
+
+template <typename T>
+static int ensure(mcx_ctx *ctx, T **p, int64_t *cap, int64_t need) {
+    if (*cap >= need && *p) return MCX_OK;
+    if (*p) CK(cudaFree(*p));
+    *p = nullptr;
+    int64_t c = need + need / 8 + 16;
+    CK(dev_alloc(p, (size_t)c));
+    *cap = c;
+    return MCX_OK;
+}
+
+static int ensure_temp(mcx_ctx *ctx, size_t bytes) {
+    if (ctx->temp_bytes >= bytes && ctx->d_temp) return MCX_OK;
+    if (ctx->d_temp) CK(cudaFree(ctx->d_temp));
+    ctx->d_temp = nullptr;
+    CK(cudaMalloc(&ctx->d_temp, bytes + bytes / 8 + 256));
+    ctx->temp_bytes = bytes + bytes / 8 + 256;
+    return MCX_OK;
+}
+
+extern "C" const char *mcx_version(void) { return "mcx 0.1 (sm_100a)"; }
+extern "C" const char *mcx_last_error(mcx_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+// seed index: one open-addressing table per word pattern over the murphy10 letters of the database
+static int build_index(mcx_ctx *ctx, const mcx_db *db) {
+    const int ns = db->n_subj;
+    const int64_t nres = db->off[ns];
+    std::vector<uint8_t> red((size_t)nres);
+    for (int64_t g = 0; g < nres; ++g) red[(size_t)g] = db->res[g] < 20 ? MURPHY10[db->res[g]] : 10;
+    std::vector<uint32_t> post_all;
+    post_all.reserve((size_t)nres * N_PAT);
+    for (int p = 0; p < N_PAT; ++p) {
+        std::vector<unsigned long long> ent;
+        ent.reserve((size_t)nres);
+        for (int s = 0; s < ns; ++s) {
+            const int n = db->off[s + 1] - db->off[s];
+            if (n >= 2048) return fail(ctx, MCX_EINVAL, "subject longer than 2047 residues");
+            const uint8_t *r = red.data() + db->off[s];
+            for (int j = 0; j + PAT_LEN[p] <= n; ++j) {
+                uint32_t c = 0; bool ok = true;
+                for (int k = 0; k < PAT_LEN[p]; ++k) {
+                    if (k == PAT_WILD[p]) continue;
+                    if (r[j + k] >= 10) { ok = false; break; }
+                    c = c * 10 + r[j + k];
+                }
+                if (ok) ent.push_back(((unsigned long long)c << 32) | ((uint32_t)s << 11) | (uint32_t)j);
+            }
+        }
+        std::sort(ent.begin(), ent.end());
+        size_t distinct = 0;
+        for (size_t k = 0; k < ent.size(); ++k) distinct += (k == 0 || (ent[k] >> 32) != (ent[k - 1] >> 32));
+        uint32_t size = 1024; int bits = 10;
+        while (size < distinct * 2) { size <<= 1; ++bits; }
+        std::vector<uint32_t> hk(size, 0xffffffffu), hv(size, 0);
+        const uint32_t base = (uint32_t)post_all.size();
+        for (size_t k = 0; k < ent.size(); ++k) {
+            const uint32_t code = (uint32_t)(ent[k] >> 32);
+            const bool first = k == 0 || (ent[k - 1] >> 32) != code;
+            const bool last = k + 1 == ent.size() || (ent[k + 1] >> 32) != code;
+            post_all.push_back((uint32_t)(ent[k] & 0x7fffffffu) | (last ? 0x80000000u : 0u));
+            if (first) {
+                uint32_t slot = (code * 2654435761u) >> (32 - bits);
+                while (hk[slot] != 0xffffffffu) slot = (slot + 1) & (size - 1);
+                hk[slot] = code; hv[slot] = base + (uint32_t)(k);
+            }
+        }
+        uint32_t *dk = nullptr, *dv = nullptr;
+        CK(dev_alloc(&dk, size)); ctx->db_allocs.push_back(dk);
+        CK(dev_alloc(&dv, size)); ctx->db_allocs.push_back(dv);
+        CK(cudaMemcpy(dk, hk.data(), size * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dv, hv.data(), size * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        ctx->db.hkey[p] = dk; ctx->db.hval[p] = dv; ctx->db.hmask[p] = size - 1; ctx->db.hshift[p] = 32 - bits;
+    }
+    uint32_t *dp = nullptr;
+    CK(dev_alloc(&dp, post_all.size())); ctx->db_allocs.push_back(dp);
+    CK(cudaMemcpy(dp, post_all.data(), post_all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    ctx->db.post = dp;
+    return MCX_OK;
+}
+
+static int upload_tables(mcx_ctx *ctx) {
+    double lnfac[256], ln20[256], ent[13 * 13];
+    for (int i = 0; i < 256; ++i) { lnfac[i] = lgamma((double)i + 1.0); ln20[i] = (double)i * log(20.0); }
+    lnfac[0] = 0.0; lnfac[1] = 0.0;
+    for (int t = 0; t <= SEG_WINDOW; ++t)
+        for (int c = 0; c <= SEG_WINDOW; ++c)
+            ent[t * 13 + c] = (c == 0 || t == 0 || c > t) ? 0.0 : -((double)c / (double)t) * (log((double)c / (double)t) / log(2.0));
+    int8_t bl[21 * 32];
+    for (int a = 0; a < 21; ++a)
+        for (int b = 0; b < 32; ++b) bl[a * 32 + b] = (a < 20 && b < 20) ? BLOSUM62[a][b] : (int8_t)-5;
+    uint8_t codon[64];
+    for (int i = 0; i < 64; ++i) {
+        const char *p = strchr(AA_ORDER, CODON_AA[i]);
+        codon[i] = (p && CODON_AA[i] != '.') ? (uint8_t)(p - AA_ORDER) : (uint8_t)AA_STOP;
+    }
+    CK(cudaMemcpyToSymbol(c_lnfac, lnfac, sizeof lnfac));
+    CK(cudaMemcpyToSymbol(c_ln20, ln20, sizeof ln20));
+    CK(cudaMemcpyToSymbol(c_ent, ent, sizeof ent));
+    CK(cudaMemcpyToSymbol(c_blosum, bl, sizeof bl));
+    CK(cudaMemcpyToSymbol(c_codon, codon, sizeof codon));
+    return MCX_OK;
+}
+
+extern "C" int mcx_create(mcx_ctx **out, const mcx_db *db, int device) {
+    if (!out || !db || !db->off || !db->res || !db->fam || db->n_subj <= 0 || db->n_subj >= 32768)
+        return fail(nullptr, MCX_EINVAL, "mcx_create: bad database descriptor");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, MCX_ECUDA, std::string("mcx_create: no CUDA device (") + cudaGetErrorString(e) +
+                                            "); libmcx has no CPU path");
+    if (device < 0 || device >= ndev) return fail(nullptr, MCX_EINVAL, "mcx_create: device index out of range");
+    mcx_ctx *ctx = new mcx_ctx();
+    ctx->device = device;
+    int rc = MCX_OK;
+    auto body = [&]() -> int {
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        for (auto &ev : ctx->ev) CK(cudaEventCreate(&ev));
+        const int ns = db->n_subj;
+        const int64_t nres = db->off[ns];
+        int32_t *doff = nullptr; uint8_t *dres = nullptr, *dfam = nullptr;
+        CK(dev_alloc(&doff, (size_t)ns + 1)); ctx->db_allocs.push_back(doff);
+        CK(dev_alloc(&dres, (size_t)nres)); ctx->db_allocs.push_back(dres);
+        CK(dev_alloc(&dfam, (size_t)ns)); ctx->db_allocs.push_back(dfam);
+        CK(cudaMemcpy(doff, db->off, ((size_t)ns + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dres, db->res, (size_t)nres, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dfam, db->fam, (size_t)ns, cudaMemcpyHostToDevice));
+        ctx->db.n_subj = ns; ctx->db.off = doff; ctx->db.res = dres; ctx->db.fam = dfam;
+        ctx->n_subj = ns;
+        int r = upload_tables(ctx); if (r) return r;
+        r = build_index(ctx, db); if (r) return r;
+        CK(dev_alloc(&ctx->d_cnt, 16));
+        CK(dev_alloc(&ctx->d_acc, 3 + 2 * MCX_N_FAM));
+        CK(dev_alloc(&ctx->d_abl, (size_t)MCX_N_FAM * MCX_LEN_BINS));
+        return MCX_OK;
+    };
+    rc = body();
+    if (rc != MCX_OK) { g_err = ctx->err; mcx_destroy(ctx); return rc; }
+    *out = ctx;
+    return MCX_OK;
+}
+
+extern "C" void mcx_destroy(mcx_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (void *p : ctx->db_allocs) cudaFree(p);
+    if (ctx->own_reads) { cudaFree(ctx->d_bases); cudaFree(ctx->d_quals); cudaFree(ctx->d_offs); }
+    void *bufs[] = {ctx->d_code, ctx->d_flag, ctx->d_pos, ctx->d_kept, ctx->d_surv, ctx->d_hsp, ctx->d_hits_out,
+                    ctx->d_keys, ctx->d_idx, ctx->d_best, ctx->d_hflag, ctx->d_hpos, ctx->d_keep, ctx->d_cnt,
+                    ctx->d_acc, ctx->d_abl, ctx->d_temp};
+    for (void *p : bufs) if (p) cudaFree(p);
+    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int mcx_set_params(mcx_ctx *ctx, const mcx_params *p) {
+    if (!ctx || !p) return fail(ctx, MCX_EINVAL, "mcx_set_params: null argument");
+    if (p->read_length < 27 || p->read_length > 3 * MAX_FRAME)
+        return fail(ctx, MCX_EINVAL, "mcx_set_params: read_length must be within 27..504");
+    if (p->filter_dups)
+        return fail(ctx, MCX_EINVAL, "mcx_set_params: filter_dups (-d) is not implemented on the device yet");
+    for (int f = 0; f < MCX_N_FAM; ++f)
+        if (p->cut[f].stat < 0 || p->cut[f].stat > 2) return fail(ctx, MCX_EINVAL, "mcx_set_params: bad aln_stat");
+    CK(cudaSetDevice(ctx->device));
+    ctx->par = *p;
+    ctx->have_par = true;
+    CK(cudaMemcpyToSymbol(c_cut, p->cut, sizeof(mcx_cutoff) * MCX_N_FAM));
+    return MCX_OK;
+}
+
+static int run_qc(mcx_ctx *ctx) {
+    const int64_t n = ctx->n_reads;
+    const mcx_params &P = ctx->par;
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_code, &ctx->cap_reads, n)) != MCX_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_flag, &ctx->cap_flag, n + 1)) != MCX_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_pos, &ctx->cap_pos, n + 1)) != MCX_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_kept, &ctx->cap_kept, n + 1)) != MCX_OK) return rc;
+    CK(cudaEventRecord(ctx->ev[1], st));
+    if (n > 0) {
+        const int NT = 256;
+        int64_t blocks = (n * 32 + NT - 1) / NT;
+        k_qc<<<(unsigned)blocks, NT, 0, st>>>(ctx->d_bases, P.has_quality ? ctx->d_quals : nullptr, ctx->d_offs, n,
+                                             P.read_length, P.quality_offset, P.min_quality, P.mean_quality,
+                                             P.max_unknown, ctx->d_code);
+        k_keep_flags<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_code, n, ctx->d_flag);
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->d_flag, ctx->d_pos, (int)(n + 1), st);
+        if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
+        CK(cudaMemsetAsync(ctx->d_flag + n, 0, sizeof(int32_t), st));
+        cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, ctx->d_flag, ctx->d_pos, (int)(n + 1), st);
+        k_scatter_kept<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_code, ctx->d_pos, n, ctx->d_kept);
+        CK(cudaMemsetAsync(ctx->d_cnt, 0, 16 * sizeof(unsigned long long), st));
+        k_count_codes<<<592, 256, 0, st>>>(ctx->d_code, n, ctx->d_cnt);
+        ctx->launches += 6;
+    }
+    CK(cudaEventRecord(ctx->ev[2], st));
+    unsigned long long cnt[4] = {0, 0, 0, 0};
+    if (n > 0) CK(cudaMemcpyAsync(cnt, ctx->d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    ctx->qc.n_reads = n; ctx->qc.kept = (int64_t)cnt[0]; ctx->qc.too_short = (int64_t)cnt[1];
+    ctx->qc.low_qual = (int64_t)cnt[2]; ctx->qc.dups = (int64_t)cnt[3];
+    ctx->kept = (int64_t)cnt[0];
+    CK(cudaEventElapsedTime(&ctx->ms[1], ctx->ev[1], ctx->ev[2]));
+    ctx->pushed = true; ctx->searched = false;
+    return MCX_OK;
+}
+
+extern "C" int mcx_push_reads(mcx_ctx *ctx, const uint8_t *bases, const uint8_t *quals, const int64_t *offsets,
+                              int64_t n) {
+    if (!ctx || !offsets || n < 0 || (n > 0 && !bases)) return fail(ctx, MCX_EINVAL, "mcx_push_reads: bad argument");
+    if (!ctx->have_par) return fail(ctx, MCX_ESTATE, "mcx_push_reads: call mcx_set_params first");
+    if (n >= (1ll << 27)) return fail(ctx, MCX_EINVAL, "mcx_push_reads: at most 2^27 reads per call");
+    if (ctx->par.has_quality && !quals && n > 0) return fail(ctx, MCX_EINVAL, "mcx_push_reads: FASTQ parameters but no qualities");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->own_reads) { ctx->d_bases = nullptr; ctx->d_quals = nullptr; ctx->d_offs = nullptr; ctx->cap_bases = ctx->cap_quals = ctx->cap_offs = 0; }
+    ctx->own_reads = true;
+    const int64_t total = n > 0 ? offsets[n] : 0;
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_bases, &ctx->cap_bases, total + 16)) != MCX_OK) return rc;
+    if (quals && (rc = ensure(ctx, &ctx->d_quals, &ctx->cap_quals, total + 16)) != MCX_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_offs, &ctx->cap_offs, n + 1)) != MCX_OK) return rc;
+    ctx->launches = 0;
+    memset(ctx->ms, 0, sizeof ctx->ms);
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (total > 0) CK(cudaMemcpyAsync(ctx->d_bases, bases, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+    if (quals && total > 0) CK(cudaMemcpyAsync(ctx->d_quals, quals, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_offs, offsets, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    ctx->n_reads = n; ctx->total_bytes = total;
+    rc = run_qc(ctx);
+    if (rc == MCX_OK) cudaEventElapsedTime(&ctx->ms[0], ctx->ev[0], ctx->ev[1]);
+    return rc;
+}
+
+extern "C" int mcx_push_reads_dev(mcx_ctx *ctx, const uint8_t *d_bases, const uint8_t *d_quals,
+                                  const int64_t *d_offsets, int64_t n, int64_t total_bytes) {
+    if (!ctx || !d_offsets || n < 0 || (n > 0 && !d_bases)) return fail(ctx, MCX_EINVAL, "mcx_push_reads_dev: bad argument");
+    if (!ctx->have_par) return fail(ctx, MCX_ESTATE, "mcx_push_reads_dev: call mcx_set_params first");
+    if (n >= (1ll << 27)) return fail(ctx, MCX_EINVAL, "mcx_push_reads_dev: at most 2^27 reads per call");
+    if (ctx->par.has_quality && !d_quals && n > 0) return fail(ctx, MCX_EINVAL, "mcx_push_reads_dev: FASTQ parameters but no qualities");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->own_reads) {
+        cudaFree(ctx->d_bases); cudaFree(ctx->d_quals); cudaFree(ctx->d_offs);
+        ctx->cap_bases = ctx->cap_quals = ctx->cap_offs = 0;
+    }
+    ctx->own_reads = false;
+    ctx->d_bases = const_cast<uint8_t *>(d_bases); ctx->d_quals = const_cast<uint8_t *>(d_quals);
+    ctx->d_offs = const_cast<int64_t *>(d_offsets);
+    ctx->n_reads = n; ctx->total_bytes = total_bytes;
+    ctx->launches = 0;
+    memset(ctx->ms, 0, sizeof ctx->ms);
+    return run_qc(ctx);
+}
+
+extern "C" int mcx_qc_counts(mcx_ctx *ctx, mcx_qc *out) {
+    if (!ctx || !out) return fail(ctx, MCX_EINVAL, "mcx_qc_counts: null argument");
+    if (!ctx->pushed) return fail(ctx, MCX_ESTATE, "mcx_qc_counts: no reads pushed");
+    *out = ctx->qc;
+    return MCX_OK;
+}
+
+template <int NT>
+static int launch_seed(mcx_ctx *ctx, const SeedArgs &A, int maxm) {
+    size_t smem = 13 * 13 * sizeof(double) + (size_t)maxm * NT;
+    CK(cudaFuncSetAttribute(k_seed<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t threads = A.n_search * 6;
+    int64_t blocks = (threads + NT - 1) / NT;
+    k_seed<NT><<<(unsigned)blocks, NT, smem, ctx->stream>>>(A);
+    return MCX_OK;
+}
+template <int NT>
+static int launch_gapped(mcx_ctx *ctx, const GapArgs &A, int maxm) {
+    size_t smem = 13 * 13 * sizeof(double) + (size_t)maxm * NT;
+    CK(cudaFuncSetAttribute(k_gapped<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = (A.n_surv + NT - 1) / NT;
+    k_gapped<NT><<<(unsigned)blocks, NT, smem, ctx->stream>>>(A);
+    return MCX_OK;
+}
+
+extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
+    if (!ctx) return fail(ctx, MCX_EINVAL, "mcx_search: null context");
+    if (!ctx->pushed) return fail(ctx, MCX_ESTATE, "mcx_search: no reads pushed");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const mcx_params &P = ctx->par;
+    const int64_t n = ctx->n_reads;
+    const int64_t n_search = (quota < 0 || quota > ctx->kept) ? ctx->kept : quota;
+    int rc;
+    mcx_result &R = ctx->res;
+    memset(&R, 0, sizeof R);
+    R.sampled_reads = n_search;
+    // counters up to the read that filled the quota (mc.py:356 breaks out of the loop there)
+    if (n_search == ctx->kept) {
+        R.too_short = ctx->qc.too_short; R.low_qual = ctx->qc.low_qual; R.dups = ctx->qc.dups;
+    } else if (n_search > 0) {
+        int32_t cut = 0;
+        CK(cudaMemcpyAsync(&cut, ctx->d_kept + (n_search - 1), sizeof cut, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemsetAsync(ctx->d_cnt, 0, 16 * sizeof(unsigned long long), st));
+        k_count_codes<<<592, 256, 0, st>>>(ctx->d_code, (int64_t)cut + 1, ctx->d_cnt);
+        ++ctx->launches;
+        unsigned long long cnt[4];
+        CK(cudaMemcpyAsync(cnt, ctx->d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        R.too_short = (int64_t)cnt[1]; R.low_qual = (int64_t)cnt[2]; R.dups = (int64_t)cnt[3];
+    }
+    // buffers
+    int64_t per_read = 8;
+    if (const char *e = getenv("MCX_SURV_PER_READ")) per_read = std::max(1, atoi(e));
+    const int64_t want = std::max<int64_t>(n_search * per_read, 1 << 16);
+    if (ctx->cap_surv < want) {
+        void *old[] = {ctx->d_surv, ctx->d_hsp, ctx->d_hits_out, ctx->d_keys, ctx->d_idx, ctx->d_hflag, ctx->d_hpos, ctx->d_keep};
+        for (void *p : old) if (p) cudaFree(p);
+        ctx->d_surv = nullptr; ctx->d_hsp = nullptr; ctx->d_hits_out = nullptr; ctx->d_keys = nullptr;
+        ctx->d_idx = nullptr; ctx->d_hflag = nullptr; ctx->d_hpos = nullptr; ctx->d_keep = nullptr;
+        CK(dev_alloc(&ctx->d_surv, (size_t)want)); CK(dev_alloc(&ctx->d_hsp, (size_t)want));
+        CK(dev_alloc(&ctx->d_hits_out, (size_t)want)); CK(dev_alloc(&ctx->d_keys, (size_t)want));
+        CK(dev_alloc(&ctx->d_idx, (size_t)want)); CK(dev_alloc(&ctx->d_hflag, (size_t)want + 1));
+        CK(dev_alloc(&ctx->d_hpos, (size_t)want + 1)); CK(dev_alloc(&ctx->d_keep, (size_t)want));
+        ctx->cap_surv = want;
+    }
+    if ((rc = ensure(ctx, &ctx->d_best, &ctx->cap_best, n + 1)) != MCX_OK) return rc;
+    CK(cudaMemsetAsync(ctx->d_cnt, 0, 16 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ctx->d_acc, 0, (3 + 2 * MCX_N_FAM) * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ctx->d_abl, 0, (size_t)MCX_N_FAM * MCX_LEN_BINS * sizeof(unsigned long long), st));
+    if (n > 0) { k_fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_best, n, -1); ++ctx->launches; }
+    const int maxm = (P.read_length + 2) / 3;
+    // an ungapped HSP of 49+ can still grow in the gapped stage, so it survives whatever the floor is
+    const int thr = std::max(1, std::min(P.min_report_raw, 49));
+
+    CK(cudaEventRecord(ctx->ev[2], st));
+    unsigned long long n_surv = 0;
+    if (n_search > 0) {
+        SeedArgs A;
+        A.bases = ctx->d_bases; A.offs = ctx->d_offs; A.kept = ctx->d_kept; A.n_search = n_search;
+        A.L = P.read_length; A.thr_report = thr; A.db = ctx->db; A.surv = ctx->d_surv;
+        A.n_surv = ctx->d_cnt + 8; A.cap_surv = (unsigned long long)ctx->cap_surv;
+        if ((rc = launch_seed<192>(ctx, A, maxm)) != MCX_OK) return rc;
+        ++ctx->launches;
+        CK(cudaMemcpyAsync(&n_surv, ctx->d_cnt + 8, sizeof n_surv, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaEventRecord(ctx->ev[3], st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if ((int64_t)n_surv > ctx->cap_surv)
+        return fail(ctx, MCX_ENOMEM, "mcx_search: survivor buffer overflow (" + std::to_string(n_surv) + " > " +
+                                         std::to_string(ctx->cap_surv) + "); raise MCX_SURV_PER_READ");
+    R.n_seed_hits = (int64_t)n_surv;
+    const int64_t ns = (int64_t)n_surv;
+    if (ns > 0) {
+        GapArgs G;
+        G.bases = ctx->d_bases; G.offs = ctx->d_offs; G.L = P.read_length; G.db = ctx->db; G.surv = ctx->d_surv;
+        G.n_surv = ns; G.hsp = ctx->d_hsp; G.keys = ctx->d_keys; G.idx = ctx->d_idx; G.counters = ctx->d_cnt + 10;
+        if ((rc = launch_gapped<128>(ctx, G, maxm)) != MCX_OK) return rc;
+        ++ctx->launches;
+    }
+    CK(cudaEventRecord(ctx->ev[4], st));
+    if (ns > 0) {
+        size_t tb = 0;
+        cub::DeviceMergeSort::SortPairs(nullptr, tb, ctx->d_keys, ctx->d_idx, ns, SortKeyLess(), st);
+        if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
+        cub::DeviceMergeSort::SortPairs(ctx->d_temp, tb, ctx->d_keys, ctx->d_idx, ns, SortKeyLess(), st);
+        ctx->launches += 3;
+    }
+    CK(cudaEventRecord(ctx->ev[5], st));
+    if (ns > 0) {
+        ClsArgs C;
+        C.hsp = ctx->d_hsp; C.idx = ctx->d_idx; C.n = ns; C.L = P.read_length; C.min_report = P.min_report_raw;
+        C.db = ctx->db; C.keep = ctx->d_keep; C.best_subject = ctx->d_best; C.acc = ctx->d_acc; C.aln_by_len = ctx->d_abl;
+        k_classify<<<(unsigned)((ns + 127) / 128), 128, 0, st>>>(C);
+        ++ctx->launches;
+    }
+    CK(cudaEventRecord(ctx->ev[6], st));
+    std::vector<unsigned long long> acc(3 + 2 * MCX_N_FAM), abl((size_t)MCX_N_FAM * MCX_LEN_BINS);
+    unsigned long long gc[2] = {0, 0};
+    CK(cudaMemcpyAsync(acc.data(), ctx->d_acc, acc.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(abl.data(), ctx->d_abl, abl.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(gc, ctx->d_cnt + 10, sizeof gc, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev[7], st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    R.reads_with_hits = (int64_t)acc[0]; R.reads_classified = (int64_t)acc[1]; R.n_hsp = (int64_t)acc[2];
+    R.n_gapped = (int64_t)gc[0]; R.gapped_cells = (int64_t)gc[1];
+    for (int f = 0; f < MCX_N_FAM; ++f) { R.fam_hits[f] = (int64_t)acc[3 + f]; R.fam_aln[f] = (int64_t)acc[3 + MCX_N_FAM + f]; }
+    for (size_t k = 0; k < abl.size(); ++k) R.aln_by_len[k] = (int64_t)abl[k];
+    cudaEventElapsedTime(&ctx->ms[2], ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->ms[3], ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&ctx->ms[4], ctx->ev[4], ctx->ev[5]);
+    cudaEventElapsedTime(&ctx->ms[5], ctx->ev[5], ctx->ev[6]);
+    cudaEventElapsedTime(&ctx->ms[6], ctx->ev[6], ctx->ev[7]);
+    ctx->n_hsp_sorted = ns;
+    ctx->searched = true;
+    return MCX_OK;
+}
+
+extern "C" int mcx_result_get(mcx_ctx *ctx, mcx_result *out) {
+    if (!ctx || !out) return fail(ctx, MCX_EINVAL, "mcx_result_get: null argument");
+    if (!ctx->searched) return fail(ctx, MCX_ESTATE, "mcx_result_get: no search has run");
+    *out = ctx->res;
+    return MCX_OK;
+}
+
+extern "C" int mcx_get_hits(mcx_ctx *ctx, mcx_hit *out, int64_t cap, int64_t *n) {
+    if (!ctx || !n) return fail(ctx, MCX_EINVAL, "mcx_get_hits: null argument");
+    if (!ctx->searched) return fail(ctx, MCX_ESTATE, "mcx_get_hits: no search has run");
+    CK(cudaSetDevice(ctx->device));
+    *n = ctx->res.n_hsp;
+    const int64_t ns = ctx->n_hsp_sorted;
+    if (!out || cap <= 0 || ns == 0) return MCX_OK;
+    cudaStream_t st = ctx->stream;
+    int rc;
+    k_keep_sorted<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(ctx->d_idx, ctx->d_keep, ns, ctx->d_hflag);
+    CK(cudaMemsetAsync(ctx->d_hflag + ns, 0, sizeof(int32_t), st));
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->d_hflag, ctx->d_hpos, (int)(ns + 1), st);
+    if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
+    cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, ctx->d_hflag, ctx->d_hpos, (int)(ns + 1), st);
+    k_gather_hits<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(ctx->d_hsp, ctx->d_idx, ctx->d_keep, ctx->d_hpos, ns, ctx->d_hits_out);
+    const int64_t take = std::min<int64_t>(cap, ctx->res.n_hsp);
+    CK(cudaMemcpyAsync(out, ctx->d_hits_out, (size_t)take * sizeof(mcx_hit), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return MCX_OK;
+}
+
+extern "C" int mcx_get_classified(mcx_ctx *ctx, int32_t *best_subject, int64_t n) {
+    if (!ctx || !best_subject) return fail(ctx, MCX_EINVAL, "mcx_get_classified: null argument");
+    if (!ctx->searched) return fail(ctx, MCX_ESTATE, "mcx_get_classified: no search has run");
+    if (n > ctx->n_reads) n = ctx->n_reads;
+    CK(cudaSetDevice(ctx->device));
+    if (n > 0) CK(cudaMemcpyAsync(best_subject, ctx->d_best, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MCX_OK;
+}
+
+extern "C" int mcx_timings(mcx_ctx *ctx, float ms[8], int64_t *launches) {
+    if (!ctx || !ms) return fail(ctx, MCX_EINVAL, "mcx_timings: null argument");
+    memcpy(ms, ctx->ms, sizeof(float) * 8);
+    if (launches) *launches = ctx->launches;
+    return MCX_OK;
+}

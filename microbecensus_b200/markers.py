@@ -1,0 +1,89 @@
+"""Marker database blob (``data/markers.mcxdb.gz``, written by tools/build_marker_db.py).
+
+One file replaces the reference's data/rapdb_2.15 (RAPsearch2 database), gene_fam.map, gene_len.map,
+pars.map, coefficients.map, weights.map and read_len.map (loaders: find_opt_pars / read_dic,
+microbe_census.py:61-88).
+"""
+import gzip
+import math
+import os
+import struct
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_PATH = os.path.join(_HERE, "data", "markers.mcxdb.gz")
+STAT_NAMES = ("hits", "cov", "aln")
+
+# Raw-score floor of the HSPs RAPsearch2 reports with `-e 1` (log10 E <= 1) for single-HSP hits, by read
+# length.  E = K * space * exp(-lambda * S) with the gapped BLOSUM62 11/1 set (lambda 0.267, K 0.041);
+# `space` is RAPsearch2's length-adjusted search space, measured from its output at these lengths
+# (tools/blackbox/evalue_floor.py); the floor only decides which HSPs count as "reported", every family
+# cutoff of pars.map lies at or above it.
+_EVALUE_SPACE = {50: 6.41e7, 100: 1.005e8, 150: 1.006e8, 500: 2.08e8}
+
+
+def bits_printed(raw):
+    """Bit score as RAPsearch2 prints it: (0.267 S + ln(1/0.041)) / ln 2 with two decimals."""
+    return float("%.2f" % ((0.267 * raw + math.log(1.0 / 0.041)) / math.log(2.0)))
+
+
+def min_raw_for_bits(cutoff):
+    """Smallest raw score whose printed bit score is >= cutoff (mc.py:425 compares the printed text)."""
+    s = 1
+    while bits_printed(s) < cutoff:
+        s += 1
+    return s
+
+
+def report_floor(read_length):
+    lens = sorted(_EVALUE_SPACE)
+    if read_length <= lens[0]:
+        space = _EVALUE_SPACE[lens[0]]
+    elif read_length >= lens[-1]:
+        space = _EVALUE_SPACE[lens[-1]]
+    else:
+        lo = max(l for l in lens if l <= read_length)
+        hi = min(l for l in lens if l >= read_length)
+        space = _EVALUE_SPACE[lo] if lo == hi else _EVALUE_SPACE[lo] + (_EVALUE_SPACE[hi] - _EVALUE_SPACE[lo]) * (read_length - lo) / (hi - lo)
+    s = 1
+    while 0.041 * space * math.exp(-0.267 * s) > 10.0:
+        s += 1
+    return s
+
+
+class Markers:
+    def __init__(self, path=None):
+        path = path or DEFAULT_PATH
+        opener = gzip.open if path.endswith(".gz") else open
+        with opener(path, "rb") as fh:
+            blob = fh.read()
+        if blob[:8] != b"MCXDB001":
+            raise ValueError("not a marker blob: %s" % path)
+        n_subj, n_res, n_fam, n_len, names_bytes = struct.unpack_from("<5i", blob, 8)
+        p = 8 + 32
+        self.off = np.frombuffer(blob, np.int32, n_subj + 1, p).copy(); p += 4 * (n_subj + 1)
+        self.fam = np.frombuffer(blob, np.uint8, n_subj, p).copy(); p += (n_subj + 3) & ~3
+        self.res = np.frombuffer(blob, np.uint8, n_res, p).copy(); p += (n_res + 3) & ~3
+        self.read_lengths = [int(x) for x in np.frombuffer(blob, np.int32, n_len, p)]; p += 4 * n_len
+        self.fam_names = [blob[p + 8 * i:p + 8 * i + 8].rstrip(b"\0").decode() for i in range(n_fam)]; p += 8 * n_fam
+        rec = np.dtype([("min_cov", "<f8"), ("max_aaid", "<f8"), ("min_score", "<f8"), ("stat", "<i4"), ("pad", "<i4")])
+        self.pars = np.frombuffer(blob, rec, n_len * n_fam, p).reshape(n_len, n_fam).copy(); p += 32 * n_len * n_fam
+        self.coeff = np.frombuffer(blob, np.float64, n_len * n_fam, p).reshape(n_len, n_fam).copy(); p += 8 * n_len * n_fam
+        self.weight = np.frombuffer(blob, np.float64, n_len * n_fam, p).reshape(n_len, n_fam).copy(); p += 8 * n_len * n_fam
+        self.names = blob[p:p + names_bytes].decode().split("\n")
+        self.n_subj, self.n_res, self.n_fam = n_subj, n_res, n_fam
+        self.subj_len = np.diff(self.off)
+
+    def length_index(self, read_length):
+        try:
+            return self.read_lengths.index(int(read_length))
+        except ValueError:
+            raise ValueError("read length %s is not one of %s" % (read_length, self.read_lengths))
+
+    def cutoffs(self, read_length):
+        """Rows of pars.map at this read length, family order = self.fam_names."""
+        return self.pars[self.length_index(read_length)]
+
+    def raw_cutoffs(self, read_length):
+        return [min_raw_for_bits(float(r["min_score"])) for r in self.cutoffs(read_length)]

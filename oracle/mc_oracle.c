@@ -496,7 +496,7 @@ static int ungapped_walk(const uint8_t *q, const uint8_t *t, int step, int nq, i
     int best = score0, cur = score0, n = 0, id = 0;
     for (;;) {
         cur += oc_blosum(q[n * step], t[n * step]);
-        id += (q[n * step] == t[n * step]);
+        id += (q[n * step] == t[n * step] && q[n * step] < 20);
         ++n;
         if (cur > best) { best = cur; *ext = n; *ident = id; }
         if (n >= nt || n >= nq) break;
@@ -585,7 +585,7 @@ static void gapped_xdrop(const uint8_t *q, const uint8_t *t, int step, int nQ, i
             if (i < 0 || j < 0) { fprintf(stderr, "oracle: gapped traceback ran off the matrix\n"); abort(); }
             g->aln++;
             if (c == 's') {
-                if (q[(i - 1) * step] == t[(j - 1) * step]) g->ident++;
+                if (q[(i - 1) * step] == t[(j - 1) * step] && q[(i - 1) * step] < 20) g->ident++;
                 --i; --j; prev = 's'; c = AT(M, i, j);
             } else if (c == 'd' || c == 'D') {
                 g->gapcols++; if (prev != 'd') g->gapopens++;
@@ -614,13 +614,18 @@ static void extend_seed(const uint8_t *q, int m, const uint8_t *t, int n, int qb
     h->aln = len + fe + be; h->gapo = 0;
     int gapcols = 0;
     if ((double)h->score >= GAP_TRIGGER) {
+        /* The product bounds the subject side of a gapped extension to query length + 63 columns
+         * (fixed-size DP rows on the device); RAPsearch2 has no such bound, but no alignment of the
+         * reference comes near 63 net gap columns (maximum observed: 17). */
         int ql = m - (h->q1 + 1), tl = n - (h->t1 + 1);
         if (ql > 2 && tl > 2) {
+            if (tl > ql + OC_GAP_SLACK) tl = ql + OC_GAP_SLACK;
             gext_t g; gapped_xdrop(q + h->q1 + 1, t + h->t1 + 1, 1, ql, tl, &g);
             if (g.gain > 0) { h->score += g.gain; h->ident += g.ident; h->q1 += g.eq; h->t1 += g.et; h->aln += g.aln; h->gapo += g.gapopens; gapcols += g.gapcols; }
         }
         ql = h->q0; tl = h->t0;
         if (ql > 2 && tl > 2) {
+            if (tl > ql + OC_GAP_SLACK) tl = ql + OC_GAP_SLACK;
             gext_t g; gapped_xdrop(q + h->q0 - 1, t + h->t0 - 1, -1, ql, tl, &g);
             if (g.gain > 0) { h->score += g.gain; h->ident += g.ident; h->q0 -= g.eq; h->t0 -= g.et; h->aln += g.aln; h->gapo += g.gapopens; gapcols += g.gapcols; }
         }
@@ -819,4 +824,43 @@ void oc_fingerprint(const uint8_t *seq, int len, uint64_t fp[2]) {
     }
     f1 += (uint64_t)len * 0xD6E8FEB86659FD93ull; r1 += (uint64_t)len * 0xD6E8FEB86659FD93ull;
     if (f1 < r1 || (f1 == r1 && f2 <= r2)) { fp[0] = f1; fp[1] = f2; } else { fp[0] = r1; fp[1] = r2; }
+}
+
+/* ------------------------------------------------------------------ batch helpers ----- */
+/* search reads [0,n) given as concatenated ASCII + offsets (only the first L bases of each are used);
+ * hits get read = index; returns the number of hits written (stops at cap) */
+int64_t oc_search_batch(const oc_index *ix, const uint8_t *bases, const int64_t *offs, int64_t n, int L,
+                        int use_seg, int min_raw, oc_hit *out, int64_t cap, int64_t *n_seeds) {
+    int64_t nh = 0;
+    enum { PER = 65536 };
+    oc_hit *buf = (oc_hit *)malloc(sizeof(oc_hit) * PER);
+    for (int64_t r = 0; r < n; ++r) {
+        if (offs[r + 1] - offs[r] < L) continue;
+        int k = oc_search_read(ix, bases + offs[r], L, 0, use_seg, min_raw, buf, PER, n_seeds, NULL);
+        for (int i = 0; i < k && nh < cap; ++i) { buf[i].read = (int32_t)r; out[nh++] = buf[i]; }
+    }
+    free(buf);
+    return nh;
+}
+
+/* mc.py:328-367 over a batch: codes per read (0 keep, 1 too short, 2 low quality, 3 duplicate, 4 = beyond
+ * the -n cut) ; returns the number of sampled reads; counters[0..2] = too_short, low_qual, dups counted up
+ * to the read that filled the quota, exactly as the reference's loop does. */
+int64_t oc_process_reads(const uint8_t *bases, const uint8_t *quals, const int64_t *offs, int64_t n, int L,
+                         int quality_offset, int min_quality, int mean_quality, int max_unknown,
+                         int64_t nreads /* <0: all */, uint8_t *code, int64_t *counters) {
+    int64_t sampled = 0;
+    counters[0] = counters[1] = counters[2] = 0;
+    int64_t r = 0;
+    for (; r < n; ++r) {
+        const uint8_t *q = quals ? quals + offs[r] : NULL;
+        int c = oc_read_qc(bases + offs[r], q, (int)(offs[r + 1] - offs[r]), L, quality_offset, min_quality,
+                           mean_quality, max_unknown);
+        code[r] = (uint8_t)c;
+        if (c == 1) counters[0]++;
+        else if (c == 2) counters[1]++;
+        else { ++sampled; if (nreads >= 0 && sampled == nreads) { ++r; break; } }
+    }
+    for (; r < n; ++r) code[r] = 4;
+    return sampled;
 }

@@ -29,6 +29,7 @@ extern "C" {
 
 #define OC_AA_STOP 20      /* '.' : stop codon, codon with a non-ACGT base, DB 'X' */
 #define OC_MAX_FRAME 168   /* 500 bp / 3 rounded up */
+#define OC_GAP_SLACK 63    /* subject columns beyond the query length in a gapped extension */
 
 /* one alignment record (best HSP of one read x subject pair) */
 typedef struct {
@@ -112,6 +113,13 @@ int64_t oc_classify(const oc_db *db, const oc_hit *hits, int64_t n_hits, int L,
 /* mc.py:265-279 + 342-356: per-read verdict. codes: 0 keep, 1 too_short, 2 low_qual (dup handled by caller) */
 int  oc_read_qc(const uint8_t *seq, const uint8_t *qual /*nullable*/, int len, int L,
                 int quality_offset, int min_quality, int mean_quality, int max_unknown);
+
+/* batch helpers used by tests/ and bench.py's cpu_baseline leg */
+int64_t oc_search_batch(const oc_index *ix, const uint8_t *bases, const int64_t *offs, int64_t n, int L,
+                        int use_seg, int min_raw, oc_hit *out, int64_t cap, int64_t *n_seeds);
+int64_t oc_process_reads(const uint8_t *bases, const uint8_t *quals, const int64_t *offs, int64_t n, int L,
+                         int quality_offset, int min_quality, int mean_quality, int max_unknown,
+                         int64_t nreads, uint8_t *code, int64_t *counters);
 
 /* 128-bit canonical fingerprint of the UNTRIMMED read (min over strand), for -d */
 void oc_fingerprint(const uint8_t *seq, int len, uint64_t fp[2]);

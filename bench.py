@@ -1,0 +1,337 @@
+#!/usr/bin/env python3
+"""Benchmark of the MicrobeCensus hot path on B200: reads/s end-to-end AGS (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--impl ours|reference]
+
+One step = one pass of the whole hot path over one batch of synthetic reads: read QC -> 6-frame
+translation + SEG + seeding + ungapped X-drop -> gapped X-drop -> per-read classification -> per-family
+sums (-> NCCL all-reduce for N > 1) -> weighted AGS estimate on the host.
+
+workloads (BASELINE.json configs):  c2 = 2,000,000 synthetic 100 bp single-end reads, -l 100 (default);
+c3 = 150 bp paired files with -q 5 -m 20 -u 5 (5M + 5M reads).  Per-GPU work is fixed (weak scaling): rank r
+owns reads [r*n, (r+1)*n) of the deterministic stream (microbecensus_b200/synth.py).
+
+`value`  = reads/s with the reads resident in HBM when the clock starts (device path only);
+`e2e`    = the same through the public host API: pinned host buffers -> libmcx (H2D inside) -> results on host;
+`roofline` = the seed+ungapped kernel against measured HBM bandwidth (algorithmic bytes);
+`cpu_baseline` = the unmodified reference (baseline/_ref: its Python stages + rapsearch_Linux_2.15 -z <cores>)
+on a bounded prefix of the same reads, or the CPU oracle port when the reference install is absent.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c2": dict(name="2M synthetic 100 bp single-end reads, -l 100", config_id=2, reads=2_000_000, L=100, fastq=False,
+               qc=dict(min_quality=-5, mean_quality=-5, max_unknown=100)),
+    "c3": dict(name="10M synthetic 150 bp paired-end reads with -q 5 -m 20 -u 5", config_id=3, reads=10_000_000, L=150,
+               fastq=True, qc=dict(min_quality=5, mean_quality=20, max_unknown=5)),
+}
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    p.add_argument("--reads-per-gpu", type=int, default=None)
+    p.add_argument("--ref-sample", type=int, default=20000, help="reads per step of the CPU reference arm")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = sorted(int(float(r[1])) for r in self.rows if r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU reference arm
+def reference_available():
+    ref = os.path.join(ROOT, "baseline", "_ref", "microbe_census")
+    return all(os.path.exists(os.path.join(ref, p)) for p in ("microbe_census.py", "bin/rapsearch_Linux_2.15", "data/rapdb_2.15"))
+
+
+def run_reference_once(batch, wl, threads, tmpdir):
+    """The unmodified reference's hot path (mc.py:611-626) on `batch`: process_seqfile -> search_seqs
+    (rapsearch child, -z threads) -> classify_reads -> aggregate_hits -> estimate.  Returns (seconds, AGS, sampled)."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+    from microbe_census import microbe_census as mc
+    from microbecensus_b200 import synth
+    path = os.path.join(tmpdir, "sample.fq" if wl["fastq"] else "sample.fa")
+    (synth.write_fastq if wl["fastq"] else synth.write_fasta)(batch, path)
+    os.chmod(os.path.join(ROOT, "baseline", "_ref", "microbe_census", "bin", "rapsearch_Linux_2.15"), 0o755)
+    args = {"seqfiles": [path], "verbose": False, "nreads": batch.n, "threads": threads, "read_length": wl["L"]}
+    args.update(wl["qc"])
+    t0 = time.perf_counter()
+    paths = mc.get_relative_paths(args)
+    mc.impute_missing_args(args)
+    mc.process_seqfile(args, paths)
+    mc.search_seqs(args, paths)
+    best = mc.classify_reads(args, paths)
+    agg = mc.aggregate_hits(args, paths, best)
+    mc.clean_up(paths)
+    ags = mc.estimate_average_genome_size(args, paths, agg)
+    return time.perf_counter() - t0, ags, args["sampled_reads"]
+
+
+def run_oracle_port_once(batch, wl, threads, tmpdir):
+    """CPU oracle port (oracle/oracle_cli, pthreads over reads) when the reference install is absent."""
+    from microbecensus_b200 import synth
+    import gzip
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "oracle_cli"], stdout=subprocess.DEVNULL)
+    fa = os.path.join(tmpdir, "sample.fa")
+    synth.write_fasta(batch, fa)
+    db = os.path.join(tmpdir, "markers.mcxdb")
+    if not os.path.exists(db):
+        open(db, "wb").write(gzip.open(os.path.join(ROOT, "microbecensus_b200", "data", "markers.mcxdb.gz")).read())
+    env = dict(os.environ, ORACLE_THREADS=str(threads))
+    t0 = time.perf_counter()
+    subprocess.check_call([os.path.join(ROOT, "oracle", "oracle_cli"), db, fa, str(wl["L"]), "16", "1", "49", os.path.join(tmpdir, "o.m8")],
+                          env=env, stderr=subprocess.DEVNULL)
+    return time.perf_counter() - t0, None, batch.n
+
+
+def cpu_baseline(wl, sample_reads, steps=1, warmup=0):
+    from microbecensus_b200 import synth
+    cores = os.cpu_count() or 1
+    if wl["fastq"]:
+        batch = synth.reads(wl["config_id"], 0, sample_reads, wl["L"], with_quals=True)
+    else:
+        batch = synth.reads(wl["config_id"], 0, sample_reads, wl["L"])
+    kind = "reference" if reference_available() else "port"
+    fn = run_reference_once if kind == "reference" else run_oracle_port_once
+    times, ags, sampled = [], None, sample_reads
+    with tempfile.TemporaryDirectory() as tmp:
+        for i in range(warmup + steps):
+            dt, ags, sampled = fn(batch, wl, cores, tmp)
+            if i >= warmup:
+                times.append(dt)
+    sec = sum(times) / len(times)
+    return {"value": sampled / sec, "unit": "reads/s", "cores": cores, "kind": kind,
+            "sample": "first %d reads of the workload stream; whole reference hot path (process_seqfile, rapsearch -z %d, "
+                      "classify_reads, aggregate_hits, estimate)" % (sample_reads, cores) if kind == "reference" else
+                      "first %d reads; CPU oracle port, %d pthreads" % (sample_reads, cores),
+            "seconds_per_step": sec, "ags": ags}
+
+
+# ---------------------------------------------------------------------------------------------- main
+def main():
+    a = parse()
+    wl = WORKLOADS[a.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        cb = cpu_baseline(wl, a.ref_sample, steps=a.steps, warmup=min(a.warmup, 1))
+        line = {"impl": "reference", "metric": "reads/sec end-to-end AGS", "value": cb["value"], "unit": "reads/s",
+                "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": 1e3 * cb["seconds_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": {"workload": wl["name"], "sample_reads_per_step": a.ref_sample, "read_length": wl["L"]},
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "ags": cb["ags"]}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from microbecensus_b200 import synth
+    from microbecensus_b200.engine import MarkerSearch, ReadBatch
+    from microbecensus_b200.markers import Markers
+    from microbecensus_b200 import microbe_census as mcb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the search has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    n = a.reads_per_gpu or (wl["reads"] if a.workload == "c2" else wl["reads"] // 2)
+    L = wl["L"]
+    lo, hi = rank * n, (rank + 1) * n
+
+    markers = Markers()
+    eng = MarkerSearch(markers, local)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    eng.set_params(L, quality_offset=33 if wl["fastq"] else None, **wl["qc"])
+
+    # ---- synthetic shard, generated on the host (untimed), staged in pinned memory
+    if a.workload == "c3":
+        r1, r2 = synth.paired_reads(wl["config_id"], lo // 2, lo // 2 + n // 2, L)
+        batch = mcb.concat_batches([r1, r2])        # files are processed one after the other (mc.py:337)
+    else:
+        batch = synth.reads(wl["config_id"], lo, hi, L, with_quals=wl["fastq"])
+    pin = lambda arr: torch.from_numpy(arr).pin_memory()
+    h_bases, h_offs = pin(batch.bases), pin(batch.offsets)
+    h_quals = pin(batch.quals) if batch.quals is not None else None
+    host_batch = ReadBatch(h_bases.numpy(), h_offs.numpy(), None if h_quals is None else h_quals.numpy())
+    d_bases, d_offs = h_bases.to(dev), h_offs.to(dev)
+    d_quals = h_quals.to(dev) if h_quals is not None else None
+    h2d_bytes = batch.nbytes
+    fam_names = markers.fam_names
+
+    def finish(res):
+        """counts -> (all-reduce) -> agg_hits -> AGS, as run_pipeline does after the search"""
+        if world > 1:
+            v = torch.from_numpy(res.counts_vector()).to(dev)
+            dist.all_reduce(v)
+            res.load_counts_vector(v.cpu().numpy())
+        args = {"read_length": L, "sampled_reads": res.sampled_reads, "verbose": False}
+        return mcb.estimate_average_genome_size(args, None, res.agg_hits()), res
+
+    def step_device():
+        eng.push_device(d_bases.data_ptr(), d_quals.data_ptr() if d_quals is not None else 0, d_offs.data_ptr(), n, int(d_bases.numel()))
+        return finish(eng.search(-1))
+
+    def step_e2e():
+        eng.push(host_batch)
+        return finish(eng.search(-1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            out = fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage = {}
+        launches = 0
+        e0.record()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = fn()
+            tm, nl = eng.timings()
+            launches += nl
+            for k, v in tm.items():
+                stage[k] = stage.get(k, 0.0) + v
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1]) / 1e3
+        return ms / steps, wall / steps, {k: v / steps for k, v in stage.items()}, launches, out
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_dev, wall_dev, stage_dev, launches, (ags, res) = timed(step_device, a.steps, max(a.warmup, 3))
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, wall_e2e, stage_e2e, _, (ags2, res2) = timed(step_e2e, a.steps, 1)
+    # device events bracket only GPU work; the step also holds host work (counter read-back, AGS estimate),
+    # so the step time is the larger of the two clocks
+    t_dev = max(ms_dev / 1e3, wall_dev)
+    t_e2e = max(ms_e2e / 1e3, wall_e2e)
+    total_reads = res.sampled_reads            # all ranks (after the all-reduce)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs")
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if hbm else "fallback 6650 GB/s (B200_PROFILING.md)"
+    hbm = hbm or 6650.0
+    # algorithmic bytes of the seed+ungapped kernel per searched read: the read's L bases,
+    # its 8-byte offset and 4-byte kept index, and one 4-byte hash slot per seed-word probe
+    m = [(L - o) // 3 for o in (0, 1, 2)]
+    probes = 2 * sum(max(0, x - 8) + 4 * max(0, x - 9) for x in m)
+    bytes_per_read = L + 12 + 4 * probes
+    per_gpu_reads = total_reads / world
+    k_ms = stage_dev["seed_ungapped"]
+    achieved = per_gpu_reads * bytes_per_read / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_seed (translate + SEG + seed lookup + ungapped X-drop)",
+                "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_read": bytes_per_read, "kernel_ms": k_ms,
+                "kernel_share_of_step": k_ms / (t_dev * 1e3)}
+    prof = os.path.join(ROOT, "profiles", "r01_k_seed_traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    gcups = res.gapped_cells / world / (stage_dev["gapped"] * 1e-3) / 1e9 if stage_dev.get("gapped") else None
+
+    line = {"metric": "reads/sec end-to-end AGS", "value": total_reads / t_dev, "unit": "reads/s", "n_gpus": world,
+            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": t_dev * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": wl["name"], "reads_per_gpu": n, "read_length": L, "parallelism": "reads sharded x%d, marker index replicated" % world,
+                       "l2": "inputs (%d MB per GPU) larger than L2, no flush needed" % (h2d_bytes >> 20)},
+            "e2e": {"value": total_reads / t_e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": int(res.counts_vector().nbytes), "ms_per_step": t_e2e * 1e3},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "stages_ms": stage_dev, "stages_ms_e2e": stage_e2e,
+            "gapped_gcups": gcups, "ags": ags, "ags_e2e": ags2,
+            "counts": {"sampled_reads": res.sampled_reads, "reads_with_hits": res.reads_with_hits,
+                       "reads_classified": res.reads_classified, "n_hsp": res.n_hsp, "n_seed_hits": res.n_seed_hits,
+                       "n_gapped": res.n_gapped, "gapped_cells": res.gapped_cells, "low_qual": res.low_qual}}
+    if world == 1 and not a.no_cpu_baseline:
+        try:
+            cb = cpu_baseline(wl, a.ref_sample)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["ags_on_sample"] = cb["ags"]
+        except Exception as exc:      # the baseline is reporting only; never lose the GPU line over it
+            line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(exc)[:200]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

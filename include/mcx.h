@@ -107,6 +107,9 @@ typedef struct {
 int  mcx_create(mcx_ctx **out, const mcx_db *db, int device);
 void mcx_destroy(mcx_ctx *ctx);
 int  mcx_set_params(mcx_ctx *ctx, const mcx_params *p);
+/* run on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream) instead of
+ * the context's own; lets the caller bracket calls with its own CUDA events */
+int  mcx_set_stream(mcx_ctx *ctx, void *cuda_stream);
 
 /* Reads as ASCII bytes, read i = bases[offsets[i] .. offsets[i+1]); quals may be NULL (FASTA) and
  * otherwise shares the offsets.  Host pointers (pinned or pageable).  Replaces any reads pushed before. */

@@ -52,7 +52,7 @@ class Hit(C.Structure):
                                          "q0", "q1", "t0", "t1")]
 
 
-EXPORTS = ("mcx_create", "mcx_destroy", "mcx_set_params", "mcx_push_reads", "mcx_push_reads_dev",
+EXPORTS = ("mcx_create", "mcx_destroy", "mcx_set_params", "mcx_set_stream", "mcx_push_reads", "mcx_push_reads_dev",
            "mcx_qc_counts", "mcx_search", "mcx_result_get", "mcx_get_hits", "mcx_get_classified",
            "mcx_timings", "mcx_last_error", "mcx_version")
 
@@ -73,6 +73,7 @@ def load():
     lib.mcx_destroy.argtypes = [vp]
     lib.mcx_destroy.restype = None
     lib.mcx_set_params.argtypes = [vp, C.POINTER(Params)]
+    lib.mcx_set_stream.argtypes = [vp, vp]
     lib.mcx_push_reads.argtypes = [vp, vp, vp, vp, i64]
     lib.mcx_push_reads_dev.argtypes = [vp, vp, vp, vp, i64, i64]
     lib.mcx_qc_counts.argtypes = [vp, C.POINTER(Qc)]

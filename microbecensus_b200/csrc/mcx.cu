@@ -719,6 +719,7 @@ __global__ void k_keep_sorted(const int32_t *__restrict__ idx, const uint8_t *__
 struct mcx_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    bool own_stream = true;
     std::string err;
     mcx_params par{};
     bool have_par = false;
@@ -927,8 +928,17 @@ extern "C" void mcx_destroy(mcx_ctx *ctx) {
                     ctx->d_acc, ctx->d_abl, ctx->d_temp};
     for (void *p : bufs) if (p) cudaFree(p);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+extern "C" int mcx_set_stream(mcx_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return fail(ctx, MCX_EINVAL, "mcx_set_stream: null context");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->stream && ctx->own_stream) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaStreamDestroy(ctx->stream)); }
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return MCX_OK;
 }
 
 extern "C" int mcx_set_params(mcx_ctx *ctx, const mcx_params *p) {

@@ -154,6 +154,10 @@ class MarkerSearch:
         self.read_length = int(read_length)
         self.min_report_raw = int(p.min_report_raw)
 
+    def set_stream(self, cuda_stream):
+        """Run on the caller's stream (int handle of a cudaStream_t)."""
+        self._ck(self.lib.mcx_set_stream(self.ctx, C.c_void_p(int(cuda_stream))))
+
     def push(self, batch):
         """Host -> device copy of the reads + QC kernel.  Returns the QC counters over all pushed reads."""
         self._batch = batch  # keep the arrays alive

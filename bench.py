@@ -287,15 +287,16 @@ def main():
     hbm = peaks.get("hbm_gbs")
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if hbm else "fallback 6650 GB/s (B200_PROFILING.md)"
     hbm = hbm or 6650.0
-    # algorithmic bytes of the seed+ungapped kernel per searched read: the read's L bases,
-    # its 8-byte offset and 4-byte kept index, and one 4-byte hash slot per seed-word probe
+    # algorithmic bytes of the probe kernel per searched read: the read's L bases, its 8-byte
+    # offset and 4-byte kept index, one 4-byte hash slot per seed-word probe, and the six frames written to the
+    # frame store
     m = [(L - o) // 3 for o in (0, 1, 2)]
     probes = 2 * sum(max(0, x - 8) + 4 * max(0, x - 9) for x in m)
-    bytes_per_read = L + 12 + 4 * probes
+    bytes_per_read = L + 12 + 4 * probes + sum(m) * 2
     per_gpu_reads = total_reads / world
-    k_ms = stage_dev["seed_ungapped"]
+    k_ms = stage_dev["probe"]
     achieved = per_gpu_reads * bytes_per_read / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_seed (translate + SEG + seed lookup + ungapped X-drop)",
+    roofline = {"bound": "hbm", "kernel": "k_probe (6-frame translation + SEG + murphy10 seed-word lookup)",
                 "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_read": bytes_per_read, "kernel_ms": k_ms,
                 "kernel_share_of_step": k_ms / (t_dev * 1e3)}

@@ -3,9 +3,11 @@
 // One context = one GPU.  The hot path is five hand-written kernels (no CPU fallback anywhere):
 //
 //   k_qc        read QC                      mc.py:265-279, 342-356      one warp per read, HBM-bound
-//   k_seed      6-frame translation + SEG + murphy10 seed lookup + ungapped X-drop extension
-//               (RAPsearch2 BuildQHash / Searching / ExtendSeq2Set / AlignFwd / AlignBwd)
-//               one thread per (read, frame), frames staged in shared memory, seed index in L2/HBM
+//   k_probe     6-frame translation + SEG + murphy10 seed-word lookup (RAPsearch2 BuildQHash / Searching /
+//               FindSeeds): one thread per (read, frame), frames staged in shared memory and written to a
+//               global frame store, word hits queued as candidates
+//   k_extend    seed growth, acceptance and ungapped X-drop extension (ExtendSeq2Set / AlignFwd / AlignBwd):
+//               one thread per candidate, survivors appended to the HSP list
 //   k_gapped    gapped X-drop extension with alignment statistics carried forward
 //               (RAPsearch2 AlignSeqs / AlignGapped / CalRes)   one thread per surviving HSP
 //   k_classify  HSP de-duplication per (read, subject), the three cutoffs, best hit per read and the
@@ -23,6 +25,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <climits>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -68,7 +71,7 @@ struct DevDB {
     const uint32_t *post;          // (subject << 11 | position), bit 31 = last posting of the word
 };
 
-struct Surv {                      // ungapped HSP that reached the report floor (16 bytes)
+struct Surv {                      // ungapped HSP that reached the report floor (20 bytes)
     int32_t read;
     uint16_t subject;
     uint8_t frame, q0;
@@ -76,6 +79,7 @@ struct Surv {                      // ungapped HSP that reached the report floor
     uint16_t t0;
     int16_t score;
     uint16_t pad;
+    uint32_t gframe;               // row of the frame store (within the chunk the survivor came from)
 };
 
 struct SortKey {                   // (read, subject, score desc, frame, q0 | q1, t0, t1, aln, ident)
@@ -88,11 +92,12 @@ struct SortKeyLess {
 };
 
 // ------------------------------------------------------------------------------------------------
-// frame construction: translation + SEG hard mask.  Frames live in shared memory, k-major
-// (element k of thread t at k*NT + t) so that a warp touching "its" residue k hits 32 distinct bytes
-// of 8 consecutive words: conflict-free.
+// frame construction: translation + SEG hard mask.  Frames live in shared memory, one row per thread
+// with a stride of an odd number of 32-bit words: "every lane touches residue k of its own frame" and
+// "all lanes touch consecutive residues of one frame" (cooperative extension) are both conflict-free.
 // ------------------------------------------------------------------------------------------------
-#define FR(k) s_aa[(k) * NT + tid]
+#define FR(k) fr[(k)]
+__host__ __device__ inline int frame_stride(int maxm) { int w = (maxm + 3) / 4; return 4 * (w | 1); }
 
 __device__ __forceinline__ int base_code(uint8_t c) {  // T C A G -> 0..3, anything else 4
     return c == 'T' ? 0 : c == 'C' ? 1 : c == 'A' ? 2 : c == 'G' ? 3 : 4;
@@ -132,77 +137,77 @@ struct Comp {                      // composition of a <=12-residue window, nibb
     }
 };
 
-template <int NT>
-__device__ double seg_win_entropy(const uint8_t *s_aa, int tid, int start, const double *ent) {
-    Comp w; w.clear();
-    for (int k = 0; k < SEG_WINDOW; ++k) w.add(FR(start + k));
-    return w.entropy(ent);
-}
+__device__ __forceinline__ bool mbit(const unsigned long long *m, int k) { return (m[k >> 6] >> (k & 63)) & 1; }
 
-// seg.c getprob() of residues [start, start+len): lnass + lnperm - len*ln20 on the sorted composition
-template <int NT>
-__device__ double seg_getprob(const uint8_t *s_aa, int tid, int start, int len) {
-    uint8_t sv[21];
-    for (int a = 0; a < 21; ++a) sv[a] = 0;
-    for (int k = 0; k < len; ++k) { int a = FR(start + k); if (a < 20) sv[a]++; }
-    for (int i = 1; i < 20; ++i) {                 // insertion sort, descending
-        uint8_t v = sv[i]; int j = i - 1;
-        while (j >= 0 && sv[j] < v) { sv[j + 1] = sv[j]; --j; }
-        sv[j + 1] = v;
+// seg.c getprob() = lnass + lnperm - len*ln20 from the histogram of letter counts: nc[c] = number of letters
+// occurring c times.  Walking c downwards visits the counts in exactly the order of seg.c's sorted state vector,
+// so the floating-point operations (and their order) are those of the reference and of the oracle.
+__device__ double seg_getprob(const uint8_t *nc, int maxc, int len) {
+    double lnperm = c_lnfac[len], lnass = c_lnfac[20];
+    int nz = 0;
+    for (int c = maxc; c >= 1; --c) {
+        const int n = nc[c];
+        if (!n) continue;
+        for (int r = 0; r < n; ++r) lnperm -= c_lnfac[c];
+        lnass -= c_lnfac[n];
+        nz += n;
     }
-    double lnperm = c_lnfac[len];
-    for (int i = 0; sv[i] != 0; ++i) lnperm -= c_lnfac[sv[i]];
-    double lnass = c_lnfac[20];
-    if (sv[0] != 0) {
-        int total = 20, cls = 1, svim1 = sv[0], svi, i = 0;
-        for (;;) {
-            if (++i == 20) { lnass -= c_lnfac[cls]; break; }
-            svi = sv[i];
-            if (svi == svim1) { cls++; continue; }
-            total -= cls;
-            lnass -= c_lnfac[cls];
-            if (svi == 0) { lnass -= c_lnfac[total]; break; }
-            cls = 1; svim1 = svi;
-        }
-    }
+    if (nz > 0 && nz < 20) lnass -= c_lnfac[20 - nz];
     return lnass + lnperm - c_ln20[len];
 }
 
-// Seg::segseq as it behaves inside RAPsearch2 (downset 0, upset 1): rare path, run only for frames
-// that hold a window with entropy <= 2.2.  The recursion of seg.c only adds segments, so the left
-// parts are queued on a small work list instead.
-template <int NT>
-__device__ void seg_full(const uint8_t *s_aa, int tid, int m, const double *ent, unsigned long long mask[3]) {
+// Seg::trim: the sub-window of [off, off+tl) with the lowest probability, longest first, leftmost first.
+// The composition slides by one residue per step instead of being rebuilt.
+__device__ void seg_trim(const uint8_t *fr, int off, int tl, int &leftend, int &rightend) {
+    uint8_t base[20], cur[20], nc[MAX_FRAME + 2];
+    for (int a = 0; a < 20; ++a) base[a] = 0;
+    for (int k = 0; k < tl; ++k) { const int a = fr[off + k]; if (a < 20) base[a]++; }
+    int lend = 0, rend = tl - 1, minlen = 1;
+    if (tl - SEG_MAXTRIM > minlen) minlen = tl - SEG_MAXTRIM;
+    double minprob = 1.0;
+    for (int len = tl; len > minlen; --len) {
+        int maxc = 0;
+        for (int c = 0; c <= len; ++c) nc[c] = 0;
+        for (int a = 0; a < 20; ++a) { const int c = base[a]; cur[a] = (uint8_t)c; if (c) { nc[c]++; maxc = c > maxc ? c : maxc; } }
+        for (int st = 0;; ++st) {
+            const double prob = seg_getprob(nc, maxc, len);
+            if (prob < minprob) { minprob = prob; lend = st; rend = len + st - 1; }
+            if (st + len >= tl) break;
+            const int a = fr[off + st], b = fr[off + st + len];
+            if (a < 20) { const int c = cur[a]; nc[c]--; if (c > 1) nc[c - 1]++; cur[a] = (uint8_t)(c - 1); }
+            if (b < 20) { const int c = cur[b]; if (c) nc[c]--; nc[c + 1]++; cur[b] = (uint8_t)(c + 1); if (c + 1 > maxc) maxc = c + 1; }
+            while (maxc > 0 && nc[maxc] == 0) --maxc;
+        }
+        const int a = fr[off + len - 1];
+        if (a < 20) base[a]--;
+    }
+    rightend -= (tl - rend - 1);
+    leftend += lend;
+}
+
+// Seg::segseq as it behaves inside RAPsearch2 (downset 0, upset 1), for frames that hold a window with entropy
+// <= 2.2.  lom / him: bit w set when the 12-window starting at w has entropy <= locut / <= hicut (the windows of a
+// sub-sequence are windows of the frame, with the last one repeated for its tail positions).  The recursion of seg.c
+// only adds segments, so the left parts are queued on a small work list instead.
+__device__ void seg_full(const uint8_t *fr, int m, const unsigned long long *lom, const unsigned long long *him,
+                         unsigned long long mask[3]) {
     int wl_off[12], wl_len[12], nwl = 1;
     wl_off[0] = 0; wl_len[0] = m;
     while (nwl > 0) {
         --nwl;
-        int off = wl_off[nwl], slen = wl_len[nwl];
+        const int off = wl_off[nwl], slen = wl_len[nwl];
         if (SEG_WINDOW > slen) continue;
-        int last = slen - 1, lowlim = 0, wmax = slen - SEG_WINDOW;
+        const int last = slen - 1, wmax = slen - SEG_WINDOW;
+        int lowlim = 0;
         for (int i = 0; i <= last; ++i) {
-            double Hi = seg_win_entropy<NT>(s_aa, tid, off + (i < wmax ? i : wmax), ent);
-            if (!(Hi <= SEG_LOCUT)) continue;
+            if (!mbit(lom, off + (i < wmax ? i : wmax))) continue;
             int j, loi, hii;
-            for (j = i; j >= lowlim; --j)
-                if (seg_win_entropy<NT>(s_aa, tid, off + (j < wmax ? j : wmax), ent) > SEG_HICUT) break;
+            for (j = i; j >= lowlim; --j) if (!mbit(him, off + (j < wmax ? j : wmax))) break;
             loi = j + 1;
-            for (j = i; j <= last; ++j)
-                if (seg_win_entropy<NT>(s_aa, tid, off + (j < wmax ? j : wmax), ent) > SEG_HICUT) break;
+            for (j = i; j <= last; ++j) if (!mbit(him, off + (j < wmax ? j : wmax))) break;
             hii = j - 1;
             int leftend = loi, rightend = hii;
-            {   // Seg::trim
-                int tl = rightend - leftend + 1, lend = 0, rend = tl - 1, minlen = 1;
-                if (tl - SEG_MAXTRIM > minlen) minlen = tl - SEG_MAXTRIM;
-                double minprob = 1.0;
-                for (int len = tl; len > minlen; --len)
-                    for (int s = 0; s + len <= tl; ++s) {
-                        double prob = seg_getprob<NT>(s_aa, tid, off + leftend + s, len);
-                        if (prob < minprob) { minprob = prob; lend = s; rend = len + s - 1; }
-                    }
-                rightend -= (tl - rend - 1);
-                leftend += lend;
-            }
+            seg_trim(fr, off + leftend, rightend - leftend + 1, leftend, rightend);
             if (i < leftend && nwl < 12) { wl_off[nwl] = off + loi; wl_len[nwl] = leftend - loi; ++nwl; }
             for (j = off + leftend; j <= off + rightend; ++j) mask[j >> 6] |= 1ull << (j & 63);
             i = hii < rightend ? hii : rightend;
@@ -211,41 +216,41 @@ __device__ void seg_full(const uint8_t *s_aa, int tid, int m, const double *ent,
     }
 }
 
-// translate frame `frame` of the read trimmed to L into FR(0..m) and hard-mask it; returns m
-template <int NT>
-__device__ int build_frame(uint8_t *s_aa, int tid, const uint8_t *__restrict__ rd, int L, int frame,
-                           const double *ent) {
-    int o = frame % 3, m = (L - o) / 3;
+// translate frame `frame` of the read trimmed to L into fr[0..m); returns m
+__device__ int translate_frame(uint8_t *fr, const uint8_t *__restrict__ rd, int L, int frame) {
+    const int o = frame % 3, m = (L - o) / 3;
     if (frame < 3) {
         for (int k = 0; k < m; ++k) {
-            int p = o + 3 * k;
-            int b0 = base_code(rd[p]), b1 = base_code(rd[p + 1]), b2 = base_code(rd[p + 2]);
-            FR(k) = ((b0 | b1 | b2) & 4) ? AA_STOP : c_codon[16 * b0 + 4 * b1 + b2];
+            const int p = o + 3 * k;
+            const int b0 = base_code(rd[p]), b1 = base_code(rd[p + 1]), b2 = base_code(rd[p + 2]);
+            fr[k] = ((b0 | b1 | b2) & 4) ? AA_STOP : c_codon[16 * b0 + 4 * b1 + b2];
         }
     } else {
         for (int k = 0; k < m; ++k) {
-            int p = L - 1 - (o + 3 * k);
-            int b0 = base_code(rd[p]), b1 = base_code(rd[p - 1]), b2 = base_code(rd[p - 2]);
-            FR(k) = ((b0 | b1 | b2) & 4) ? AA_STOP : c_codon[16 * (b0 ^ 2) + 4 * (b1 ^ 2) + (b2 ^ 2)];
-        }
-    }
-    if (m >= SEG_WINDOW) {
-        // fast path: slide the 12-window once; almost every frame has no window at or below locut
-        Comp w; w.clear();
-        for (int k = 0; k < SEG_WINDOW; ++k) w.add(FR(k));
-        bool trig = w.entropy(ent) <= SEG_LOCUT;
-        for (int s = 1; s + SEG_WINDOW <= m && !trig; ++s) {
-            w.sub(FR(s - 1)); w.add(FR(s + SEG_WINDOW - 1));
-            trig = w.entropy(ent) <= SEG_LOCUT;
-        }
-        if (trig) {
-            unsigned long long mask[3] = {0, 0, 0};
-            seg_full<NT>(s_aa, tid, m, ent, mask);
-            for (int k = 0; k < m; ++k)
-                if ((mask[k >> 6] >> (k & 63)) & 1) FR(k) = AA_STOP;
+            const int p = L - 1 - (o + 3 * k);
+            const int b0 = base_code(rd[p]), b1 = base_code(rd[p - 1]), b2 = base_code(rd[p - 2]);
+            fr[k] = ((b0 | b1 | b2) & 4) ? AA_STOP : c_codon[16 * (b0 ^ 2) + 4 * (b1 ^ 2) + (b2 ^ 2)];
         }
     }
     return m;
+}
+
+// entropy of every 12-window against locut / hicut; returns true when some window is at or below locut
+__device__ bool seg_window_masks(const uint8_t *fr, int m, const double *ent, unsigned long long lom[3],
+                                 unsigned long long him[3]) {
+    lom[0] = lom[1] = lom[2] = 0; him[0] = him[1] = him[2] = 0;
+    if (m < SEG_WINDOW) return false;
+    Comp w; w.clear();
+    for (int k = 0; k < SEG_WINDOW; ++k) w.add(fr[k]);
+    bool trig = false;
+    for (int st = 0;; ++st) {
+        const double e = w.entropy(ent);
+        if (e <= SEG_LOCUT) { lom[st >> 6] |= 1ull << (st & 63); trig = true; }
+        if (e <= SEG_HICUT) him[st >> 6] |= 1ull << (st & 63);
+        if (st + SEG_WINDOW >= m) break;
+        w.sub(fr[st]); w.add(fr[st + SEG_WINDOW]);
+    }
+    return trig;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -305,54 +310,213 @@ __global__ void k_count_codes(const uint8_t *__restrict__ code, int64_t upto, un
 // ------------------------------------------------------------------------------------------------
 // K2: seeds + ungapped extension.  One thread per (kept read, frame).
 // ------------------------------------------------------------------------------------------------
-struct SeedArgs {
+// K2a: one thread per (kept read, frame): translate, test every 12-window against the SEG cut-offs and write the
+// frame to the global frame store (each warp copies its 32 rows as words).  Frames holding a low-entropy window
+// (a few per cent) are queued for k_seg instead of running the irregular SEG code with one lane alive.
+struct FrameArgs {
     const uint8_t *bases;
     const int64_t *offs;
     const int32_t *kept;
-    int64_t n_search;
+    int64_t first, n_search;       // kept reads [first, first + n_search) in this launch
     int L;
+    uint8_t *frames;               // rows of fstride bytes, one per (read, frame)
+    uint32_t *segq;                // frames that need the full SEG
+    unsigned long long *n_segq;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_frames(FrameArgs A, int fstride) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    double *s_ent = reinterpret_cast<double *>(smem);
+    uint8_t *s_aa = smem + 13 * 13 * sizeof(double);
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int k = tid; k < 13 * 13; k += NT) s_ent[k] = c_ent[k];
+    for (int k = tid; k < NT * fstride / 4; k += NT) reinterpret_cast<uint32_t *>(s_aa)[k] = 0x14141414u;  // AA_STOP
+    __syncthreads();
+    const int64_t g = (int64_t)blockIdx.x * NT + tid;          // frame row within this launch
+    const int64_t ki = g / 6;
+    uint8_t *fr = s_aa + tid * fstride;
+    bool trig = false;
+    if (ki < A.n_search) {
+        const int frame = (int)(g - ki * 6);
+        const int read = A.kept[A.first + ki];
+        const int m = translate_frame(fr, A.bases + A.offs[read], A.L, frame);
+        unsigned long long lom[3], him[3];
+        trig = seg_window_masks(fr, m, s_ent, lom, him);
+    }
+    const uint32_t tm = __ballot_sync(0xffffffffu, trig);
+    if (tm) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(A.n_segq, (unsigned long long)__popc(tm));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (trig) A.segq[base + __popc(tm & ((1u << lane) - 1))] = (uint32_t)g;
+    }
+    __syncwarp();
+    const int64_t row0 = (int64_t)blockIdx.x * NT + (tid - lane);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(A.frames + row0 * fstride);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(s_aa + (tid - lane) * fstride);
+    for (int k = lane; k < 32 * fstride / 4; k += 32) dst[k] = src[k];
+}
+
+// K2a': full SEG for the queued frames, one thread each; masked residues are overwritten in the frame store
+__global__ void k_seg(uint8_t *frames, int fstride, int L, const uint32_t *__restrict__ segq, int64_t n) {
+    __shared__ double s_ent[13 * 13];
+    for (int k = threadIdx.x; k < 13 * 13; k += blockDim.x) s_ent[k] = c_ent[k];
+    __syncthreads();
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const uint32_t row = segq[g];
+    uint8_t *fr = frames + (int64_t)row * fstride;
+    const int m = (L - (int)(row % 6u) % 3) / 3;
+    unsigned long long lom[3], him[3], mask[3] = {0, 0, 0};
+    seg_window_masks(fr, m, s_ent, lom, him);
+    seg_full(fr, m, lom, him, mask);
+    for (int k = 0; k < m; ++k)
+        if ((mask[k >> 6] >> (k & 63)) & 1) fr[k] = AA_STOP;
+}
+
+// K2b: one thread per frame of the store: slide the 10-letter murphy10 window, probe the five word tables and
+// queue every posting of every word hit as a candidate (gframe, subject, subject position, query position,
+// pattern).  Space for a whole posting list is reserved with one atomic.
+struct Cand {                      // 12 bytes
+    uint32_t gframe;               // row of the frame store
+    uint32_t sj;                   // subject << 11 | subject position
+    uint32_t ip;                   // query position << 8 | pattern
+};
+
+struct ProbeArgs {
+    int64_t n_frames;
+    int L;
+    DevDB db;
+    const uint8_t *frames;
+    Cand *cand;
+    unsigned long long *n_cand;
+    unsigned long long cap_cand;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
+    extern __shared__ __align__(16) uint8_t s_aa[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    {   // each warp stages its 32 rows
+        const int64_t row0 = (int64_t)blockIdx.x * NT + (tid - lane);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(A.frames + row0 * fstride);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_aa + (tid - lane) * fstride);
+        for (int k = lane; k < 32 * fstride / 4; k += 32) dst[k] = src[k];
+    }
+    __syncwarp();
+    const int64_t g = (int64_t)blockIdx.x * NT + tid;
+    if (g >= A.n_frames) return;
+    const uint8_t *fr = s_aa + tid * fstride;
+    const int m = (A.L - (int)(g % 6) % 3) / 3;
+    // reduced letters of the 10-window [i, i+10) as nibbles (letter k at bits 4k); 15 past the end
+    unsigned long long win = 0;
+    for (int k = 0; k < 10; ++k) win |= (unsigned long long)(k < m ? red_of(fr[k]) : 15) << (4 * k);
+    for (int i = 0; i + 9 <= m; ++i) {
+        uint32_t code[N_PAT], slot[N_PAT], key[N_PAT];
+        int bad9 = 0;
+        {
+            uint32_t c9 = 0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { uint32_t r = (uint32_t)(win >> (4 * k)) & 15; bad9 |= (r >= 10); c9 = c9 * 10 + r; }
+            code[0] = c9;
+        }
+        const int bad10 = bad9 | ((((uint32_t)(win >> 36)) & 15) >= 10);
+#pragma unroll
+        for (int p = 1; p < N_PAT; ++p) {
+            uint32_t c = 0;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) if (k != p + 2) c = c * 10 + ((uint32_t)(win >> (4 * k)) & 15);
+            code[p] = c;
+        }
+        // all five first-slot loads are in flight together
+#pragma unroll
+        for (int p = 0; p < N_PAT; ++p) {
+            slot[p] = (code[p] * 2654435761u) >> A.db.hshift[p];
+            key[p] = (p == 0 ? !bad9 : !bad10) ? __ldg(A.db.hkey[p] + slot[p]) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int p = 0; p < N_PAT; ++p) {
+            uint32_t k = key[p], sl = slot[p];
+            if (k == 0xffffffffu) continue;
+            while (k != 0xffffffffu && k != code[p]) { sl = (sl + 1) & A.db.hmask[p]; k = __ldg(A.db.hkey[p] + sl); }
+            if (k != code[p]) continue;
+            const uint32_t v = __ldg(A.db.hval[p] + sl);
+            const uint32_t pi = v & 0x1ffffffu, extra = v >> 25;      // 25-bit start, 7-bit (count - 1), 127 = longer
+            uint32_t cnt = extra + 1;
+            if (extra == 127) { cnt = 128; while (!(__ldg(A.db.post + pi + cnt - 1) & 0x80000000u)) ++cnt; }
+            const unsigned long long base = atomicAdd(A.n_cand, (unsigned long long)cnt);
+            if (base + cnt > A.cap_cand) continue;
+            const uint32_t ip = ((uint32_t)i << 8) | (uint32_t)p;
+            for (uint32_t q = 0; q < cnt; ++q) {
+                Cand c; c.gframe = (uint32_t)g; c.sj = __ldg(A.db.post + pi + q) & 0x7fffffffu; c.ip = ip;
+                A.cand[base + q] = c;
+            }
+        }
+        const int nx = i + 10;
+        win = (win >> 4) | ((unsigned long long)(nx < m ? red_of(fr[nx]) : 15) << 36);
+    }
+}
+
+// K2b: one thread per candidate: grow the word to the maximal murphy10-identical stretch, apply the seed
+// acceptance test and walk the ungapped X-drop extension both ways (ExtendSeq2Set 0x413fc4-0x414073, AlignFwd /
+// AlignBwd).  HSPs reaching the report floor are appended to the survivor list.
+struct ExtArgs {
+    const int32_t *kept;
+    int64_t first;
+    int L, fstride;
     int thr_report;                // ungapped HSPs at or above this raw score survive
     DevDB db;
+    const uint8_t *frames;
+    const Cand *cand;
+    int64_t n_cand;
     Surv *surv;
     unsigned long long *n_surv;
     unsigned long long cap_surv;
 };
 
 template <int NT>
-__device__ __forceinline__ void try_seed(const SeedArgs &A, const uint8_t *s_aa, int tid, int m, int read,
-                                         int frame, int p, int i, uint32_t posting) {
-    const int s = (int)((posting & 0x7fffffffu) >> 11), j = (int)(posting & 0x7ff);
-    const int32_t o = A.db.off[s];
-    const int n = A.db.off[s + 1] - o;
+__global__ void __launch_bounds__(NT) k_extend(ExtArgs A) {
+    __shared__ int8_t s_bl[21 * 32];
+    for (int k = threadIdx.x; k < 21 * 32; k += NT) s_bl[k] = c_blosum[k];
+    __syncthreads();
+    const int64_t g = (int64_t)blockIdx.x * NT + threadIdx.x;
+    if (g >= A.n_cand) return;
+    const Cand c = A.cand[g];
+    const int frame = (int)(c.gframe % 6u);
+    const int m = (A.L - frame % 3) / 3;
+    const uint8_t *__restrict__ fr = A.frames + (int64_t)c.gframe * A.fstride;
+    const int s = (int)(c.sj >> 11), j = (int)(c.sj & 0x7ff), i = (int)(c.ip >> 8), p = (int)(c.ip & 0xff);
+    const int32_t o = __ldg(A.db.off + s);
+    const int n = __ldg(A.db.off + s + 1) - o;
     const uint8_t *__restrict__ t = A.db.res + o;
     if (p == 0) {                  // exact words: left-maximal only (ExtendSeq2Set 0x4140c0-0x414113)
-        if (i > 0 && j > 0 && red_eq(FR(i - 1), t[j - 1])) return;
+        if (i > 0 && j > 0 && red_eq(fr[i - 1], t[j - 1])) return;
     } else {                       // one-substitution words: the replaced letter differs by construction;
-        int w = p + 2;             // keep one window per substituted position (all give the same seed)
-        if (red_of(FR(i + w)) == red_of(t[j + w])) return;
-        if (w >= 4 && i + 10 < m && j + 10 < n && red_eq(FR(i + 10), t[j + 10])) return;
+        const int w = p + 2;       // keep one window per substituted position (all windows give the same seed)
+        if (red_of(fr[i + w]) == red_of(t[j + w])) return;
+        if (w >= 4 && i + 10 < m && j + 10 < n && red_eq(fr[i + 10], t[j + 10])) return;
     }
-    // grow the word to the maximal murphy10-identical stretch (right, then left)
     int qb = i, sb = j, len = p == 0 ? 9 : 10;
-    while (qb + len < m && sb + len < n && red_eq(FR(qb + len), t[sb + len])) ++len;
-    while (qb > 0 && sb > 0 && red_eq(FR(qb - 1), t[sb - 1])) { --qb; --sb; ++len; }
+    while (qb + len < m && sb + len < n && red_eq(fr[qb + len], t[sb + len])) ++len;
+    while (qb > 0 && sb > 0 && red_eq(fr[qb - 1], t[sb - 1])) { --qb; --sb; ++len; }
     int score0 = 0, id0 = 0;
     for (int k = 0; k < len; ++k) {
-        int a = FR(qb + k), b = t[sb + k];
-        score0 += c_blosum[a * 32 + b];
+        const int a = fr[qb + k], b = t[sb + k];
+        score0 += s_bl[a * 32 + b];
         id0 += (a == b && a < 20);
     }
     if (score0 < SEED_MIN_SCORE || id0 < SEED_MIN_IDENT) return;
-    // AlignFwd / AlignBwd: both walks start from the seed score; stop after a residue that leaves the
-    // running score below -20 or at least 9 (> 8.94) under the best so far
+    // both walks start from the seed score; stop after a residue that leaves the running score below -20 or
+    // at least 9 (> 8.94) under the best so far
     int fe = 0, fid = 0, gf = 0, be = 0, bid = 0, gb = 0;
     {
-        int nq = m - qb - len, nt = n - sb - len;
+        const int nq = m - qb - len, nt = n - sb - len;
         if (nq > 0 && nt > 0) {
             int best = score0, cur = score0, k = 0, id = 0;
             for (;;) {
-                int a = FR(qb + len + k), b = t[sb + len + k];
-                cur += c_blosum[a * 32 + b];
+                const int a = fr[qb + len + k], b = t[sb + len + k];
+                cur += s_bl[a * 32 + b];
                 id += (a == b && a < 20);
                 ++k;
                 if (cur > best) { best = cur; fe = k; fid = id; }
@@ -363,12 +527,12 @@ __device__ __forceinline__ void try_seed(const SeedArgs &A, const uint8_t *s_aa,
         }
     }
     {
-        int nq = qb, nt = sb;
+        const int nq = qb, nt = sb;
         if (nq > 0 && nt > 0) {
             int best = score0, cur = score0, k = 0, id = 0;
             for (;;) {
-                int a = FR(qb - 1 - k), b = t[sb - 1 - k];
-                cur += c_blosum[a * 32 + b];
+                const int a = fr[qb - 1 - k], b = t[sb - 1 - k];
+                cur += s_bl[a * 32 + b];
                 id += (a == b && a < 20);
                 ++k;
                 if (cur > best) { best = cur; be = k; bid = id; }
@@ -378,80 +542,22 @@ __device__ __forceinline__ void try_seed(const SeedArgs &A, const uint8_t *s_aa,
             gb = best - score0;
         }
     }
-    int total = score0 + gf + gb;
+    const int total = score0 + gf + gb;
     if (total < A.thr_report) return;
-    unsigned long long idx = atomicAdd(A.n_surv, 1ull);
+    const uint32_t mask = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(A.n_surv, (unsigned long long)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    const unsigned long long idx = base + __popc(mask & ((1u << lane) - 1));
     if (idx >= A.cap_surv) return;
     Surv v;
-    v.read = read; v.subject = (uint16_t)s; v.frame = (uint8_t)frame;
+    v.read = A.kept[A.first + c.gframe / 6u]; v.subject = (uint16_t)s; v.frame = (uint8_t)frame;
     v.q0 = (uint8_t)(qb - be); v.q1 = (uint8_t)(qb + len + fe - 1);
     v.ident = (uint8_t)(id0 + fid + bid); v.t0 = (uint16_t)(sb - be);
-    v.score = (int16_t)total; v.pad = 0;
+    v.score = (int16_t)total; v.pad = (uint16_t)0;
+    v.gframe = c.gframe;
     A.surv[idx] = v;
-}
-
-template <int NT>
-__device__ __forceinline__ void probe(const SeedArgs &A, const uint8_t *s_aa, int tid, int m, int read, int frame,
-                                      int p, int i, uint32_t code) {
-    const uint32_t *__restrict__ hk = A.db.hkey[p];
-    uint32_t slot = (code * 2654435761u) >> A.db.hshift[p];
-    for (;;) {
-        uint32_t k = __ldg(hk + slot);
-        if (k == 0xffffffffu) return;
-        if (k == code) break;
-        slot = (slot + 1) & A.db.hmask[p];
-    }
-    uint32_t pi = __ldg(A.db.hval[p] + slot);
-    for (;;) {
-        uint32_t posting = __ldg(A.db.post + pi);
-        try_seed<NT>(A, s_aa, tid, m, read, frame, p, i, posting);
-        if (posting & 0x80000000u) break;
-        ++pi;
-    }
-}
-
-template <int NT>
-__global__ void __launch_bounds__(NT) k_seed(SeedArgs A) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    double *s_ent = reinterpret_cast<double *>(smem);
-    uint8_t *s_aa = smem + 13 * 13 * sizeof(double);
-    const int tid = threadIdx.x;
-    for (int k = tid; k < 13 * 13; k += NT) s_ent[k] = c_ent[k];
-    __syncthreads();
-    int64_t g = (int64_t)blockIdx.x * NT + tid;
-    int64_t ki = g / 6;
-    if (ki >= A.n_search) return;
-    const int frame = (int)(g - ki * 6);
-    const int read = A.kept[ki];
-    const uint8_t *rd = A.bases + A.offs[read];
-    const int m = build_frame<NT>(s_aa, tid, rd, A.L, frame, s_ent);
-    if (m < 9) return;
-    // reduced letters of the 10-window [i, i+10) as nibbles (letter k at bits 4k); 15 past the end
-    unsigned long long win = 0;
-    for (int k = 0; k < 10; ++k) win |= (unsigned long long)(k < m ? red_of(FR(k)) : 15) << (4 * k);
-    for (int i = 0; i + 9 <= m; ++i) {
-        // invalid letters are 10 (stop / mask) or 15 (past the end): bit 3 and bit 1 set, or 15
-        unsigned long long w = win;
-        int bad9 = 0, bad10;
-        uint32_t c9 = 0;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) { uint32_t r = (uint32_t)(w >> (4 * k)) & 15; bad9 |= (r >= 10); c9 = c9 * 10 + r; }
-        uint32_t r9 = (uint32_t)(w >> 36) & 15;
-        bad10 = bad9 | (r9 >= 10);
-        if (!bad9) probe<NT>(A, s_aa, tid, m, read, frame, 0, i, c9);
-        if (!bad10) {
-#pragma unroll
-            for (int p = 1; p < N_PAT; ++p) {
-                const int wl = p + 2;
-                uint32_t c = 0;
-#pragma unroll
-                for (int k = 0; k < 10; ++k) if (k != wl) c = c * 10 + ((uint32_t)(w >> (4 * k)) & 15);
-                probe<NT>(A, s_aa, tid, m, read, frame, p, i, c);
-            }
-        }
-        int nx = i + 10;
-        win = (win >> 4) | ((unsigned long long)(nx < m ? red_of(FR(nx)) : 15) << 36);
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -470,8 +576,7 @@ constexpr int GROW = MAX_FRAME + GAP_SLACK + 2;
 
 struct GExt { int gain, eq, et; uint32_t st; int cells; };
 
-template <int NT>
-__device__ void gapped_xdrop(const uint8_t *s_aa, int tid, int q_first, int qstep, const uint8_t *__restrict__ t,
+__device__ void gapped_xdrop(const uint8_t *fr, int q_first, int qstep, const uint8_t *__restrict__ t,
                              int tstep, int nQ, int nD, GExt &g) {
     g.gain = 0; g.eq = 0; g.et = 0; g.st = 0; g.cells = 0;
     const int GI = GAP_OPEN, GE = GAP_EXT, GIE = GAP_OPEN + GAP_EXT;
@@ -546,12 +651,11 @@ __device__ void gapped_xdrop(const uint8_t *s_aa, int tid, int q_first, int qste
 }
 
 struct GapArgs {
-    const uint8_t *bases;
-    const int64_t *offs;
-    int L;
+    int L, fstride;
     DevDB db;
-    const Surv *surv;
-    int64_t n_surv;
+    const uint8_t *frames;         // frame store of the chunk the survivors came from
+    const Surv *surv;              // survivors [first, first + n_surv) of the global list
+    int64_t first, n_surv;
     mcx_hit *hsp;
     SortKey *keys;
     int32_t *idx;
@@ -560,17 +664,12 @@ struct GapArgs {
 
 template <int NT>
 __global__ void __launch_bounds__(NT) k_gapped(GapArgs A) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    double *s_ent = reinterpret_cast<double *>(smem);
-    uint8_t *s_aa = smem + 13 * 13 * sizeof(double);
-    const int tid = threadIdx.x;
-    for (int k = tid; k < 13 * 13; k += NT) s_ent[k] = c_ent[k];
-    __syncthreads();
-    int64_t g = (int64_t)blockIdx.x * NT + tid;
+    int64_t g = (int64_t)blockIdx.x * NT + threadIdx.x;
     if (g >= A.n_surv) return;
+    g += A.first;
     const Surv v = A.surv[g];
-    const uint8_t *rd = A.bases + A.offs[v.read];
-    const int m = build_frame<NT>(s_aa, tid, rd, A.L, v.frame, s_ent);
+    const uint8_t *__restrict__ fr = A.frames + (int64_t)v.gframe * A.fstride;
+    const int m = (A.L - v.frame % 3) / 3;
     const int32_t o = A.db.off[v.subject];
     const int n = A.db.off[v.subject + 1] - o;
     const uint8_t *t = A.db.res + o;
@@ -581,7 +680,7 @@ __global__ void __launch_bounds__(NT) k_gapped(GapArgs A) {
         int ql = m - (q1 + 1), tl = n - (t1 + 1);
         if (ql > 2 && tl > 2) {
             if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
-            GExt e; gapped_xdrop<NT>(s_aa, tid, q1 + 1, 1, t + t1 + 1, 1, ql, tl, e);
+            GExt e; gapped_xdrop(fr, q1 + 1, 1, t + t1 + 1, 1, ql, tl, e);
             ++ng; nc += e.cells;
             if (e.gain > 0) {
                 score += e.gain; q1 += e.eq; t1 += e.et;
@@ -591,7 +690,7 @@ __global__ void __launch_bounds__(NT) k_gapped(GapArgs A) {
         ql = q0; tl = t0;
         if (ql > 2 && tl > 2) {
             if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
-            GExt e; gapped_xdrop<NT>(s_aa, tid, q0 - 1, -1, t + t0 - 1, -1, ql, tl, e);
+            GExt e; gapped_xdrop(fr, q0 - 1, -1, t + t0 - 1, -1, ql, tl, e);
             ++ng; nc += e.cells;
             if (e.gain > 0) {
                 score += e.gain; q0 -= e.eq; t0 -= e.et;
@@ -741,6 +840,11 @@ struct mcx_ctx {
     bool pushed = false, searched = false;
     // search buffers
     Surv *d_surv = nullptr;
+    uint8_t *d_frames = nullptr;
+    uint32_t *d_segq = nullptr;
+    int64_t cap_segq = 0, n_segq_last = 0;
+    Cand *d_cand = nullptr;
+    int64_t cap_frames = 0, cap_cand = 0, n_cand_last = 0;
     mcx_hit *d_hsp = nullptr, *d_hits_out = nullptr;
     SortKey *d_keys = nullptr;
     int32_t *d_idx = nullptr, *d_best = nullptr, *d_hflag = nullptr, *d_hpos = nullptr;
@@ -783,6 +887,32 @@ static int ensure(mcx_ctx *ctx, T **p, int64_t *cap, int64_t need) {
     int64_t c = need + need / 8 + 16;
     CK(dev_alloc(p, (size_t)c));
     *cap = c;
+    return MCX_OK;
+}
+
+template <typename T>
+static int grow_keep(mcx_ctx *ctx, T **p, int64_t keep, int64_t cap) {
+    T *q = nullptr;
+    CK(dev_alloc(&q, (size_t)cap));
+    if (*p && keep > 0) CK(cudaMemcpyAsync(q, *p, (size_t)keep * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (*p) CK(cudaFree(*p));
+    *p = q;
+    return MCX_OK;
+}
+
+// survivor-sized buffers: keep the first `keep` entries of the ones that carry state across chunks
+static int grow_survivors(mcx_ctx *ctx, int64_t keep, int64_t cap) {
+    int rc;
+    if ((rc = grow_keep(ctx, &ctx->d_surv, keep, cap)) != MCX_OK) return rc;
+    if ((rc = grow_keep(ctx, &ctx->d_hsp, keep, cap)) != MCX_OK) return rc;
+    if ((rc = grow_keep(ctx, &ctx->d_keys, keep, cap)) != MCX_OK) return rc;
+    if ((rc = grow_keep(ctx, &ctx->d_idx, keep, cap)) != MCX_OK) return rc;
+    if ((rc = grow_keep(ctx, &ctx->d_hits_out, 0, cap)) != MCX_OK) return rc;
+    if ((rc = grow_keep(ctx, &ctx->d_hflag, 0, cap + 1)) != MCX_OK) return rc;
+    if ((rc = grow_keep(ctx, &ctx->d_hpos, 0, cap + 1)) != MCX_OK) return rc;
+    if ((rc = grow_keep(ctx, &ctx->d_keep, 0, cap)) != MCX_OK) return rc;
+    ctx->cap_surv = cap;
     return MCX_OK;
 }
 
@@ -838,7 +968,10 @@ static int build_index(mcx_ctx *ctx, const mcx_db *db) {
             if (first) {
                 uint32_t slot = (code * 2654435761u) >> (32 - bits);
                 while (hk[slot] != 0xffffffffu) slot = (slot + 1) & (size - 1);
-                hk[slot] = code; hv[slot] = base + (uint32_t)(k);
+                size_t e = k;
+                while (e + 1 < ent.size() && (ent[e + 1] >> 32) == code) ++e;
+                const uint32_t cnt = (uint32_t)(e - k + 1);
+                hk[slot] = code; hv[slot] = (base + (uint32_t)k) | ((cnt > 127 ? 127u : cnt - 1) << 25);
             }
         }
         uint32_t *dk = nullptr, *dv = nullptr;
@@ -848,6 +981,7 @@ static int build_index(mcx_ctx *ctx, const mcx_db *db) {
         CK(cudaMemcpy(dv, hv.data(), size * sizeof(uint32_t), cudaMemcpyHostToDevice));
         ctx->db.hkey[p] = dk; ctx->db.hval[p] = dv; ctx->db.hmask[p] = size - 1; ctx->db.hshift[p] = 32 - bits;
     }
+    if (post_all.size() >= (1u << 25)) return fail(ctx, MCX_EINVAL, "seed index too large for 25-bit posting offsets");
     uint32_t *dp = nullptr;
     CK(dev_alloc(&dp, post_all.size())); ctx->db_allocs.push_back(dp);
     CK(cudaMemcpy(dp, post_all.data(), post_all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -925,7 +1059,7 @@ extern "C" void mcx_destroy(mcx_ctx *ctx) {
     if (ctx->own_reads) { cudaFree(ctx->d_bases); cudaFree(ctx->d_quals); cudaFree(ctx->d_offs); }
     void *bufs[] = {ctx->d_code, ctx->d_flag, ctx->d_pos, ctx->d_kept, ctx->d_surv, ctx->d_hsp, ctx->d_hits_out,
                     ctx->d_keys, ctx->d_idx, ctx->d_best, ctx->d_hflag, ctx->d_hpos, ctx->d_keep, ctx->d_cnt,
-                    ctx->d_acc, ctx->d_abl, ctx->d_temp};
+                    ctx->d_acc, ctx->d_abl, ctx->d_temp, ctx->d_frames, ctx->d_cand, ctx->d_segq};
     for (void *p : bufs) if (p) cudaFree(p);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -1050,24 +1184,6 @@ extern "C" int mcx_qc_counts(mcx_ctx *ctx, mcx_qc *out) {
     return MCX_OK;
 }
 
-template <int NT>
-static int launch_seed(mcx_ctx *ctx, const SeedArgs &A, int maxm) {
-    size_t smem = 13 * 13 * sizeof(double) + (size_t)maxm * NT;
-    CK(cudaFuncSetAttribute(k_seed<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t threads = A.n_search * 6;
-    int64_t blocks = (threads + NT - 1) / NT;
-    k_seed<NT><<<(unsigned)blocks, NT, smem, ctx->stream>>>(A);
-    return MCX_OK;
-}
-template <int NT>
-static int launch_gapped(mcx_ctx *ctx, const GapArgs &A, int maxm) {
-    size_t smem = 13 * 13 * sizeof(double) + (size_t)maxm * NT;
-    CK(cudaFuncSetAttribute(k_gapped<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t blocks = (A.n_surv + NT - 1) / NT;
-    k_gapped<NT><<<(unsigned)blocks, NT, smem, ctx->stream>>>(A);
-    return MCX_OK;
-}
-
 extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     if (!ctx) return fail(ctx, MCX_EINVAL, "mcx_search: null context");
     if (!ctx->pushed) return fail(ctx, MCX_ESTATE, "mcx_search: no reads pushed");
@@ -1099,17 +1215,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     int64_t per_read = 8;
     if (const char *e = getenv("MCX_SURV_PER_READ")) per_read = std::max(1, atoi(e));
     const int64_t want = std::max<int64_t>(n_search * per_read, 1 << 16);
-    if (ctx->cap_surv < want) {
-        void *old[] = {ctx->d_surv, ctx->d_hsp, ctx->d_hits_out, ctx->d_keys, ctx->d_idx, ctx->d_hflag, ctx->d_hpos, ctx->d_keep};
-        for (void *p : old) if (p) cudaFree(p);
-        ctx->d_surv = nullptr; ctx->d_hsp = nullptr; ctx->d_hits_out = nullptr; ctx->d_keys = nullptr;
-        ctx->d_idx = nullptr; ctx->d_hflag = nullptr; ctx->d_hpos = nullptr; ctx->d_keep = nullptr;
-        CK(dev_alloc(&ctx->d_surv, (size_t)want)); CK(dev_alloc(&ctx->d_hsp, (size_t)want));
-        CK(dev_alloc(&ctx->d_hits_out, (size_t)want)); CK(dev_alloc(&ctx->d_keys, (size_t)want));
-        CK(dev_alloc(&ctx->d_idx, (size_t)want)); CK(dev_alloc(&ctx->d_hflag, (size_t)want + 1));
-        CK(dev_alloc(&ctx->d_hpos, (size_t)want + 1)); CK(dev_alloc(&ctx->d_keep, (size_t)want));
-        ctx->cap_surv = want;
-    }
+    if (ctx->cap_surv < want && (rc = grow_survivors(ctx, 0, want)) != MCX_OK) return rc;
     if ((rc = ensure(ctx, &ctx->d_best, &ctx->cap_best, n + 1)) != MCX_OK) return rc;
     CK(cudaMemsetAsync(ctx->d_cnt, 0, 16 * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(ctx->d_acc, 0, (3 + 2 * MCX_N_FAM) * sizeof(unsigned long long), st));
@@ -1119,32 +1225,101 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     // an ungapped HSP of 49+ can still grow in the gapped stage, so it survives whatever the floor is
     const int thr = std::max(1, std::min(P.min_report_raw, 49));
 
-    CK(cudaEventRecord(ctx->ev[2], st));
-    unsigned long long n_surv = 0;
-    if (n_search > 0) {
-        SeedArgs A;
-        A.bases = ctx->d_bases; A.offs = ctx->d_offs; A.kept = ctx->d_kept; A.n_search = n_search;
-        A.L = P.read_length; A.thr_report = thr; A.db = ctx->db; A.surv = ctx->d_surv;
-        A.n_surv = ctx->d_cnt + 8; A.cap_surv = (unsigned long long)ctx->cap_surv;
-        if ((rc = launch_seed<192>(ctx, A, maxm)) != MCX_OK) return rc;
-        ++ctx->launches;
-        CK(cudaMemcpyAsync(&n_surv, ctx->d_cnt + 8, sizeof n_surv, cudaMemcpyDeviceToHost, st));
+    // K2a/K2b/K3 run per chunk of reads so that the frame store and the candidate queue stay bounded
+    const int fstride = frame_stride(maxm);
+    int64_t chunk = 2000000, cand_per_read = 96;
+    if (const char *e = getenv("MCX_CHUNK_READS")) chunk = std::max(1, atoi(e));
+    if (const char *e = getenv("MCX_CAND_PER_READ")) cand_per_read = std::max(1, atoi(e));
+    chunk = std::min<int64_t>(chunk, std::max<int64_t>(n_search, 1));
+    {
+        const int64_t need_fr = (chunk * 6 + 512) * fstride, need_cand = std::max<int64_t>(chunk * cand_per_read, 1 << 16);
+        if ((rc = ensure(ctx, &ctx->d_frames, &ctx->cap_frames, need_fr)) != MCX_OK) return rc;
+        if ((rc = ensure(ctx, &ctx->d_cand, &ctx->cap_cand, need_cand)) != MCX_OK) return rc;
+        if ((rc = ensure(ctx, &ctx->d_segq, &ctx->cap_segq, chunk * 6 + 512)) != MCX_OK) return rc;
     }
-    CK(cudaEventRecord(ctx->ev[3], st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
-    if ((int64_t)n_surv > ctx->cap_surv)
-        return fail(ctx, MCX_ENOMEM, "mcx_search: survivor buffer overflow (" + std::to_string(n_surv) + " > " +
-                                         std::to_string(ctx->cap_surv) + "); raise MCX_SURV_PER_READ");
+    float ms_probe = 0, ms_ext = 0, ms_gap = 0;
+    unsigned long long n_surv = 0, n_cand_total = 0;
+    for (int64_t first = 0; first < n_search; first += chunk) {
+        const int64_t nr = std::min(chunk, n_search - first);
+        CK(cudaMemsetAsync(ctx->d_cnt + 9, 0, sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(ctx->d_cnt + 12, 0, sizeof(unsigned long long), st));
+        CK(cudaEventRecord(ctx->ev[2], st));
+        constexpr int NTF = 192;
+        {
+            FrameArgs F;
+            F.bases = ctx->d_bases; F.offs = ctx->d_offs; F.kept = ctx->d_kept; F.first = first; F.n_search = nr;
+            F.L = P.read_length; F.frames = ctx->d_frames; F.segq = ctx->d_segq; F.n_segq = ctx->d_cnt + 12;
+            const size_t smem = 13 * 13 * sizeof(double) + (size_t)fstride * NTF;
+            CK(cudaFuncSetAttribute(k_frames<NTF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_frames<NTF><<<(unsigned)((nr * 6 + NTF - 1) / NTF), NTF, smem, st>>>(F, fstride);
+            ++ctx->launches;
+        }
+        unsigned long long n_segq = 0;
+        CK(cudaMemcpyAsync(&n_segq, ctx->d_cnt + 12, sizeof n_segq, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        if (n_segq > 0) {
+            k_seg<<<(unsigned)((n_segq + 63) / 64), 64, 0, st>>>(ctx->d_frames, fstride, P.read_length, ctx->d_segq, (int64_t)n_segq);
+            ++ctx->launches;
+        }
+        ctx->n_segq_last = (int64_t)n_segq;
+        unsigned long long n_cand = 0;
+        for (int attempt = 0;; ++attempt) {
+            ProbeArgs A;
+            A.n_frames = nr * 6; A.L = P.read_length; A.db = ctx->db; A.frames = ctx->d_frames; A.cand = ctx->d_cand;
+            A.n_cand = ctx->d_cnt + 9; A.cap_cand = (unsigned long long)ctx->cap_cand;
+            const size_t smem = (size_t)fstride * NTF;
+            CK(cudaFuncSetAttribute(k_probe<NTF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_probe<NTF><<<(unsigned)((nr * 6 + NTF - 1) / NTF), NTF, smem, st>>>(A, fstride);
+            ++ctx->launches;
+            CK(cudaMemcpyAsync(&n_cand, ctx->d_cnt + 9, sizeof n_cand, cudaMemcpyDeviceToHost, st));
+            if (attempt == 0) CK(cudaEventRecord(ctx->ev[3], st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+            if ((int64_t)n_cand <= ctx->cap_cand) break;
+            if (attempt) return fail(ctx, MCX_ENOMEM, "mcx_search: candidate queue overflow after regrowth");
+            // the count is exact: size the queue for it and probe this chunk again
+            if ((rc = ensure(ctx, &ctx->d_cand, &ctx->cap_cand, (int64_t)n_cand)) != MCX_OK) return rc;
+            CK(cudaMemsetAsync(ctx->d_cnt + 9, 0, sizeof(unsigned long long), st));
+        }
+        n_cand_total += n_cand;
+        const unsigned long long surv_before = n_surv;
+        for (int attempt = 0; n_cand > 0; ++attempt) {
+            ExtArgs E;
+            E.kept = ctx->d_kept; E.first = first; E.L = P.read_length; E.fstride = fstride; E.thr_report = thr; E.db = ctx->db;
+            E.frames = ctx->d_frames; E.cand = ctx->d_cand; E.n_cand = (int64_t)n_cand; E.surv = ctx->d_surv;
+            E.n_surv = ctx->d_cnt + 8; E.cap_surv = (unsigned long long)ctx->cap_surv;
+            k_extend<256><<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(E);
+            ++ctx->launches;
+            CK(cudaMemcpyAsync(&n_surv, ctx->d_cnt + 8, sizeof n_surv, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+            if ((int64_t)n_surv <= ctx->cap_surv) break;
+            if (attempt) return fail(ctx, MCX_ENOMEM, "mcx_search: survivor buffer overflow after regrowth");
+            if ((rc = grow_survivors(ctx, (int64_t)surv_before, (int64_t)n_surv + (int64_t)n_surv / 4)) != MCX_OK) return rc;
+            CK(cudaMemcpyAsync(ctx->d_cnt + 8, &surv_before, sizeof surv_before, cudaMemcpyHostToDevice, st));
+            n_surv = surv_before;
+        }
+        CK(cudaEventRecord(ctx->ev[8], st));
+        if (n_surv > surv_before) {
+            GapArgs G;
+            G.L = P.read_length; G.fstride = fstride; G.db = ctx->db; G.frames = ctx->d_frames; G.surv = ctx->d_surv;
+            G.first = (int64_t)surv_before; G.n_surv = (int64_t)(n_surv - surv_before);
+            G.hsp = ctx->d_hsp; G.keys = ctx->d_keys; G.idx = ctx->d_idx; G.counters = ctx->d_cnt + 10;
+            k_gapped<128><<<(unsigned)((G.n_surv + 127) / 128), 128, 0, st>>>(G);
+            ++ctx->launches;
+        }
+        CK(cudaEventRecord(ctx->ev[9], st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        float t;
+        cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3]); ms_probe += t;
+        cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[8]); ms_ext += t;
+        cudaEventElapsedTime(&t, ctx->ev[8], ctx->ev[9]); ms_gap += t;
+    }
     R.n_seed_hits = (int64_t)n_surv;
+    ctx->n_cand_last = (int64_t)n_cand_total;
     const int64_t ns = (int64_t)n_surv;
-    if (ns > 0) {
-        GapArgs G;
-        G.bases = ctx->d_bases; G.offs = ctx->d_offs; G.L = P.read_length; G.db = ctx->db; G.surv = ctx->d_surv;
-        G.n_surv = ns; G.hsp = ctx->d_hsp; G.keys = ctx->d_keys; G.idx = ctx->d_idx; G.counters = ctx->d_cnt + 10;
-        if ((rc = launch_gapped<128>(ctx, G, maxm)) != MCX_OK) return rc;
-        ++ctx->launches;
-    }
     CK(cudaEventRecord(ctx->ev[4], st));
     if (ns > 0) {
         size_t tb = 0;
@@ -1174,8 +1349,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     R.n_gapped = (int64_t)gc[0]; R.gapped_cells = (int64_t)gc[1];
     for (int f = 0; f < MCX_N_FAM; ++f) { R.fam_hits[f] = (int64_t)acc[3 + f]; R.fam_aln[f] = (int64_t)acc[3 + MCX_N_FAM + f]; }
     for (size_t k = 0; k < abl.size(); ++k) R.aln_by_len[k] = (int64_t)abl[k];
-    cudaEventElapsedTime(&ctx->ms[2], ctx->ev[2], ctx->ev[3]);
-    cudaEventElapsedTime(&ctx->ms[3], ctx->ev[3], ctx->ev[4]);
+    ctx->ms[2] = ms_probe; ctx->ms[7] = ms_ext; ctx->ms[3] = ms_gap;
     cudaEventElapsedTime(&ctx->ms[4], ctx->ev[4], ctx->ev[5]);
     cudaEventElapsedTime(&ctx->ms[5], ctx->ev[5], ctx->ev[6]);
     cudaEventElapsedTime(&ctx->ms[6], ctx->ev[6], ctx->ev[7]);

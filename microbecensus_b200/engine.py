@@ -196,7 +196,7 @@ class MarkerSearch:
         ms = (C.c_float * 8)()
         launches = C.c_int64(0)
         self._ck(self.lib.mcx_timings(self.ctx, C.byref(ms), C.byref(launches)))
-        names = ("h2d", "qc", "seed_ungapped", "gapped", "sort", "classify", "d2h")
+        names = ("h2d", "qc", "probe", "gapped", "sort", "classify", "d2h", "extend")
         return {k: float(ms[i]) for i, k in enumerate(names)}, int(launches.value)
 
 

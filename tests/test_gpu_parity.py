@@ -1,0 +1,173 @@
+"""CUDA path (through the libmcx C ABI) against the CPU oracle and the golden fixtures.  Needs a B200."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import golden_io
+from microbecensus_b200 import microbe_census as mcb, synth
+from microbecensus_b200.engine import MarkerSearch, ReadBatch
+from oracle_lib import MCX_ORDER
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(markers):
+    e = MarkerSearch(markers, 0)
+    yield e
+    e.close()
+
+
+def gpu_vs_oracle(eng, oracle, markers, batch, L, quota=-1):
+    eng.set_params(L)
+    eng.push(batch)
+    res = eng.search(quota)
+    hits = eng.hits()
+    oh, _ = oracle.search(batch, L, eng.min_report_raw)
+    assert hits.shape == oh[:, MCX_ORDER].shape
+    assert np.array_equal(hits, oh[:, MCX_ORDER])          # every reported HSP, every field: bit-exact
+    oc = oracle.classify(oh, L, markers, batch.n)
+    assert res.reads_classified == oc["classified"]
+    assert np.array_equal(res.fam_hits, oc["fam_hits"])
+    assert np.array_equal(res.fam_aln, oc["fam_aln"])
+    assert np.array_equal(res.aln_by_len, oc["aln_by_len"])
+    assert np.array_equal(eng.classified(batch.n), oc["best_subject"])
+    assert res.n_hsp == len(oh)
+    assert res.reads_with_hits == len(set(oh[:, 0].tolist()))
+    return res
+
+
+@pytest.mark.parametrize("fname,L", [("meta.fa.gz", 100), ("meta50.fa.gz", 50), ("long.fa.gz", 500), ("long.fa.gz", 250),
+                                     ("long.fa.gz", 150), ("long.fa.gz", 60), ("long.fa.gz", 300)])
+def test_golden_reads_bit_exact(eng, oracle, markers, fname, L):
+    gpu_vs_oracle(eng, oracle, markers, ReadBatch.from_strings(golden_io.read_fasta(fname)), L)
+
+
+@pytest.mark.parametrize("L,n", [(100, 20000), (150, 8000), (70, 8000), (400, 2000)])
+def test_seeded_synthetic_reads_bit_exact(eng, oracle, markers, L, n):
+    res = gpu_vs_oracle(eng, oracle, markers, synth.reads(7, 0, n, L), L)
+    assert res.reads_classified > 0
+
+
+def test_classification_against_reference_golden(eng, markers):
+    """GPU classification vs what the reference's classify_reads made of RAPsearch2's own output."""
+    for fname, name, L in (("meta.fa.gz", "meta", 100), ("meta50.fa.gz", "meta50", 50)):
+        batch = ReadBatch.from_strings(golden_io.read_fasta(fname))
+        eng.set_params(L); eng.push(batch); eng.search(-1)
+        best = eng.classified(batch.n)
+        exp = golden_io.read_json("%s.L%d.json" % (name, L))
+        ref_cls = {int(k): v["fam"] for k, v in exp["classified"].items()}
+        ours = {int(i): markers.fam_names[markers.fam[s]] for i, s in enumerate(best) if s >= 0}
+        assert set(ref_cls) == set(ours)
+        assert all(ref_cls[k] == ours[k] for k in ours)
+
+
+def test_qc_counters_match_reference_and_oracle(eng, oracle, markers):
+    recs = golden_io.read_fastq("short.fq.gz")
+    batch = ReadBatch.from_strings([r[1] for r in recs], [r[2] for r in recs])
+    for case in golden_io.read_json("short.qc.json"):
+        o = case["opts"]
+        L = case["read_length"]
+        eng.set_params(L, quality_offset=case["quality_offset"], min_quality=o.get("min_quality", -5),
+                       mean_quality=o.get("mean_quality", -5), max_unknown=o.get("max_unknown", 100))
+        eng.push(batch)
+        res = eng.search(o.get("nreads", 1000000))
+        assert (res.sampled_reads, res.too_short, res.low_qual, res.dups) == (case["sampled"], case["too_short"], case["low_qual"], 0), case
+        sampled, code, cnt = oracle.process_reads(batch, L, case["quality_offset"], o.get("min_quality", -5), o.get("mean_quality", -5),
+                                                  o.get("max_unknown", 100), o.get("nreads", 1000000))
+        assert sampled == res.sampled_reads
+        # the searched reads are exactly the oracle's kept reads: same HSPs on that subset
+        kept = np.flatnonzero(code == 0)
+        sub = ReadBatch.from_strings([recs[i][1] for i in kept])
+        oh, _ = oracle.search(sub, L, eng.min_report_raw)
+        hits = eng.hits()
+        assert len(hits) == len(oh)
+        assert np.array_equal(hits[:, 1:], oh[:, MCX_ORDER][:, 1:])
+        assert np.array_equal(hits[:, 0], kept[oh[:, 0]])
+
+
+def test_edge_cases(eng, oracle, markers):
+    # empty input
+    eng.set_params(100)
+    eng.push(ReadBatch.from_strings([]))
+    res = eng.search(-1)
+    assert res.sampled_reads == 0 and res.n_hsp == 0 and res.reads_classified == 0
+    # all too short / unknown bases / lower case / ragged lengths
+    good = golden_io.read_fasta("meta.fa.gz")[:40]
+    seqs = ["ACGT" * 10, "N" * 100, good[0].lower(), good[1][:50] + "N" + good[1][51:], good[2] + "ACGTACGT", good[3][:99]] + good[4:]
+    batch = ReadBatch.from_strings(seqs)
+    eng.push(batch)
+    res = eng.search(-1)
+    assert res.too_short == 2 and res.sampled_reads == len(seqs) - 2
+    kept = [s for s in seqs if len(s) >= 100]
+    oh, _ = oracle.search(ReadBatch.from_strings(kept), 100, eng.min_report_raw)
+    assert res.n_hsp == len(oh)
+    # max_unknown filter: the all-N read goes
+    eng.set_params(100, max_unknown=10)
+    eng.push(batch)
+    assert eng.search(-1).low_qual == 1
+
+
+def test_full_size_invariants(eng, markers):
+    """BASELINE config 2 size (2M x 100 bp): size-independent properties instead of an oracle run --
+    idempotence, additivity of the integer sums over a split of the reads (checksum of checksums), the -n quota
+    equals a search of the prefix, and agreement of the host API with device-resident input."""
+    import torch
+    n, L = 2_000_000, 100
+    batch = synth.reads(2, 0, n, L)
+    eng.set_params(L)
+    eng.push(batch)
+    whole = eng.search(-1)
+    again = eng.search(-1)
+    assert np.array_equal(whole.counts_vector(), again.counts_vector())
+    assert whole.sampled_reads == n and whole.reads_classified > 10000
+    parts = []
+    for lo, hi in ((0, 700_001), (700_001, n)):
+        eng.push(batch.slice(lo, hi))
+        parts.append(eng.search(-1).counts_vector())
+    total = parts[0] + parts[1]
+    assert np.array_equal(total, whole.counts_vector())
+    eng.push(batch)
+    q = eng.search(700_001)
+    assert np.array_equal(q.counts_vector(), parts[0])
+    d_b = torch.from_numpy(batch.bases).cuda(); d_o = torch.from_numpy(batch.offsets).cuda()
+    eng.push_device(d_b.data_ptr(), 0, d_o.data_ptr(), n, d_b.numel())
+    assert np.array_equal(eng.search(-1).counts_vector(), whole.counts_vector())
+    ags = mcb.estimate_average_genome_size({"read_length": L, "sampled_reads": n, "verbose": False}, None, whole.agg_hits())
+    assert 1.0e6 < ags < 4.0e6
+
+
+def test_run_pipeline_drop_in(eng, oracle, markers, tmp_path, capsys):
+    """run_pipeline(args) on a FASTQ file: same args keys, verbose lines and AGS as the oracle-derived numbers."""
+    recs = golden_io.read_fastq("short.fq.gz")
+    path = os.path.join(os.path.dirname(golden_io.GOLD), "golden", "short.fq.gz")
+    args = {"seqfiles": [path], "verbose": True, "nreads": 2000, "mean_quality": 25}
+    est, out = mcb.run_pipeline(args)
+    text = capsys.readouterr().out
+    assert out["file_type"] == "fastq" and out["quality_offset"] == 32 and out["read_length"] == 100
+    batch = ReadBatch.from_strings([r[1] for r in recs], [r[2] for r in recs])
+    sampled, code, cnt = oracle.process_reads(batch, 100, 32, -5, 25, 100, 2000)
+    assert out["sampled_reads"] == sampled
+    assert "\t%d reads shorter than 100 bp and skipped" % cnt["too_short"] in text
+    assert "\t%d low quality reads found and skipped" % cnt["low_qual"] in text
+    sub = ReadBatch.from_strings([recs[i][1] for i in np.flatnonzero(code == 0)])
+    oh, _ = oracle.search(sub, 100, mcb.get_engine(0).min_report_raw)
+    oc = oracle.classify(oh, 100, markers, sub.n)
+    assert "\t%d reads assigned to a marker protein" % oc["classified"] in text
+    from microbecensus_b200.engine import SearchResult
+
+    class Raw:
+        pass
+    raw = Raw()
+    for k in ("too_short", "low_qual", "dups", "reads_with_hits", "n_hsp", "n_seed_hits", "n_gapped", "gapped_cells"):
+        setattr(raw, k, 0)
+    raw.sampled_reads = sampled; raw.reads_classified = oc["classified"]
+    raw.fam_hits = oc["fam_hits"]; raw.fam_aln = oc["fam_aln"]; raw.aln_by_len = oc["aln_by_len"].ravel()
+    want = mcb.estimate_average_genome_size({"read_length": 100, "sampled_reads": sampled, "verbose": False}, None,
+                                            SearchResult(raw, markers, 100).agg_hits())
+    assert est == want
+    out["outfile"] = str(tmp_path / "r.txt")
+    mcb.report_results(out, est, mcb.count_bases(out))
+    assert open(out["outfile"]).read().startswith("Parameters\nmetagenome:\t")

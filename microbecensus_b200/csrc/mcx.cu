@@ -69,7 +69,13 @@ struct DevDB {
     uint32_t hmask[N_PAT];
     int hshift[N_PAT];
     const uint32_t *post;          // (subject << 11 | position), bit 31 = last posting of the word
+    const uint32_t *bloom;         // 2^28-bit presence filter over (pattern, word): absorbs ~94 % of the probes in L2
 };
+
+#define BLOOM_BITS 28
+__host__ __device__ __forceinline__ uint32_t bloom_index(int p, uint32_t code) {
+    return ((code ^ ((uint32_t)p * 0x3243F6A9u)) * 2246822519u) >> (32 - BLOOM_BITS);
+}
 
 struct Surv {                      // ungapped HSP that reached the report floor (20 bytes)
     int32_t read;
@@ -287,6 +293,58 @@ __global__ void k_qc(const uint8_t *__restrict__ bases, const uint8_t *__restric
     }
 }
 
+// -d (mc.py:345, 355): the reference keeps the set of whole untrimmed strings of the reads it has written and
+// skips a read whose string or reverse complement is in it.  Restated with a 128-bit polynomial fingerprint that is
+// canonical over strands (same definition as the oracle's oc_fingerprint): a read that is long enough is a
+// duplicate iff an earlier KEPT read has the same fingerprint.  Per fingerprint group in index order: everything
+// after the first kept read is a duplicate; reads before it keep their QC verdict.
+struct FpKey { unsigned long long a, b; uint32_t idx; uint32_t pad; };
+struct FpLess {
+    __device__ __forceinline__ bool operator()(const FpKey &x, const FpKey &y) const {
+        return x.a < y.a || (x.a == y.a && (x.b < y.b || (x.b == y.b && x.idx < y.idx)));
+    }
+};
+#define FP_B1 0x9E3779B97F4A7C15ull
+#define FP_B2 0xC2B2AE3D27D4EB4Full
+#define FP_LEN 0xD6E8FEB86659FD93ull
+__device__ __forceinline__ unsigned long long fp_code(uint8_t c) {
+    return c == 'A' ? 1 : c == 'C' ? 2 : c == 'G' ? 3 : c == 'T' ? 4 : c == 'N' ? 5 : 6 + (c & 0x7f);
+}
+__global__ void k_fingerprint(const uint8_t *__restrict__ bases, const int64_t *__restrict__ offs, int64_t n,
+                              FpKey *__restrict__ keys) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int64_t b = offs[r];
+    const int len = (int)(offs[r + 1] - b);
+    unsigned long long f1 = 0, f2 = 0, r1 = 0, r2 = 0, p1 = 1, p2 = 1;
+    for (int i = 0; i < len; ++i) {
+        const unsigned long long c = fp_code(bases[b + i]);
+        const unsigned long long rc = (c >= 1 && c <= 4) ? 5 - c : c;
+        f1 = f1 * FP_B1 + c; f2 = f2 * FP_B2 + c;
+        r1 += rc * p1; r2 += rc * p2; p1 *= FP_B1; p2 *= FP_B2;
+    }
+    f1 += (unsigned long long)len * FP_LEN; r1 += (unsigned long long)len * FP_LEN;
+    FpKey k;
+    if (f1 < r1 || (f1 == r1 && f2 <= r2)) { k.a = f1; k.b = f2; } else { k.a = r1; k.b = r2; }
+    k.idx = (uint32_t)r; k.pad = 0;
+    keys[r] = k;
+}
+__global__ void k_mark_dups(const FpKey *__restrict__ keys, int64_t n, uint8_t *__restrict__ code) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const FpKey k = keys[p];
+    if (p > 0 && keys[p - 1].a == k.a && keys[p - 1].b == k.b) return;   // not the first of its group
+    bool seen_kept = false;
+    for (int64_t e = p; e < n; ++e) {
+        const FpKey q = keys[e];
+        if (q.a != k.a || q.b != k.b) break;
+        const uint8_t c = code[q.idx];
+        if (c == 1) continue;                  // too short is decided before the duplicate test
+        if (seen_kept) code[q.idx] = 3;
+        else if (c == 0) seen_kept = true;
+    }
+}
+
 __global__ void k_keep_flags(const uint8_t *__restrict__ code, int64_t n, int32_t *__restrict__ flag) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) flag[i] = code[i] == 0;
@@ -389,10 +447,11 @@ struct ProbeArgs {
     int L;
     DevDB db;
     const uint8_t *frames;
-    Cand *cand;
-    unsigned long long *n_cand;
-    unsigned long long cap_cand;
+    Cand *cand;                    // NQ sub-queues of cap_cand entries each (spreads the append atomics)
+    unsigned long long *n_cand;    // NQ counters
+    unsigned long long cap_cand;   // per sub-queue
 };
+constexpr int NQ = 64;
 
 template <int NT>
 __global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
@@ -429,11 +488,17 @@ __global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
             for (int k = 0; k < 10; ++k) if (k != p + 2) c = c * 10 + ((uint32_t)(win >> (4 * k)) & 15);
             code[p] = c;
         }
-        // all five first-slot loads are in flight together
+        // five filter words in flight together, then the table slots of the words the filter lets through
+        uint32_t bw[N_PAT], bi[N_PAT];
+#pragma unroll
+        for (int p = 0; p < N_PAT; ++p) {
+            bi[p] = bloom_index(p, code[p]);
+            bw[p] = (p == 0 ? !bad9 : !bad10) ? __ldg(A.db.bloom + (bi[p] >> 5)) : 0u;
+        }
 #pragma unroll
         for (int p = 0; p < N_PAT; ++p) {
             slot[p] = (code[p] * 2654435761u) >> A.db.hshift[p];
-            key[p] = (p == 0 ? !bad9 : !bad10) ? __ldg(A.db.hkey[p] + slot[p]) : 0xffffffffu;
+            key[p] = ((bw[p] >> (bi[p] & 31)) & 1) ? __ldg(A.db.hkey[p] + slot[p]) : 0xffffffffu;
         }
 #pragma unroll
         for (int p = 0; p < N_PAT; ++p) {
@@ -445,12 +510,14 @@ __global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
             const uint32_t pi = v & 0x1ffffffu, extra = v >> 25;      // 25-bit start, 7-bit (count - 1), 127 = longer
             uint32_t cnt = extra + 1;
             if (extra == 127) { cnt = 128; while (!(__ldg(A.db.post + pi + cnt - 1) & 0x80000000u)) ++cnt; }
-            const unsigned long long base = atomicAdd(A.n_cand, (unsigned long long)cnt);
+            const int sq = blockIdx.x & (NQ - 1);
+            const unsigned long long base = atomicAdd(A.n_cand + sq, (unsigned long long)cnt);
             if (base + cnt > A.cap_cand) continue;
+            Cand *dst = A.cand + (unsigned long long)sq * A.cap_cand + base;
             const uint32_t ip = ((uint32_t)i << 8) | (uint32_t)p;
             for (uint32_t q = 0; q < cnt; ++q) {
                 Cand c; c.gframe = (uint32_t)g; c.sj = __ldg(A.db.post + pi + q) & 0x7fffffffu; c.ip = ip;
-                A.cand[base + q] = c;
+                dst[q] = c;
             }
         }
         const int nx = i + 10;
@@ -469,7 +536,9 @@ struct ExtArgs {
     DevDB db;
     const uint8_t *frames;
     const Cand *cand;
-    int64_t n_cand;
+    int64_t n_cand;                // total over the sub-queues
+    unsigned long long cap_cand;   // per sub-queue
+    unsigned long long qstart[NQ + 1];   // exclusive prefix of the sub-queue fills
     Surv *surv;
     unsigned long long *n_surv;
     unsigned long long cap_surv;
@@ -482,7 +551,10 @@ __global__ void __launch_bounds__(NT) k_extend(ExtArgs A) {
     __syncthreads();
     const int64_t g = (int64_t)blockIdx.x * NT + threadIdx.x;
     if (g >= A.n_cand) return;
-    const Cand c = A.cand[g];
+    int sq = 0;
+#pragma unroll
+    for (int step = NQ / 2; step; step >>= 1) if ((unsigned long long)g >= A.qstart[sq + step]) sq += step;
+    const Cand c = A.cand[(unsigned long long)sq * A.cap_cand + ((unsigned long long)g - A.qstart[sq])];
     const int frame = (int)(c.gframe % 6u);
     const int m = (A.L - frame % 3) / 3;
     const uint8_t *__restrict__ fr = A.frames + (int64_t)c.gframe * A.fstride;
@@ -758,16 +830,19 @@ __global__ void k_classify(ClsArgs A) {
     if (p >= A.n) return;
     const int read = A.hsp[A.idx[p]].read;
     if (p > 0 && A.hsp[A.idx[p - 1]].read == read) return;   // not the first HSP of its read
-    int cur_subj = -1, nk = 0, nrep = 0, best = -1, best_score = -1;
+    // pass 1: which HSPs are printed -- at or above the floor and, per subject in score order, disjoint in query
+    // and subject range from every HSP already kept for that subject
+    int cur_subj = -1, nk = 0, nrep = 0;
     int kqs[8], kqe[8], kt0[8], kt1[8];
-    for (int64_t e = p; e < A.n; ++e) {
+    int64_t end = p;
+    for (int64_t e = p; e < A.n; ++e, ++end) {
         const int id = A.idx[e];
         const mcx_hit h = A.hsp[id];
         if (h.read != read) break;
         if (h.subject != cur_subj) { cur_subj = h.subject; nk = 0; }
         int qs, qe;
         dna_coords(A.L, h.frame, h.q0, h.q1, qs, qe);
-        int lo = qs < qe ? qs : qe, hi = qs < qe ? qe : qs;
+        const int lo = qs < qe ? qs : qe, hi = qs < qe ? qe : qs;
         bool keep = h.score >= A.min_report;
         for (int k = 0; k < nk && keep; ++k)
             if (!(hi < kqs[k] || kqe[k] < lo) || !(h.t1 < kt0[k] || kt1[k] < h.t0)) keep = false;
@@ -775,6 +850,38 @@ __global__ void k_classify(ClsArgs A) {
         if (!keep) continue;
         if (nk < 8) { kqs[nk] = lo; kqe[nk] = hi; kt0[nk] = h.t0; kt1[nk] = h.t1; ++nk; }
         ++nrep;
+    }
+    // RAPsearch2 prints at most 500 lines per query (-v default), best first: keep the 500 highest scores, ties at
+    // the cut score in (subject, ...) order.  Rare; the cut score is found by bisection over the kept HSPs.
+    if (nrep > MAX_LINES) {
+        int lo = A.min_report, hi = 2047;                    // largest T with count(score >= T) >= 500
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            int c = 0;
+            for (int64_t e = p; e < end; ++e) { const int id = A.idx[e]; if (A.keep[id] && min(A.hsp[id].score, 2047) >= mid) ++c; }
+            if (c >= MAX_LINES) lo = mid; else hi = mid - 1;
+        }
+        const int T = lo;
+        int above = 0;
+        for (int64_t e = p; e < end; ++e) { const int id = A.idx[e]; if (A.keep[id] && min(A.hsp[id].score, 2047) > T) ++above; }
+        int allow = MAX_LINES - above;
+        for (int64_t e = p; e < end; ++e) {
+            const int id = A.idx[e];
+            if (!A.keep[id]) continue;
+            const int sc = min(A.hsp[id].score, 2047);
+            if (sc > T || (sc == T && allow-- > 0)) continue;
+            A.keep[id] = 0;
+        }
+        nrep = MAX_LINES;
+    }
+    // pass 2: cutoffs and best hit among the printed HSPs (mc.py:420-453)
+    int best = -1, best_score = -1;
+    for (int64_t e = p; e < end; ++e) {
+        const int id = A.idx[e];
+        if (!A.keep[id]) continue;
+        const mcx_hit h = A.hsp[id];
+        int qs, qe;
+        dna_coords(A.L, h.frame, h.q0, h.q1, qs, qe);
         const int fam = A.db.fam[h.subject];
         const int slen = A.db.off[h.subject + 1] - A.db.off[h.subject];
         const mcx_cutoff c = c_cut[fam];
@@ -833,6 +940,8 @@ struct mcx_ctx {
     bool own_reads = false;
     int64_t cap_bases = 0, cap_quals = 0, cap_offs = 0;
     uint8_t *d_code = nullptr;
+    FpKey *d_fp = nullptr;
+    int64_t cap_fp = 0;
     int32_t *d_flag = nullptr, *d_pos = nullptr, *d_kept = nullptr;
     int64_t cap_reads = 0, cap_flag = 0, cap_pos = 0, cap_kept = 0;
     int64_t kept = 0;
@@ -851,6 +960,7 @@ struct mcx_ctx {
     uint8_t *d_keep = nullptr;
     int64_t cap_surv = 0, cap_best = 0;
     unsigned long long *d_cnt = nullptr;     // 16 scalar counters
+    unsigned long long *d_qcnt = nullptr;    // NQ candidate sub-queue fills
     unsigned long long *d_acc = nullptr;     // 3 + 60
     unsigned long long *d_abl = nullptr;     // 30 * 1280
     void *d_temp = nullptr;
@@ -934,7 +1044,7 @@ static int build_index(mcx_ctx *ctx, const mcx_db *db) {
     const int64_t nres = db->off[ns];
     std::vector<uint8_t> red((size_t)nres);
     for (int64_t g = 0; g < nres; ++g) red[(size_t)g] = db->res[g] < 20 ? MURPHY10[db->res[g]] : 10;
-    std::vector<uint32_t> post_all;
+    std::vector<uint32_t> post_all, bloom((size_t)1 << (BLOOM_BITS - 5), 0u);
     post_all.reserve((size_t)nres * N_PAT);
     for (int p = 0; p < N_PAT; ++p) {
         std::vector<unsigned long long> ent;
@@ -966,6 +1076,8 @@ static int build_index(mcx_ctx *ctx, const mcx_db *db) {
             const bool last = k + 1 == ent.size() || (ent[k + 1] >> 32) != code;
             post_all.push_back((uint32_t)(ent[k] & 0x7fffffffu) | (last ? 0x80000000u : 0u));
             if (first) {
+                const uint32_t b = bloom_index(p, code);
+                bloom[b >> 5] |= 1u << (b & 31);
                 uint32_t slot = (code * 2654435761u) >> (32 - bits);
                 while (hk[slot] != 0xffffffffu) slot = (slot + 1) & (size - 1);
                 size_t e = k;
@@ -986,6 +1098,10 @@ static int build_index(mcx_ctx *ctx, const mcx_db *db) {
     CK(dev_alloc(&dp, post_all.size())); ctx->db_allocs.push_back(dp);
     CK(cudaMemcpy(dp, post_all.data(), post_all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     ctx->db.post = dp;
+    uint32_t *db_ = nullptr;
+    CK(dev_alloc(&db_, bloom.size())); ctx->db_allocs.push_back(db_);
+    CK(cudaMemcpy(db_, bloom.data(), bloom.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    ctx->db.bloom = db_;
     return MCX_OK;
 }
 
@@ -1042,6 +1158,7 @@ extern "C" int mcx_create(mcx_ctx **out, const mcx_db *db, int device) {
         int r = upload_tables(ctx); if (r) return r;
         r = build_index(ctx, db); if (r) return r;
         CK(dev_alloc(&ctx->d_cnt, 16));
+        CK(dev_alloc(&ctx->d_qcnt, NQ));
         CK(dev_alloc(&ctx->d_acc, 3 + 2 * MCX_N_FAM));
         CK(dev_alloc(&ctx->d_abl, (size_t)MCX_N_FAM * MCX_LEN_BINS));
         return MCX_OK;
@@ -1059,7 +1176,7 @@ extern "C" void mcx_destroy(mcx_ctx *ctx) {
     if (ctx->own_reads) { cudaFree(ctx->d_bases); cudaFree(ctx->d_quals); cudaFree(ctx->d_offs); }
     void *bufs[] = {ctx->d_code, ctx->d_flag, ctx->d_pos, ctx->d_kept, ctx->d_surv, ctx->d_hsp, ctx->d_hits_out,
                     ctx->d_keys, ctx->d_idx, ctx->d_best, ctx->d_hflag, ctx->d_hpos, ctx->d_keep, ctx->d_cnt,
-                    ctx->d_acc, ctx->d_abl, ctx->d_temp, ctx->d_frames, ctx->d_cand, ctx->d_segq};
+                    ctx->d_acc, ctx->d_abl, ctx->d_temp, ctx->d_frames, ctx->d_cand, ctx->d_segq, ctx->d_qcnt, ctx->d_fp};
     for (void *p : bufs) if (p) cudaFree(p);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -1079,8 +1196,6 @@ extern "C" int mcx_set_params(mcx_ctx *ctx, const mcx_params *p) {
     if (!ctx || !p) return fail(ctx, MCX_EINVAL, "mcx_set_params: null argument");
     if (p->read_length < 27 || p->read_length > 3 * MAX_FRAME)
         return fail(ctx, MCX_EINVAL, "mcx_set_params: read_length must be within 27..504");
-    if (p->filter_dups)
-        return fail(ctx, MCX_EINVAL, "mcx_set_params: filter_dups (-d) is not implemented on the device yet");
     for (int f = 0; f < MCX_N_FAM; ++f)
         if (p->cut[f].stat < 0 || p->cut[f].stat > 2) return fail(ctx, MCX_EINVAL, "mcx_set_params: bad aln_stat");
     CK(cudaSetDevice(ctx->device));
@@ -1106,6 +1221,16 @@ static int run_qc(mcx_ctx *ctx) {
         k_qc<<<(unsigned)blocks, NT, 0, st>>>(ctx->d_bases, P.has_quality ? ctx->d_quals : nullptr, ctx->d_offs, n,
                                              P.read_length, P.quality_offset, P.min_quality, P.mean_quality,
                                              P.max_unknown, ctx->d_code);
+        if (P.filter_dups) {
+            if ((rc = ensure(ctx, &ctx->d_fp, &ctx->cap_fp, n)) != MCX_OK) return rc;
+            k_fingerprint<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->d_bases, ctx->d_offs, n, ctx->d_fp);
+            size_t tbs = 0;
+            cub::DeviceMergeSort::SortKeys(nullptr, tbs, ctx->d_fp, n, FpLess(), st);
+            if ((rc = ensure_temp(ctx, tbs)) != MCX_OK) return rc;
+            cub::DeviceMergeSort::SortKeys(ctx->d_temp, tbs, ctx->d_fp, n, FpLess(), st);
+            k_mark_dups<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_fp, n, ctx->d_code);
+            ctx->launches += 5;
+        }
         k_keep_flags<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_code, n, ctx->d_flag);
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->d_flag, ctx->d_pos, (int)(n + 1), st);
@@ -1241,7 +1366,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     unsigned long long n_surv = 0, n_cand_total = 0;
     for (int64_t first = 0; first < n_search; first += chunk) {
         const int64_t nr = std::min(chunk, n_search - first);
-        CK(cudaMemsetAsync(ctx->d_cnt + 9, 0, sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(ctx->d_qcnt, 0, NQ * sizeof(unsigned long long), st));
         CK(cudaMemsetAsync(ctx->d_cnt + 12, 0, sizeof(unsigned long long), st));
         CK(cudaEventRecord(ctx->ev[2], st));
         constexpr int NTF = 192;
@@ -1263,24 +1388,27 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             ++ctx->launches;
         }
         ctx->n_segq_last = (int64_t)n_segq;
-        unsigned long long n_cand = 0;
+        unsigned long long n_cand = 0, qfill[NQ];
         for (int attempt = 0;; ++attempt) {
             ProbeArgs A;
             A.n_frames = nr * 6; A.L = P.read_length; A.db = ctx->db; A.frames = ctx->d_frames; A.cand = ctx->d_cand;
-            A.n_cand = ctx->d_cnt + 9; A.cap_cand = (unsigned long long)ctx->cap_cand;
+            A.n_cand = ctx->d_qcnt; A.cap_cand = (unsigned long long)(ctx->cap_cand / NQ);
             const size_t smem = (size_t)fstride * NTF;
             CK(cudaFuncSetAttribute(k_probe<NTF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_probe<NTF><<<(unsigned)((nr * 6 + NTF - 1) / NTF), NTF, smem, st>>>(A, fstride);
             ++ctx->launches;
-            CK(cudaMemcpyAsync(&n_cand, ctx->d_cnt + 9, sizeof n_cand, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(qfill, ctx->d_qcnt, sizeof qfill, cudaMemcpyDeviceToHost, st));
             if (attempt == 0) CK(cudaEventRecord(ctx->ev[3], st));
             CK(cudaStreamSynchronize(st));
             CK(cudaGetLastError());
-            if ((int64_t)n_cand <= ctx->cap_cand) break;
+            unsigned long long worst = 0;
+            n_cand = 0;
+            for (int q = 0; q < NQ; ++q) { n_cand += qfill[q]; worst = std::max(worst, qfill[q]); }
+            if ((int64_t)worst <= ctx->cap_cand / NQ) break;
             if (attempt) return fail(ctx, MCX_ENOMEM, "mcx_search: candidate queue overflow after regrowth");
-            // the count is exact: size the queue for it and probe this chunk again
-            if ((rc = ensure(ctx, &ctx->d_cand, &ctx->cap_cand, (int64_t)n_cand)) != MCX_OK) return rc;
-            CK(cudaMemsetAsync(ctx->d_cnt + 9, 0, sizeof(unsigned long long), st));
+            // the fills are exact: size every sub-queue for the fullest one and probe this chunk again
+            if ((rc = ensure(ctx, &ctx->d_cand, &ctx->cap_cand, (int64_t)(worst + worst / 16 + 1024) * NQ)) != MCX_OK) return rc;
+            CK(cudaMemsetAsync(ctx->d_qcnt, 0, NQ * sizeof(unsigned long long), st));
         }
         n_cand_total += n_cand;
         const unsigned long long surv_before = n_surv;
@@ -1288,6 +1416,9 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             ExtArgs E;
             E.kept = ctx->d_kept; E.first = first; E.L = P.read_length; E.fstride = fstride; E.thr_report = thr; E.db = ctx->db;
             E.frames = ctx->d_frames; E.cand = ctx->d_cand; E.n_cand = (int64_t)n_cand; E.surv = ctx->d_surv;
+            E.cap_cand = (unsigned long long)(ctx->cap_cand / NQ);
+            E.qstart[0] = 0;
+            for (int q = 0; q < NQ; ++q) E.qstart[q + 1] = E.qstart[q] + qfill[q];
             E.n_surv = ctx->d_cnt + 8; E.cap_surv = (unsigned long long)ctx->cap_surv;
             k_extend<256><<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(E);
             ++ctx->launches;

@@ -10,6 +10,7 @@ namespace mcx {
 
 constexpr int AA_STOP = 20;        // '.', SEG-masked 'x', database 'X': scores -5 against everything
 constexpr int MAX_FRAME = 168;     // aa per frame at 500 bp
+constexpr int MAX_LINES = 500;     // RAPsearch2 -v default: lines printed per query
 constexpr int GAP_SLACK = 63;      // subject columns beyond the query length in a gapped extension
 constexpr int GAP_OPEN = 11;       // CHashSearch +0x40358
 constexpr int GAP_EXT = 1;         // CHashSearch +0x4035c

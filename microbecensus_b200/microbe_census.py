@@ -8,7 +8,8 @@ Public surface kept from the reference (file:line in /root/reference/microbe_cen
 pipeline fills in, the verbose messages and the ``sys.exit`` texts.  What changed: the four calls at
 :611-:620 (process_seqfile, search_seqs -> RAPsearch2 child process, classify_reads, aggregate_hits) are one
 GPU search; ``-t`` is accepted and ignored by the search; ``-r`` (alternative rapsearch binary) has nothing
-to point at and is ignored.  ``-d`` is not available on the device yet and raises.
+to point at and is ignored.  ``-d`` compares 128-bit strand-canonical fingerprints of the untrimmed reads
+instead of whole strings (the reference's KeyError on non-ACGTN characters under ``-d`` is not reproduced).
 """
 import bz2
 import gzip
@@ -351,8 +352,6 @@ def sample_and_search(args, engine=None):
     Files are taken in order and concatenated (mc.py:337: paired files are processed one after the other);
     the device applies the filter chain too-short -> low-quality per read and the `-n` cut as "first nreads
     kept reads"; counters are those of the reference loop up to the read that filled the quota."""
-    if args.get("filter_dups"):
-        raise NotImplementedError("-d (filter_dups) is not implemented in the GPU path yet")
     eng = engine or get_engine(int(os.environ.get("MCX_DEVICE", "0")))
     if args["verbose"]:
         print("====Estimating Average Genome Size====")
@@ -361,7 +360,7 @@ def sample_and_search(args, engine=None):
     fastq = args["file_type"] == "fastq"
     eng.set_params(L, quality_offset=args.get("quality_offset") if fastq else None,
                    min_quality=args["min_quality"], mean_quality=args["mean_quality"],
-                   max_unknown=args["max_unknown"], filter_dups=False)
+                   max_unknown=args["max_unknown"], filter_dups=bool(args.get("filter_dups")))
     nreads = args["nreads"]
     batch = concat_batches([load_reads(f, args["file_type"]) for f in args["seqfiles"]])
     if fastq and batch.quals is None:

@@ -749,6 +749,22 @@ int oc_search_read(const oc_index *ix, const uint8_t *read, int L, int W, int us
         }
         if (keep) out[u++] = out[k];
     }
+    /* RAPsearch2 prints at most 500 lines per query (-v default), best E-value first.  Restated as: the 500
+     * highest raw scores; among lines tied at the cut score the ones first in (subject, ...) order stay
+     * (RAPsearch2's own order among equal E-values is unspecified). */
+    if (u > OC_MAX_LINES) {
+        int hist[2048];
+        memset(hist, 0, sizeof hist);
+        for (int k = 0; k < u; ++k) hist[out[k].score > 2047 ? 2047 : out[k].score]++;
+        int T = 2047, above = 0;
+        while (T > 0 && above + hist[T] < OC_MAX_LINES) { above += hist[T]; --T; }
+        int allow = OC_MAX_LINES - above, w = 0;
+        for (int k = 0; k < u; ++k) {
+            int sc = out[k].score > 2047 ? 2047 : out[k].score;
+            if (sc > T || (sc == T && allow-- > 0)) out[w++] = out[k];
+        }
+        u = w;
+    }
     return u;
 }
 
@@ -849,18 +865,47 @@ int64_t oc_search_batch(const oc_index *ix, const uint8_t *bases, const int64_t 
 int64_t oc_process_reads(const uint8_t *bases, const uint8_t *quals, const int64_t *offs, int64_t n, int L,
                          int quality_offset, int min_quality, int mean_quality, int max_unknown,
                          int64_t nreads /* <0: all */, uint8_t *code, int64_t *counters) {
+    return oc_process_reads_d(bases, quals, offs, n, L, quality_offset, min_quality, mean_quality, max_unknown, 0,
+                              nreads, code, counters);
+}
+
+/* same with -d: a read that is long enough is skipped as a duplicate when the fingerprint of its untrimmed
+ * string (either strand) equals that of a read already kept (mc.py:345, 355); the test comes before QC. */
+int64_t oc_process_reads_d(const uint8_t *bases, const uint8_t *quals, const int64_t *offs, int64_t n, int L,
+                           int quality_offset, int min_quality, int mean_quality, int max_unknown, int filter_dups,
+                           int64_t nreads /* <0: all */, uint8_t *code, int64_t *counters) {
     int64_t sampled = 0;
     counters[0] = counters[1] = counters[2] = 0;
+    size_t cap = 1; while (cap < (size_t)(2 * n + 16)) cap <<= 1;
+    uint64_t *set = filter_dups ? (uint64_t *)calloc(cap * 2, sizeof(uint64_t)) : NULL;   /* (0,0) = empty */
     int64_t r = 0;
     for (; r < n; ++r) {
         const uint8_t *q = quals ? quals + offs[r] : NULL;
-        int c = oc_read_qc(bases + offs[r], q, (int)(offs[r + 1] - offs[r]), L, quality_offset, min_quality,
-                           mean_quality, max_unknown);
+        int len = (int)(offs[r + 1] - offs[r]);
+        int c = oc_read_qc(bases + offs[r], q, len, L, quality_offset, min_quality, mean_quality, max_unknown);
+        uint64_t fp[2] = {0, 0}; size_t slot = 0;
+        if (filter_dups && c != 1) {
+            oc_fingerprint(bases + offs[r], len, fp);
+            if (fp[0] == 0 && fp[1] == 0) fp[1] = 1;
+            slot = (size_t)(fp[0] * 0x9E3779B97F4A7C15ull >> 20) & (cap - 1);
+            int dup = 0;
+            while (set[2 * slot] || set[2 * slot + 1]) {
+                if (set[2 * slot] == fp[0] && set[2 * slot + 1] == fp[1]) { dup = 1; break; }
+                slot = (slot + 1) & (cap - 1);
+            }
+            if (dup) c = 3;
+        }
         code[r] = (uint8_t)c;
         if (c == 1) counters[0]++;
         else if (c == 2) counters[1]++;
-        else { ++sampled; if (nreads >= 0 && sampled == nreads) { ++r; break; } }
+        else if (c == 3) counters[2]++;
+        else {
+            if (filter_dups) { set[2 * slot] = fp[0]; set[2 * slot + 1] = fp[1]; }
+            ++sampled;
+            if (nreads >= 0 && sampled == nreads) { ++r; break; }
+        }
     }
     for (; r < n; ++r) code[r] = 4;
+    free(set);
     return sampled;
 }

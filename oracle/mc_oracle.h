@@ -29,6 +29,7 @@ extern "C" {
 
 #define OC_AA_STOP 20      /* '.' : stop codon, codon with a non-ACGT base, DB 'X' */
 #define OC_MAX_FRAME 168   /* 500 bp / 3 rounded up */
+#define OC_MAX_LINES 500   /* RAPsearch2 -v default: lines printed per query */
 #define OC_GAP_SLACK 63    /* subject columns beyond the query length in a gapped extension */
 
 /* one alignment record (best HSP of one read x subject pair) */
@@ -120,6 +121,10 @@ int64_t oc_search_batch(const oc_index *ix, const uint8_t *bases, const int64_t 
 int64_t oc_process_reads(const uint8_t *bases, const uint8_t *quals, const int64_t *offs, int64_t n, int L,
                          int quality_offset, int min_quality, int mean_quality, int max_unknown,
                          int64_t nreads, uint8_t *code, int64_t *counters);
+
+int64_t oc_process_reads_d(const uint8_t *bases, const uint8_t *quals, const int64_t *offs, int64_t n, int L,
+                           int quality_offset, int min_quality, int mean_quality, int max_unknown, int filter_dups,
+                           int64_t nreads, uint8_t *code, int64_t *counters);
 
 /* 128-bit canonical fingerprint of the UNTRIMMED read (min over strand), for -d */
 void oc_fingerprint(const uint8_t *seq, int len, uint64_t fp[2]);

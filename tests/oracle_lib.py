@@ -45,9 +45,9 @@ class Oracle:
         L.oc_classify.restype = C.c_int64
         L.oc_classify.argtypes = [C.POINTER(OcDb), C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_int64]
-        L.oc_process_reads.restype = C.c_int64
-        L.oc_process_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
-                                       C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+        L.oc_process_reads_d.restype = C.c_int64
+        L.oc_process_reads_d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
         L.oc_bits.restype = C.c_double
         L.oc_bits.argtypes = [C.c_int]
         L.oc_min_raw_for_bits.restype = C.c_int
@@ -87,13 +87,14 @@ class Oracle:
         return {"classified": int(nc), "fam_hits": fam_hits, "fam_aln": fam_aln, "aln_by_len": abl.reshape(30, 1280),
                 "best_subject": best[:n_reads]}
 
-    def process_reads(self, batch, L, quality_offset, min_quality, mean_quality, max_unknown, nreads):
+    def process_reads(self, batch, L, quality_offset, min_quality, mean_quality, max_unknown, nreads, filter_dups=False):
         code = np.zeros(max(batch.n, 1), np.uint8)
         counters = np.zeros(3, np.int64)
         q = batch.quals.ctypes.data if batch.quals is not None else None
-        sampled = self.lib.oc_process_reads(batch.bases.ctypes.data, q, batch.offsets.ctypes.data, batch.n, int(L),
-                                            int(quality_offset or 0), int(min_quality), int(mean_quality), int(max_unknown),
-                                            -1 if nreads is None else int(nreads), code.ctypes.data, counters.ctypes.data)
+        sampled = self.lib.oc_process_reads_d(batch.bases.ctypes.data, q, batch.offsets.ctypes.data, batch.n, int(L),
+                                              int(quality_offset or 0), int(min_quality), int(mean_quality), int(max_unknown),
+                                              1 if filter_dups else 0, -1 if nreads is None else int(nreads),
+                                              code.ctypes.data, counters.ctypes.data)
         return int(sampled), code[:batch.n], {"too_short": int(counters[0]), "low_qual": int(counters[1]), "dups": int(counters[2])}
 
     def frame(self, seq, L, frame, use_seg=True):

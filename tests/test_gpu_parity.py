@@ -171,3 +171,18 @@ def test_run_pipeline_drop_in(eng, oracle, markers, tmp_path, capsys):
     out["outfile"] = str(tmp_path / "r.txt")
     mcb.report_results(out, est, mcb.count_bases(out))
     assert open(out["outfile"]).read().startswith("Parameters\nmetagenome:\t")
+
+
+def test_duplicate_filter_matches_oracle(eng, oracle, markers):
+    """-d on the device (fingerprint + sort + first-kept-wins) against the oracle's sequential set, with QC and -n"""
+    from test_host import dup_batch
+    seqs, quals = dup_batch(n=20000, seed=11)
+    batch = ReadBatch.from_strings(seqs, quals)
+    for opts in (dict(minq=-5, meanq=-5, maxunk=100, nreads=None), dict(minq=3, meanq=21, maxunk=5, nreads=None),
+                 dict(minq=-5, meanq=22, maxunk=100, nreads=9000)):
+        eng.set_params(100, quality_offset=33, min_quality=opts["minq"], mean_quality=opts["meanq"], max_unknown=opts["maxunk"], filter_dups=True)
+        qc = eng.push(batch)
+        res = eng.search(-1 if opts["nreads"] is None else opts["nreads"])
+        sampled, code, cnt = oracle.process_reads(batch, 100, 33, opts["minq"], opts["meanq"], opts["maxunk"], opts["nreads"], filter_dups=True)
+        assert (res.sampled_reads, res.too_short, res.low_qual, res.dups) == (sampled, cnt["too_short"], cnt["low_qual"], cnt["dups"]), opts
+        assert res.dups > 300

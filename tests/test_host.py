@@ -169,3 +169,58 @@ dist.destroy_process_group()
 ''' % (ROOT, ROOT))
     subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                            "--master-port", "29517", str(script)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+
+
+def dup_batch(n=3000, L=100, seed=5):
+    """reads with injected exact and reverse-complement duplicates, ragged lengths, N's and varied qualities"""
+    rng = np.random.default_rng(seed)
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+    seqs, quals = [], []
+    for i in range(n):
+        u = rng.random()
+        if i > 10 and u < 0.08:
+            s = seqs[int(rng.integers(0, i))]
+        elif i > 10 and u < 0.12:
+            s = "".join(comp[c] for c in reversed(seqs[int(rng.integers(0, i))]))
+        else:
+            ln = int(rng.choice([L - 20, L, L + 7, L + 30]))
+            s = "".join(rng.choice(list("ACGT"), ln))
+            if rng.random() < 0.05:
+                s = s[:5] + "N" * 12 + s[17:]
+        seqs.append(s)
+        lowq = 2 if rng.random() < 0.2 else 12
+        quals.append("".join(chr(33 + int(q)) for q in rng.integers(lowq, 41, len(s))))
+    return seqs, quals
+
+
+def reference_loop(seqs, quals, L, qoff, minq, meanq, maxunk, dups, nreads):
+    """process_seqfile (mc.py:328-367) re-typed over in-memory records: the known answer for the -d semantics"""
+    comp = {"A": "T", "T": "A", "G": "C", "C": "G", "N": "N"}
+    seen, kept, too_short, low_qual, ndup = set(), [], 0, 0, 0
+    for i, (s, q) in enumerate(zip(seqs, quals)):
+        if len(s) < L:
+            too_short += 1; continue
+        if dups and (s in seen or "".join(comp[c] for c in s[::-1]) in seen):
+            ndup += 1; continue
+        t = s[:L]
+        ph = [ord(c) - qoff for c in q[:L]]
+        if 100 * t.count("N") / float(len(t)) > maxunk or float(np.mean(ph)) < meanq or min(ph) < minq:
+            low_qual += 1; continue
+        kept.append(i)
+        if dups:
+            seen.add(s)
+        if len(kept) == nreads:
+            break
+    return kept, too_short, low_qual, ndup
+
+
+def test_oracle_duplicate_filter_matches_reference_semantics(oracle):
+    seqs, quals = dup_batch()
+    batch = ReadBatch.from_strings(seqs, quals)
+    for opts in (dict(minq=-5, meanq=-5, maxunk=100, nreads=10**9), dict(minq=3, meanq=21, maxunk=5, nreads=10**9),
+                 dict(minq=-5, meanq=22, maxunk=100, nreads=1500)):
+        kept, ts, lq, nd = reference_loop(seqs, quals, 100, 33, opts["minq"], opts["meanq"], opts["maxunk"], True, opts["nreads"])
+        sampled, code, cnt = oracle.process_reads(batch, 100, 33, opts["minq"], opts["meanq"], opts["maxunk"], opts["nreads"], filter_dups=True)
+        assert sampled == len(kept) and list(np.flatnonzero(code == 0)) == kept
+        assert (cnt["too_short"], cnt["low_qual"], cnt["dups"]) == (ts, lq, nd)
+        assert nd > 60

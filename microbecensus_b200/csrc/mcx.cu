@@ -416,21 +416,134 @@ __global__ void __launch_bounds__(NT) k_frames(FrameArgs A, int fstride) {
     for (int k = lane; k < 32 * fstride / 4; k += 32) dst[k] = src[k];
 }
 
-// K2a': full SEG for the queued frames, one thread each; masked residues are overwritten in the frame store
-__global__ void k_seg(uint8_t *frames, int fstride, int L, const uint32_t *__restrict__ segq, int64_t n) {
-    __shared__ double s_ent[13 * 13];
-    for (int k = threadIdx.x; k < 13 * 13; k += blockDim.x) s_ent[k] = c_ent[k];
+// K2a': full SEG for the queued frames, one WARP per frame; masked residues are overwritten in the frame store.
+// The control flow of Seg::segseq is warp-uniform (every lane runs the same scalar code on masks held in shared
+// memory); the expensive part, Seg::trim, evaluates the windows of one length in parallel, one lane per window
+// start, from a prefix-count table of the segment, and takes the minimum with seg.c's scan order as tie-break
+// (longer windows first, then leftmost).  First version: one thread per frame, 24 ms for 2M reads with 2 of 32
+// lanes active on average (profiles/); this one keeps the warp busy.
+__device__ __forceinline__ bool sbit(const uint32_t *m, int k) { return (m[k >> 5] >> (k & 31)) & 1; }
+
+__device__ void coop_trim(const uint8_t *fr, int off, int tl, uint8_t *P, uint8_t *nc, int lane, int &leftend, int &rightend) {
+    __syncwarp();
+    if (lane < 20) {                       // P[k][a] = occurrences of letter a among the first k residues
+        int acc = 0;
+        P[lane] = 0;
+        for (int k = 0; k < tl; ++k) { acc += (fr[off + k] == lane); P[(k + 1) * 20 + lane] = (uint8_t)acc; }
+    }
+    __syncwarp();
+    int lend = 0, rend = tl - 1, minlen = 1;
+    if (tl - SEG_MAXTRIM > minlen) minlen = tl - SEG_MAXTRIM;
+    double minprob = 1.0;
+    // windows in seg.c's scan order: length tl, tl-1, ... minlen+1, starts left to right; row d = tl - len holds
+    // d + 1 windows, so window number w sits in row d with d(d+1)/2 <= w < (d+1)(d+2)/2.  32 windows per round.
+    const int D = tl - minlen, NW = D * (D + 1) / 2;
+    for (int base = 0; base < NW; base += 32) {
+        const int w = base + lane;
+        double prob = 1.0e300;
+        int st = 0, len = tl;
+        if (w < NW) {
+            int d = (int)((sqrtf(8.0f * (float)w + 1.0f) - 1.0f) * 0.5f);
+            while (d * (d + 1) / 2 > w) --d;
+            while ((d + 1) * (d + 2) / 2 <= w) ++d;
+            len = tl - d; st = w - d * (d + 1) / 2;
+            const uint8_t *p0 = P + st * 20, *p1 = P + (st + len) * 20;
+            int comp[20], maxc = 0;
+#pragma unroll
+            for (int a = 0; a < 20; ++a) {
+                const int c = (int)p1[a] - (int)p0[a];
+                comp[a] = c;
+                if (c) { nc[c]++; maxc = c > maxc ? c : maxc; }
+            }
+            prob = seg_getprob(nc, maxc, len);
+#pragma unroll
+            for (int a = 0; a < 20; ++a) nc[comp[a]] = 0;
+        }
+        double best = prob;
+        int bl = lane;
+#pragma unroll
+        for (int dd = 16; dd; dd >>= 1) {
+            const double o = __shfl_xor_sync(0xffffffffu, best, dd);
+            const int ol = __shfl_xor_sync(0xffffffffu, bl, dd);
+            if (o < best || (o == best && ol < bl)) { best = o; bl = ol; }
+        }
+        if (best < minprob) {
+            minprob = best;
+            lend = __shfl_sync(0xffffffffu, st, bl);
+            rend = __shfl_sync(0xffffffffu, len, bl) + lend - 1;
+        }
+    }
+    rightend -= (tl - rend - 1);
+    leftend += lend;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_seg(uint8_t *frames, int fstride, int L, const uint32_t *__restrict__ segq,
+                                                    int64_t n, int maxm) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    double *s_ent = reinterpret_cast<double *>(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per_warp = fstride + (maxm + 1) * 20 + 4 - ((fstride + (maxm + 1) * 20) & 3) + 18 * 4;
+    uint8_t *wbase = smem + 13 * 13 * sizeof(double) + (size_t)warp * per_warp;
+    uint32_t *s_m = reinterpret_cast<uint32_t *>(wbase);       // [0..5] lo, [6..11] hi, [12..17] result mask
+    uint8_t *fr = wbase + 18 * 4;
+    uint8_t *P = fr + fstride;
+    for (int k = threadIdx.x; k < 13 * 13; k += WARPS * 32) s_ent[k] = c_ent[k];
     __syncthreads();
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t g = (int64_t)blockIdx.x * WARPS + warp;
     if (g >= n) return;
     const uint32_t row = segq[g];
-    uint8_t *fr = frames + (int64_t)row * fstride;
+    uint8_t *gfr = frames + (int64_t)row * fstride;
     const int m = (L - (int)(row % 6u) % 3) / 3;
-    unsigned long long lom[3], him[3], mask[3] = {0, 0, 0};
-    seg_window_masks(fr, m, s_ent, lom, him);
-    seg_full(fr, m, lom, him, mask);
-    for (int k = 0; k < m; ++k)
-        if ((mask[k >> 6] >> (k & 63)) & 1) fr[k] = AA_STOP;
+    for (int k = lane; k < fstride / 4; k += 32) reinterpret_cast<uint32_t *>(fr)[k] = reinterpret_cast<const uint32_t *>(gfr)[k];
+    uint8_t nc[MAX_FRAME + 2];
+    for (int k = 0; k < MAX_FRAME + 2; ++k) nc[k] = 0;
+    __syncwarp();
+    // entropy of every 12-window against the two cut-offs, one window per lane
+    for (int r = 0; r < 6; ++r) {
+        const int w = r * 32 + lane;
+        bool lo = false, hi = false;
+        if (w + SEG_WINDOW <= m) {
+            Comp c; c.clear();
+            for (int k = 0; k < SEG_WINDOW; ++k) c.add(fr[w + k]);
+            const double e = c.entropy(s_ent);
+            lo = e <= SEG_LOCUT; hi = e <= SEG_HICUT;
+        }
+        const uint32_t bl = __ballot_sync(0xffffffffu, lo), bh = __ballot_sync(0xffffffffu, hi);
+        if (lane == 0) { s_m[r] = bl; s_m[6 + r] = bh; s_m[12 + r] = 0; }
+    }
+    __syncwarp();
+    const uint32_t *lom = s_m, *him = s_m + 6;
+    uint32_t *mask = s_m + 12;
+    // Seg::segseq (downset 0, upset 1); the recursion of seg.c only adds segments, so the left parts are queued
+    int wl_off[12], wl_len[12], nwl = 1;
+    wl_off[0] = 0; wl_len[0] = m;
+    while (nwl > 0) {
+        --nwl;
+        const int off = wl_off[nwl], slen = wl_len[nwl];
+        if (SEG_WINDOW > slen) continue;
+        const int last = slen - 1, wmax = slen - SEG_WINDOW;
+        int lowlim = 0;
+        for (int i = 0; i <= last; ++i) {
+            if (!sbit(lom, off + (i < wmax ? i : wmax))) continue;
+            int j, loi, hii;
+            for (j = i; j >= lowlim; --j) if (!sbit(him, off + (j < wmax ? j : wmax))) break;
+            loi = j + 1;
+            for (j = i; j <= last; ++j) if (!sbit(him, off + (j < wmax ? j : wmax))) break;
+            hii = j - 1;
+            int leftend = loi, rightend = hii;
+            coop_trim(fr, off + leftend, rightend - leftend + 1, P, nc, lane, leftend, rightend);
+            if (i < leftend && nwl < 12) { wl_off[nwl] = off + loi; wl_len[nwl] = leftend - loi; ++nwl; }
+            __syncwarp();
+            if (lane == 0) for (j = off + leftend; j <= off + rightend; ++j) mask[j >> 5] |= 1u << (j & 31);
+            __syncwarp();
+            i = hii < rightend ? hii : rightend;
+            lowlim = i + 1;
+        }
+    }
+    __syncwarp();
+    for (int k = lane; k < m; k += 32)
+        if (sbit(mask, k)) gfr[k] = AA_STOP;
 }
 
 // K2b: one thread per frame of the store: slide the 10-letter murphy10 window, probe the five word tables and
@@ -1384,7 +1497,12 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
         if (n_segq > 0) {
-            k_seg<<<(unsigned)((n_segq + 63) / 64), 64, 0, st>>>(ctx->d_frames, fstride, P.read_length, ctx->d_segq, (int64_t)n_segq);
+            constexpr int SW = 4;
+            const int pw = fstride + (maxm + 1) * 20;
+            const size_t smem = 13 * 13 * sizeof(double) + (size_t)SW * (pw + 4 - (pw & 3) + 18 * 4);
+            CK(cudaFuncSetAttribute(k_seg<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_seg<SW><<<(unsigned)((n_segq + SW - 1) / SW), SW * 32, smem, st>>>(ctx->d_frames, fstride, P.read_length, ctx->d_segq,
+                                                                           (int64_t)n_segq, maxm);
             ++ctx->launches;
         }
         ctx->n_segq_last = (int64_t)n_segq;

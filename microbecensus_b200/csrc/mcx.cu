@@ -757,10 +757,9 @@ __global__ void __launch_bounds__(NT) k_extend(ExtArgs A) {
 #define ST_ALN 0x100u
 #define ST_GAPCOL 0x20000u
 #define ST_GAPRUN 0x4000000u
-constexpr int GROW = MAX_FRAME + GAP_SLACK + 2;
-
 struct GExt { int gain, eq, et; uint32_t st; int cells; };
 
+template <int GROW>                // row capacity: longest frame + GAP_SLACK + 2
 __device__ void gapped_xdrop(const uint8_t *fr, int q_first, int qstep, const uint8_t *__restrict__ t,
                              int tstep, int nQ, int nD, GExt &g) {
     g.gain = 0; g.eq = 0; g.et = 0; g.st = 0; g.cells = 0;
@@ -847,7 +846,7 @@ struct GapArgs {
     unsigned long long *counters;  // [0] gapped extensions, [1] cells
 };
 
-template <int NT>
+template <int NT, int GROW>
 __global__ void __launch_bounds__(NT) k_gapped(GapArgs A) {
     int64_t g = (int64_t)blockIdx.x * NT + threadIdx.x;
     if (g >= A.n_surv) return;
@@ -865,7 +864,7 @@ __global__ void __launch_bounds__(NT) k_gapped(GapArgs A) {
         int ql = m - (q1 + 1), tl = n - (t1 + 1);
         if (ql > 2 && tl > 2) {
             if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
-            GExt e; gapped_xdrop(fr, q1 + 1, 1, t + t1 + 1, 1, ql, tl, e);
+            GExt e; gapped_xdrop<GROW>(fr, q1 + 1, 1, t + t1 + 1, 1, ql, tl, e);
             ++ng; nc += e.cells;
             if (e.gain > 0) {
                 score += e.gain; q1 += e.eq; t1 += e.et;
@@ -875,7 +874,7 @@ __global__ void __launch_bounds__(NT) k_gapped(GapArgs A) {
         ql = q0; tl = t0;
         if (ql > 2 && tl > 2) {
             if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
-            GExt e; gapped_xdrop(fr, q0 - 1, -1, t + t0 - 1, -1, ql, tl, e);
+            GExt e; gapped_xdrop<GROW>(fr, q0 - 1, -1, t + t0 - 1, -1, ql, tl, e);
             ++ng; nc += e.cells;
             if (e.gain > 0) {
                 score += e.gain; q0 -= e.eq; t0 -= e.et;
@@ -1555,7 +1554,9 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             G.L = P.read_length; G.fstride = fstride; G.db = ctx->db; G.frames = ctx->d_frames; G.surv = ctx->d_surv;
             G.first = (int64_t)surv_before; G.n_surv = (int64_t)(n_surv - surv_before);
             G.hsp = ctx->d_hsp; G.keys = ctx->d_keys; G.idx = ctx->d_idx; G.counters = ctx->d_cnt + 10;
-            k_gapped<128><<<(unsigned)((G.n_surv + 127) / 128), 128, 0, st>>>(G);
+            if (maxm + GAP_SLACK + 2 <= 104) k_gapped<128, 104><<<(unsigned)((G.n_surv + 127) / 128), 128, 0, st>>>(G);
+            else if (maxm + GAP_SLACK + 2 <= 152) k_gapped<128, 152><<<(unsigned)((G.n_surv + 127) / 128), 128, 0, st>>>(G);
+            else k_gapped<128, MAX_FRAME + GAP_SLACK + 2><<<(unsigned)((G.n_surv + 127) / 128), 128, 0, st>>>(G);
             ++ctx->launches;
         }
         CK(cudaEventRecord(ctx->ev[9], st));

@@ -120,6 +120,11 @@ int  mcx_push_reads_dev(mcx_ctx *ctx, const uint8_t *d_bases, const uint8_t *d_q
                         const int64_t *d_offsets, int64_t n, int64_t total_bytes);
 
 int  mcx_qc_counts(mcx_ctx *ctx, mcx_qc *out);
+/* Per-read verdicts of the pushed reads (0 keep, 1 too short, 2 low quality, 3 duplicate) and, optionally,
+ * the 128-bit strand-canonical fingerprints of the untrimmed reads (2 x uint64 per read) to host memory;
+ * mcx_qc_import replaces the verdicts (e.g. duplicates decided across GPUs, mc.py:345) and rebuilds the kept list. */
+int  mcx_qc_export(mcx_ctx *ctx, uint8_t *code, uint64_t *fingerprints);
+int  mcx_qc_import(mcx_ctx *ctx, const uint8_t *code);
 /* search the first `quota` kept reads (quota < 0: all of them) */
 int  mcx_search(mcx_ctx *ctx, int64_t quota);
 int  mcx_result_get(mcx_ctx *ctx, mcx_result *out);

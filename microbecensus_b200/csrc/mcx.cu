@@ -1414,6 +1414,65 @@ extern "C" int mcx_push_reads_dev(mcx_ctx *ctx, const uint8_t *d_bases, const ui
     return run_qc(ctx);
 }
 
+static int refresh_kept(mcx_ctx *ctx) {
+    const int64_t n = ctx->n_reads;
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if (n > 0) {
+        k_keep_flags<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_code, n, ctx->d_flag);
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->d_flag, ctx->d_pos, (int)(n + 1), st);
+        if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
+        CK(cudaMemsetAsync(ctx->d_flag + n, 0, sizeof(int32_t), st));
+        cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, ctx->d_flag, ctx->d_pos, (int)(n + 1), st);
+        k_scatter_kept<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_code, ctx->d_pos, n, ctx->d_kept);
+        CK(cudaMemsetAsync(ctx->d_cnt, 0, 16 * sizeof(unsigned long long), st));
+        k_count_codes<<<592, 256, 0, st>>>(ctx->d_code, n, ctx->d_cnt);
+        ctx->launches += 5;
+    }
+    unsigned long long cnt[4] = {0, 0, 0, 0};
+    if (n > 0) CK(cudaMemcpyAsync(cnt, ctx->d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    ctx->qc.n_reads = n; ctx->qc.kept = (int64_t)cnt[0]; ctx->qc.too_short = (int64_t)cnt[1];
+    ctx->qc.low_qual = (int64_t)cnt[2]; ctx->qc.dups = (int64_t)cnt[3];
+    ctx->kept = (int64_t)cnt[0];
+    ctx->searched = false;
+    return MCX_OK;
+}
+
+extern "C" int mcx_qc_export(mcx_ctx *ctx, uint8_t *code, uint64_t *fingerprints) {
+    if (!ctx || !code) return fail(ctx, MCX_EINVAL, "mcx_qc_export: null argument");
+    if (!ctx->pushed) return fail(ctx, MCX_ESTATE, "mcx_qc_export: no reads pushed");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t n = ctx->n_reads;
+    cudaStream_t st = ctx->stream;
+    if (n == 0) return MCX_OK;
+    CK(cudaMemcpyAsync(code, ctx->d_code, (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (fingerprints) {
+        int rc;
+        if ((rc = ensure(ctx, &ctx->d_fp, &ctx->cap_fp, n)) != MCX_OK) return rc;
+        k_fingerprint<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->d_bases, ctx->d_offs, n, ctx->d_fp);
+        ++ctx->launches;
+        std::vector<FpKey> h((size_t)n);
+        CK(cudaMemcpyAsync(h.data(), ctx->d_fp, (size_t)n * sizeof(FpKey), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int64_t i = 0; i < n; ++i) { fingerprints[2 * i] = h[(size_t)i].a; fingerprints[2 * i + 1] = h[(size_t)i].b; }
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return MCX_OK;
+}
+
+extern "C" int mcx_qc_import(mcx_ctx *ctx, const uint8_t *code) {
+    if (!ctx || !code) return fail(ctx, MCX_EINVAL, "mcx_qc_import: null argument");
+    if (!ctx->pushed) return fail(ctx, MCX_ESTATE, "mcx_qc_import: no reads pushed");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n_reads > 0)
+        CK(cudaMemcpyAsync(ctx->d_code, code, (size_t)ctx->n_reads, cudaMemcpyHostToDevice, ctx->stream));
+    return refresh_kept(ctx);
+}
+
 extern "C" int mcx_qc_counts(mcx_ctx *ctx, mcx_qc *out) {
     if (!ctx || !out) return fail(ctx, MCX_EINVAL, "mcx_qc_counts: null argument");
     if (!ctx->pushed) return fail(ctx, MCX_ESTATE, "mcx_qc_counts: no reads pushed");
@@ -1433,8 +1492,9 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     mcx_result &R = ctx->res;
     memset(&R, 0, sizeof R);
     R.sampled_reads = n_search;
-    // counters up to the read that filled the quota (mc.py:356 breaks out of the loop there)
-    if (n_search == ctx->kept) {
+    // counters up to the read that filled the quota (mc.py:356 breaks out of the loop there); when the quota is
+    // not reached the loop runs to the end of the input and every rejected read counts
+    if (quota < 0 || quota > ctx->kept) {
         R.too_short = ctx->qc.too_short; R.low_qual = ctx->qc.low_qual; R.dups = ctx->qc.dups;
     } else if (n_search > 0) {
         int32_t cut = 0;

@@ -174,6 +174,19 @@ class MarkerSearch:
         self._ck(self.lib.mcx_qc_counts(self.ctx, C.byref(q)))
         return {"n_reads": q.n_reads, "kept": q.kept, "too_short": q.too_short, "low_qual": q.low_qual, "dups": q.dups}
 
+    def qc_export(self, with_fingerprints=False):
+        """(codes uint8[n], fingerprints uint64[n, 2] or None) of the pushed reads"""
+        n = self.qc()["n_reads"]
+        code = np.zeros(max(n, 1), np.uint8)
+        fp = np.zeros((max(n, 1), 2), np.uint64) if with_fingerprints else None
+        self._ck(self.lib.mcx_qc_export(self.ctx, _ptr(code), _ptr(fp)))
+        return code[:n], (None if fp is None else fp[:n])
+
+    def qc_import(self, code):
+        code = np.ascontiguousarray(code, np.uint8)
+        self._ck(self.lib.mcx_qc_import(self.ctx, _ptr(code)))
+        return self.qc()
+
     def search(self, quota=-1):
         self._ck(self.lib.mcx_search(self.ctx, -1 if quota is None else int(quota)))
         raw = _lib.Result()

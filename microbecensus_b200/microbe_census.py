@@ -365,8 +365,26 @@ def sample_and_search(args, engine=None):
     batch = concat_batches([load_reads(f, args["file_type"]) for f in args["seqfiles"]])
     if fastq and batch.quals is None:
         raise ValueError("FASTQ input without qualities")
-    eng.push(batch if fastq else ReadBatch(batch.bases, batch.offsets, None))
-    res = eng.search(-1 if nreads is None else nreads)
+    if not fastq:
+        batch = ReadBatch(batch.bases, batch.offsets, None)
+    # under torchrun every rank parses the input and searches its contiguous block of the read stream; -n, -d and
+    # the sums are made global by microbecensus_b200.distributed (one all-reduce + two small all-gathers)
+    world, rank = 1, 0
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            world, rank = dist.get_world_size(), dist.get_rank()
+    except ImportError:
+        pass
+    if world > 1:
+        from .distributed import sharded_search
+        eng.set_params(L, quality_offset=args.get("quality_offset") if fastq else None, min_quality=args["min_quality"],
+                       mean_quality=args["mean_quality"], max_unknown=args["max_unknown"], filter_dups=False)
+        lo, hi = rank * batch.n // world, (rank + 1) * batch.n // world
+        res = sharded_search(eng, batch.slice(lo, hi), lo, nreads=nreads, filter_dups=bool(args.get("filter_dups")))
+    else:
+        eng.push(batch)
+        res = eng.search(-1 if nreads is None else nreads)
     if res.sampled_reads == 0:
         sys.exit("\nError! No reads remaining after filtering!")
     args["sampled_reads"] = res.sampled_reads

@@ -57,6 +57,7 @@ class Oracle:
         L.oc_frame.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.oc_alignment_coverage.restype = C.c_double
         L.oc_alignment_coverage.argtypes = [C.c_double] * 7
+        L.oc_fingerprint.argtypes = [C.c_char_p, C.c_int, C.c_void_p]
         self.ix = L.oc_index_build(C.byref(self.db))
 
     def close(self):

@@ -186,3 +186,26 @@ def test_duplicate_filter_matches_oracle(eng, oracle, markers):
         sampled, code, cnt = oracle.process_reads(batch, 100, 33, opts["minq"], opts["meanq"], opts["maxunk"], opts["nreads"], filter_dups=True)
         assert (res.sampled_reads, res.too_short, res.low_qual, res.dups) == (sampled, cnt["too_short"], cnt["low_qual"], cnt["dups"]), opts
         assert res.dups > 300
+
+
+def test_verdict_export_import_roundtrip(eng, oracle, markers):
+    """mcx_qc_export / mcx_qc_import (the hooks the cross-GPU -n / -d logic uses): exported verdicts and fingerprints
+    equal the oracle's, and importing verdicts decided elsewhere drives the search."""
+    import ctypes
+    from test_host import dup_batch
+    seqs, quals = dup_batch(n=5000, seed=4)
+    batch = ReadBatch.from_strings(seqs, quals)
+    eng.set_params(100, quality_offset=33, min_quality=3, mean_quality=21, max_unknown=5)
+    eng.push(batch)
+    code, fp = eng.qc_export(True)
+    _, ocode, _ = oracle.process_reads(batch, 100, 33, 3, 21, 5, None)
+    assert np.array_equal(code, ocode)
+    for i in range(0, len(seqs), 37):
+        buf = (ctypes.c_uint64 * 2)()
+        oracle.lib.oc_fingerprint(seqs[i].encode(), len(seqs[i]), buf)
+        assert (int(fp[i, 0]), int(fp[i, 1])) == (buf[0], buf[1])
+    sampled, dcode, cnt = oracle.process_reads(batch, 100, 33, 3, 21, 5, None, filter_dups=True)
+    qc = eng.qc_import(dcode)
+    assert qc["kept"] == sampled and qc["dups"] == cnt["dups"]
+    res = eng.search(-1)
+    assert (res.sampled_reads, res.dups, res.low_qual, res.too_short) == (sampled, cnt["dups"], cnt["low_qual"], cnt["too_short"])

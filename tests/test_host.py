@@ -224,3 +224,43 @@ def test_oracle_duplicate_filter_matches_reference_semantics(oracle):
         assert sampled == len(kept) and list(np.flatnonzero(code == 0)) == kept
         assert (cnt["too_short"], cnt["low_qual"], cnt["dups"]) == (ts, lq, nd)
         assert nd > 60
+
+
+def test_sharded_quota_and_duplicates_equal_the_whole(oracle):
+    """Cross-GPU logic on CPU: three contiguous shards + shard_quota + resolve_duplicates reproduce the verdicts and
+    counters of one pass over everything (oracle = reference loop) for -d with QC and a -n cut."""
+    from microbecensus_b200.distributed import shard_quota, resolve_duplicates
+    seqs, quals = dup_batch(n=4000, seed=21)
+    whole = ReadBatch.from_strings(seqs, quals)
+    fp = np.zeros((len(seqs), 2), np.uint64)
+    for i, s in enumerate(seqs):
+        buf = (ctypes.c_uint64 * 2)()
+        oracle.lib.oc_fingerprint(s.encode(), len(s), buf)
+        fp[i] = (buf[0], buf[1])
+    bounds = [0, 1100, 2900, 4000]
+    for nreads in (None, 1700, 2500):
+        sampled, code, cnt = oracle.process_reads(whole, 100, 33, 3, 21, 5, nreads, filter_dups=True)
+        # per shard: local QC without -d
+        local = []
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            _, c, _ = oracle.process_reads(whole.slice(lo, hi), 100, 33, 3, 21, 5, None, filter_dups=False)
+            local.append(c)
+        allc = np.concatenate(local)
+        ok = np.flatnonzero(allc == 0)
+        resolved = [resolve_duplicates(c, fp[lo:hi], lo, fp[ok], ok) for c, (lo, hi) in zip(local, zip(bounds[:-1], bounds[1:]))]
+        kept = [int((c == 0).sum()) for c in resolved]
+        quotas = [shard_quota(kept, nreads, r) for r in range(3)]
+        tot = {"sampled": 0, "too_short": 0, "low_qual": 0, "dups": 0}
+        for c, q in zip(resolved, quotas):
+            if q == 0:
+                continue
+            if q < 0:
+                upto = len(c)
+                tot["sampled"] += int((c == 0).sum())
+            else:
+                upto = int(np.flatnonzero(c == 0)[q - 1]) + 1
+                tot["sampled"] += q
+            tot["too_short"] += int((c[:upto] == 1).sum()); tot["low_qual"] += int((c[:upto] == 2).sum()); tot["dups"] += int((c[:upto] == 3).sum())
+        assert tot == {"sampled": sampled, "too_short": cnt["too_short"], "low_qual": cnt["low_qual"], "dups": cnt["dups"]}, (nreads, tot, cnt)
+        searched = np.concatenate(resolved)
+        assert np.array_equal(np.flatnonzero(searched == 0)[:sampled], np.flatnonzero(code == 0))

@@ -8,7 +8,7 @@ translation + SEG + seeding + ungapped X-drop -> gapped X-drop -> per-read class
 sums (-> NCCL all-reduce for N > 1) -> weighted AGS estimate on the host.
 
 workloads (BASELINE.json configs):  c2 = 2,000,000 synthetic 100 bp single-end reads, -l 100 (default);
-c3 = 150 bp paired files with -q 5 -m 20 -u 5 (5M + 5M reads).  Per-GPU work is fixed (weak scaling): rank r
+c3 = 150 bp paired files with -q 5 -m 20 -u 5 (5M + 5M reads); c4 = 150 bp with -d, 12.5M reads per GPU.  Per-GPU work is fixed (weak scaling): rank r
 owns reads [r*n, (r+1)*n) of the deterministic stream (microbecensus_b200/synth.py).
 
 `value`  = reads/s with the reads resident in HBM when the clock starts (device path only);
@@ -29,11 +29,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+SEED_DUPS = 20260104
+
 WORKLOADS = {
     "c2": dict(name="2M synthetic 100 bp single-end reads, -l 100", config_id=2, reads=2_000_000, L=100, fastq=False,
                qc=dict(min_quality=-5, mean_quality=-5, max_unknown=100)),
     "c3": dict(name="10M synthetic 150 bp paired-end reads with -q 5 -m 20 -u 5", config_id=3, reads=10_000_000, L=150,
                fastq=True, qc=dict(min_quality=5, mean_quality=20, max_unknown=5)),
+    "c4": dict(name="100M synthetic 150 bp reads with -d (5 % exact + 1 % reverse-complement duplicates), 12.5M per GPU",
+               config_id=4, reads=12_500_000, L=150, fastq=False, dups=True,
+               qc=dict(min_quality=-5, mean_quality=-5, max_unknown=100)),
 }
 
 
@@ -191,14 +196,15 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    n = a.reads_per_gpu or (wl["reads"] if a.workload == "c2" else wl["reads"] // 2)
+    n = a.reads_per_gpu or (wl["reads"] // 2 if a.workload == "c3" else wl["reads"])
     L = wl["L"]
     lo, hi = rank * n, (rank + 1) * n
 
     markers = Markers()
     eng = MarkerSearch(markers, local)
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
-    eng.set_params(L, quality_offset=33 if wl["fastq"] else None, **wl["qc"])
+    dups = bool(wl.get("dups"))
+    eng.set_params(L, quality_offset=33 if wl["fastq"] else None, filter_dups=dups and world == 1, **wl["qc"])
 
     # ---- synthetic shard, generated on the host (untimed), staged in pinned memory
     if a.workload == "c3":
@@ -206,6 +212,16 @@ def main():
         batch = mcb.concat_batches([r1, r2])        # files are processed one after the other (mc.py:337)
     else:
         batch = synth.reads(wl["config_id"], lo, hi, L, with_quals=wl["fastq"])
+    if dups:                                   # copies of earlier reads of the same shard, 1 in 6 reverse-complemented
+        rng = np.random.default_rng(SEED_DUPS + rank)
+        mat = batch.bases.reshape(n, L)
+        comp = np.zeros(256, np.uint8); comp[[65, 67, 71, 84, 78]] = [84, 71, 67, 65, 78]
+        idx = np.flatnonzero(rng.random(n) < 0.06)
+        idx = idx[idx > 0]
+        src = (rng.random(len(idx)) * idx).astype(np.int64)
+        rc = rng.random(len(idx)) < 1.0 / 6.0
+        mat[idx[~rc]] = mat[src[~rc]]
+        mat[idx[rc]] = comp[mat[src[rc]][:, ::-1]]
     pin = lambda arr: torch.from_numpy(arr).pin_memory()
     h_bases, h_offs = pin(batch.bases), pin(batch.offsets)
     h_quals = pin(batch.quals) if batch.quals is not None else None
@@ -224,11 +240,24 @@ def main():
         args = {"read_length": L, "sampled_reads": res.sampled_reads, "verbose": False}
         return mcb.estimate_average_genome_size(args, None, res.agg_hits()), res
 
+    from microbecensus_b200.distributed import sharded_search
+
+    def finish_reduced(res):
+        args = {"read_length": L, "sampled_reads": res.sampled_reads, "verbose": False}
+        return mcb.estimate_average_genome_size(args, None, res.agg_hits()), res
+
+    def push_dev():
+        return eng.push_device(d_bases.data_ptr(), d_quals.data_ptr() if d_quals is not None else 0, d_offs.data_ptr(), n, int(d_bases.numel()))
+
     def step_device():
-        eng.push_device(d_bases.data_ptr(), d_quals.data_ptr() if d_quals is not None else 0, d_offs.data_ptr(), n, int(d_bases.numel()))
+        if dups and world > 1:                 # -d needs the cross-rank exchange of fingerprints
+            return finish_reduced(sharded_search(eng, None, lo, nreads=None, filter_dups=True, push=push_dev))
+        push_dev()
         return finish(eng.search(-1))
 
     def step_e2e():
+        if dups and world > 1:
+            return finish_reduced(sharded_search(eng, host_batch, lo, nreads=None, filter_dups=True))
         eng.push(host_batch)
         return finish(eng.search(-1))
 
@@ -320,7 +349,7 @@ def main():
             "gapped_gcups": gcups, "ags": ags, "ags_e2e": ags2,
             "counts": {"sampled_reads": res.sampled_reads, "reads_with_hits": res.reads_with_hits,
                        "reads_classified": res.reads_classified, "n_hsp": res.n_hsp, "n_seed_hits": res.n_seed_hits,
-                       "n_gapped": res.n_gapped, "gapped_cells": res.gapped_cells, "low_qual": res.low_qual}}
+                       "n_gapped": res.n_gapped, "gapped_cells": res.gapped_cells, "low_qual": res.low_qual, "dups": res.dups}}
     if world == 1 and not a.no_cpu_baseline:
         try:
             cb = cpu_baseline(wl, a.ref_sample)

@@ -60,15 +60,16 @@ def resolve_duplicates(codes, fps, first_index, passing_fps, passing_index):
     return codes
 
 
-def sharded_search(engine, batch, first_index, nreads=None, filter_dups=False, group=None, device=None):
+def sharded_search(engine, batch, first_index, nreads=None, filter_dups=False, group=None, device=None, push=None):
     """Search this rank's block of reads (already `set_params`-ed engine) and return the all-reduced SearchResult.
 
-    Without an initialised process group this is the single-GPU path."""
+    `push` (optional) replaces `engine.push(batch)`, e.g. to push device-resident buffers.
+    Without an initialised process group this is the single-GPU path (the engine's own -d is used then)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
-    qc = engine.push(batch)
+    qc = push() if push is not None else engine.push(batch)
     if world == 1:
         return engine.search(-1 if nreads is None else nreads)
     dev = device or (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu"))

@@ -83,7 +83,7 @@ def load():
     lib.mcx_result_get.argtypes = [vp, C.POINTER(Result)]
     lib.mcx_get_hits.argtypes = [vp, vp, i64, C.POINTER(i64)]
     lib.mcx_get_classified.argtypes = [vp, vp, i64]
-    lib.mcx_timings.argtypes = [vp, C.POINTER(C.c_float * 8), C.POINTER(i64)]
+    lib.mcx_timings.argtypes = [vp, C.POINTER(C.c_float * 10), C.POINTER(i64)]
     lib.mcx_last_error.argtypes = [vp]
     lib.mcx_last_error.restype = C.c_char_p
     lib.mcx_version.restype = C.c_char_p

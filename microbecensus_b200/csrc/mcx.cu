@@ -1079,9 +1079,9 @@ struct mcx_ctx {
     size_t temp_bytes = 0;
     int64_t n_hsp_sorted = 0;
     mcx_result res{};
-    float ms[8] = {0};
+    float ms[12] = {0};
     int64_t launches = 0;
-    cudaEvent_t ev[10] = {nullptr};
+    cudaEvent_t ev[16] = {nullptr};
 };
 
 static thread_local std::string g_err;
@@ -1534,7 +1534,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         if ((rc = ensure(ctx, &ctx->d_cand, &ctx->cap_cand, need_cand)) != MCX_OK) return rc;
         if ((rc = ensure(ctx, &ctx->d_segq, &ctx->cap_segq, chunk * 6 + 512)) != MCX_OK) return rc;
     }
-    float ms_probe = 0, ms_ext = 0, ms_gap = 0;
+    float ms_frames = 0, ms_seg = 0, ms_probe = 0, ms_ext = 0, ms_gap = 0;
     unsigned long long n_surv = 0, n_cand_total = 0;
     for (int64_t first = 0; first < n_search; first += chunk) {
         const int64_t nr = std::min(chunk, n_search - first);
@@ -1551,6 +1551,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             k_frames<NTF><<<(unsigned)((nr * 6 + NTF - 1) / NTF), NTF, smem, st>>>(F, fstride);
             ++ctx->launches;
         }
+        CK(cudaEventRecord(ctx->ev[10], st));
         unsigned long long n_segq = 0;
         CK(cudaMemcpyAsync(&n_segq, ctx->d_cnt + 12, sizeof n_segq, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -1565,6 +1566,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             ++ctx->launches;
         }
         ctx->n_segq_last = (int64_t)n_segq;
+        CK(cudaEventRecord(ctx->ev[11], st));
         unsigned long long n_cand = 0, qfill[NQ];
         for (int attempt = 0;; ++attempt) {
             ProbeArgs A;
@@ -1623,7 +1625,9 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
         float t;
-        cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3]); ms_probe += t;
+        cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[10]); ms_frames += t;
+        cudaEventElapsedTime(&t, ctx->ev[10], ctx->ev[11]); ms_seg += t;
+        cudaEventElapsedTime(&t, ctx->ev[11], ctx->ev[3]); ms_probe += t;
         cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[8]); ms_ext += t;
         cudaEventElapsedTime(&t, ctx->ev[8], ctx->ev[9]); ms_gap += t;
     }
@@ -1659,7 +1663,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     R.n_gapped = (int64_t)gc[0]; R.gapped_cells = (int64_t)gc[1];
     for (int f = 0; f < MCX_N_FAM; ++f) { R.fam_hits[f] = (int64_t)acc[3 + f]; R.fam_aln[f] = (int64_t)acc[3 + MCX_N_FAM + f]; }
     for (size_t k = 0; k < abl.size(); ++k) R.aln_by_len[k] = (int64_t)abl[k];
-    ctx->ms[2] = ms_probe; ctx->ms[7] = ms_ext; ctx->ms[3] = ms_gap;
+    ctx->ms[2] = ms_probe; ctx->ms[7] = ms_ext; ctx->ms[3] = ms_gap; ctx->ms[8] = ms_frames; ctx->ms[9] = ms_seg;
     cudaEventElapsedTime(&ctx->ms[4], ctx->ev[4], ctx->ev[5]);
     cudaEventElapsedTime(&ctx->ms[5], ctx->ev[5], ctx->ev[6]);
     cudaEventElapsedTime(&ctx->ms[6], ctx->ev[6], ctx->ev[7]);
@@ -1708,9 +1712,9 @@ extern "C" int mcx_get_classified(mcx_ctx *ctx, int32_t *best_subject, int64_t n
     return MCX_OK;
 }
 
-extern "C" int mcx_timings(mcx_ctx *ctx, float ms[8], int64_t *launches) {
+extern "C" int mcx_timings(mcx_ctx *ctx, float ms[10], int64_t *launches) {
     if (!ctx || !ms) return fail(ctx, MCX_EINVAL, "mcx_timings: null argument");
-    memcpy(ms, ctx->ms, sizeof(float) * 8);
+    memcpy(ms, ctx->ms, sizeof(float) * 10);
     if (launches) *launches = ctx->launches;
     return MCX_OK;
 }

@@ -206,10 +206,10 @@ class MarkerSearch:
         return out
 
     def timings(self):
-        ms = (C.c_float * 8)()
+        ms = (C.c_float * 10)()
         launches = C.c_int64(0)
         self._ck(self.lib.mcx_timings(self.ctx, C.byref(ms), C.byref(launches)))
-        names = ("h2d", "qc", "probe", "gapped", "sort", "classify", "d2h", "extend")
+        names = ("h2d", "qc", "probe", "gapped", "sort", "classify", "d2h", "extend", "frames", "seg")
         return {k: float(ms[i]) for i, k in enumerate(names)}, int(launches.value)
 
 

@@ -131,13 +131,26 @@ struct Comp {                      // composition of a <=12-residue window, nibb
         if (c > 1) nc += 1ull << (4 * (c - 1));
         --tot;
     }
+    // number of distinct letters = sum of the nibbles of nc
+    __device__ __forceinline__ int distinct() const {
+        const unsigned long long s = (nc & 0x0f0f0f0f0f0f0f0full) + ((nc >> 4) & 0x0f0f0f0f0f0f0f0full);
+        return (int)((s * 0x0101010101010101ull) >> 56);
+    }
+    // A window of <= 12 counted residues with 8 or more distinct letters has entropy > hicut whatever the counts
+    // (the flattest-possible tail (t-7, 1 x 7) gives 2.617 / 2.73 / 2.85 / 2.95 / 3.0 bits for t = 12..8), so the sum
+    // is only formed for the few windows that can be at or below a cut-off.
+    __device__ __forceinline__ bool cannot_be_low() const { return distinct() >= 8; }
     // seg.c entropy(): terms added in descending-count order (the oracle sums its sorted state vector)
     __device__ __forceinline__ double entropy(const double *ent) const {
         double e = 0.0;
         if (tot == 0) return 0.0;
-        for (int c = SEG_WINDOW; c >= 1; --c) {
-            int n = (int)((nc >> (4 * c)) & 15);
-            for (int r = 0; r < n; ++r) e += ent[tot * 13 + c];
+        unsigned long long rest = nc;
+        while (rest) {                                   // highest count first
+            const int c = (63 - __clzll((long long)rest)) >> 2;
+            const int n = (int)((rest >> (4 * c)) & 15);
+            const double t = ent[tot * 13 + c];
+            for (int r = 0; r < n; ++r) e += t;
+            rest &= ~(15ull << (4 * c));
         }
         return e;
     }
@@ -250,9 +263,11 @@ __device__ bool seg_window_masks(const uint8_t *fr, int m, const double *ent, un
     for (int k = 0; k < SEG_WINDOW; ++k) w.add(fr[k]);
     bool trig = false;
     for (int st = 0;; ++st) {
-        const double e = w.entropy(ent);
-        if (e <= SEG_LOCUT) { lom[st >> 6] |= 1ull << (st & 63); trig = true; }
-        if (e <= SEG_HICUT) him[st >> 6] |= 1ull << (st & 63);
+        if (!w.cannot_be_low()) {
+            const double e = w.entropy(ent);
+            if (e <= SEG_LOCUT) { lom[st >> 6] |= 1ull << (st & 63); trig = true; }
+            if (e <= SEG_HICUT) him[st >> 6] |= 1ull << (st & 63);
+        }
         if (st + SEG_WINDOW >= m) break;
         w.sub(fr[st]); w.add(fr[st + SEG_WINDOW]);
     }
@@ -506,8 +521,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_seg(uint8_t *frames, int fstride
         if (w + SEG_WINDOW <= m) {
             Comp c; c.clear();
             for (int k = 0; k < SEG_WINDOW; ++k) c.add(fr[w + k]);
-            const double e = c.entropy(s_ent);
-            lo = e <= SEG_LOCUT; hi = e <= SEG_HICUT;
+            if (!c.cannot_be_low()) {
+                const double e = c.entropy(s_ent);
+                lo = e <= SEG_LOCUT; hi = e <= SEG_HICUT;
+            }
         }
         const uint32_t bl = __ballot_sync(0xffffffffu, lo), bh = __ballot_sync(0xffffffffu, hi);
         if (lane == 0) { s_m[r] = bl; s_m[6 + r] = bh; s_m[12 + r] = 0; }

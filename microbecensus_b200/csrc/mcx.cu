@@ -105,8 +105,10 @@ struct SortKeyLess {
 #define FR(k) fr[(k)]
 __host__ __device__ inline int frame_stride(int maxm) { int w = (maxm + 3) / 4; return 4 * (w | 1); }
 
-__device__ __forceinline__ int base_code(uint8_t c) {  // T C A G -> 0..3, anything else 4
-    return c == 'T' ? 0 : c == 'C' ? 1 : c == 'A' ? 2 : c == 'G' ? 3 : 4;
+__device__ __forceinline__ int base_code(uint8_t c) {  // T C A G -> 0..3, anything else 4; branch-free
+    const int idx = (c >> 1) & 3;                          // A 0, C 1, T 2, G 3 for the four upper-case letters
+    const bool valid = ((0x47544341u >> (8 * idx)) & 0xffu) == (uint32_t)c;
+    return valid ? (int)((0x3012u >> (4 * idx)) & 3u) : 4;
 }
 
 struct Comp {                      // composition of a <=12-residue window, nibble-packed
@@ -237,19 +239,15 @@ __device__ void seg_full(const uint8_t *fr, int m, const unsigned long long *lom
 
 // translate frame `frame` of the read trimmed to L into fr[0..m); returns m
 __device__ int translate_frame(uint8_t *fr, const uint8_t *__restrict__ rd, int L, int frame) {
+    // one code path for both strands (lanes of a warp hold all six frames): the reverse frames walk the read
+    // backwards and complement each base (T<->A, C<->G = code ^ 2)
     const int o = frame % 3, m = (L - o) / 3;
-    if (frame < 3) {
-        for (int k = 0; k < m; ++k) {
-            const int p = o + 3 * k;
-            const int b0 = base_code(rd[p]), b1 = base_code(rd[p + 1]), b2 = base_code(rd[p + 2]);
-            fr[k] = ((b0 | b1 | b2) & 4) ? AA_STOP : c_codon[16 * b0 + 4 * b1 + b2];
-        }
-    } else {
-        for (int k = 0; k < m; ++k) {
-            const int p = L - 1 - (o + 3 * k);
-            const int b0 = base_code(rd[p]), b1 = base_code(rd[p - 1]), b2 = base_code(rd[p - 2]);
-            fr[k] = ((b0 | b1 | b2) & 4) ? AA_STOP : c_codon[16 * (b0 ^ 2) + 4 * (b1 ^ 2) + (b2 ^ 2)];
-        }
+    const bool rev = frame >= 3;
+    const int step = rev ? -1 : 1, flip = rev ? 2 : 0;
+    int p = rev ? L - 1 - o : o;
+    for (int k = 0; k < m; ++k, p += 3 * step) {
+        const int b0 = base_code(rd[p]), b1 = base_code(rd[p + step]), b2 = base_code(rd[p + 2 * step]);
+        fr[k] = ((b0 | b1 | b2) & 4) ? AA_STOP : c_codon[16 * (b0 ^ flip) + 4 * (b1 ^ flip) + (b2 ^ flip)];
     }
     return m;
 }

@@ -895,55 +895,99 @@ __device__ void gapped_xdrop(const uint8_t *fr, int q_first, int qstep, const ui
     if (best > 0) { g.gain = best; g.eq = brow; g.et = bcol; g.st = bst; }
 }
 
+struct GExtRec { int32_t gain; uint16_t eq, et; uint32_t st; uint32_t cells; };   // result of one direction
+
 struct GapArgs {
     int L, fstride;
     DevDB db;
     const uint8_t *frames;         // frame store of the chunk the survivors came from
     const Surv *surv;              // survivors [first, first + n_surv) of the global list
     int64_t first, n_surv;
+    uint32_t *items;               // work list: (survivor - first) << 1 | direction
+    unsigned long long *n_items;
+    GExtRec *ext;                  // [2 * (survivor - first) + direction], zeroed before the launch
     mcx_hit *hsp;
     SortKey *keys;
     int32_t *idx;
     unsigned long long *counters;  // [0] gapped extensions, [1] cells
 };
 
+// K3a: which (survivor, direction) pairs get a gapped extension (AlignSeqs 0x4134c8-0x4135b4: ungapped total >= 48.17
+// and more than two residues left on both sequences on that side).  Compaction again: the DP kernel only sees work.
+__global__ void k_gap_list(GapArgs A) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool f = false, b = false;
+    if (g < A.n_surv) {
+        const Surv v = A.surv[A.first + g];
+        if (v.score >= 49) {
+            const int m = (A.L - v.frame % 3) / 3;
+            const int n = A.db.off[v.subject + 1] - A.db.off[v.subject];
+            const int t1 = v.t0 + (v.q1 - v.q0);
+            f = (m - (v.q1 + 1) > 2) && (n - (t1 + 1) > 2);
+            b = (v.q0 > 2) && (v.t0 > 2);
+        }
+    }
+    const int lane = threadIdx.x & 31;
+    const uint32_t mf = __ballot_sync(0xffffffffu, f), mb = __ballot_sync(0xffffffffu, b);
+    const int tot = __popc(mf) + __popc(mb);
+    if (tot == 0) return;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(A.n_items, (unsigned long long)tot);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const uint32_t lt = (1u << lane) - 1;
+    if (f) A.items[base + __popc(mf & lt)] = (uint32_t)(g << 1);
+    if (b) A.items[base + __popc(mf) + __popc(mb & lt)] = (uint32_t)(g << 1) | 1u;
+}
+
+// K3b: one thread per gapped extension
 template <int NT, int GROW>
-__global__ void __launch_bounds__(NT) k_gapped(GapArgs A) {
-    int64_t g = (int64_t)blockIdx.x * NT + threadIdx.x;
-    if (g >= A.n_surv) return;
-    g += A.first;
-    const Surv v = A.surv[g];
+__global__ void __launch_bounds__(NT) k_gap_dir(GapArgs A, int64_t n_items) {
+    const int64_t w = (int64_t)blockIdx.x * NT + threadIdx.x;
+    if (w >= n_items) return;
+    const uint32_t item = A.items[w];
+    const int64_t g = item >> 1;
+    const int dir = item & 1;
+    const Surv v = A.surv[A.first + g];
     const uint8_t *__restrict__ fr = A.frames + (int64_t)v.gframe * A.fstride;
     const int m = (A.L - v.frame % 3) / 3;
     const int32_t o = A.db.off[v.subject];
     const int n = A.db.off[v.subject + 1] - o;
     const uint8_t *t = A.db.res + o;
+    const int q0 = v.q0, q1 = v.q1, t0 = v.t0, t1 = v.t0 + (v.q1 - v.q0);
+    GExt e;
+    if (dir == 0) {
+        int ql = m - (q1 + 1), tl = n - (t1 + 1);
+        if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
+        gapped_xdrop<GROW>(fr, q1 + 1, 1, t + t1 + 1, 1, ql, tl, e);
+    } else {
+        int ql = q0, tl = t0;
+        if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
+        gapped_xdrop<GROW>(fr, q0 - 1, -1, t + t0 - 1, -1, ql, tl, e);
+    }
+    GExtRec r;
+    r.gain = e.gain; r.eq = (uint16_t)e.eq; r.et = (uint16_t)e.et; r.st = e.st; r.cells = (uint32_t)e.cells;
+    A.ext[2 * g + dir] = r;
+}
+
+// K3c: one thread per survivor: add the two extensions to the ungapped HSP, write the HSP record and its sort key
+__global__ void k_gap_finish(GapArgs A) {
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= A.n_surv) return;
+    const GExtRec ef = A.ext[2 * g], eb = A.ext[2 * g + 1];
+    g += A.first;
+    const Surv v = A.surv[g];
     int q0 = v.q0, q1 = v.q1, t0 = v.t0, t1 = v.t0 + (v.q1 - v.q0);
     int score = v.score, ident = v.ident, aln = q1 - q0 + 1, gapcols = 0, gapo = 0;
-    if (score >= 49) {                                       // >= 48.17: gapped extension from both ends
-        unsigned long long ng = 0, nc = 0;
-        int ql = m - (q1 + 1), tl = n - (t1 + 1);
-        if (ql > 2 && tl > 2) {
-            if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
-            GExt e; gapped_xdrop<GROW>(fr, q1 + 1, 1, t + t1 + 1, 1, ql, tl, e);
-            ++ng; nc += e.cells;
-            if (e.gain > 0) {
-                score += e.gain; q1 += e.eq; t1 += e.et;
-                ident += e.st & 0xff; aln += (e.st >> 8) & 0x1ff; gapcols += (e.st >> 17) & 0x1ff; gapo += e.st >> 26;
-            }
-        }
-        ql = q0; tl = t0;
-        if (ql > 2 && tl > 2) {
-            if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
-            GExt e; gapped_xdrop<GROW>(fr, q0 - 1, -1, t + t0 - 1, -1, ql, tl, e);
-            ++ng; nc += e.cells;
-            if (e.gain > 0) {
-                score += e.gain; q0 -= e.eq; t0 -= e.et;
-                ident += e.st & 0xff; aln += (e.st >> 8) & 0x1ff; gapcols += (e.st >> 17) & 0x1ff; gapo += e.st >> 26;
-            }
-        }
-        if (ng) { atomicAdd(&A.counters[0], ng); atomicAdd(&A.counters[1], nc); }
+    if (ef.gain > 0) {
+        score += ef.gain; q1 += ef.eq; t1 += ef.et;
+        ident += ef.st & 0xff; aln += (ef.st >> 8) & 0x1ff; gapcols += (ef.st >> 17) & 0x1ff; gapo += ef.st >> 26;
     }
+    if (eb.gain > 0) {
+        score += eb.gain; q0 -= eb.eq; t0 -= eb.et;
+        ident += eb.st & 0xff; aln += (eb.st >> 8) & 0x1ff; gapcols += (eb.st >> 17) & 0x1ff; gapo += eb.st >> 26;
+    }
+    const unsigned long long nc = (unsigned long long)ef.cells + eb.cells;
+    if (nc) atomicAdd(&A.counters[1], nc);
     mcx_hit h;
     h.read = v.read; h.subject = v.subject; h.frame = v.frame; h.score = score;
     h.aln = aln; h.ident = ident; h.mism = aln - ident - gapcols; h.gapo = gapo;
@@ -1123,7 +1167,9 @@ struct mcx_ctx {
     // search buffers
     Surv *d_surv = nullptr;
     uint8_t *d_frames = nullptr;
-    uint32_t *d_segq = nullptr;
+    uint32_t *d_segq = nullptr, *d_gitems = nullptr;
+    GExtRec *d_gext = nullptr;
+    int64_t cap_gitems = 0, cap_gext = 0;
     int64_t cap_segq = 0, n_segq_last = 0;
     Cand *d_cand = nullptr;
     int64_t cap_frames = 0, cap_cand = 0, n_cand_last = 0;
@@ -1349,7 +1395,7 @@ extern "C" void mcx_destroy(mcx_ctx *ctx) {
     if (ctx->own_reads) { cudaFree(ctx->d_bases); cudaFree(ctx->d_quals); cudaFree(ctx->d_offs); }
     void *bufs[] = {ctx->d_code, ctx->d_flag, ctx->d_pos, ctx->d_kept, ctx->d_surv, ctx->d_hsp, ctx->d_hits_out,
                     ctx->d_keys, ctx->d_idx, ctx->d_best, ctx->d_hflag, ctx->d_hpos, ctx->d_keep, ctx->d_cnt,
-                    ctx->d_acc, ctx->d_abl, ctx->d_temp, ctx->d_frames, ctx->d_cand, ctx->d_segq, ctx->d_qcnt, ctx->d_fp};
+                    ctx->d_acc, ctx->d_abl, ctx->d_temp, ctx->d_frames, ctx->d_cand, ctx->d_segq, ctx->d_qcnt, ctx->d_fp, ctx->d_gitems, ctx->d_gext};
     for (void *p : bufs) if (p) cudaFree(p);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -1596,7 +1642,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         if ((rc = ensure(ctx, &ctx->d_segq, &ctx->cap_segq, chunk * 6 + 512)) != MCX_OK) return rc;
     }
     float ms_frames = 0, ms_seg = 0, ms_probe = 0, ms_ext = 0, ms_gap = 0;
-    unsigned long long n_surv = 0, n_cand_total = 0;
+    unsigned long long n_surv = 0, n_cand_total = 0, n_gapped_total = 0;
     for (int64_t first = 0; first < n_search; first += chunk) {
         const int64_t nr = std::min(chunk, n_search - first);
         CK(cudaMemsetAsync(ctx->d_qcnt, 0, NQ * sizeof(unsigned long long), st));
@@ -1677,10 +1723,24 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             G.L = P.read_length; G.fstride = fstride; G.db = ctx->db; G.frames = ctx->d_frames; G.surv = ctx->d_surv;
             G.first = (int64_t)surv_before; G.n_surv = (int64_t)(n_surv - surv_before);
             G.hsp = ctx->d_hsp; G.keys = ctx->d_keys; G.idx = ctx->d_idx; G.counters = ctx->d_cnt + 10;
-            if (maxm + GAP_SLACK + 2 <= 104) k_gapped<128, 104><<<(unsigned)((G.n_surv + 127) / 128), 128, 0, st>>>(G);
-            else if (maxm + GAP_SLACK + 2 <= 152) k_gapped<128, 152><<<(unsigned)((G.n_surv + 127) / 128), 128, 0, st>>>(G);
-            else k_gapped<128, MAX_FRAME + GAP_SLACK + 2><<<(unsigned)((G.n_surv + 127) / 128), 128, 0, st>>>(G);
-            ++ctx->launches;
+            if ((rc = ensure(ctx, &ctx->d_gitems, &ctx->cap_gitems, 2 * G.n_surv)) != MCX_OK) return rc;
+            if ((rc = ensure(ctx, &ctx->d_gext, &ctx->cap_gext, 2 * G.n_surv)) != MCX_OK) return rc;
+            G.items = ctx->d_gitems; G.ext = ctx->d_gext; G.n_items = ctx->d_cnt + 13;
+            CK(cudaMemsetAsync(ctx->d_gext, 0, (size_t)(2 * G.n_surv) * sizeof(GExtRec), st));
+            CK(cudaMemsetAsync(ctx->d_cnt + 13, 0, sizeof(unsigned long long), st));
+            k_gap_list<<<(unsigned)((G.n_surv + 255) / 256), 256, 0, st>>>(G);
+            unsigned long long n_items = 0;
+            CK(cudaMemcpyAsync(&n_items, ctx->d_cnt + 13, sizeof n_items, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (n_items > 0) {
+                const unsigned gb = (unsigned)((n_items + 127) / 128);
+                if (maxm + GAP_SLACK + 2 <= 104) k_gap_dir<128, 104><<<gb, 128, 0, st>>>(G, (int64_t)n_items);
+                else if (maxm + GAP_SLACK + 2 <= 152) k_gap_dir<128, 152><<<gb, 128, 0, st>>>(G, (int64_t)n_items);
+                else k_gap_dir<128, MAX_FRAME + GAP_SLACK + 2><<<gb, 128, 0, st>>>(G, (int64_t)n_items);
+                n_gapped_total += n_items;
+            }
+            k_gap_finish<<<(unsigned)((G.n_surv + 255) / 256), 256, 0, st>>>(G);
+            ctx->launches += 3;
         }
         CK(cudaEventRecord(ctx->ev[9], st));
         CK(cudaStreamSynchronize(st));
@@ -1721,7 +1781,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     R.reads_with_hits = (int64_t)acc[0]; R.reads_classified = (int64_t)acc[1]; R.n_hsp = (int64_t)acc[2];
-    R.n_gapped = (int64_t)gc[0]; R.gapped_cells = (int64_t)gc[1];
+    R.n_gapped = (int64_t)n_gapped_total; R.gapped_cells = (int64_t)gc[1];
     for (int f = 0; f < MCX_N_FAM; ++f) { R.fam_hits[f] = (int64_t)acc[3 + f]; R.fam_aln[f] = (int64_t)acc[3 + MCX_N_FAM + f]; }
     for (size_t k = 0; k < abl.size(); ++k) R.aln_by_len[k] = (int64_t)abl[k];
     ctx->ms[2] = ms_probe; ctx->ms[7] = ms_ext; ctx->ms[3] = ms_gap; ctx->ms[8] = ms_frames; ctx->ms[9] = ms_seg;

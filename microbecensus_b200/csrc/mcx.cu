@@ -820,51 +820,59 @@ __global__ void __launch_bounds__(NT) k_extend(ExtArgs A) {
 #define ST_GAPRUN 0x4000000u
 struct GExt { int gain, eq, et; uint32_t st; int cells; };
 
-template <int GROW>                // row capacity: longest frame + GAP_SLACK + 2
+template <int GROW, bool STATS>    // GROW = row capacity (longest frame + GAP_SLACK + 2); STATS = carry the alignment statistics
 __device__ void gapped_xdrop(const uint8_t *fr, int q_first, int qstep, const uint8_t *__restrict__ t,
                              int tstep, int nQ, int nD, GExt &g) {
     g.gain = 0; g.eq = 0; g.et = 0; g.st = 0; g.cells = 0;
     const int GI = GAP_OPEN, GE = GAP_EXT, GIE = GAP_OPEN + GAP_EXT;
     const int limit = 15;                      // (int)((26.98 - 11) / 1)
     int H[GROW], F[GROW];
-    uint32_t HS[GROW], FS[GROW];
-    H[0] = 0; F[0] = -GI; HS[0] = 0; FS[0] = 0;
+    uint32_t HS[STATS ? GROW : 1], FS[STATS ? GROW : 1];
+    H[0] = 0; F[0] = -GI;
+    if (STATS) { HS[0] = 0; FS[0] = 0; }
     {
         int r = -GI;
         for (int j = 1; j <= limit && j <= nD; ++j) {
             r -= GE; H[j] = r; F[j] = r - GI;
-            HS[j] = (uint32_t)j * (ST_ALN + ST_GAPCOL) + ST_GAPRUN; FS[j] = HS[j];
+            if (STATS) { HS[j] = (uint32_t)j * (ST_ALN + ST_GAPCOL) + ST_GAPRUN; FS[j] = HS[j]; }
         }
     }
     int cs = 1, ce = limit, best = 0, bcol = 0, brow = 0, cells = 0;
     uint32_t bst = 0;
     for (int i = 1; i <= nQ; ++i) {
         int diag = H[cs - 1];
-        uint32_t dst = HS[cs - 1];
-        // boundary cell (i, cs-1): value max(H-12, F-1), always traced as a vertical gap column
-        uint32_t bs = (i == 1 ? HS[cs - 1] + ST_GAPRUN : FS[cs - 1]) + ST_ALN + ST_GAPCOL;
+        uint32_t dst = 0, bs = 0;
+        if (STATS) {
+            dst = HS[cs - 1];
+            // boundary cell (i, cs-1): value max(H-12, F-1), always traced as a vertical gap column
+            bs = (i == 1 ? HS[cs - 1] + ST_GAPRUN : FS[cs - 1]) + ST_ALN + ST_GAPCOL;
+        }
         int v = H[cs - 1] - GIE, f1 = F[cs - 1] - GE;
         if (v < f1) v = f1;
-        F[cs - 1] = v; H[cs - 1] = v; HS[cs - 1] = bs; FS[cs - 1] = bs;
+        F[cs - 1] = v; H[cs - 1] = v;
+        if (STATS) { HS[cs - 1] = bs; FS[cs - 1] = bs; }
         int E = v - GI, hl = v, j = cs;
         uint32_t ES = bs, hls = bs;
         bool skip_tail = false;
-        const int qa = FR(q_first + (i - 1) * qstep);
+        const int qa = fr[q_first + (i - 1) * qstep];
         if (!(cs > ce || cs > nD)) {
             for (;;) {
                 ++cells;
                 int a = hl - GIE, b = E - GE;
-                if (a >= b) { E = a; ES = hls + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { E = b; ES += ST_ALN + ST_GAPCOL; }
+                if (a >= b) { E = a; if (STATS) ES = hls + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { E = b; if (STATS) ES += ST_ALN + ST_GAPCOL; }
                 int c = H[j] - GIE, d = F[j] - GE, Fv;
-                uint32_t FSv;
-                if (c >= d) { Fv = c; FSv = HS[j] + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { Fv = d; FSv = FS[j] + ST_ALN + ST_GAPCOL; }
+                uint32_t FSv = 0;
+                if (c >= d) { Fv = c; if (STATS) FSv = HS[j] + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { Fv = d; if (STATS) FSv = FS[j] + ST_ALN + ST_GAPCOL; }
                 const int tb = t[(j - 1) * tstep];
                 int h = diag + c_blosum[qa * 32 + tb];
-                uint32_t hs = dst + ST_ALN + (uint32_t)(qa == tb && qa < 20);
+                uint32_t hs = 0;
+                if (STATS) hs = dst + ST_ALN + (uint32_t)(qa == tb && qa < 20);
                 if (E > h) { h = E; hs = ES; }
                 if (h < Fv) { h = Fv; hs = FSv; }
-                diag = H[j]; dst = HS[j];
-                H[j] = h; HS[j] = hs; F[j] = Fv; FS[j] = FSv; hl = h; hls = hs;
+                diag = H[j];
+                if (STATS) dst = HS[j];
+                H[j] = h; F[j] = Fv; hl = h;
+                if (STATS) { HS[j] = hs; FS[j] = FSv; hls = hs; }
                 if (h > best) { best = h; bcol = j; brow = i; bst = hs; }
                 else if (h <= best - 27 && j > bcol) {       // h < best - 26.98
                     if (j >= ce) { ce = j; break; }
@@ -878,8 +886,9 @@ __device__ void gapped_xdrop(const uint8_t *fr, int q_first, int qstep, const ui
             for (int jj = ce + 1; jj <= nD; ++jj) {          // run on along the row by horizontal gaps
                 ++cells;
                 int a = hl - GIE, b = E - GE;
-                if (a > b) { E = a; ES = hls + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { E = b; ES += ST_ALN + ST_GAPCOL; }
-                H[jj] = E; HS[jj] = ES; F[jj] = E - GI; FS[jj] = ES; hl = E; hls = ES;
+                if (a > b) { E = a; if (STATS) ES = hls + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { E = b; if (STATS) ES += ST_ALN + ST_GAPCOL; }
+                H[jj] = E; F[jj] = E - GI; hl = E;
+                if (STATS) { HS[jj] = ES; FS[jj] = ES; hls = ES; }
                 if (E > best) { best = E; bcol = jj; brow = i; bst = ES; }
                 else if (E <= best - 27) { ce = jj; break; }
             }
@@ -939,34 +948,50 @@ __global__ void k_gap_list(GapArgs A) {
     if (b) A.items[base + __popc(mf) + __popc(mb & lt)] = (uint32_t)(g << 1) | 1u;
 }
 
-// K3b: one thread per gapped extension
-template <int NT, int GROW>
-__global__ void __launch_bounds__(NT) k_gap_dir(GapArgs A, int64_t n_items) {
+// K3b: one thread per gapped extension.  First a score-only pass over all of them (two DP rows); only the ~20 % that
+// gain anything are queued for the second pass, which repeats the same DP carrying the alignment statistics.
+template <int NT, int GROW, bool STATS>
+__global__ void __launch_bounds__(NT) k_gap_dir(GapArgs A, const uint32_t *__restrict__ items, int64_t n_items,
+                                                uint32_t *__restrict__ items2, unsigned long long *n_items2) {
     const int64_t w = (int64_t)blockIdx.x * NT + threadIdx.x;
-    if (w >= n_items) return;
-    const uint32_t item = A.items[w];
-    const int64_t g = item >> 1;
-    const int dir = item & 1;
-    const Surv v = A.surv[A.first + g];
-    const uint8_t *__restrict__ fr = A.frames + (int64_t)v.gframe * A.fstride;
-    const int m = (A.L - v.frame % 3) / 3;
-    const int32_t o = A.db.off[v.subject];
-    const int n = A.db.off[v.subject + 1] - o;
-    const uint8_t *t = A.db.res + o;
-    const int q0 = v.q0, q1 = v.q1, t0 = v.t0, t1 = v.t0 + (v.q1 - v.q0);
-    GExt e;
-    if (dir == 0) {
-        int ql = m - (q1 + 1), tl = n - (t1 + 1);
-        if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
-        gapped_xdrop<GROW>(fr, q1 + 1, 1, t + t1 + 1, 1, ql, tl, e);
-    } else {
-        int ql = q0, tl = t0;
-        if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
-        gapped_xdrop<GROW>(fr, q0 - 1, -1, t + t0 - 1, -1, ql, tl, e);
+    bool again = false;
+    uint32_t item = 0;
+    if (w < n_items) {
+        item = items[w];
+        const int64_t g = item >> 1;
+        const int dir = item & 1;
+        const Surv v = A.surv[A.first + g];
+        const uint8_t *__restrict__ fr = A.frames + (int64_t)v.gframe * A.fstride;
+        const int m = (A.L - v.frame % 3) / 3;
+        const int32_t o = A.db.off[v.subject];
+        const int n = A.db.off[v.subject + 1] - o;
+        const uint8_t *t = A.db.res + o;
+        const int q0 = v.q0, q1 = v.q1, t0 = v.t0, t1 = v.t0 + (v.q1 - v.q0);
+        GExt e;
+        if (dir == 0) {
+            int ql = m - (q1 + 1), tl = n - (t1 + 1);
+            if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
+            gapped_xdrop<GROW, STATS>(fr, q1 + 1, 1, t + t1 + 1, 1, ql, tl, e);
+        } else {
+            int ql = q0, tl = t0;
+            if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
+            gapped_xdrop<GROW, STATS>(fr, q0 - 1, -1, t + t0 - 1, -1, ql, tl, e);
+        }
+        GExtRec r;
+        r.gain = e.gain; r.eq = (uint16_t)e.eq; r.et = (uint16_t)e.et; r.st = e.st; r.cells = (uint32_t)e.cells;
+        A.ext[2 * g + dir] = r;
+        again = !STATS && e.gain > 0;
     }
-    GExtRec r;
-    r.gain = e.gain; r.eq = (uint16_t)e.eq; r.et = (uint16_t)e.et; r.st = e.st; r.cells = (uint32_t)e.cells;
-    A.ext[2 * g + dir] = r;
+    if (!STATS) {
+        const int lane = threadIdx.x & 31;
+        const uint32_t ma = __ballot_sync(0xffffffffu, again);
+        if (ma) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(n_items2, (unsigned long long)__popc(ma));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (again) items2[base + __popc(ma & ((1u << lane) - 1))] = item;
+        }
+    }
 }
 
 // K3c: one thread per survivor: add the two extensions to the ungapped HSP, write the HSP record and its sort key
@@ -988,6 +1013,7 @@ __global__ void k_gap_finish(GapArgs A) {
     }
     const unsigned long long nc = (unsigned long long)ef.cells + eb.cells;
     if (nc) atomicAdd(&A.counters[1], nc);
+    { const int ng = (ef.gain > 0) + (eb.gain > 0); if (ng) atomicAdd(&A.counters[0], (unsigned long long)ng); }
     mcx_hit h;
     h.read = v.read; h.subject = v.subject; h.frame = v.frame; h.score = score;
     h.aln = aln; h.ident = ident; h.mism = aln - ident - gapcols; h.gapo = gapo;
@@ -1723,7 +1749,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             G.L = P.read_length; G.fstride = fstride; G.db = ctx->db; G.frames = ctx->d_frames; G.surv = ctx->d_surv;
             G.first = (int64_t)surv_before; G.n_surv = (int64_t)(n_surv - surv_before);
             G.hsp = ctx->d_hsp; G.keys = ctx->d_keys; G.idx = ctx->d_idx; G.counters = ctx->d_cnt + 10;
-            if ((rc = ensure(ctx, &ctx->d_gitems, &ctx->cap_gitems, 2 * G.n_surv)) != MCX_OK) return rc;
+            if ((rc = ensure(ctx, &ctx->d_gitems, &ctx->cap_gitems, 4 * G.n_surv)) != MCX_OK) return rc;
             if ((rc = ensure(ctx, &ctx->d_gext, &ctx->cap_gext, 2 * G.n_surv)) != MCX_OK) return rc;
             G.items = ctx->d_gitems; G.ext = ctx->d_gext; G.n_items = ctx->d_cnt + 13;
             CK(cudaMemsetAsync(ctx->d_gext, 0, (size_t)(2 * G.n_surv) * sizeof(GExtRec), st));
@@ -1733,10 +1759,23 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             CK(cudaMemcpyAsync(&n_items, ctx->d_cnt + 13, sizeof n_items, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             if (n_items > 0) {
+                uint32_t *items2 = ctx->d_gitems + G.n_surv * 2;     // second half of the work-list buffer
+                CK(cudaMemsetAsync(ctx->d_cnt + 14, 0, sizeof(unsigned long long), st));
                 const unsigned gb = (unsigned)((n_items + 127) / 128);
-                if (maxm + GAP_SLACK + 2 <= 104) k_gap_dir<128, 104><<<gb, 128, 0, st>>>(G, (int64_t)n_items);
-                else if (maxm + GAP_SLACK + 2 <= 152) k_gap_dir<128, 152><<<gb, 128, 0, st>>>(G, (int64_t)n_items);
-                else k_gap_dir<128, MAX_FRAME + GAP_SLACK + 2><<<gb, 128, 0, st>>>(G, (int64_t)n_items);
+                const int grow = maxm + GAP_SLACK + 2;
+                if (grow <= 104) k_gap_dir<128, 104, false><<<gb, 128, 0, st>>>(G, G.items, (int64_t)n_items, items2, ctx->d_cnt + 14);
+                else if (grow <= 152) k_gap_dir<128, 152, false><<<gb, 128, 0, st>>>(G, G.items, (int64_t)n_items, items2, ctx->d_cnt + 14);
+                else k_gap_dir<128, MAX_FRAME + GAP_SLACK + 2, false><<<gb, 128, 0, st>>>(G, G.items, (int64_t)n_items, items2, ctx->d_cnt + 14);
+                unsigned long long n2 = 0;
+                CK(cudaMemcpyAsync(&n2, ctx->d_cnt + 14, sizeof n2, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if (n2 > 0) {
+                    const unsigned gb2 = (unsigned)((n2 + 127) / 128);
+                    if (grow <= 104) k_gap_dir<128, 104, true><<<gb2, 128, 0, st>>>(G, items2, (int64_t)n2, nullptr, nullptr);
+                    else if (grow <= 152) k_gap_dir<128, 152, true><<<gb2, 128, 0, st>>>(G, items2, (int64_t)n2, nullptr, nullptr);
+                    else k_gap_dir<128, MAX_FRAME + GAP_SLACK + 2, true><<<gb2, 128, 0, st>>>(G, items2, (int64_t)n2, nullptr, nullptr);
+                    ++ctx->launches;
+                }
                 n_gapped_total += n_items;
             }
             k_gap_finish<<<(unsigned)((G.n_surv + 255) / 256), 256, 0, st>>>(G);
@@ -1782,6 +1821,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     CK(cudaGetLastError());
     R.reads_with_hits = (int64_t)acc[0]; R.reads_classified = (int64_t)acc[1]; R.n_hsp = (int64_t)acc[2];
     R.n_gapped = (int64_t)n_gapped_total; R.gapped_cells = (int64_t)gc[1];
+    if (getenv("MCX_DEBUG")) fprintf(stderr, "[mcx] gapped extensions %llu, with gain > 0: %llu, cells %llu\n", n_gapped_total, gc[0], gc[1]);
     for (int f = 0; f < MCX_N_FAM; ++f) { R.fam_hits[f] = (int64_t)acc[3 + f]; R.fam_aln[f] = (int64_t)acc[3 + MCX_N_FAM + f]; }
     for (size_t k = 0; k < abl.size(); ++k) R.aln_by_len[k] = (int64_t)abl[k];
     ctx->ms[2] = ms_probe; ctx->ms[7] = ms_ext; ctx->ms[3] = ms_gap; ctx->ms[8] = ms_frames; ctx->ms[9] = ms_seg;

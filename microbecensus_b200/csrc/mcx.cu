@@ -35,12 +35,13 @@ using namespace mcx;
 // ------------------------------------------------------------------------------------------------
 // device-side constants
 // ------------------------------------------------------------------------------------------------
-__constant__ double c_lnfac[256];     // ln(i!)
-__constant__ double c_ln20[256];      // i * ln 20
-__constant__ double c_ent[13 * 13];   // [tot][c] = -(c/tot) log2(c/tot)
-__constant__ int8_t c_blosum[21 * 32];
-__constant__ uint8_t c_codon[64];
 __constant__ mcx_cutoff c_cut[MCX_N_FAM];
+// Look-up tables live in global memory and are staged in shared memory by the blocks that index them per lane:
+// constant-bank reads with a per-lane index are serialised (k_extend once spent 11 % of its time filling its
+// BLOSUM62 copy from a __constant__ array, k_frames 11 % on the codon table).
+__device__ __align__(16) int8_t g_blosum[21 * 32];
+__device__ double g_lnfac[256];       // ln(i!)
+__device__ double g_ln20[256];        // i * ln 20
 
 // murphy10 letters of residues 0..15 / 16..20, one nibble each (built from MURPHY10 at compile time)
 constexpr unsigned long long pack_m10(int first, int last) {
@@ -69,12 +70,19 @@ struct DevDB {
     uint32_t hmask[N_PAT];
     int hshift[N_PAT];
     const uint32_t *post;          // (subject << 11 | position), bit 31 = last posting of the word
-    const uint32_t *bloom;         // 2^28-bit presence filter over (pattern, word): absorbs ~94 % of the probes in L2
+    const uint32_t *bloom;         // 2^28-bit presence filter over (pattern, word): absorbs ~97 % of the probes in L2
 };
 
-#define BLOOM_BITS 28
-__host__ __device__ __forceinline__ uint32_t bloom_index(int p, uint32_t code) {
-    return ((code ^ ((uint32_t)p * 0x3243F6A9u)) * 2246822519u) >> (32 - BLOOM_BITS);
+// presence filter: 2^23 words of 32 bits; a key sets two bits of ONE word (same L2 sector traffic as a one-bit filter,
+// false-positive rate ~1.3 % instead of 5.6 % at this load, so fewer than half as many table lookups follow)
+#define BLOOM_WORD_BITS 23
+__host__ __device__ __forceinline__ uint32_t bloom_hash(int p, uint32_t code) {
+    return (code ^ ((uint32_t)p * 0x3243F6A9u)) * 2246822519u;
+}
+__host__ __device__ __forceinline__ uint32_t bloom_word(uint32_t h) { return h >> (32 - BLOOM_WORD_BITS); }
+__host__ __device__ __forceinline__ uint32_t bloom_mask(uint32_t h) {
+    const uint32_t h2 = h * 0x85EBCA6Bu;
+    return (1u << (h2 >> 27)) | (1u << ((h2 >> 22) & 31u));
 }
 
 struct Surv {                      // ungapped HSP that reached the report floor (20 bytes)
@@ -111,165 +119,58 @@ __device__ __forceinline__ int base_code(uint8_t c) {  // T C A G -> 0..3, anyth
     return valid ? (int)((0x3012u >> (4 * idx)) & 3u) : 4;
 }
 
-struct Comp {                      // composition of a <=12-residue window, nibble-packed
-    unsigned long long lo, hi, nc; // counts of letters 0..15 / 16..19 / number of letters having count c
-    int tot;
-    __device__ __forceinline__ void clear() { lo = hi = nc = 0; tot = 0; }
-    __device__ __forceinline__ void add(int a) {
+// SEG window test in integers.  The entropy of a window is a function of its sorted letter counts only, and for a
+// fixed number of counted residues `tot` it is monotone in G = sum over letters of g(count), g(c) = c log2 c:
+// H = log2 tot - G / tot.  G is kept in 2^-24 fixed point and updated as the window slides (one table value per
+// residue entering or leaving); "H <= cut" becomes "G >= thr[tot]".  upload_tables() derives thr[tot] from the
+// double-precision sums the reference forms (seg.c entropy(): -(c/tot) log2(c/tot), highest count first) over every
+// partition of tot <= 12 and refuses to start unless the integer test separates them exactly, so the verdicts are
+// those of the floating-point code and of the oracle.  (First version: nibble-packed count histogram + FP64 sum in
+// descending-count order for every window with < 8 distinct letters -- 24 % of k_frames' instructions at 6 of 32
+// lanes active.)
+constexpr int SEG_TAB = 176;       // entries of ln(i!) / i ln 20 staged per block (window lengths <= MAX_FRAME)
+struct SegTab { int dg[16]; int2 thr[16]; };    // dg[c] = g(c+1) - g(c); thr[tot] = (locut, hicut) thresholds on G
+__device__ SegTab g_segtab;
+
+struct WinG {                       // composition of a <= 12-residue window
+    unsigned long long lo, hi;      // counts of letters 0..15 / 16..19, one nibble each
+    int G, tot;
+    __device__ __forceinline__ void clear() { lo = hi = 0; G = 0; tot = 0; }
+    __device__ __forceinline__ void add(int a, const SegTab &T) {
         if (a >= 20) return;
         int c;
         if (a < 16) { c = (int)((lo >> (4 * a)) & 15); lo += 1ull << (4 * a); }
         else { c = (int)((hi >> (4 * (a - 16))) & 15); hi += 1ull << (4 * (a - 16)); }
-        if (c) nc -= 1ull << (4 * c);
-        nc += 1ull << (4 * (c + 1));
+        G += T.dg[c];
         ++tot;
     }
-    __device__ __forceinline__ void sub(int a) {
+    __device__ __forceinline__ void sub(int a, const SegTab &T) {
         if (a >= 20) return;
         int c;
         if (a < 16) { c = (int)((lo >> (4 * a)) & 15); lo -= 1ull << (4 * a); }
         else { c = (int)((hi >> (4 * (a - 16))) & 15); hi -= 1ull << (4 * (a - 16)); }
-        nc -= 1ull << (4 * c);
-        if (c > 1) nc += 1ull << (4 * (c - 1));
+        G -= T.dg[c - 1];
         --tot;
     }
-    // number of distinct letters = sum of the nibbles of nc
-    __device__ __forceinline__ int distinct() const {
-        const unsigned long long s = (nc & 0x0f0f0f0f0f0f0f0full) + ((nc >> 4) & 0x0f0f0f0f0f0f0f0full);
-        return (int)((s * 0x0101010101010101ull) >> 56);
-    }
-    // A window of <= 12 counted residues with 8 or more distinct letters has entropy > hicut whatever the counts
-    // (the flattest-possible tail (t-7, 1 x 7) gives 2.617 / 2.73 / 2.85 / 2.95 / 3.0 bits for t = 12..8), so the sum
-    // is only formed for the few windows that can be at or below a cut-off.
-    __device__ __forceinline__ bool cannot_be_low() const { return distinct() >= 8; }
-    // seg.c entropy(): terms added in descending-count order (the oracle sums its sorted state vector)
-    __device__ __forceinline__ double entropy(const double *ent) const {
-        double e = 0.0;
-        if (tot == 0) return 0.0;
-        unsigned long long rest = nc;
-        while (rest) {                                   // highest count first
-            const int c = (63 - __clzll((long long)rest)) >> 2;
-            const int n = (int)((rest >> (4 * c)) & 15);
-            const double t = ent[tot * 13 + c];
-            for (int r = 0; r < n; ++r) e += t;
-            rest &= ~(15ull << (4 * c));
-        }
-        return e;
-    }
+    __device__ __forceinline__ bool low(const SegTab &T) const { return G >= T.thr[tot].x; }    // entropy <= locut
+    __device__ __forceinline__ bool high(const SegTab &T) const { return G >= T.thr[tot].y; }   // entropy <= hicut
 };
-
-__device__ __forceinline__ bool mbit(const unsigned long long *m, int k) { return (m[k >> 6] >> (k & 63)) & 1; }
 
 // seg.c getprob() = lnass + lnperm - len*ln20 from the histogram of letter counts: nc[c] = number of letters
 // occurring c times.  Walking c downwards visits the counts in exactly the order of seg.c's sorted state vector,
 // so the floating-point operations (and their order) are those of the reference and of the oracle.
-__device__ double seg_getprob(const uint8_t *nc, int maxc, int len) {
-    double lnperm = c_lnfac[len], lnass = c_lnfac[20];
+__device__ double seg_getprob(const uint8_t *nc, int maxc, int len, const double *lnfac, const double *ln20) {
+    double lnperm = lnfac[len], lnass = lnfac[20];
     int nz = 0;
     for (int c = maxc; c >= 1; --c) {
         const int n = nc[c];
         if (!n) continue;
-        for (int r = 0; r < n; ++r) lnperm -= c_lnfac[c];
-        lnass -= c_lnfac[n];
+        for (int r = 0; r < n; ++r) lnperm -= lnfac[c];
+        lnass -= lnfac[n];
         nz += n;
     }
-    if (nz > 0 && nz < 20) lnass -= c_lnfac[20 - nz];
-    return lnass + lnperm - c_ln20[len];
-}
-
-// Seg::trim: the sub-window of [off, off+tl) with the lowest probability, longest first, leftmost first.
-// The composition slides by one residue per step instead of being rebuilt.
-__device__ void seg_trim(const uint8_t *fr, int off, int tl, int &leftend, int &rightend) {
-    uint8_t base[20], cur[20], nc[MAX_FRAME + 2];
-    for (int a = 0; a < 20; ++a) base[a] = 0;
-    for (int k = 0; k < tl; ++k) { const int a = fr[off + k]; if (a < 20) base[a]++; }
-    int lend = 0, rend = tl - 1, minlen = 1;
-    if (tl - SEG_MAXTRIM > minlen) minlen = tl - SEG_MAXTRIM;
-    double minprob = 1.0;
-    for (int len = tl; len > minlen; --len) {
-        int maxc = 0;
-        for (int c = 0; c <= len; ++c) nc[c] = 0;
-        for (int a = 0; a < 20; ++a) { const int c = base[a]; cur[a] = (uint8_t)c; if (c) { nc[c]++; maxc = c > maxc ? c : maxc; } }
-        for (int st = 0;; ++st) {
-            const double prob = seg_getprob(nc, maxc, len);
-            if (prob < minprob) { minprob = prob; lend = st; rend = len + st - 1; }
-            if (st + len >= tl) break;
-            const int a = fr[off + st], b = fr[off + st + len];
-            if (a < 20) { const int c = cur[a]; nc[c]--; if (c > 1) nc[c - 1]++; cur[a] = (uint8_t)(c - 1); }
-            if (b < 20) { const int c = cur[b]; if (c) nc[c]--; nc[c + 1]++; cur[b] = (uint8_t)(c + 1); if (c + 1 > maxc) maxc = c + 1; }
-            while (maxc > 0 && nc[maxc] == 0) --maxc;
-        }
-        const int a = fr[off + len - 1];
-        if (a < 20) base[a]--;
-    }
-    rightend -= (tl - rend - 1);
-    leftend += lend;
-}
-
-// Seg::segseq as it behaves inside RAPsearch2 (downset 0, upset 1), for frames that hold a window with entropy
-// <= 2.2.  lom / him: bit w set when the 12-window starting at w has entropy <= locut / <= hicut (the windows of a
-// sub-sequence are windows of the frame, with the last one repeated for its tail positions).  The recursion of seg.c
-// only adds segments, so the left parts are queued on a small work list instead.
-__device__ void seg_full(const uint8_t *fr, int m, const unsigned long long *lom, const unsigned long long *him,
-                         unsigned long long mask[3]) {
-    int wl_off[12], wl_len[12], nwl = 1;
-    wl_off[0] = 0; wl_len[0] = m;
-    while (nwl > 0) {
-        --nwl;
-        const int off = wl_off[nwl], slen = wl_len[nwl];
-        if (SEG_WINDOW > slen) continue;
-        const int last = slen - 1, wmax = slen - SEG_WINDOW;
-        int lowlim = 0;
-        for (int i = 0; i <= last; ++i) {
-            if (!mbit(lom, off + (i < wmax ? i : wmax))) continue;
-            int j, loi, hii;
-            for (j = i; j >= lowlim; --j) if (!mbit(him, off + (j < wmax ? j : wmax))) break;
-            loi = j + 1;
-            for (j = i; j <= last; ++j) if (!mbit(him, off + (j < wmax ? j : wmax))) break;
-            hii = j - 1;
-            int leftend = loi, rightend = hii;
-            seg_trim(fr, off + leftend, rightend - leftend + 1, leftend, rightend);
-            if (i < leftend && nwl < 12) { wl_off[nwl] = off + loi; wl_len[nwl] = leftend - loi; ++nwl; }
-            for (j = off + leftend; j <= off + rightend; ++j) mask[j >> 6] |= 1ull << (j & 63);
-            i = hii < rightend ? hii : rightend;
-            lowlim = i + 1;
-        }
-    }
-}
-
-// translate frame `frame` of the read trimmed to L into fr[0..m); returns m
-__device__ int translate_frame(uint8_t *fr, const uint8_t *__restrict__ rd, int L, int frame) {
-    // one code path for both strands (lanes of a warp hold all six frames): the reverse frames walk the read
-    // backwards and complement each base (T<->A, C<->G = code ^ 2)
-    const int o = frame % 3, m = (L - o) / 3;
-    const bool rev = frame >= 3;
-    const int step = rev ? -1 : 1, flip = rev ? 2 : 0;
-    int p = rev ? L - 1 - o : o;
-    for (int k = 0; k < m; ++k, p += 3 * step) {
-        const int b0 = base_code(rd[p]), b1 = base_code(rd[p + step]), b2 = base_code(rd[p + 2 * step]);
-        fr[k] = ((b0 | b1 | b2) & 4) ? AA_STOP : c_codon[16 * (b0 ^ flip) + 4 * (b1 ^ flip) + (b2 ^ flip)];
-    }
-    return m;
-}
-
-// entropy of every 12-window against locut / hicut; returns true when some window is at or below locut
-__device__ bool seg_window_masks(const uint8_t *fr, int m, const double *ent, unsigned long long lom[3],
-                                 unsigned long long him[3]) {
-    lom[0] = lom[1] = lom[2] = 0; him[0] = him[1] = him[2] = 0;
-    if (m < SEG_WINDOW) return false;
-    Comp w; w.clear();
-    for (int k = 0; k < SEG_WINDOW; ++k) w.add(fr[k]);
-    bool trig = false;
-    for (int st = 0;; ++st) {
-        if (!w.cannot_be_low()) {
-            const double e = w.entropy(ent);
-            if (e <= SEG_LOCUT) { lom[st >> 6] |= 1ull << (st & 63); trig = true; }
-            if (e <= SEG_HICUT) him[st >> 6] |= 1ull << (st & 63);
-        }
-        if (st + SEG_WINDOW >= m) break;
-        w.sub(fr[st]); w.add(fr[st + SEG_WINDOW]);
-    }
-    return trig;
+    if (nz > 0 && nz < 20) lnass -= lnfac[20 - nz];
+    return lnass + lnperm - ln20[len];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -395,25 +296,54 @@ struct FrameArgs {
     unsigned long long *n_segq;
 };
 
+// Translation goes through a 2 x 125-entry table in shared memory indexed by three base codes (T C A G = 0..3,
+// anything else 4 -> '.'), one half per strand: the reverse frames walk the read backwards and the table holds the
+// codon of the complemented bases, so both strands share one code path and no lane tests for invalid bases.  The
+// block first decodes the bases of its NT/6 reads into shared memory once (each base is used by all six frames).
+__device__ uint8_t g_codon_lut[256];
+
 template <int NT>
 __global__ void __launch_bounds__(NT) k_frames(FrameArgs A, int fstride) {
     extern __shared__ __align__(16) uint8_t smem[];
-    double *s_ent = reinterpret_cast<double *>(smem);
-    uint8_t *s_aa = smem + 13 * 13 * sizeof(double);
-    const int tid = threadIdx.x, lane = tid & 31;
-    for (int k = tid; k < 13 * 13; k += NT) s_ent[k] = c_ent[k];
+    constexpr int RPB = NT / 6;                                  // reads per block
+    SegTab *s_tab = reinterpret_cast<SegTab *>(smem);
+    uint8_t *s_lut = smem + sizeof(SegTab);                      // 256 bytes
+    uint8_t *s_aa = s_lut + 256;                                 // NT rows of fstride bytes
+    uint8_t *s_code = s_aa + NT * fstride;                       // RPB reads of L base codes
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int L = A.L;
+    for (int k = tid; k < (int)(sizeof(SegTab) / 4); k += NT) reinterpret_cast<uint32_t *>(s_tab)[k] = reinterpret_cast<const uint32_t *>(&g_segtab)[k];
+    for (int k = tid; k < 64; k += NT) reinterpret_cast<uint32_t *>(s_lut)[k] = reinterpret_cast<const uint32_t *>(g_codon_lut)[k];
     for (int k = tid; k < NT * fstride / 4; k += NT) reinterpret_cast<uint32_t *>(s_aa)[k] = 0x14141414u;  // AA_STOP
+    const int64_t read0 = (int64_t)blockIdx.x * RPB;
+    for (int r = warp; r < RPB; r += NT / 32) {
+        if (read0 + r >= A.n_search) break;
+        const uint8_t *__restrict__ rd = A.bases + A.offs[A.kept[A.first + read0 + r]];
+        for (int k = lane; k < L; k += 32) s_code[r * L + k] = (uint8_t)base_code(rd[k]);
+    }
     __syncthreads();
     const int64_t g = (int64_t)blockIdx.x * NT + tid;          // frame row within this launch
-    const int64_t ki = g / 6;
+    const int r = tid / 6, frame = tid - r * 6;
     uint8_t *fr = s_aa + tid * fstride;
     bool trig = false;
-    if (ki < A.n_search) {
-        const int frame = (int)(g - ki * 6);
-        const int read = A.kept[A.first + ki];
-        const int m = translate_frame(fr, A.bases + A.offs[read], A.L, frame);
-        unsigned long long lom[3], him[3];
-        trig = seg_window_masks(fr, m, s_ent, lom, him);
+    if (read0 + r < A.n_search) {
+        const int o = frame % 3, m = (L - o) / 3;
+        const bool rev = frame >= 3;
+        const int step = rev ? -1 : 1;
+        const uint8_t *cd = s_code + r * L + (rev ? L - 1 - o : o);
+        const uint8_t *lut = s_lut + (rev ? 125 : 0);
+        for (int k = 0; k < m; ++k, cd += 3 * step) fr[k] = lut[25 * cd[0] + 5 * cd[step] + cd[2 * step]];
+        // does any 12-window have entropy <= locut?  (Seg::segseq only acts on frames that have one)
+        if (m >= SEG_WINDOW) {
+            const SegTab &T = *s_tab;
+            WinG w; w.clear();
+            for (int k = 0; k < SEG_WINDOW; ++k) w.add(fr[k], T);
+            for (int st = 0;; ++st) {
+                trig |= w.low(T);
+                if (st + SEG_WINDOW >= m) break;
+                w.sub(fr[st], T); w.add(fr[st + SEG_WINDOW], T);
+            }
+        }
     }
     const uint32_t tm = __ballot_sync(0xffffffffu, trig);
     if (tm) {
@@ -436,8 +366,38 @@ __global__ void __launch_bounds__(NT) k_frames(FrameArgs A, int fstride) {
 // (longer windows first, then leftmost).  First version: one thread per frame, 24 ms for 2M reads with 2 of 32
 // lanes active on average (profiles/); this one keeps the warp busy.
 __device__ __forceinline__ bool sbit(const uint32_t *m, int k) { return (m[k >> 5] >> (k & 31)) & 1; }
+// smallest k in [from, to] whose bit is set (SET) or clear (!SET); -1 if none
+template <bool SET>
+__device__ __forceinline__ int next_bit(const uint32_t *m, int from, int to) {
+    if (from > to) return -1;
+    int w = from >> 5;
+    const int wl = to >> 5;
+    uint32_t x = (SET ? m[w] : ~m[w]) & (0xffffffffu << (from & 31));
+    for (;;) {
+        if (w == wl) x &= 0xffffffffu >> (31 - (to & 31));
+        if (x) return (w << 5) + __ffs(x) - 1;
+        if (w == wl) return -1;
+        ++w;
+        x = SET ? m[w] : ~m[w];
+    }
+}
+// largest k in [down_to, from] whose bit is clear; -1 if none
+__device__ __forceinline__ int prev_clear_bit(const uint32_t *m, int from, int down_to) {
+    if (from < down_to) return -1;
+    int w = from >> 5;
+    const int wl = down_to >> 5;
+    uint32_t x = ~m[w] & (0xffffffffu >> (31 - (from & 31)));
+    for (;;) {
+        if (w == wl) x &= 0xffffffffu << (down_to & 31);
+        if (x) return (w << 5) + 31 - __clz(x);
+        if (w == wl) return -1;
+        --w;
+        x = ~m[w];
+    }
+}
 
-__device__ void coop_trim(const uint8_t *fr, int off, int tl, uint8_t *P, uint8_t *nc, int lane, int &leftend, int &rightend) {
+__device__ void coop_trim(const uint8_t *fr, int off, int tl, uint8_t *P, uint8_t *nc, int lane, const double *lnfac,
+                          const double *ln20, int &leftend, int &rightend) {
     __syncwarp();
     if (lane < 20) {                       // P[k][a] = occurrences of letter a among the first k residues
         int acc = 0;
@@ -468,7 +428,7 @@ __device__ void coop_trim(const uint8_t *fr, int off, int tl, uint8_t *P, uint8_
                 comp[a] = c;
                 if (c) { nc[c]++; maxc = c > maxc ? c : maxc; }
             }
-            prob = seg_getprob(nc, maxc, len);
+            prob = seg_getprob(nc, maxc, len, lnfac, ln20);
 #pragma unroll
             for (int a = 0; a < 20; ++a) nc[comp[a]] = 0;
         }
@@ -494,71 +454,89 @@ template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_seg(uint8_t *frames, int fstride, int L, const uint32_t *__restrict__ segq,
                                                     int64_t n, int maxm) {
     extern __shared__ __align__(16) uint8_t smem[];
-    double *s_ent = reinterpret_cast<double *>(smem);
+    double *s_lnfac = reinterpret_cast<double *>(smem);        // [SEG_TAB] ln(i!)
+    double *s_ln20 = s_lnfac + SEG_TAB;                         // [SEG_TAB] i ln 20
+    SegTab *s_tab = reinterpret_cast<SegTab *>(s_ln20 + SEG_TAB);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per_warp = fstride + (maxm + 1) * 20 + 4 - ((fstride + (maxm + 1) * 20) & 3) + 18 * 4;
-    uint8_t *wbase = smem + 13 * 13 * sizeof(double) + (size_t)warp * per_warp;
+    uint8_t *wbase = smem + 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + (size_t)warp * per_warp;
     uint32_t *s_m = reinterpret_cast<uint32_t *>(wbase);       // [0..5] lo, [6..11] hi, [12..17] result mask
     uint8_t *fr = wbase + 18 * 4;
     uint8_t *P = fr + fstride;
-    for (int k = threadIdx.x; k < 13 * 13; k += WARPS * 32) s_ent[k] = c_ent[k];
+    for (int k = threadIdx.x; k < SEG_TAB; k += WARPS * 32) { s_lnfac[k] = g_lnfac[k]; s_ln20[k] = g_ln20[k]; }
+    for (int k = threadIdx.x; k < (int)(sizeof(SegTab) / 4); k += WARPS * 32) reinterpret_cast<uint32_t *>(s_tab)[k] = reinterpret_cast<const uint32_t *>(&g_segtab)[k];
     __syncthreads();
-    const int64_t g = (int64_t)blockIdx.x * WARPS + warp;
-    if (g >= n) return;
-    const uint32_t row = segq[g];
-    uint8_t *gfr = frames + (int64_t)row * fstride;
-    const int m = (L - (int)(row % 6u) % 3) / 3;
-    for (int k = lane; k < fstride / 4; k += 32) reinterpret_cast<uint32_t *>(fr)[k] = reinterpret_cast<const uint32_t *>(gfr)[k];
     uint8_t nc[MAX_FRAME + 2];
     for (int k = 0; k < MAX_FRAME + 2; ++k) nc[k] = 0;
-    __syncwarp();
-    // entropy of every 12-window against the two cut-offs, one window per lane
-    for (int r = 0; r < 6; ++r) {
-        const int w = r * 32 + lane;
-        bool lo = false, hi = false;
-        if (w + SEG_WINDOW <= m) {
-            Comp c; c.clear();
-            for (int k = 0; k < SEG_WINDOW; ++k) c.add(fr[w + k]);
-            if (!c.cannot_be_low()) {
-                const double e = c.entropy(s_ent);
-                lo = e <= SEG_LOCUT; hi = e <= SEG_HICUT;
-            }
-        }
-        const uint32_t bl = __ballot_sync(0xffffffffu, lo), bh = __ballot_sync(0xffffffffu, hi);
-        if (lane == 0) { s_m[r] = bl; s_m[6 + r] = bh; s_m[12 + r] = 0; }
-    }
-    __syncwarp();
     const uint32_t *lom = s_m, *him = s_m + 6;
     uint32_t *mask = s_m + 12;
-    // Seg::segseq (downset 0, upset 1); the recursion of seg.c only adds segments, so the left parts are queued
-    int wl_off[12], wl_len[12], nwl = 1;
-    wl_off[0] = 0; wl_len[0] = m;
-    while (nwl > 0) {
-        --nwl;
-        const int off = wl_off[nwl], slen = wl_len[nwl];
-        if (SEG_WINDOW > slen) continue;
-        const int last = slen - 1, wmax = slen - SEG_WINDOW;
-        int lowlim = 0;
-        for (int i = 0; i <= last; ++i) {
-            if (!sbit(lom, off + (i < wmax ? i : wmax))) continue;
-            int j, loi, hii;
-            for (j = i; j >= lowlim; --j) if (!sbit(him, off + (j < wmax ? j : wmax))) break;
-            loi = j + 1;
-            for (j = i; j <= last; ++j) if (!sbit(him, off + (j < wmax ? j : wmax))) break;
-            hii = j - 1;
-            int leftend = loi, rightend = hii;
-            coop_trim(fr, off + leftend, rightend - leftend + 1, P, nc, lane, leftend, rightend);
-            if (i < leftend && nwl < 12) { wl_off[nwl] = off + loi; wl_len[nwl] = leftend - loi; ++nwl; }
-            __syncwarp();
-            if (lane == 0) for (j = off + leftend; j <= off + rightend; ++j) mask[j >> 5] |= 1u << (j & 31);
-            __syncwarp();
-            i = hii < rightend ? hii : rightend;
-            lowlim = i + 1;
+    // blocks stride over the queue so that the tables above are staged once per block, not once per four frames
+    for (int64_t g = (int64_t)blockIdx.x * WARPS + warp; g < n; g += (int64_t)gridDim.x * WARPS) {
+        const uint32_t row = segq[g];
+        uint8_t *gfr = frames + (int64_t)row * fstride;
+        const int m = (L - (int)(row % 6u) % 3) / 3;
+        __syncwarp();
+        for (int k = lane; k < fstride / 4; k += 32) reinterpret_cast<uint32_t *>(fr)[k] = reinterpret_cast<const uint32_t *>(gfr)[k];
+        __syncwarp();
+        // entropy of every 12-window against the two cut-offs, one window per lane
+        for (int r = 0; r < 6; ++r) {
+            uint32_t bl = 0, bh = 0;
+            if (r * 32 + SEG_WINDOW <= m) {
+                const int w = r * 32 + lane;
+                bool lo = false, hi = false;
+                if (w + SEG_WINDOW <= m) {
+                    WinG c; c.clear();
+                    for (int k = 0; k < SEG_WINDOW; ++k) c.add(fr[w + k], *s_tab);
+                    lo = c.low(*s_tab); hi = c.high(*s_tab);
+                }
+                bl = __ballot_sync(0xffffffffu, lo); bh = __ballot_sync(0xffffffffu, hi);
+            }
+            if (lane == 0) { s_m[r] = bl; s_m[6 + r] = bh; s_m[12 + r] = 0; }
         }
+        __syncwarp();
+        // Seg::segseq (downset 0, upset 1); the recursion of seg.c only adds segments, so the left parts are queued.
+        // Position i of a sub-sequence [off, off + slen) looks at the frame's window off + min(i, wmax); the scans
+        // over positions are searches for the next set / clear bit of the two window masks.
+        int wl_off[12], wl_len[12], nwl = 1;
+        wl_off[0] = 0; wl_len[0] = m;
+        while (nwl > 0) {
+            --nwl;
+            const int off = wl_off[nwl], slen = wl_len[nwl];
+            if (SEG_WINDOW > slen) continue;
+            const int last = slen - 1, wmax = slen - SEG_WINDOW;
+            int lowlim = 0;
+            for (int i = 0; i <= last; ++i) {
+                if (i <= wmax) {
+                    const int k = next_bit<true>(lom, off + i, off + wmax);
+                    if (k < 0) break;              // the positions past wmax repeat window wmax, which is clear
+                    i = k - off;
+                } else if (!sbit(lom, off + wmax)) break;
+                // a window at or below locut is at or below hicut: position i itself is set in `him`
+                int loi = lowlim, hii = last;
+                if (lowlim <= wmax) {
+                    const int k = prev_clear_bit(him, off + (i < wmax ? i : wmax), off + lowlim);
+                    if (k >= 0) loi = k - off + 1;
+                }
+                if (i <= wmax) {
+                    const int k = next_bit<false>(him, off + i, off + wmax);
+                    if (k >= 0) hii = k - off - 1;
+                }
+                int leftend = loi, rightend = hii;
+                coop_trim(fr, off + leftend, rightend - leftend + 1, P, nc, lane, s_lnfac, s_ln20, leftend, rightend);
+                if (i < leftend && nwl < 12) { wl_off[nwl] = off + loi; wl_len[nwl] = leftend - loi; ++nwl; }
+                if (lane < 6) {                    // mask[off + leftend .. off + rightend], one word per lane
+                    const int b0 = max(off + leftend, lane * 32), b1 = min(off + rightend, lane * 32 + 31);
+                    if (b0 <= b1) mask[lane] |= (0xffffffffu >> (31 - (b1 - b0))) << (b0 & 31);
+                }
+                __syncwarp();
+                i = hii < rightend ? hii : rightend;
+                lowlim = i + 1;
+            }
+        }
+        __syncwarp();
+        for (int k = lane; k < m; k += 32)
+            if (sbit(mask, k)) gfr[k] = AA_STOP;
     }
-    __syncwarp();
-    for (int k = lane; k < m; k += 32)
-        if (sbit(mask, k)) gfr[k] = AA_STOP;
 }
 
 // K2b: one thread per frame of the store: slide the 10-letter murphy10 window, probe the five word tables and
@@ -635,22 +613,23 @@ __global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
             code[p] = c;
         }
         // five filter words in flight together
-        uint32_t bw[N_PAT], bi[N_PAT];
+        uint32_t bw[N_PAT], bh[N_PAT];
 #pragma unroll
         for (int p = 0; p < N_PAT; ++p) {
-            bi[p] = bloom_index(p, code[p]);
-            bw[p] = (p == 0 ? !bad9 : !bad10) ? __ldg(A.db.bloom + (bi[p] >> 5)) : 0u;
+            bh[p] = bloom_hash(p, code[p]);
+            bw[p] = (p == 0 ? !bad9 : !bad10) ? __ldg(A.db.bloom + bloom_word(bh[p])) : 0u;
         }
+        bool pass[N_PAT];
         int npass = 0;
 #pragma unroll
-        for (int p = 0; p < N_PAT; ++p) npass += (bw[p] >> (bi[p] & 31)) & 1;
+        for (int p = 0; p < N_PAT; ++p) { const uint32_t mk = bloom_mask(bh[p]); pass[p] = (bw[p] & mk) == mk; npass += pass[p]; }
         const int incl = warp_scan_add(npass, lane);
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         if (total > 0) {
             int o = incl - npass;
 #pragma unroll
             for (int p = 0; p < N_PAT; ++p)
-                if ((bw[p] >> (bi[p] & 31)) & 1) { qcode[o] = code[p]; qmeta[o] = (uint8_t)((lane << 3) | p); ++o; }
+                if (pass[p]) { qcode[o] = code[p]; qmeta[o] = (uint8_t)((lane << 3) | p); ++o; }
             __syncwarp();
             for (int base = 0; base < total; base += 32) {
                 const int t = base + lane;
@@ -665,9 +644,9 @@ __global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
                     while (k != 0xffffffffu && k != c) { sl = (sl + 1) & A.db.hmask[p]; k = __ldg(hk + sl); }
                     if (k == c) {
                         const uint32_t v = __ldg(A.db.hval[p] + sl);
-                        pi = v & 0x1ffffffu;                              // 25-bit start, 7-bit (count - 1), 127 = longer
+                        pi = v & 0x1ffffffu;                              // 25-bit start, 7-bit (count - 1)
                         cnt = (v >> 25) + 1;
-                        if ((v >> 25) == 127) { cnt = 128; while (!(__ldg(A.db.post + pi + cnt - 1) & 0x80000000u)) ++cnt; }
+                        if ((v >> 25) == 127) { cnt = __ldg(A.db.post + pi); ++pi; }   // longer lists start with their length
                     }
                 }
                 const int inc2 = warp_scan_add((int)cnt, lane);
@@ -720,8 +699,8 @@ struct ExtArgs {
 
 template <int NT>
 __global__ void __launch_bounds__(NT) k_extend(ExtArgs A) {
-    __shared__ int8_t s_bl[21 * 32];
-    for (int k = threadIdx.x; k < 21 * 32; k += NT) s_bl[k] = c_blosum[k];
+    __shared__ __align__(4) int8_t s_bl[21 * 32];
+    for (int k = threadIdx.x; k < 21 * 32 / 4; k += NT) reinterpret_cast<uint32_t *>(s_bl)[k] = reinterpret_cast<const uint32_t *>(g_blosum)[k];
     __syncthreads();
     const int64_t g = (int64_t)blockIdx.x * NT + threadIdx.x;
     if (g >= A.n_cand) return;
@@ -820,59 +799,113 @@ __global__ void __launch_bounds__(NT) k_extend(ExtArgs A) {
 #define ST_GAPRUN 0x4000000u
 struct GExt { int gain, eq, et; uint32_t st; int cells; };
 
-template <int GROW, bool STATS>    // GROW = row capacity (longest frame + GAP_SLACK + 2); STATS = carry the alignment statistics
+// one DP column of the row being overwritten: H and F (and, in the statistics pass, the statistics words of the
+// alignments they end); one aligned local-memory access per cell instead of two or four
+template <bool STATS> struct DPCell;
+template <> struct __align__(8) DPCell<false> { int h, f; };
+template <> struct __align__(16) DPCell<true> { int h, f; uint32_t hs, fs; };
+
+// The DP row lives in shared memory, column-major over the block's threads: cell j of thread t at [j * NT + t], so
+// lanes sitting at different columns never share a bank.  H and F fit 16 bits each (|values| < 2,000).  (First
+// version: per-thread local arrays -- 832 B x 2,048 resident threads do not fit L1, and 35 % of the kernel's
+// samples waited on the load of H[j] / F[j] with ~9 of 32 lanes active.)
+template <bool STATS> struct RowShared;
+template <> struct RowShared<false> {
+    uint32_t *p; int nt;
+    __device__ __forceinline__ DPCell<false> get(int j) const {
+        const uint32_t v = p[j * nt];
+        DPCell<false> c; c.h = (int)(short)(v & 0xffffu); c.f = (int)v >> 16;
+        return c;
+    }
+    __device__ __forceinline__ void set(int j, const DPCell<false> &c) { p[j * nt] = ((uint32_t)c.h & 0xffffu) | ((uint32_t)c.f << 16); }
+};
+template <> struct RowShared<true> {
+    uint32_t *p; int nt, plane;                  // three planes: (H, F), statistics of H, statistics of F
+    __device__ __forceinline__ DPCell<true> get(int j) const {
+        const uint32_t v = p[j * nt];
+        DPCell<true> c; c.h = (int)(short)(v & 0xffffu); c.f = (int)v >> 16; c.hs = p[plane + j * nt]; c.fs = p[2 * plane + j * nt];
+        return c;
+    }
+    __device__ __forceinline__ void set(int j, const DPCell<true> &c) {
+        p[j * nt] = ((uint32_t)c.h & 0xffffu) | ((uint32_t)c.f << 16); p[plane + j * nt] = c.hs; p[2 * plane + j * nt] = c.fs;
+    }
+};
+
+// STATS = carry the alignment statistics; bl = BLOSUM62 rows of 32 in shared memory.  The inner loop loads the next
+// cell, subject residue and substitution score one iteration ahead.
+template <bool STATS>
 __device__ void gapped_xdrop(const uint8_t *fr, int q_first, int qstep, const uint8_t *__restrict__ t,
-                             int tstep, int nQ, int nD, GExt &g) {
+                             int tstep, int nQ, int nD, const int8_t *bl, RowShared<STATS> R, GExt &g) {
     g.gain = 0; g.eq = 0; g.et = 0; g.st = 0; g.cells = 0;
     const int GI = GAP_OPEN, GE = GAP_EXT, GIE = GAP_OPEN + GAP_EXT;
     const int limit = 15;                      // (int)((26.98 - 11) / 1)
-    int H[GROW], F[GROW];
-    uint32_t HS[STATS ? GROW : 1], FS[STATS ? GROW : 1];
-    H[0] = 0; F[0] = -GI;
-    if (STATS) { HS[0] = 0; FS[0] = 0; }
+    typedef DPCell<STATS> Cell;
     {
+        Cell w; w.h = 0; w.f = -GI;
+        if constexpr (STATS) { w.hs = 0; w.fs = 0; }
+        R.set(0, w);
         int r = -GI;
         for (int j = 1; j <= limit && j <= nD; ++j) {
-            r -= GE; H[j] = r; F[j] = r - GI;
-            if (STATS) { HS[j] = (uint32_t)j * (ST_ALN + ST_GAPCOL) + ST_GAPRUN; FS[j] = HS[j]; }
+            r -= GE; w.h = r; w.f = r - GI;
+            if constexpr (STATS) { w.hs = (uint32_t)j * (ST_ALN + ST_GAPCOL) + ST_GAPRUN; w.fs = w.hs; }
+            R.set(j, w);
         }
     }
     int cs = 1, ce = limit, best = 0, bcol = 0, brow = 0, cells = 0;
     uint32_t bst = 0;
     for (int i = 1; i <= nQ; ++i) {
-        int diag = H[cs - 1];
+        const Cell left = R.get(cs - 1);
+        int diag = left.h;
         uint32_t dst = 0, bs = 0;
-        if (STATS) {
-            dst = HS[cs - 1];
+        if constexpr (STATS) {
+            dst = left.hs;
             // boundary cell (i, cs-1): value max(H-12, F-1), always traced as a vertical gap column
-            bs = (i == 1 ? HS[cs - 1] + ST_GAPRUN : FS[cs - 1]) + ST_ALN + ST_GAPCOL;
+            bs = (i == 1 ? left.hs + ST_GAPRUN : left.fs) + ST_ALN + ST_GAPCOL;
         }
-        int v = H[cs - 1] - GIE, f1 = F[cs - 1] - GE;
+        int v = left.h - GIE;
+        const int f1 = left.f - GE;
         if (v < f1) v = f1;
-        F[cs - 1] = v; H[cs - 1] = v;
-        if (STATS) { HS[cs - 1] = bs; FS[cs - 1] = bs; }
+        {
+            Cell w; w.h = v; w.f = v;
+            if constexpr (STATS) { w.hs = bs; w.fs = bs; }
+            R.set(cs - 1, w);
+        }
         int E = v - GI, hl = v, j = cs;
         uint32_t ES = bs, hls = bs;
         bool skip_tail = false;
         const int qa = fr[q_first + (i - 1) * qstep];
+        const int8_t *brow_bl = bl + qa * 32;
         if (!(cs > ce || cs > nD)) {
+            Cell cur = R.get(j);
+            int tb = t[(j - 1) * tstep];
+            int sc = brow_bl[tb];
             for (;;) {
                 ++cells;
-                int a = hl - GIE, b = E - GE;
-                if (a >= b) { E = a; if (STATS) ES = hls + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { E = b; if (STATS) ES += ST_ALN + ST_GAPCOL; }
-                int c = H[j] - GIE, d = F[j] - GE, Fv;
+                Cell nxt = cur;
+                int tbn = 0, scn = 0;
+                if (j < nD) { nxt = R.get(j + 1); tbn = t[j * tstep]; scn = brow_bl[tbn]; }
+                const int a = hl - GIE, b = E - GE;
+                if (a >= b) { E = a; if constexpr (STATS) ES = hls + ST_ALN + ST_GAPCOL + ST_GAPRUN; }
+                else { E = b; if constexpr (STATS) ES += ST_ALN + ST_GAPCOL; }
+                const int c = cur.h - GIE, d = cur.f - GE;
+                int Fv;
                 uint32_t FSv = 0;
-                if (c >= d) { Fv = c; if (STATS) FSv = HS[j] + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { Fv = d; if (STATS) FSv = FS[j] + ST_ALN + ST_GAPCOL; }
-                const int tb = t[(j - 1) * tstep];
-                int h = diag + c_blosum[qa * 32 + tb];
+                if (c >= d) { Fv = c; if constexpr (STATS) FSv = cur.hs + ST_ALN + ST_GAPCOL + ST_GAPRUN; }
+                else { Fv = d; if constexpr (STATS) FSv = cur.fs + ST_ALN + ST_GAPCOL; }
+                int h = diag + sc;
                 uint32_t hs = 0;
-                if (STATS) hs = dst + ST_ALN + (uint32_t)(qa == tb && qa < 20);
+                if constexpr (STATS) hs = dst + ST_ALN + (uint32_t)(qa == tb && qa < 20);
                 if (E > h) { h = E; hs = ES; }
                 if (h < Fv) { h = Fv; hs = FSv; }
-                diag = H[j];
-                if (STATS) dst = HS[j];
-                H[j] = h; F[j] = Fv; hl = h;
-                if (STATS) { HS[j] = hs; FS[j] = FSv; hls = hs; }
+                diag = cur.h;
+                if constexpr (STATS) dst = cur.hs;
+                {
+                    Cell w; w.h = h; w.f = Fv;
+                    if constexpr (STATS) { w.hs = hs; w.fs = FSv; }
+                    R.set(j, w);
+                }
+                hl = h;
+                if constexpr (STATS) hls = hs;
                 if (h > best) { best = h; bcol = j; brow = i; bst = hs; }
                 else if (h <= best - 27 && j > bcol) {       // h < best - 26.98
                     if (j >= ce) { ce = j; break; }
@@ -880,22 +913,29 @@ __device__ void gapped_xdrop(const uint8_t *fr, int q_first, int qstep, const ui
                 }
                 ++j;
                 if (j > nD || j > ce) break;
+                cur = nxt; tb = tbn; sc = scn;
             }
         }
         if (!skip_tail) {
             for (int jj = ce + 1; jj <= nD; ++jj) {          // run on along the row by horizontal gaps
                 ++cells;
-                int a = hl - GIE, b = E - GE;
-                if (a > b) { E = a; if (STATS) ES = hls + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { E = b; if (STATS) ES += ST_ALN + ST_GAPCOL; }
-                H[jj] = E; F[jj] = E - GI; hl = E;
-                if (STATS) { HS[jj] = ES; FS[jj] = ES; hls = ES; }
+                const int a = hl - GIE, b = E - GE;
+                if (a > b) { E = a; if constexpr (STATS) ES = hls + ST_ALN + ST_GAPCOL + ST_GAPRUN; }
+                else { E = b; if constexpr (STATS) ES += ST_ALN + ST_GAPCOL; }
+                {
+                    Cell w; w.h = E; w.f = E - GI;
+                    if constexpr (STATS) { w.hs = ES; w.fs = ES; }
+                    R.set(jj, w);
+                }
+                hl = E;
+                if constexpr (STATS) hls = ES;
                 if (E > best) { best = E; bcol = jj; brow = i; bst = ES; }
                 else if (E <= best - 27) { ce = jj; break; }
             }
             if (cs <= bcol) {                                // drop dead cells on the left
-                int thr = best - 27;
-                if (H[bcol] <= thr) cs = bcol;
-                else for (int c = bcol - 1; c >= cs; --c) if (H[c] <= thr) { cs = c; break; }
+                const int thr = best - 27;
+                if (R.get(bcol).h <= thr) cs = bcol;
+                else for (int c = bcol - 1; c >= cs; --c) if (R.get(c).h <= thr) { cs = c; break; }
             }
         }
         if (!(cs < ce)) break;
@@ -950,9 +990,16 @@ __global__ void k_gap_list(GapArgs A) {
 
 // K3b: one thread per gapped extension.  First a score-only pass over all of them (two DP rows); only the ~20 % that
 // gain anything are queued for the second pass, which repeats the same DP carrying the alignment statistics.
-template <int NT, int GROW, bool STATS>
+template <int NT, bool STATS>
 __global__ void __launch_bounds__(NT) k_gap_dir(GapArgs A, const uint32_t *__restrict__ items, int64_t n_items,
-                                                uint32_t *__restrict__ items2, unsigned long long *n_items2) {
+                                                uint32_t *__restrict__ items2, unsigned long long *n_items2, int grow) {
+    extern __shared__ __align__(16) uint32_t s_rows[];             // [1 or 3 planes][grow][NT]
+    __shared__ __align__(4) int8_t s_bl[21 * 32];
+    RowShared<STATS> R;
+    R.p = s_rows + threadIdx.x; R.nt = NT;
+    if constexpr (STATS) R.plane = grow * NT;
+    for (int k = threadIdx.x; k < 21 * 32 / 4; k += NT) reinterpret_cast<uint32_t *>(s_bl)[k] = reinterpret_cast<const uint32_t *>(g_blosum)[k];
+    __syncthreads();
     const int64_t w = (int64_t)blockIdx.x * NT + threadIdx.x;
     bool again = false;
     uint32_t item = 0;
@@ -971,11 +1018,11 @@ __global__ void __launch_bounds__(NT) k_gap_dir(GapArgs A, const uint32_t *__res
         if (dir == 0) {
             int ql = m - (q1 + 1), tl = n - (t1 + 1);
             if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
-            gapped_xdrop<GROW, STATS>(fr, q1 + 1, 1, t + t1 + 1, 1, ql, tl, e);
+            gapped_xdrop<STATS>(fr, q1 + 1, 1, t + t1 + 1, 1, ql, tl, s_bl, R, e);
         } else {
             int ql = q0, tl = t0;
             if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
-            gapped_xdrop<GROW, STATS>(fr, q0 - 1, -1, t + t0 - 1, -1, ql, tl, e);
+            gapped_xdrop<STATS>(fr, q0 - 1, -1, t + t0 - 1, -1, ql, tl, s_bl, R, e);
         }
         GExtRec r;
         r.gain = e.gain; r.eq = (uint16_t)e.eq; r.et = (uint16_t)e.et; r.st = e.st; r.cells = (uint32_t)e.cells;
@@ -1055,95 +1102,133 @@ __device__ double alignment_coverage(int L, int qs_, int qe_, int t0, int t1, in
     return (double)aln_ / maxaln;
 }
 
+// The sorted key of an HSP (k_gap_finish) holds every field the classifier needs, so K4 streams the 16-byte keys in
+// sorted order and never gathers the 48-byte records.
+struct KeyHit { int read, subject, score, frame, q0, q1, t0, t1, aln, ident; };
+__device__ __forceinline__ KeyHit key_decode(const SortKey &k) {
+    KeyHit h;
+    h.read = (int)(k.k1 >> 37); h.subject = (int)(k.k1 >> 22) & 0x7fff; h.score = 2047 - ((int)(k.k1 >> 11) & 0x7ff);
+    h.frame = (int)(k.k1 >> 8) & 7; h.q0 = (int)k.k1 & 0xff;
+    h.q1 = (int)(k.k2 >> 48); h.t0 = (int)(k.k2 >> 37) & 0x7ff; h.t1 = (int)(k.k2 >> 26) & 0x7ff;
+    h.aln = (int)(k.k2 >> 17) & 0x1ff; h.ident = (int)(k.k2 >> 8) & 0x1ff;
+    return h;
+}
+
 struct ClsArgs {
-    const mcx_hit *hsp;
-    const int32_t *idx;            // sorted order
+    const SortKey *keys;           // sorted: (read, subject, score desc, ...)
     int64_t n;
     int L;
     int min_report;
     DevDB db;
-    uint8_t *keep;                 // per hsp: 1 = reported line
+    uint8_t *keep;                 // per sorted position: 1 = reported line
+    int32_t *nrep;                 // per pushed read: reported lines (before the 500-line cap), zeroed
+    unsigned long long *bestkey;   // per pushed read: (score + 1) << 32 | ~position of the best passing line, zeroed
     int32_t *best_subject;         // per pushed read
     unsigned long long *acc;       // [0] reads_with_hits [1] classified [2] n_hsp, then fam_hits[30], fam_aln[30]
     unsigned long long *aln_by_len;
 };
 
-__global__ void k_classify(ClsArgs A) {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// K4a: one thread per (read, subject) group of the sorted list (1-2 HSPs almost always): which HSPs are printed -- at
+// or above the floor and, in score order, disjoint in query and subject range from every HSP already kept for that
+// subject.
+__global__ void k_cls_groups(ClsArgs A) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= A.n) return;
-    const int read = A.hsp[A.idx[p]].read;
-    if (p > 0 && A.hsp[A.idx[p - 1]].read == read) return;   // not the first HSP of its read
-    // pass 1: which HSPs are printed -- at or above the floor and, per subject in score order, disjoint in query
-    // and subject range from every HSP already kept for that subject
-    int cur_subj = -1, nk = 0, nrep = 0;
+    const unsigned long long grp = A.keys[p].k1 >> 22;
+    if (p > 0 && (A.keys[p - 1].k1 >> 22) == grp) return;
+    int nk = 0, nrep = 0;
     int kqs[8], kqe[8], kt0[8], kt1[8];
-    int64_t end = p;
-    for (int64_t e = p; e < A.n; ++e, ++end) {
-        const int id = A.idx[e];
-        const mcx_hit h = A.hsp[id];
-        if (h.read != read) break;
-        if (h.subject != cur_subj) { cur_subj = h.subject; nk = 0; }
+    for (int64_t e = p; e < A.n; ++e) {
+        const SortKey k = A.keys[e];
+        if ((k.k1 >> 22) != grp) break;
+        const KeyHit h = key_decode(k);
         int qs, qe;
         dna_coords(A.L, h.frame, h.q0, h.q1, qs, qe);
         const int lo = qs < qe ? qs : qe, hi = qs < qe ? qe : qs;
         bool keep = h.score >= A.min_report;
-        for (int k = 0; k < nk && keep; ++k)
-            if (!(hi < kqs[k] || kqe[k] < lo) || !(h.t1 < kt0[k] || kt1[k] < h.t0)) keep = false;
-        A.keep[id] = keep;
+        for (int j = 0; j < nk && keep; ++j)
+            if (!(hi < kqs[j] || kqe[j] < lo) || !(h.t1 < kt0[j] || kt1[j] < h.t0)) keep = false;
+        A.keep[e] = keep;
         if (!keep) continue;
         if (nk < 8) { kqs[nk] = lo; kqe[nk] = hi; kt0[nk] = h.t0; kt1[nk] = h.t1; ++nk; }
         ++nrep;
     }
-    // RAPsearch2 prints at most 500 lines per query (-v default), best first: keep the 500 highest scores, ties at
-    // the cut score in (subject, ...) order.  Rare; the cut score is found by bisection over the kept HSPs.
-    if (nrep > MAX_LINES) {
-        int lo = A.min_report, hi = 2047;                    // largest T with count(score >= T) >= 500
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            int c = 0;
-            for (int64_t e = p; e < end; ++e) { const int id = A.idx[e]; if (A.keep[id] && min(A.hsp[id].score, 2047) >= mid) ++c; }
-            if (c >= MAX_LINES) lo = mid; else hi = mid - 1;
+    if (nrep) atomicAdd(&A.nrep[(int)(grp >> 15)], nrep);
+}
+
+// K4b: one thread per read of the sorted list: count it, and apply RAPsearch2's limit of 500 printed lines per
+// query (-v default), best first: keep the 500 highest scores, ties at the cut score in (subject, ...) order.
+// Rare; the cut score is found by bisection over the kept HSPs.
+__global__ void k_cls_cap(ClsArgs A) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int nrep = 0;
+    if (p < A.n) {
+        const int read = (int)(A.keys[p].k1 >> 37);
+        if (p == 0 || (int)(A.keys[p - 1].k1 >> 37) != read) nrep = A.nrep[read];
+        if (nrep > MAX_LINES) {
+            int64_t end = p;
+            while (end < A.n && (int)(A.keys[end].k1 >> 37) == read) ++end;
+            int lo = A.min_report, hi = 2047;                    // largest T with count(score >= T) >= 500
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                int c = 0;
+                for (int64_t e = p; e < end; ++e) if (A.keep[e] && key_decode(A.keys[e]).score >= mid) ++c;
+                if (c >= MAX_LINES) lo = mid; else hi = mid - 1;
+            }
+            const int T = lo;
+            int above = 0;
+            for (int64_t e = p; e < end; ++e) if (A.keep[e] && key_decode(A.keys[e]).score > T) ++above;
+            int allow = MAX_LINES - above;
+            for (int64_t e = p; e < end; ++e) {
+                if (!A.keep[e]) continue;
+                const int sc = key_decode(A.keys[e]).score;
+                if (sc > T || (sc == T && allow-- > 0)) continue;
+                A.keep[e] = 0;
+            }
+            nrep = MAX_LINES;
         }
-        const int T = lo;
-        int above = 0;
-        for (int64_t e = p; e < end; ++e) { const int id = A.idx[e]; if (A.keep[id] && min(A.hsp[id].score, 2047) > T) ++above; }
-        int allow = MAX_LINES - above;
-        for (int64_t e = p; e < end; ++e) {
-            const int id = A.idx[e];
-            if (!A.keep[id]) continue;
-            const int sc = min(A.hsp[id].score, 2047);
-            if (sc > T || (sc == T && allow-- > 0)) continue;
-            A.keep[id] = 0;
-        }
-        nrep = MAX_LINES;
     }
-    // pass 2: cutoffs and best hit among the printed HSPs (mc.py:420-453)
-    int best = -1, best_score = -1;
-    for (int64_t e = p; e < end; ++e) {
-        const int id = A.idx[e];
-        if (!A.keep[id]) continue;
-        const mcx_hit h = A.hsp[id];
-        int qs, qe;
-        dna_coords(A.L, h.frame, h.q0, h.q1, qs, qe);
-        const int fam = A.db.fam[h.subject];
-        const int slen = A.db.off[h.subject + 1] - A.db.off[h.subject];
-        const mcx_cutoff c = c_cut[fam];
-        if (alignment_coverage(A.L, qs, qe, h.t0, h.t1, h.aln, slen) < c.min_cov) continue;
-        if (h.score < c.min_raw) continue;
-        if ((double)(100 * h.ident) > c.max_aaid * (double)h.aln) continue;
-        if (best < 0 || best_score < h.score) { best = id; best_score = h.score; }
-    }
-    if (nrep) { atomicAdd(&A.acc[0], 1ull); atomicAdd(&A.acc[2], (unsigned long long)nrep); }
-    if (best >= 0) {
-        const mcx_hit h = A.hsp[best];
-        const int fam = A.db.fam[h.subject];
-        const int slen = A.db.off[h.subject + 1] - A.db.off[h.subject];
-        atomicAdd(&A.acc[1], 1ull);
-        atomicAdd(&A.acc[3 + fam], 1ull);
-        atomicAdd(&A.acc[3 + MCX_N_FAM + fam], (unsigned long long)h.aln);
-        atomicAdd(&A.aln_by_len[fam * MCX_LEN_BINS + slen], (unsigned long long)h.aln);
-        A.best_subject[read] = h.subject;
-    }
+    const uint32_t any = __ballot_sync(0xffffffffu, nrep > 0);
+    if (!any) return;
+    int lines = nrep;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) lines += __shfl_xor_sync(0xffffffffu, lines, d);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&A.acc[0], (unsigned long long)__popc(any)); atomicAdd(&A.acc[2], (unsigned long long)lines); }
+}
+
+// K4c: one thread per HSP: the three cutoffs of its subject's family (mc.py:420-430); the best passing line of a
+// read is the highest score, first in sorted order on ties (mc.py:450-453) -- one atomicMax per passing line.
+__global__ void k_cls_filter(ClsArgs A) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.n || !A.keep[p]) return;
+    const KeyHit h = key_decode(A.keys[p]);
+    int qs, qe;
+    dna_coords(A.L, h.frame, h.q0, h.q1, qs, qe);
+    const int fam = A.db.fam[h.subject];
+    const int slen = A.db.off[h.subject + 1] - A.db.off[h.subject];
+    const mcx_cutoff c = c_cut[fam];
+    if (alignment_coverage(A.L, qs, qe, h.t0, h.t1, h.aln, slen) < c.min_cov) return;
+    if (h.score < c.min_raw) return;
+    if ((double)(100 * h.ident) > c.max_aaid * (double)h.aln) return;
+    atomicMax(&A.bestkey[h.read], ((unsigned long long)(h.score + 1) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)p));
+}
+
+// K4d: one thread per read of the sorted list: per-family sums of the classified reads (mc.py:462-472)
+__global__ void k_cls_sum(ClsArgs A) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.n) return;
+    const int read = (int)(A.keys[p].k1 >> 37);
+    if (p > 0 && (int)(A.keys[p - 1].k1 >> 37) == read) return;
+    const unsigned long long b = A.bestkey[read];
+    if (!b) return;
+    const KeyHit h = key_decode(A.keys[0xffffffffu - (uint32_t)b]);
+    const int fam = A.db.fam[h.subject];
+    const int slen = A.db.off[h.subject + 1] - A.db.off[h.subject];
+    atomicAdd(&A.acc[1], 1ull);
+    atomicAdd(&A.acc[3 + fam], 1ull);
+    atomicAdd(&A.acc[3 + MCX_N_FAM + fam], (unsigned long long)h.aln);
+    atomicAdd(&A.aln_by_len[fam * MCX_LEN_BINS + slen], (unsigned long long)h.aln);
+    A.best_subject[read] = h.subject;
 }
 
 __global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v) {
@@ -1154,12 +1239,11 @@ __global__ void k_gather_hits(const mcx_hit *__restrict__ hsp, const int32_t *__
                               const uint8_t *__restrict__ keep, const int32_t *__restrict__ pos, int64_t n,
                               mcx_hit *__restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && keep[idx[i]]) out[pos[i]] = hsp[idx[i]];
+    if (i < n && keep[i]) out[pos[i]] = hsp[idx[i]];
 }
-__global__ void k_keep_sorted(const int32_t *__restrict__ idx, const uint8_t *__restrict__ keep, int64_t n,
-                              int32_t *__restrict__ flag) {
+__global__ void k_keep_sorted(const uint8_t *__restrict__ keep, int64_t n, int32_t *__restrict__ flag) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flag[i] = keep[idx[i]];
+    if (i < n) flag[i] = keep[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1203,7 +1287,9 @@ struct mcx_ctx {
     SortKey *d_keys = nullptr;
     int32_t *d_idx = nullptr, *d_best = nullptr, *d_hflag = nullptr, *d_hpos = nullptr;
     uint8_t *d_keep = nullptr;
-    int64_t cap_surv = 0, cap_best = 0;
+    int32_t *d_nrep = nullptr;
+    unsigned long long *d_bestkey = nullptr;
+    int64_t cap_surv = 0, cap_best = 0, cap_nrep = 0, cap_bestkey = 0;
     unsigned long long *d_cnt = nullptr;     // 16 scalar counters
     unsigned long long *d_qcnt = nullptr;    // NQ candidate sub-queue fills
     unsigned long long *d_acc = nullptr;     // 3 + 60
@@ -1289,7 +1375,7 @@ static int build_index(mcx_ctx *ctx, const mcx_db *db) {
     const int64_t nres = db->off[ns];
     std::vector<uint8_t> red((size_t)nres);
     for (int64_t g = 0; g < nres; ++g) red[(size_t)g] = db->res[g] < 20 ? MURPHY10[db->res[g]] : 10;
-    std::vector<uint32_t> post_all, bloom((size_t)1 << (BLOOM_BITS - 5), 0u);
+    std::vector<uint32_t> post_all, bloom((size_t)1 << BLOOM_WORD_BITS, 0u);
     post_all.reserve((size_t)nres * N_PAT);
     for (int p = 0; p < N_PAT; ++p) {
         std::vector<unsigned long long> ent;
@@ -1314,22 +1400,19 @@ static int build_index(mcx_ctx *ctx, const mcx_db *db) {
         uint32_t size = 1024; int bits = 10;
         while (size < distinct * 2) { size <<= 1; ++bits; }
         std::vector<uint32_t> hk(size, 0xffffffffu), hv(size, 0);
-        const uint32_t base = (uint32_t)post_all.size();
-        for (size_t k = 0; k < ent.size(); ++k) {
+        for (size_t k = 0; k < ent.size();) {
             const uint32_t code = (uint32_t)(ent[k] >> 32);
-            const bool first = k == 0 || (ent[k - 1] >> 32) != code;
-            const bool last = k + 1 == ent.size() || (ent[k + 1] >> 32) != code;
-            post_all.push_back((uint32_t)(ent[k] & 0x7fffffffu) | (last ? 0x80000000u : 0u));
-            if (first) {
-                const uint32_t b = bloom_index(p, code);
-                bloom[b >> 5] |= 1u << (b & 31);
-                uint32_t slot = (code * 2654435761u) >> (32 - bits);
-                while (hk[slot] != 0xffffffffu) slot = (slot + 1) & (size - 1);
-                size_t e = k;
-                while (e + 1 < ent.size() && (ent[e + 1] >> 32) == code) ++e;
-                const uint32_t cnt = (uint32_t)(e - k + 1);
-                hk[slot] = code; hv[slot] = (base + (uint32_t)k) | ((cnt > 127 ? 127u : cnt - 1) << 25);
-            }
+            size_t e = k;
+            while (e + 1 < ent.size() && (ent[e + 1] >> 32) == code) ++e;
+            const uint32_t cnt = (uint32_t)(e - k + 1);
+            const uint32_t h = bloom_hash(p, code);
+            bloom[bloom_word(h)] |= bloom_mask(h);
+            uint32_t slot = (code * 2654435761u) >> (32 - bits);
+            while (hk[slot] != 0xffffffffu) slot = (slot + 1) & (size - 1);
+            hk[slot] = code; hv[slot] = (uint32_t)post_all.size() | ((cnt > 127 ? 127u : cnt - 1) << 25);
+            if (cnt > 127) post_all.push_back(cnt);          // lists too long for the 7-bit field start with their length
+            for (size_t q = k; q <= e; ++q) post_all.push_back((uint32_t)(ent[q] & 0x7fffffffu) | (q == e ? 0x80000000u : 0u));
+            k = e + 1;
         }
         uint32_t *dk = nullptr, *dv = nullptr;
         CK(dev_alloc(&dk, size)); ctx->db_allocs.push_back(dk);
@@ -1365,11 +1448,57 @@ static int upload_tables(mcx_ctx *ctx) {
         const char *p = strchr(AA_ORDER, CODON_AA[i]);
         codon[i] = (p && CODON_AA[i] != '.') ? (uint8_t)(p - AA_ORDER) : (uint8_t)AA_STOP;
     }
-    CK(cudaMemcpyToSymbol(c_lnfac, lnfac, sizeof lnfac));
-    CK(cudaMemcpyToSymbol(c_ln20, ln20, sizeof ln20));
-    CK(cudaMemcpyToSymbol(c_ent, ent, sizeof ent));
-    CK(cudaMemcpyToSymbol(c_blosum, bl, sizeof bl));
-    CK(cudaMemcpyToSymbol(c_codon, codon, sizeof codon));
+    // integer form of the SEG window test (see SegTab): thresholds taken from the reference's own double sums
+    {
+        SegTab T;
+        memset(&T, 0, sizeof T);
+        long long gfix[13];
+        gfix[0] = 0;
+        for (int c = 1; c <= SEG_WINDOW; ++c) gfix[c] = llround((double)c * log2((double)c) * 16777216.0);
+        for (int c = 0; c < SEG_WINDOW; ++c) T.dg[c] = (int)(gfix[c + 1] - gfix[c]);
+        for (int tot = 0; tot <= SEG_WINDOW; ++tot) {
+            long long min_yes[2] = {LLONG_MAX, LLONG_MAX}, max_no[2] = {LLONG_MIN, LLONG_MIN};
+            int part[20];
+            // every way of writing tot as at most 20 letter counts, largest first (the order seg.c sums them in)
+            auto rec = [&](auto &&self, int left, int maxpart, int np) -> void {
+                if (left == 0) {
+                    double e = 0.0;
+                    long long G = 0;
+                    for (int k = 0; k < np; ++k) { e += ent[tot * 13 + part[k]]; G += gfix[part[k]]; }
+                    const double cut[2] = {SEG_LOCUT, SEG_HICUT};
+                    for (int q = 0; q < 2; ++q) {
+                        if (e <= cut[q]) min_yes[q] = std::min(min_yes[q], G);
+                        else max_no[q] = std::max(max_no[q], G);
+                    }
+                    return;
+                }
+                if (np == 20) return;
+                for (int k = std::min(left, maxpart); k >= 1; --k) { part[np] = k; self(self, left - k, k, np + 1); }
+            };
+            rec(rec, tot, tot, 0);
+            for (int q = 0; q < 2; ++q)
+                if (max_no[q] >= min_yes[q]) return fail(ctx, MCX_EINVAL, "internal: integer SEG window test does not separate the entropy cut-offs");
+            T.thr[tot].x = (int)std::min<long long>(min_yes[0], INT_MAX);
+            T.thr[tot].y = (int)std::min<long long>(min_yes[1], INT_MAX);
+        }
+        CK(cudaMemcpyToSymbol(g_segtab, &T, sizeof T));
+    }
+    {
+        uint8_t lut[256];
+        memset(lut, AA_STOP, sizeof lut);
+        for (int rev = 0; rev < 2; ++rev)
+            for (int c0 = 0; c0 < 5; ++c0)
+                for (int c1 = 0; c1 < 5; ++c1)
+                    for (int c2 = 0; c2 < 5; ++c2) {
+                        if (c0 == 4 || c1 == 4 || c2 == 4) continue;
+                        const int f = rev ? 2 : 0;       // complement: T<->A, C<->G = code ^ 2
+                        lut[125 * rev + 25 * c0 + 5 * c1 + c2] = codon[16 * (c0 ^ f) + 4 * (c1 ^ f) + (c2 ^ f)];
+                    }
+        CK(cudaMemcpyToSymbol(g_codon_lut, lut, sizeof lut));
+    }
+    CK(cudaMemcpyToSymbol(g_blosum, bl, sizeof bl));
+    CK(cudaMemcpyToSymbol(g_lnfac, lnfac, sizeof lnfac));
+    CK(cudaMemcpyToSymbol(g_ln20, ln20, sizeof ln20));
     return MCX_OK;
 }
 
@@ -1421,7 +1550,7 @@ extern "C" void mcx_destroy(mcx_ctx *ctx) {
     if (ctx->own_reads) { cudaFree(ctx->d_bases); cudaFree(ctx->d_quals); cudaFree(ctx->d_offs); }
     void *bufs[] = {ctx->d_code, ctx->d_flag, ctx->d_pos, ctx->d_kept, ctx->d_surv, ctx->d_hsp, ctx->d_hits_out,
                     ctx->d_keys, ctx->d_idx, ctx->d_best, ctx->d_hflag, ctx->d_hpos, ctx->d_keep, ctx->d_cnt,
-                    ctx->d_acc, ctx->d_abl, ctx->d_temp, ctx->d_frames, ctx->d_cand, ctx->d_segq, ctx->d_qcnt, ctx->d_fp, ctx->d_gitems, ctx->d_gext};
+                    ctx->d_acc, ctx->d_abl, ctx->d_temp, ctx->d_frames, ctx->d_cand, ctx->d_segq, ctx->d_qcnt, ctx->d_fp, ctx->d_gitems, ctx->d_gext, ctx->d_nrep, ctx->d_bestkey};
     for (void *p : bufs) if (p) cudaFree(p);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -1647,6 +1776,10 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     const int64_t want = std::max<int64_t>(n_search * per_read, 1 << 16);
     if (ctx->cap_surv < want && (rc = grow_survivors(ctx, 0, want)) != MCX_OK) return rc;
     if ((rc = ensure(ctx, &ctx->d_best, &ctx->cap_best, n + 1)) != MCX_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_nrep, &ctx->cap_nrep, n + 1)) != MCX_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_bestkey, &ctx->cap_bestkey, n + 1)) != MCX_OK) return rc;
+    CK(cudaMemsetAsync(ctx->d_nrep, 0, (size_t)(n + 1) * sizeof(int32_t), st));
+    CK(cudaMemsetAsync(ctx->d_bestkey, 0, (size_t)(n + 1) * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(ctx->d_cnt, 0, 16 * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(ctx->d_acc, 0, (3 + 2 * MCX_N_FAM) * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(ctx->d_abl, 0, (size_t)MCX_N_FAM * MCX_LEN_BINS * sizeof(unsigned long long), st));
@@ -1679,7 +1812,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             FrameArgs F;
             F.bases = ctx->d_bases; F.offs = ctx->d_offs; F.kept = ctx->d_kept; F.first = first; F.n_search = nr;
             F.L = P.read_length; F.frames = ctx->d_frames; F.segq = ctx->d_segq; F.n_segq = ctx->d_cnt + 12;
-            const size_t smem = 13 * 13 * sizeof(double) + (size_t)fstride * NTF;
+            const size_t smem = sizeof(SegTab) + 256 + (size_t)fstride * NTF + (size_t)(NTF / 6) * P.read_length;
             CK(cudaFuncSetAttribute(k_frames<NTF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_frames<NTF><<<(unsigned)((nr * 6 + NTF - 1) / NTF), NTF, smem, st>>>(F, fstride);
             ++ctx->launches;
@@ -1692,9 +1825,9 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         if (n_segq > 0) {
             constexpr int SW = 4;
             const int pw = fstride + (maxm + 1) * 20;
-            const size_t smem = 13 * 13 * sizeof(double) + (size_t)SW * (pw + 4 - (pw & 3) + 18 * 4);
+            const size_t smem = 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + (size_t)SW * (pw + 4 - (pw & 3) + 18 * 4);
             CK(cudaFuncSetAttribute(k_seg<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_seg<SW><<<(unsigned)((n_segq + SW - 1) / SW), SW * 32, smem, st>>>(ctx->d_frames, fstride, P.read_length, ctx->d_segq,
+            k_seg<SW><<<(unsigned)std::min<unsigned long long>((n_segq + SW - 1) / SW, 148ull * 16), SW * 32, smem, st>>>(ctx->d_frames, fstride, P.read_length, ctx->d_segq,
                                                                            (int64_t)n_segq, maxm);
             ++ctx->launches;
         }
@@ -1761,19 +1894,30 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             if (n_items > 0) {
                 uint32_t *items2 = ctx->d_gitems + G.n_surv * 2;     // second half of the work-list buffer
                 CK(cudaMemsetAsync(ctx->d_cnt + 14, 0, sizeof(unsigned long long), st));
-                const unsigned gb = (unsigned)((n_items + 127) / 128);
+                // rows of `grow` columns per thread in shared memory: 4 B per cell in the score pass, 12 B with statistics
                 const int grow = maxm + GAP_SLACK + 2;
-                if (grow <= 104) k_gap_dir<128, 104, false><<<gb, 128, 0, st>>>(G, G.items, (int64_t)n_items, items2, ctx->d_cnt + 14);
-                else if (grow <= 152) k_gap_dir<128, 152, false><<<gb, 128, 0, st>>>(G, G.items, (int64_t)n_items, items2, ctx->d_cnt + 14);
-                else k_gap_dir<128, MAX_FRAME + GAP_SLACK + 2, false><<<gb, 128, 0, st>>>(G, G.items, (int64_t)n_items, items2, ctx->d_cnt + 14);
+                {
+                    const size_t smem = (size_t)grow * 128 * 4;
+                    if (smem <= 64 * 1024) {
+                        CK(cudaFuncSetAttribute(k_gap_dir<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        k_gap_dir<128, false><<<(unsigned)((n_items + 127) / 128), 128, smem, st>>>(G, G.items, (int64_t)n_items, items2, ctx->d_cnt + 14, grow);
+                    } else {
+                        CK(cudaFuncSetAttribute(k_gap_dir<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem / 2)));
+                        k_gap_dir<64, false><<<(unsigned)((n_items + 63) / 64), 64, smem / 2, st>>>(G, G.items, (int64_t)n_items, items2, ctx->d_cnt + 14, grow);
+                    }
+                }
                 unsigned long long n2 = 0;
                 CK(cudaMemcpyAsync(&n2, ctx->d_cnt + 14, sizeof n2, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
                 if (n2 > 0) {
-                    const unsigned gb2 = (unsigned)((n2 + 127) / 128);
-                    if (grow <= 104) k_gap_dir<128, 104, true><<<gb2, 128, 0, st>>>(G, items2, (int64_t)n2, nullptr, nullptr);
-                    else if (grow <= 152) k_gap_dir<128, 152, true><<<gb2, 128, 0, st>>>(G, items2, (int64_t)n2, nullptr, nullptr);
-                    else k_gap_dir<128, MAX_FRAME + GAP_SLACK + 2, true><<<gb2, 128, 0, st>>>(G, items2, (int64_t)n2, nullptr, nullptr);
+                    const size_t smem = (size_t)grow * 64 * 12;
+                    if (smem <= 120 * 1024) {
+                        CK(cudaFuncSetAttribute(k_gap_dir<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        k_gap_dir<64, true><<<(unsigned)((n2 + 63) / 64), 64, smem, st>>>(G, items2, (int64_t)n2, nullptr, nullptr, grow);
+                    } else {
+                        CK(cudaFuncSetAttribute(k_gap_dir<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem / 2)));
+                        k_gap_dir<32, true><<<(unsigned)((n2 + 31) / 32), 32, smem / 2, st>>>(G, items2, (int64_t)n2, nullptr, nullptr, grow);
+                    }
                     ++ctx->launches;
                 }
                 n_gapped_total += n_items;
@@ -1805,10 +1949,15 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     CK(cudaEventRecord(ctx->ev[5], st));
     if (ns > 0) {
         ClsArgs C;
-        C.hsp = ctx->d_hsp; C.idx = ctx->d_idx; C.n = ns; C.L = P.read_length; C.min_report = P.min_report_raw;
-        C.db = ctx->db; C.keep = ctx->d_keep; C.best_subject = ctx->d_best; C.acc = ctx->d_acc; C.aln_by_len = ctx->d_abl;
-        k_classify<<<(unsigned)((ns + 127) / 128), 128, 0, st>>>(C);
-        ++ctx->launches;
+        C.keys = ctx->d_keys; C.n = ns; C.L = P.read_length; C.min_report = P.min_report_raw;
+        C.db = ctx->db; C.keep = ctx->d_keep; C.nrep = ctx->d_nrep; C.bestkey = ctx->d_bestkey;
+        C.best_subject = ctx->d_best; C.acc = ctx->d_acc; C.aln_by_len = ctx->d_abl;
+        const unsigned cb = (unsigned)((ns + 255) / 256);
+        k_cls_groups<<<cb, 256, 0, st>>>(C);
+        k_cls_cap<<<cb, 256, 0, st>>>(C);
+        k_cls_filter<<<cb, 256, 0, st>>>(C);
+        k_cls_sum<<<cb, 256, 0, st>>>(C);
+        ctx->launches += 4;
     }
     CK(cudaEventRecord(ctx->ev[6], st));
     std::vector<unsigned long long> acc(3 + 2 * MCX_N_FAM), abl((size_t)MCX_N_FAM * MCX_LEN_BINS);
@@ -1849,7 +1998,7 @@ extern "C" int mcx_get_hits(mcx_ctx *ctx, mcx_hit *out, int64_t cap, int64_t *n)
     if (!out || cap <= 0 || ns == 0) return MCX_OK;
     cudaStream_t st = ctx->stream;
     int rc;
-    k_keep_sorted<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(ctx->d_idx, ctx->d_keep, ns, ctx->d_hflag);
+    k_keep_sorted<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(ctx->d_keep, ns, ctx->d_hflag);
     CK(cudaMemsetAsync(ctx->d_hflag + ns, 0, sizeof(int32_t), st));
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->d_hflag, ctx->d_hpos, (int)(ns + 1), st);

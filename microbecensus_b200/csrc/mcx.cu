@@ -36,6 +36,7 @@ using namespace mcx;
 // device-side constants
 // ------------------------------------------------------------------------------------------------
 __constant__ mcx_cutoff c_cut[MCX_N_FAM];
+__constant__ int8_t c_blosum[21 * 32];
 // Look-up tables live in global memory and are staged in shared memory by the blocks that index them per lane:
 // constant-bank reads with a per-lane index are serialised (k_extend once spent 11 % of its time filling its
 // BLOSUM62 copy from a __constant__ array, k_frames 11 % on the codon table).
@@ -159,11 +160,12 @@ struct WinG {                       // composition of a <= 12-residue window
 // seg.c getprob() = lnass + lnperm - len*ln20 from the histogram of letter counts: nc[c] = number of letters
 // occurring c times.  Walking c downwards visits the counts in exactly the order of seg.c's sorted state vector,
 // so the floating-point operations (and their order) are those of the reference and of the oracle.
+// nc is the calling lane's column of a [count][32 lanes] byte table in shared memory (stride 32).
 __device__ double seg_getprob(const uint8_t *nc, int maxc, int len, const double *lnfac, const double *ln20) {
     double lnperm = lnfac[len], lnass = lnfac[20];
     int nz = 0;
     for (int c = maxc; c >= 1; --c) {
-        const int n = nc[c];
+        const int n = nc[c * 32];
         if (!n) continue;
         for (int r = 0; r < n; ++r) lnperm -= lnfac[c];
         lnass -= lnfac[n];
@@ -396,6 +398,10 @@ __device__ __forceinline__ int prev_clear_bit(const uint32_t *m, int from, int d
     }
 }
 
+__host__ __device__ inline int seg_warp_bytes(int fstride, int maxm) {   // shared memory of one warp of k_seg
+    return 18 * 4 + fstride + (((maxm + 1) * 20 + 3) & ~3) + (maxm + 2) * 32;
+}
+
 __device__ void coop_trim(const uint8_t *fr, int off, int tl, uint8_t *P, uint8_t *nc, int lane, const double *lnfac,
                           const double *ln20, int &leftend, int &rightend) {
     __syncwarp();
@@ -420,17 +426,20 @@ __device__ void coop_trim(const uint8_t *fr, int off, int tl, uint8_t *P, uint8_
             while (d * (d + 1) / 2 > w) --d;
             while ((d + 1) * (d + 2) / 2 <= w) ++d;
             len = tl - d; st = w - d * (d + 1) / 2;
-            const uint8_t *p0 = P + st * 20, *p1 = P + (st + len) * 20;
-            int comp[20], maxc = 0;
+            // composition of the window = difference of two rows of the prefix table, four letters per word
+            const uint32_t *w0 = reinterpret_cast<const uint32_t *>(P + st * 20), *w1 = reinterpret_cast<const uint32_t *>(P + (st + len) * 20);
+            uint32_t cw[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) cw[q] = w1[q] - w0[q];      // no borrow: every byte of w1 >= that of w0
+            int maxc = 0;
 #pragma unroll
             for (int a = 0; a < 20; ++a) {
-                const int c = (int)p1[a] - (int)p0[a];
-                comp[a] = c;
-                if (c) { nc[c]++; maxc = c > maxc ? c : maxc; }
+                const int c = (int)((cw[a >> 2] >> (8 * (a & 3))) & 0xffu);
+                if (c) { nc[c * 32]++; maxc = c > maxc ? c : maxc; }
             }
             prob = seg_getprob(nc, maxc, len, lnfac, ln20);
 #pragma unroll
-            for (int a = 0; a < 20; ++a) nc[comp[a]] = 0;
+            for (int a = 0; a < 20; ++a) nc[((cw[a >> 2] >> (8 * (a & 3))) & 0xffu) * 32] = 0;
         }
         double best = prob;
         int bl = lane;
@@ -458,16 +467,15 @@ __global__ void __launch_bounds__(WARPS * 32) k_seg(uint8_t *frames, int fstride
     double *s_ln20 = s_lnfac + SEG_TAB;                         // [SEG_TAB] i ln 20
     SegTab *s_tab = reinterpret_cast<SegTab *>(s_ln20 + SEG_TAB);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int per_warp = fstride + (maxm + 1) * 20 + 4 - ((fstride + (maxm + 1) * 20) & 3) + 18 * 4;
-    uint8_t *wbase = smem + 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + (size_t)warp * per_warp;
+    uint8_t *wbase = smem + 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + (size_t)warp * seg_warp_bytes(fstride, maxm);
     uint32_t *s_m = reinterpret_cast<uint32_t *>(wbase);       // [0..5] lo, [6..11] hi, [12..17] result mask
     uint8_t *fr = wbase + 18 * 4;
-    uint8_t *P = fr + fstride;
+    uint8_t *P = fr + fstride;                                 // [maxm + 1][20] prefix counts of the segment being trimmed
+    uint8_t *nc = P + (((maxm + 1) * 20 + 3) & ~3) + lane;     // [maxm + 2][32 lanes] letters-per-count histogram, kept zero
     for (int k = threadIdx.x; k < SEG_TAB; k += WARPS * 32) { s_lnfac[k] = g_lnfac[k]; s_ln20[k] = g_ln20[k]; }
     for (int k = threadIdx.x; k < (int)(sizeof(SegTab) / 4); k += WARPS * 32) reinterpret_cast<uint32_t *>(s_tab)[k] = reinterpret_cast<const uint32_t *>(&g_segtab)[k];
     __syncthreads();
-    uint8_t nc[MAX_FRAME + 2];
-    for (int k = 0; k < MAX_FRAME + 2; ++k) nc[k] = 0;
+    for (int k = 0; k < maxm + 2; ++k) nc[k * 32] = 0;
     const uint32_t *lom = s_m, *him = s_m + 6;
     uint32_t *mask = s_m + 12;
     // blocks stride over the queue so that the tables above are staged once per block, not once per four frames
@@ -799,113 +807,59 @@ __global__ void __launch_bounds__(NT) k_extend(ExtArgs A) {
 #define ST_GAPRUN 0x4000000u
 struct GExt { int gain, eq, et; uint32_t st; int cells; };
 
-// one DP column of the row being overwritten: H and F (and, in the statistics pass, the statistics words of the
-// alignments they end); one aligned local-memory access per cell instead of two or four
-template <bool STATS> struct DPCell;
-template <> struct __align__(8) DPCell<false> { int h, f; };
-template <> struct __align__(16) DPCell<true> { int h, f; uint32_t hs, fs; };
-
-// The DP row lives in shared memory, column-major over the block's threads: cell j of thread t at [j * NT + t], so
-// lanes sitting at different columns never share a bank.  H and F fit 16 bits each (|values| < 2,000).  (First
-// version: per-thread local arrays -- 832 B x 2,048 resident threads do not fit L1, and 35 % of the kernel's
-// samples waited on the load of H[j] / F[j] with ~9 of 32 lanes active.)
-template <bool STATS> struct RowShared;
-template <> struct RowShared<false> {
-    uint32_t *p; int nt;
-    __device__ __forceinline__ DPCell<false> get(int j) const {
-        const uint32_t v = p[j * nt];
-        DPCell<false> c; c.h = (int)(short)(v & 0xffffu); c.f = (int)v >> 16;
-        return c;
-    }
-    __device__ __forceinline__ void set(int j, const DPCell<false> &c) { p[j * nt] = ((uint32_t)c.h & 0xffffu) | ((uint32_t)c.f << 16); }
-};
-template <> struct RowShared<true> {
-    uint32_t *p; int nt, plane;                  // three planes: (H, F), statistics of H, statistics of F
-    __device__ __forceinline__ DPCell<true> get(int j) const {
-        const uint32_t v = p[j * nt];
-        DPCell<true> c; c.h = (int)(short)(v & 0xffffu); c.f = (int)v >> 16; c.hs = p[plane + j * nt]; c.fs = p[2 * plane + j * nt];
-        return c;
-    }
-    __device__ __forceinline__ void set(int j, const DPCell<true> &c) {
-        p[j * nt] = ((uint32_t)c.h & 0xffffu) | ((uint32_t)c.f << 16); p[plane + j * nt] = c.hs; p[2 * plane + j * nt] = c.fs;
-    }
-};
-
-// STATS = carry the alignment statistics; bl = BLOSUM62 rows of 32 in shared memory.  The inner loop loads the next
-// cell, subject residue and substitution score one iteration ahead.
-template <bool STATS>
+template <int GROW, bool STATS>    // GROW = row capacity (longest frame + GAP_SLACK + 2); STATS = carry the alignment statistics
 __device__ void gapped_xdrop(const uint8_t *fr, int q_first, int qstep, const uint8_t *__restrict__ t,
-                             int tstep, int nQ, int nD, const int8_t *bl, RowShared<STATS> R, GExt &g) {
+                             int tstep, int nQ, int nD, GExt &g) {
     g.gain = 0; g.eq = 0; g.et = 0; g.st = 0; g.cells = 0;
     const int GI = GAP_OPEN, GE = GAP_EXT, GIE = GAP_OPEN + GAP_EXT;
     const int limit = 15;                      // (int)((26.98 - 11) / 1)
-    typedef DPCell<STATS> Cell;
+    int H[GROW], F[GROW];
+    uint32_t HS[STATS ? GROW : 1], FS[STATS ? GROW : 1];
+    H[0] = 0; F[0] = -GI;
+    if (STATS) { HS[0] = 0; FS[0] = 0; }
     {
-        Cell w; w.h = 0; w.f = -GI;
-        if constexpr (STATS) { w.hs = 0; w.fs = 0; }
-        R.set(0, w);
         int r = -GI;
         for (int j = 1; j <= limit && j <= nD; ++j) {
-            r -= GE; w.h = r; w.f = r - GI;
-            if constexpr (STATS) { w.hs = (uint32_t)j * (ST_ALN + ST_GAPCOL) + ST_GAPRUN; w.fs = w.hs; }
-            R.set(j, w);
+            r -= GE; H[j] = r; F[j] = r - GI;
+            if (STATS) { HS[j] = (uint32_t)j * (ST_ALN + ST_GAPCOL) + ST_GAPRUN; FS[j] = HS[j]; }
         }
     }
     int cs = 1, ce = limit, best = 0, bcol = 0, brow = 0, cells = 0;
     uint32_t bst = 0;
     for (int i = 1; i <= nQ; ++i) {
-        const Cell left = R.get(cs - 1);
-        int diag = left.h;
+        int diag = H[cs - 1];
         uint32_t dst = 0, bs = 0;
-        if constexpr (STATS) {
-            dst = left.hs;
+        if (STATS) {
+            dst = HS[cs - 1];
             // boundary cell (i, cs-1): value max(H-12, F-1), always traced as a vertical gap column
-            bs = (i == 1 ? left.hs + ST_GAPRUN : left.fs) + ST_ALN + ST_GAPCOL;
+            bs = (i == 1 ? HS[cs - 1] + ST_GAPRUN : FS[cs - 1]) + ST_ALN + ST_GAPCOL;
         }
-        int v = left.h - GIE;
-        const int f1 = left.f - GE;
+        int v = H[cs - 1] - GIE, f1 = F[cs - 1] - GE;
         if (v < f1) v = f1;
-        {
-            Cell w; w.h = v; w.f = v;
-            if constexpr (STATS) { w.hs = bs; w.fs = bs; }
-            R.set(cs - 1, w);
-        }
+        F[cs - 1] = v; H[cs - 1] = v;
+        if (STATS) { HS[cs - 1] = bs; FS[cs - 1] = bs; }
         int E = v - GI, hl = v, j = cs;
         uint32_t ES = bs, hls = bs;
         bool skip_tail = false;
         const int qa = fr[q_first + (i - 1) * qstep];
-        const int8_t *brow_bl = bl + qa * 32;
         if (!(cs > ce || cs > nD)) {
-            Cell cur = R.get(j);
-            int tb = t[(j - 1) * tstep];
-            int sc = brow_bl[tb];
             for (;;) {
                 ++cells;
-                Cell nxt = cur;
-                int tbn = 0, scn = 0;
-                if (j < nD) { nxt = R.get(j + 1); tbn = t[j * tstep]; scn = brow_bl[tbn]; }
-                const int a = hl - GIE, b = E - GE;
-                if (a >= b) { E = a; if constexpr (STATS) ES = hls + ST_ALN + ST_GAPCOL + ST_GAPRUN; }
-                else { E = b; if constexpr (STATS) ES += ST_ALN + ST_GAPCOL; }
-                const int c = cur.h - GIE, d = cur.f - GE;
-                int Fv;
+                int a = hl - GIE, b = E - GE;
+                if (a >= b) { E = a; if (STATS) ES = hls + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { E = b; if (STATS) ES += ST_ALN + ST_GAPCOL; }
+                int c = H[j] - GIE, d = F[j] - GE, Fv;
                 uint32_t FSv = 0;
-                if (c >= d) { Fv = c; if constexpr (STATS) FSv = cur.hs + ST_ALN + ST_GAPCOL + ST_GAPRUN; }
-                else { Fv = d; if constexpr (STATS) FSv = cur.fs + ST_ALN + ST_GAPCOL; }
-                int h = diag + sc;
+                if (c >= d) { Fv = c; if (STATS) FSv = HS[j] + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { Fv = d; if (STATS) FSv = FS[j] + ST_ALN + ST_GAPCOL; }
+                const int tb = t[(j - 1) * tstep];
+                int h = diag + c_blosum[qa * 32 + tb];
                 uint32_t hs = 0;
-                if constexpr (STATS) hs = dst + ST_ALN + (uint32_t)(qa == tb && qa < 20);
+                if (STATS) hs = dst + ST_ALN + (uint32_t)(qa == tb && qa < 20);
                 if (E > h) { h = E; hs = ES; }
                 if (h < Fv) { h = Fv; hs = FSv; }
-                diag = cur.h;
-                if constexpr (STATS) dst = cur.hs;
-                {
-                    Cell w; w.h = h; w.f = Fv;
-                    if constexpr (STATS) { w.hs = hs; w.fs = FSv; }
-                    R.set(j, w);
-                }
-                hl = h;
-                if constexpr (STATS) hls = hs;
+                diag = H[j];
+                if (STATS) dst = HS[j];
+                H[j] = h; F[j] = Fv; hl = h;
+                if (STATS) { HS[j] = hs; FS[j] = FSv; hls = hs; }
                 if (h > best) { best = h; bcol = j; brow = i; bst = hs; }
                 else if (h <= best - 27 && j > bcol) {       // h < best - 26.98
                     if (j >= ce) { ce = j; break; }
@@ -913,29 +867,22 @@ __device__ void gapped_xdrop(const uint8_t *fr, int q_first, int qstep, const ui
                 }
                 ++j;
                 if (j > nD || j > ce) break;
-                cur = nxt; tb = tbn; sc = scn;
             }
         }
         if (!skip_tail) {
             for (int jj = ce + 1; jj <= nD; ++jj) {          // run on along the row by horizontal gaps
                 ++cells;
-                const int a = hl - GIE, b = E - GE;
-                if (a > b) { E = a; if constexpr (STATS) ES = hls + ST_ALN + ST_GAPCOL + ST_GAPRUN; }
-                else { E = b; if constexpr (STATS) ES += ST_ALN + ST_GAPCOL; }
-                {
-                    Cell w; w.h = E; w.f = E - GI;
-                    if constexpr (STATS) { w.hs = ES; w.fs = ES; }
-                    R.set(jj, w);
-                }
-                hl = E;
-                if constexpr (STATS) hls = ES;
+                int a = hl - GIE, b = E - GE;
+                if (a > b) { E = a; if (STATS) ES = hls + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { E = b; if (STATS) ES += ST_ALN + ST_GAPCOL; }
+                H[jj] = E; F[jj] = E - GI; hl = E;
+                if (STATS) { HS[jj] = ES; FS[jj] = ES; hls = ES; }
                 if (E > best) { best = E; bcol = jj; brow = i; bst = ES; }
                 else if (E <= best - 27) { ce = jj; break; }
             }
             if (cs <= bcol) {                                // drop dead cells on the left
-                const int thr = best - 27;
-                if (R.get(bcol).h <= thr) cs = bcol;
-                else for (int c = bcol - 1; c >= cs; --c) if (R.get(c).h <= thr) { cs = c; break; }
+                int thr = best - 27;
+                if (H[bcol] <= thr) cs = bcol;
+                else for (int c = bcol - 1; c >= cs; --c) if (H[c] <= thr) { cs = c; break; }
             }
         }
         if (!(cs < ce)) break;
@@ -988,18 +935,14 @@ __global__ void k_gap_list(GapArgs A) {
     if (b) A.items[base + __popc(mf) + __popc(mb & lt)] = (uint32_t)(g << 1) | 1u;
 }
 
-// K3b: one thread per gapped extension.  First a score-only pass over all of them (two DP rows); only the ~20 % that
+// K3b: one thread per gapped extension, DP rows in local memory.  (Tried and measured slower on 2M x 100 bp: rows in
+// shared memory, column-major and conflict-free -- 6.8 ms instead of 4.9, the 53-80 KB per block leave too few warps
+// to hide the serial dependency of the cells; packed (H, F) cells with the next cell prefetched -- no change.)
+// First a score-only pass over all of them (two DP rows); only the ~20 % that
 // gain anything are queued for the second pass, which repeats the same DP carrying the alignment statistics.
-template <int NT, bool STATS>
+template <int NT, int GROW, bool STATS>
 __global__ void __launch_bounds__(NT) k_gap_dir(GapArgs A, const uint32_t *__restrict__ items, int64_t n_items,
-                                                uint32_t *__restrict__ items2, unsigned long long *n_items2, int grow) {
-    extern __shared__ __align__(16) uint32_t s_rows[];             // [1 or 3 planes][grow][NT]
-    __shared__ __align__(4) int8_t s_bl[21 * 32];
-    RowShared<STATS> R;
-    R.p = s_rows + threadIdx.x; R.nt = NT;
-    if constexpr (STATS) R.plane = grow * NT;
-    for (int k = threadIdx.x; k < 21 * 32 / 4; k += NT) reinterpret_cast<uint32_t *>(s_bl)[k] = reinterpret_cast<const uint32_t *>(g_blosum)[k];
-    __syncthreads();
+                                                uint32_t *__restrict__ items2, unsigned long long *n_items2) {
     const int64_t w = (int64_t)blockIdx.x * NT + threadIdx.x;
     bool again = false;
     uint32_t item = 0;
@@ -1018,11 +961,11 @@ __global__ void __launch_bounds__(NT) k_gap_dir(GapArgs A, const uint32_t *__res
         if (dir == 0) {
             int ql = m - (q1 + 1), tl = n - (t1 + 1);
             if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
-            gapped_xdrop<STATS>(fr, q1 + 1, 1, t + t1 + 1, 1, ql, tl, s_bl, R, e);
+            gapped_xdrop<GROW, STATS>(fr, q1 + 1, 1, t + t1 + 1, 1, ql, tl, e);
         } else {
             int ql = q0, tl = t0;
             if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
-            gapped_xdrop<STATS>(fr, q0 - 1, -1, t + t0 - 1, -1, ql, tl, s_bl, R, e);
+            gapped_xdrop<GROW, STATS>(fr, q0 - 1, -1, t + t0 - 1, -1, ql, tl, e);
         }
         GExtRec r;
         r.gain = e.gain; r.eq = (uint16_t)e.eq; r.et = (uint16_t)e.et; r.st = e.st; r.cells = (uint32_t)e.cells;
@@ -1497,6 +1440,7 @@ static int upload_tables(mcx_ctx *ctx) {
         CK(cudaMemcpyToSymbol(g_codon_lut, lut, sizeof lut));
     }
     CK(cudaMemcpyToSymbol(g_blosum, bl, sizeof bl));
+    CK(cudaMemcpyToSymbol(c_blosum, bl, sizeof bl));
     CK(cudaMemcpyToSymbol(g_lnfac, lnfac, sizeof lnfac));
     CK(cudaMemcpyToSymbol(g_ln20, ln20, sizeof ln20));
     return MCX_OK;
@@ -1824,8 +1768,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         CK(cudaGetLastError());
         if (n_segq > 0) {
             constexpr int SW = 4;
-            const int pw = fstride + (maxm + 1) * 20;
-            const size_t smem = 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + (size_t)SW * (pw + 4 - (pw & 3) + 18 * 4);
+            const size_t smem = 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + (size_t)SW * seg_warp_bytes(fstride, maxm);
             CK(cudaFuncSetAttribute(k_seg<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_seg<SW><<<(unsigned)std::min<unsigned long long>((n_segq + SW - 1) / SW, 148ull * 16), SW * 32, smem, st>>>(ctx->d_frames, fstride, P.read_length, ctx->d_segq,
                                                                            (int64_t)n_segq, maxm);
@@ -1894,30 +1837,19 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             if (n_items > 0) {
                 uint32_t *items2 = ctx->d_gitems + G.n_surv * 2;     // second half of the work-list buffer
                 CK(cudaMemsetAsync(ctx->d_cnt + 14, 0, sizeof(unsigned long long), st));
-                // rows of `grow` columns per thread in shared memory: 4 B per cell in the score pass, 12 B with statistics
+                const unsigned gb = (unsigned)((n_items + 127) / 128);
                 const int grow = maxm + GAP_SLACK + 2;
-                {
-                    const size_t smem = (size_t)grow * 128 * 4;
-                    if (smem <= 64 * 1024) {
-                        CK(cudaFuncSetAttribute(k_gap_dir<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        k_gap_dir<128, false><<<(unsigned)((n_items + 127) / 128), 128, smem, st>>>(G, G.items, (int64_t)n_items, items2, ctx->d_cnt + 14, grow);
-                    } else {
-                        CK(cudaFuncSetAttribute(k_gap_dir<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem / 2)));
-                        k_gap_dir<64, false><<<(unsigned)((n_items + 63) / 64), 64, smem / 2, st>>>(G, G.items, (int64_t)n_items, items2, ctx->d_cnt + 14, grow);
-                    }
-                }
+                if (grow <= 104) k_gap_dir<128, 104, false><<<gb, 128, 0, st>>>(G, G.items, (int64_t)n_items, items2, ctx->d_cnt + 14);
+                else if (grow <= 152) k_gap_dir<128, 152, false><<<gb, 128, 0, st>>>(G, G.items, (int64_t)n_items, items2, ctx->d_cnt + 14);
+                else k_gap_dir<128, MAX_FRAME + GAP_SLACK + 2, false><<<gb, 128, 0, st>>>(G, G.items, (int64_t)n_items, items2, ctx->d_cnt + 14);
                 unsigned long long n2 = 0;
                 CK(cudaMemcpyAsync(&n2, ctx->d_cnt + 14, sizeof n2, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
                 if (n2 > 0) {
-                    const size_t smem = (size_t)grow * 64 * 12;
-                    if (smem <= 120 * 1024) {
-                        CK(cudaFuncSetAttribute(k_gap_dir<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        k_gap_dir<64, true><<<(unsigned)((n2 + 63) / 64), 64, smem, st>>>(G, items2, (int64_t)n2, nullptr, nullptr, grow);
-                    } else {
-                        CK(cudaFuncSetAttribute(k_gap_dir<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem / 2)));
-                        k_gap_dir<32, true><<<(unsigned)((n2 + 31) / 32), 32, smem / 2, st>>>(G, items2, (int64_t)n2, nullptr, nullptr, grow);
-                    }
+                    const unsigned gb2 = (unsigned)((n2 + 127) / 128);
+                    if (grow <= 104) k_gap_dir<128, 104, true><<<gb2, 128, 0, st>>>(G, items2, (int64_t)n2, nullptr, nullptr);
+                    else if (grow <= 152) k_gap_dir<128, 152, true><<<gb2, 128, 0, st>>>(G, items2, (int64_t)n2, nullptr, nullptr);
+                    else k_gap_dir<128, MAX_FRAME + GAP_SLACK + 2, true><<<gb2, 128, 0, st>>>(G, items2, (int64_t)n2, nullptr, nullptr);
                     ++ctx->launches;
                 }
                 n_gapped_total += n_items;

@@ -22,6 +22,7 @@ import numpy as np
 from numpy import median
 
 from .engine import MarkerSearch, ReadBatch
+from .seqio import SeqFile
 from .markers import Markers
 
 __version__ = "1.1.0"
@@ -63,15 +64,6 @@ def open_file(inpath):
     return open(inpath)
 
 
-def _open_bytes(inpath):
-    ext = inpath.split(".")[-1]
-    if ext == "gz":
-        return gzip.open(inpath, "rb")
-    if ext == "bz2":
-        return bz2.BZ2File(inpath, "rb")
-    return open(inpath, "rb")
-
-
 def read_list(file, header, dtype):
     """One value per line (mc.py:90-99)."""
     conv = float if dtype == "float" else int if dtype == "int" else (lambda v: v)
@@ -101,15 +93,15 @@ def parse_seqs(fp):
     '>' or '@'; the name ends at the first space; sequence lines run until a line beginning with '@', '+'
     or '>'; after a '+' line quality lines are consumed until they are at least as long as the sequence;
     a FASTQ record cut short by EOF is yielded without qualities."""
-    pending = None
+    pending = None            # readfq's `last`: tested for truth, so an empty stripped line counts as "none"
     lines = iter(fp)
     while True:
-        if pending is None:
+        if not pending:
             for line in lines:
                 if line[0] in ">@":
                     pending = line[:-1]
                     break
-            if pending is None:
+            if not pending:
                 return
         name = pending[1:].partition(" ")[0]
         pending = None
@@ -120,9 +112,9 @@ def parse_seqs(fp):
                 break
             chunks.append(line[:-1])
         seq = "".join(chunks)
-        if pending is None or pending[0] != "+":
+        if not pending or pending[0] != "+":
             yield Sequence(name, seq)
-            if pending is None:
+            if not pending:
                 return
             continue
         got, qchunks, complete = 0, [], False
@@ -235,100 +227,24 @@ def print_parameters(args):
 
 
 # ------------------------------------------------------------------------------------------------ read loading
-class _Fallback(Exception):
-    pass
+# Files are read by libmcxio (microbecensus_b200/csrc/mcxio.cpp, include/mcxio.h): the readfq state machine of
+# parse_seqs() in C++, inflating / reading ahead in a producer thread and returning packed batches.  parse_seqs()
+# above stays as the mirror of the reference's generator (auto-detection uses it; tests check the reader against it).
+_base_counts = {}          # (path, size, mtime) -> total bases of the file, filled when a file was read to its end
 
 
-def _fast_records(data, file_type, max_records):
-    """Vectorised parse of a whole decompressed file held in `data` (bytes): 4-line FASTQ or FASTA whose
-    sequence lines contain no '@'/'+' starts.  Raises _Fallback for anything irregular so that the exact
-    readfq state machine (parse_seqs) decides."""
-    buf = np.frombuffer(data, np.uint8)
-    if len(buf) == 0:
-        return ReadBatch(np.zeros(0, np.uint8), np.zeros(1, np.int64), None), 0
-    if buf[-1] != 10:
-        # readfq strips the last character of every line (l[:-1]); a final line without a newline loses a
-        # real character in the reference, and so it does here
-        buf = buf.copy()
-        buf[-1] = 10
-    nl = np.flatnonzero(buf == 10)
-    starts = np.concatenate([[0], nl[:-1] + 1])
-    first = buf[np.minimum(starts, len(buf) - 1)]
-    empty = nl == starts
-    if file_type == "fastq":
-        if len(starts) % 4 or empty.any():
-            raise _Fallback()
-        h, s, p, q = starts[0::4], starts[1::4], starts[2::4], starts[3::4]
-        if not ((first[0::4] == 64).all() and (first[2::4] == 43).all()):
-            raise _Fallback()
-        sf = first[1::4]
-        if ((sf == 64) | (sf == 43) | (sf == 62)).any():
-            raise _Fallback()
-        slen = nl[1::4] - s
-        qlen = nl[3::4] - q
-        if (qlen < slen).any():
-            raise _Fallback()
-        n = len(h) if max_records is None else min(len(h), max_records)
-        offs = np.zeros(n + 1, np.int64)
-        offs[1:] = np.cumsum(slen[:n])
-        total = int(offs[-1])
-        idx = np.repeat(s[:n] - offs[:-1], slen[:n]) + np.arange(total)
-        bases = buf[idx]
-        qidx = np.repeat(q[:n] - offs[:-1], slen[:n]) + np.arange(total)
-        # readfq keeps the whole quality line; only the first len(seq) characters are ever used
-        return ReadBatch(bases, offs, buf[qidx]), len(h)
-    if file_type == "fasta":
-        hdr = first == 62
-        if not hdr[0]:
-            raise _Fallback()
-        body = ~hdr
-        bf = first[body]
-        if ((bf == 64) | (bf == 43)).any():
-            raise _Fallback()
-        rec_of_line = np.cumsum(hdr) - 1
-        n_all = int(rec_of_line[-1]) + 1
-        n = n_all if max_records is None else min(n_all, max_records)
-        keep_line = body & (rec_of_line < n)
-        llen = (nl - starts) * keep_line
-        per_rec = np.bincount(rec_of_line[keep_line], weights=llen[keep_line], minlength=n)[:n].astype(np.int64)
-        offs = np.zeros(n + 1, np.int64)
-        offs[1:] = np.cumsum(per_rec)
-        ls, ll = starts[keep_line], llen[keep_line]
-        out_start = np.concatenate([[0], np.cumsum(ll)[:-1]]) if len(ll) else np.zeros(0, np.int64)
-        total = int(ll.sum())
-        idx = np.repeat(ls - out_start, ll) + np.arange(total)
-        return ReadBatch(buf[idx], offs, None), n_all
-    raise _Fallback()
+def _file_key(path):
+    st = os.stat(path)
+    return (os.path.abspath(path), st.st_size, st.st_mtime_ns)
 
 
-def _slow_records(seqfile, max_records):
-    seqs, quals, any_q = [], [], False
-    with open_file(seqfile) as fh:
-        for rec in parse_seqs(fh):
-            seqs.append(rec.seq)
-            q = rec.quality
-            if q is not None:
-                any_q = True
-                # shorter-than-sequence qualities cannot come out of readfq; longer ones are cut to len(seq)
-                q = q[:len(rec.seq)].ljust(len(rec.seq), "!")
-            quals.append(q)
-            if max_records is not None and len(seqs) >= max_records:
-                break
-    if any_q:
-        quals = [q if q is not None else "~" * len(s) for q, s in zip(quals, seqs)]
-        return ReadBatch.from_strings(seqs, quals)
-    return ReadBatch.from_strings(seqs)
-
-
-def load_reads(seqfile, file_type, max_records=None):
+def load_reads(seqfile, file_type=None, max_records=None):
     """All (or the first max_records) records of one file as a ReadBatch."""
-    try:
-        with _open_bytes(seqfile) as fh:
-            data = fh.read()
-        batch, _ = _fast_records(data, file_type, max_records)
-        return batch
-    except _Fallback:
-        return _slow_records(seqfile, max_records)
+    with SeqFile(seqfile) as rd:
+        batch = rd.next_batch(max_records)
+        if rd.eof:
+            _base_counts[_file_key(seqfile)] = rd.bases_total
+    return batch
 
 
 def concat_batches(batches):
@@ -362,11 +278,6 @@ def sample_and_search(args, engine=None):
                    min_quality=args["min_quality"], mean_quality=args["mean_quality"],
                    max_unknown=args["max_unknown"], filter_dups=bool(args.get("filter_dups")))
     nreads = args["nreads"]
-    batch = concat_batches([load_reads(f, args["file_type"]) for f in args["seqfiles"]])
-    if fastq and batch.quals is None:
-        raise ValueError("FASTQ input without qualities")
-    if not fastq:
-        batch = ReadBatch(batch.bases, batch.offsets, None)
     # under torchrun every rank parses the input and searches its contiguous block of the read stream; -n, -d and
     # the sums are made global by microbecensus_b200.distributed (one all-reduce + two small all-gathers)
     world, rank = 1, 0
@@ -376,15 +287,53 @@ def sample_and_search(args, engine=None):
             world, rank = dist.get_world_size(), dist.get_rank()
     except ImportError:
         pass
-    if world > 1:
-        from .distributed import sharded_search
-        eng.set_params(L, quality_offset=args.get("quality_offset") if fastq else None, min_quality=args["min_quality"],
-                       mean_quality=args["mean_quality"], max_unknown=args["max_unknown"], filter_dups=False)
-        lo, hi = rank * batch.n // world, (rank + 1) * batch.n // world
-        res = sharded_search(eng, batch.slice(lo, hi), lo, nreads=nreads, filter_dups=bool(args.get("filter_dups")))
+
+    def checked(batch):
+        if fastq and batch.quals is None and batch.n:
+            raise ValueError("FASTQ input without qualities")
+        return batch if fastq else ReadBatch(batch.bases, batch.offsets, None)
+
+    want_total = args.get("no_equivs") is False      # the CLI will ask count_bases() next: finish the files in this pass
+    if world > 1 or args.get("filter_dups"):
+        # -d and the sharded run need the whole read stream at once (duplicates are decided over all reads)
+        batch = checked(concat_batches([load_reads(f) for f in args["seqfiles"]]))
+        if world > 1:
+            from .distributed import sharded_search
+            eng.set_params(L, quality_offset=args.get("quality_offset") if fastq else None, min_quality=args["min_quality"],
+                           mean_quality=args["mean_quality"], max_unknown=args["max_unknown"], filter_dups=False)
+            lo, hi = rank * batch.n // world, (rank + 1) * batch.n // world
+            res = sharded_search(eng, batch.slice(lo, hi), lo, nreads=nreads, filter_dups=bool(args.get("filter_dups")))
+        else:
+            eng.push(batch)
+            res = eng.search(-1 if nreads is None else nreads)
     else:
-        eng.push(batch)
-        res = eng.search(-1 if nreads is None else nreads)
+        # stream: batches of records go to the GPU as they are parsed; reading stops with the read that fills -n
+        # (mc.py:356) and the additive results of the batches are summed
+        per_batch = int(os.environ.get("MCX_BATCH_READS", "8000000"))
+        res, remaining = None, nreads
+        for path in args["seqfiles"]:
+            if remaining is not None and remaining <= 0:
+                break
+            with SeqFile(path) as rd:
+                while not rd.eof and (remaining is None or remaining > 0):
+                    batch = checked(rd.next_batch(per_batch, copy=False))
+                    if batch.n == 0:
+                        break
+                    eng.push(batch)
+                    part = eng.search(-1 if remaining is None else remaining)
+                    if remaining is not None:
+                        remaining -= part.sampled_reads
+                    if res is None:
+                        res = part
+                    else:
+                        res.load_counts_vector(res.counts_vector() + part.counts_vector())
+                if want_total and not rd.eof:
+                    rd.skip_rest()
+                if rd.eof:
+                    _base_counts[_file_key(path)] = rd.bases_total
+        if res is None:
+            eng.push(ReadBatch(np.zeros(0, np.uint8), np.zeros(1, np.int64), None if not fastq else np.zeros(0, np.uint8)))
+            res = eng.search(-1)
     if res.sampled_reads == 0:
         sys.exit("\nError! No reads remaining after filtering!")
     args["sampled_reads"] = res.sampled_reads
@@ -454,9 +403,12 @@ def count_bases(args):
     if args["verbose"]:
         print("Computing number of genome equivalents...")
     total = 0
-    file_type = args.get("file_type") or auto_detect_file_type(args["seqfiles"][0])
     for path in args["seqfiles"]:
-        total += int(load_reads(path, file_type).offsets[-1])
+        key = _file_key(path)
+        if key not in _base_counts:                  # not read to its end by the sampling pass: count it now
+            with SeqFile(path) as rd:
+                _base_counts[key] = rd.skip_rest()[1]
+        total += _base_counts[key]
     return total
 
 

@@ -57,14 +57,14 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.Result) == 8 * (10 + 30 + 30 + 30 * 1280)
 
 
-def test_fast_reader_matches_readfq_state_machine(tmp_path):
-    """The vectorised loader and the exact readfq generator agree, including multi-line FASTA, names with
-    spaces, a missing final newline and records that force the fallback path."""
+def test_reader_matches_readfq_state_machine(tmp_path):
+    """libmcxio and the readfq generator agree, including multi-line FASTA / FASTQ, names with spaces, a missing
+    final newline and '+' lines inside FASTA (more cases in tests/test_seqio.py)."""
     cases = {
         "a.fa": ">r1 desc\nACGT\nAC\n>r2\nTTTT\n>r3\n\nGG",
         "b.fq": "@q1\nACGTN\n+\nIIII#\n@q2 x\nAC\n+q2\n!!\n",
-        "c.fq": "@q1\nACGT\nAC\n+\nIIII\nII\n@q2\nGG\n+\n@@\n",       # multi-line FASTQ -> fallback
-        "d.fa": ">r1\nAC\n+weird\nGG\n>r2\nTT\n",                       # '+' line inside FASTA -> fallback
+        "c.fq": "@q1\nACGT\nAC\n+\nIIII\nII\n@q2\nGG\n+\n@@\n",       # multi-line FASTQ
+        "d.fa": ">r1\nAC\n+weird\nGG\n>r2\nTT\n",                       # '+' line inside FASTA
     }
     for name, text in cases.items():
         p = tmp_path / name

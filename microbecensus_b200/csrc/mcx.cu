@@ -86,18 +86,28 @@ __host__ __device__ __forceinline__ uint32_t bloom_mask(uint32_t h) {
     return (1u << (h2 >> 27)) | (1u << ((h2 >> 22) & 31u));
 }
 
-struct Surv {                      // ungapped HSP that reached the report floor (20 bytes)
+struct Surv {                      // ungapped HSP that reached the report floor
     int32_t read;
-    uint16_t subject;
-    uint8_t frame, q0;
-    uint8_t q1, ident;
-    uint16_t t0;
-    int16_t score;
-    uint16_t pad;
-    uint32_t gframe;               // row of the frame store (within the chunk the survivor came from)
+    int subject, frame, q0, q1, ident, t0, score;
+    uint32_t gframe;               // row of the frame store (within the chunk the survivor came from, < 2^24)
 };
+// in memory: 16 bytes, one 128-bit access.  x read | y gframe(24) ident(8) | z subject(15) t0(11) frame(3) | w q0(8) q1(8) score(16)
+__device__ __forceinline__ uint4 surv_pack(const Surv &v) {
+    uint4 p;
+    p.x = (uint32_t)v.read; p.y = v.gframe | ((uint32_t)v.ident << 24);
+    p.z = (uint32_t)v.subject | ((uint32_t)v.t0 << 15) | ((uint32_t)v.frame << 26);
+    p.w = (uint32_t)v.q0 | ((uint32_t)v.q1 << 8) | ((uint32_t)(uint16_t)(int16_t)v.score << 16);
+    return p;
+}
+__device__ __forceinline__ Surv surv_unpack(const uint4 p) {
+    Surv v;
+    v.read = (int32_t)p.x; v.gframe = p.y & 0xffffffu; v.ident = (int)(p.y >> 24);
+    v.subject = (int)(p.z & 0x7fffu); v.t0 = (int)((p.z >> 15) & 0x7ffu); v.frame = (int)((p.z >> 26) & 7u);
+    v.q0 = (int)(p.w & 0xffu); v.q1 = (int)((p.w >> 8) & 0xffu); v.score = (int)(int16_t)(uint16_t)(p.w >> 16);
+    return v;
+}
 
-struct SortKey {                   // (read, subject, score desc, frame, q0 | q1, t0, t1, aln, ident)
+struct __align__(16) SortKey {     // (read, subject, score desc, frame, q0 | q1, t0, t1, aln, ident)
     unsigned long long k1, k2;
 };
 struct SortKeyLess {
@@ -160,16 +170,34 @@ struct WinG {                       // composition of a <= 12-residue window
 // seg.c getprob() = lnass + lnperm - len*ln20 from the histogram of letter counts: nc[c] = number of letters
 // occurring c times.  Walking c downwards visits the counts in exactly the order of seg.c's sorted state vector,
 // so the floating-point operations (and their order) are those of the reference and of the oracle.
-// nc is the calling lane's column of a [count][32 lanes] byte table in shared memory (stride 32).
-__device__ double seg_getprob(const uint8_t *nc, int maxc, int len, const double *lnfac, const double *ln20) {
+// nc is the calling lane's column of a [count][32 lanes] byte table in shared memory (stride 32); the entries read
+// are reset to zero on the way.  Subtracting ln(1!) = 0 leaves a double unchanged, so counts of one are skipped.
+__device__ double seg_getprob(uint8_t *nc, int maxc, int len, const double *lnfac, const double *ln20) {
     double lnperm = lnfac[len], lnass = lnfac[20];
     int nz = 0;
     for (int c = maxc; c >= 1; --c) {
         const int n = nc[c * 32];
         if (!n) continue;
-        for (int r = 0; r < n; ++r) lnperm -= lnfac[c];
-        lnass -= lnfac[n];
+        nc[c * 32] = 0;
+        if (c > 1) { const double lf = lnfac[c]; for (int r = 0; r < n; ++r) lnperm -= lf; }
+        if (n > 1) lnass -= lnfac[n];
         nz += n;
+    }
+    if (nz > 0 && nz < 20) lnass -= lnfac[20 - nz];
+    return lnass + lnperm - ln20[len];
+}
+// the same from a register histogram, one nibble per count value 1..15 (windows of at most 15 residues: neither a
+// count nor the number of letters sharing it can exceed 15)
+__device__ __forceinline__ double seg_getprob_packed(unsigned long long h, int len, const double *lnfac, const double *ln20) {
+    double lnperm = lnfac[len], lnass = lnfac[20];
+    int nz = 0;
+    while (h) {                                              // highest count first
+        const int c = (63 - __clzll((long long)h)) >> 2;
+        const int n = (int)((h >> (4 * c)) & 15);
+        if (c > 1) { const double lf = lnfac[c]; for (int r = 0; r < n; ++r) lnperm -= lf; }
+        if (n > 1) lnass -= lnfac[n];
+        nz += n;
+        h &= ~(15ull << (4 * c));
     }
     if (nz > 0 && nz < 20) lnass -= lnfac[20 - nz];
     return lnass + lnperm - ln20[len];
@@ -431,15 +459,26 @@ __device__ void coop_trim(const uint8_t *fr, int off, int tl, uint8_t *P, uint8_
             uint32_t cw[5];
 #pragma unroll
             for (int q = 0; q < 5; ++q) cw[q] = w1[q] - w0[q];      // no borrow: every byte of w1 >= that of w0
-            int maxc = 0;
+            if (len <= 15) {
+                unsigned long long h = 0;
 #pragma unroll
-            for (int a = 0; a < 20; ++a) {
-                const int c = (int)((cw[a >> 2] >> (8 * (a & 3))) & 0xffu);
-                if (c) { nc[c * 32]++; maxc = c > maxc ? c : maxc; }
+                for (int q = 0; q < 5; ++q) {
+                    const uint32_t x = cw[q];
+                    if (x) {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) { const uint32_t c = (x >> (8 * b)) & 0xffu; if (c) h += 1ull << (4 * c); }
+                    }
+                }
+                prob = seg_getprob_packed(h, len, lnfac, ln20);
+            } else {
+                int maxc = 0;
+#pragma unroll
+                for (int a = 0; a < 20; ++a) {
+                    const int c = (int)((cw[a >> 2] >> (8 * (a & 3))) & 0xffu);
+                    if (c) { nc[c * 32]++; maxc = c > maxc ? c : maxc; }
+                }
+                prob = seg_getprob(nc, maxc, len, lnfac, ln20);
             }
-            prob = seg_getprob(nc, maxc, len, lnfac, ln20);
-#pragma unroll
-            for (int a = 0; a < 20; ++a) nc[((cw[a >> 2] >> (8 * (a & 3))) & 0xffu) * 32] = 0;
         }
         double best = prob;
         int bl = lane;
@@ -700,7 +739,7 @@ struct ExtArgs {
     int64_t n_cand;                // total over the sub-queues
     unsigned long long cap_cand;   // per sub-queue
     unsigned long long qstart[NQ + 1];   // exclusive prefix of the sub-queue fills
-    Surv *surv;
+    uint4 *surv;
     unsigned long long *n_surv;
     unsigned long long cap_surv;
 };
@@ -785,12 +824,12 @@ __global__ void __launch_bounds__(NT) k_extend(ExtArgs A) {
     const unsigned long long idx = base + __popc(mask & ((1u << lane) - 1));
     if (idx >= A.cap_surv) return;
     Surv v;
-    v.read = A.kept[A.first + c.gframe / 6u]; v.subject = (uint16_t)s; v.frame = (uint8_t)frame;
-    v.q0 = (uint8_t)(qb - be); v.q1 = (uint8_t)(qb + len + fe - 1);
-    v.ident = (uint8_t)(id0 + fid + bid); v.t0 = (uint16_t)(sb - be);
-    v.score = (int16_t)total; v.pad = (uint16_t)0;
+    v.read = A.kept[A.first + c.gframe / 6u]; v.subject = s; v.frame = frame;
+    v.q0 = qb - be; v.q1 = qb + len + fe - 1;
+    v.ident = id0 + fid + bid; v.t0 = sb - be;
+    v.score = total;
     v.gframe = c.gframe;
-    A.surv[idx] = v;
+    A.surv[idx] = surv_pack(v);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -891,13 +930,13 @@ __device__ void gapped_xdrop(const uint8_t *fr, int q_first, int qstep, const ui
     if (best > 0) { g.gain = best; g.eq = brow; g.et = bcol; g.st = bst; }
 }
 
-struct GExtRec { int32_t gain; uint16_t eq, et; uint32_t st; uint32_t cells; };   // result of one direction
+struct __align__(16) GExtRec { int32_t gain; uint16_t eq, et; uint32_t st; uint32_t cells; };   // result of one direction
 
 struct GapArgs {
     int L, fstride;
     DevDB db;
     const uint8_t *frames;         // frame store of the chunk the survivors came from
-    const Surv *surv;              // survivors [first, first + n_surv) of the global list
+    const uint4 *surv;             // survivors [first, first + n_surv) of the global list
     int64_t first, n_surv;
     uint32_t *items;               // work list: (survivor - first) << 1 | direction
     unsigned long long *n_items;
@@ -914,7 +953,7 @@ __global__ void k_gap_list(GapArgs A) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool f = false, b = false;
     if (g < A.n_surv) {
-        const Surv v = A.surv[A.first + g];
+        const Surv v = surv_unpack(A.surv[A.first + g]);
         if (v.score >= 49) {
             const int m = (A.L - v.frame % 3) / 3;
             const int n = A.db.off[v.subject + 1] - A.db.off[v.subject];
@@ -950,7 +989,7 @@ __global__ void __launch_bounds__(NT) k_gap_dir(GapArgs A, const uint32_t *__res
         item = items[w];
         const int64_t g = item >> 1;
         const int dir = item & 1;
-        const Surv v = A.surv[A.first + g];
+        const Surv v = surv_unpack(A.surv[A.first + g]);
         const uint8_t *__restrict__ fr = A.frames + (int64_t)v.gframe * A.fstride;
         const int m = (A.L - v.frame % 3) / 3;
         const int32_t o = A.db.off[v.subject];
@@ -990,7 +1029,7 @@ __global__ void k_gap_finish(GapArgs A) {
     if (g >= A.n_surv) return;
     const GExtRec ef = A.ext[2 * g], eb = A.ext[2 * g + 1];
     g += A.first;
-    const Surv v = A.surv[g];
+    const Surv v = surv_unpack(A.surv[g]);
     int q0 = v.q0, q1 = v.q1, t0 = v.t0, t1 = v.t0 + (v.q1 - v.q0);
     int score = v.score, ident = v.ident, aln = q1 - q0 + 1, gapcols = 0, gapo = 0;
     if (ef.gain > 0) {
@@ -1001,14 +1040,25 @@ __global__ void k_gap_finish(GapArgs A) {
         score += eb.gain; q0 -= eb.eq; t0 -= eb.et;
         ident += eb.st & 0xff; aln += (eb.st >> 8) & 0x1ff; gapcols += (eb.st >> 17) & 0x1ff; gapo += eb.st >> 26;
     }
-    const unsigned long long nc = (unsigned long long)ef.cells + eb.cells;
-    if (nc) atomicAdd(&A.counters[1], nc);
-    { const int ng = (ef.gain > 0) + (eb.gain > 0); if (ng) atomicAdd(&A.counters[0], (unsigned long long)ng); }
+    {   // counters: one atomic per warp, not per survivor (2M atomics on one address were half of this kernel)
+        const uint32_t am = __activemask();
+        const unsigned nc = __reduce_add_sync(am, ef.cells + eb.cells);
+        const unsigned ng = __reduce_add_sync(am, (unsigned)((ef.gain > 0) + (eb.gain > 0)));
+        if ((threadIdx.x & 31) == __ffs(am) - 1) {
+            if (nc) atomicAdd(&A.counters[1], (unsigned long long)nc);
+            if (ng) atomicAdd(&A.counters[0], (unsigned long long)ng);
+        }
+    }
     mcx_hit h;
     h.read = v.read; h.subject = v.subject; h.frame = v.frame; h.score = score;
     h.aln = aln; h.ident = ident; h.mism = aln - ident - gapcols; h.gapo = gapo;
     h.q0 = q0; h.q1 = q1; h.t0 = t0; h.t1 = t1;
-    A.hsp[g] = h;
+    {   // 48-byte record as three 128-bit stores
+        uint4 *dst = reinterpret_cast<uint4 *>(A.hsp + g);
+        dst[0] = make_uint4((uint32_t)h.read, (uint32_t)h.subject, (uint32_t)h.frame, (uint32_t)h.score);
+        dst[1] = make_uint4((uint32_t)h.aln, (uint32_t)h.ident, (uint32_t)h.mism, (uint32_t)h.gapo);
+        dst[2] = make_uint4((uint32_t)h.q0, (uint32_t)h.q1, (uint32_t)h.t0, (uint32_t)h.t1);
+    }
     SortKey k;
     k.k1 = ((unsigned long long)(uint32_t)v.read << 37) | ((unsigned long long)v.subject << 22) |
            ((unsigned long long)(2047 - score) << 11) | ((unsigned long long)v.frame << 8) | (unsigned long long)q0;
@@ -1064,6 +1114,8 @@ struct ClsArgs {
     int min_report;
     DevDB db;
     uint8_t *keep;                 // per sorted position: 1 = reported line
+    int32_t *caplist;              // sorted positions of the first HSP of reads with more than 500 reported lines
+    unsigned long long *n_cap;
     int32_t *nrep;                 // per pushed read: reported lines (before the 500-line cap), zeroed
     unsigned long long *bestkey;   // per pushed read: (score + 1) << 32 | ~position of the best passing line, zeroed
     int32_t *best_subject;         // per pushed read
@@ -1099,9 +1151,7 @@ __global__ void k_cls_groups(ClsArgs A) {
     if (nrep) atomicAdd(&A.nrep[(int)(grp >> 15)], nrep);
 }
 
-// K4b: one thread per read of the sorted list: count it, and apply RAPsearch2's limit of 500 printed lines per
-// query (-v default), best first: keep the 500 highest scores, ties at the cut score in (subject, ...) order.
-// Rare; the cut score is found by bisection over the kept HSPs.
+// K4b: one thread per read of the sorted list: count it; reads with more than 500 reported lines go on a list.
 __global__ void k_cls_cap(ClsArgs A) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int nrep = 0;
@@ -1109,34 +1159,71 @@ __global__ void k_cls_cap(ClsArgs A) {
         const int read = (int)(A.keys[p].k1 >> 37);
         if (p == 0 || (int)(A.keys[p - 1].k1 >> 37) != read) nrep = A.nrep[read];
         if (nrep > MAX_LINES) {
-            int64_t end = p;
-            while (end < A.n && (int)(A.keys[end].k1 >> 37) == read) ++end;
-            int lo = A.min_report, hi = 2047;                    // largest T with count(score >= T) >= 500
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                int c = 0;
-                for (int64_t e = p; e < end; ++e) if (A.keep[e] && key_decode(A.keys[e]).score >= mid) ++c;
-                if (c >= MAX_LINES) lo = mid; else hi = mid - 1;
-            }
-            const int T = lo;
-            int above = 0;
-            for (int64_t e = p; e < end; ++e) if (A.keep[e] && key_decode(A.keys[e]).score > T) ++above;
-            int allow = MAX_LINES - above;
-            for (int64_t e = p; e < end; ++e) {
-                if (!A.keep[e]) continue;
-                const int sc = key_decode(A.keys[e]).score;
-                if (sc > T || (sc == T && allow-- > 0)) continue;
-                A.keep[e] = 0;
-            }
+            A.caplist[atomicAdd(A.n_cap, 1ull)] = (int32_t)p;
             nrep = MAX_LINES;
         }
     }
     const uint32_t any = __ballot_sync(0xffffffffu, nrep > 0);
     if (!any) return;
-    int lines = nrep;
-#pragma unroll
-    for (int d = 16; d; d >>= 1) lines += __shfl_xor_sync(0xffffffffu, lines, d);
+    const int lines = __reduce_add_sync(0xffffffffu, nrep);
     if ((threadIdx.x & 31) == 0) { atomicAdd(&A.acc[0], (unsigned long long)__popc(any)); atomicAdd(&A.acc[2], (unsigned long long)lines); }
+}
+
+// K4b': RAPsearch2 prints at most 500 lines per query (-v default), best first: keep the 500 highest scores, ties
+// at the cut score in (subject, ...) order.  One warp per listed read: score histogram in shared memory, cut score
+// from its suffix sums, then the ties in sorted order.  (First version: one thread per read bisecting the cut score
+// with 11 passes over its HSPs -- 1 ms for a few hundred reads.)
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_cls_cap_apply(ClsArgs A) {
+    __shared__ int s_hist[WARPS][2048];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int *hist = s_hist[warp];
+    const unsigned long long ncap = *A.n_cap;
+    for (unsigned long long q = (unsigned long long)blockIdx.x * WARPS + warp; q < ncap; q += (unsigned long long)gridDim.x * WARPS) {
+        const int64_t p = A.caplist[q];
+        const int read = (int)(A.keys[p].k1 >> 37);
+        for (int k = lane; k < 2048; k += 32) hist[k] = 0;
+        __syncwarp();
+        int64_t end = p;
+        for (;; end += 32) {                                 // histogram of the kept scores; finds the end of the read
+            const int64_t e = end + lane;
+            const bool mine = e < A.n && (int)(A.keys[e].k1 >> 37) == read;
+            if (mine && A.keep[e]) atomicAdd(&hist[key_decode(A.keys[e]).score], 1);
+            const uint32_t bm = __ballot_sync(0xffffffffu, mine);
+            if (bm != 0xffffffffu) { end += __popc(bm); break; }
+        }
+        __syncwarp();
+        int T = 0, above = 0, run = 0;                       // largest T with count(score >= T) >= 500
+        for (int top = 2047; top >= 0; top -= 32) {
+            const int c = hist[top - lane];
+            int inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+            const uint32_t hit = __ballot_sync(0xffffffffu, run + inc >= MAX_LINES);
+            if (hit) {
+                const int l = __ffs(hit) - 1;
+                T = top - l;
+                above = run + __shfl_sync(0xffffffffu, inc - c, l);
+                break;
+            }
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        const int allow = MAX_LINES - above;
+        int taken = 0;
+        for (int64_t base = p; base < end; base += 32) {     // ties at T in sorted order
+            const int64_t e = base + lane;
+            bool tie = false;
+            if (e < end && A.keep[e]) {
+                const int sc = key_decode(A.keys[e]).score;
+                if (sc < T) A.keep[e] = 0;
+                tie = sc == T;
+            }
+            const uint32_t tm = __ballot_sync(0xffffffffu, tie);
+            if (tie && taken + __popc(tm & ((1u << lane) - 1)) >= allow) A.keep[e] = 0;
+            taken += __popc(tm);
+        }
+        __syncwarp();
+    }
 }
 
 // K4c: one thread per HSP: the three cutoffs of its subject's family (mc.py:420-430); the best passing line of a
@@ -1218,7 +1305,7 @@ struct mcx_ctx {
     mcx_qc qc{};
     bool pushed = false, searched = false;
     // search buffers
-    Surv *d_surv = nullptr;
+    uint4 *d_surv = nullptr;
     uint8_t *d_frames = nullptr;
     uint32_t *d_segq = nullptr, *d_gitems = nullptr;
     GExtRec *d_gext = nullptr;
@@ -1735,7 +1822,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     // K2a/K2b/K3 run per chunk of reads so that the frame store and the candidate queue stay bounded
     const int fstride = frame_stride(maxm);
     int64_t chunk = 2000000, cand_per_read = 96;
-    if (const char *e = getenv("MCX_CHUNK_READS")) chunk = std::max(1, atoi(e));
+    if (const char *e = getenv("MCX_CHUNK_READS")) chunk = std::min(2700000, std::max(1, atoi(e)));   // frame rows < 2^24
     if (const char *e = getenv("MCX_CAND_PER_READ")) cand_per_read = std::max(1, atoi(e));
     chunk = std::min<int64_t>(chunk, std::max<int64_t>(n_search, 1));
     {
@@ -1884,12 +1971,14 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         C.keys = ctx->d_keys; C.n = ns; C.L = P.read_length; C.min_report = P.min_report_raw;
         C.db = ctx->db; C.keep = ctx->d_keep; C.nrep = ctx->d_nrep; C.bestkey = ctx->d_bestkey;
         C.best_subject = ctx->d_best; C.acc = ctx->d_acc; C.aln_by_len = ctx->d_abl;
+        C.caplist = ctx->d_hflag; C.n_cap = ctx->d_cnt + 15;
         const unsigned cb = (unsigned)((ns + 255) / 256);
         k_cls_groups<<<cb, 256, 0, st>>>(C);
         k_cls_cap<<<cb, 256, 0, st>>>(C);
+        k_cls_cap_apply<4><<<148, 128, 0, st>>>(C);
         k_cls_filter<<<cb, 256, 0, st>>>(C);
         k_cls_sum<<<cb, 256, 0, st>>>(C);
-        ctx->launches += 4;
+        ctx->launches += 5;
     }
     CK(cudaEventRecord(ctx->ev[6], st));
     std::vector<unsigned long long> acc(3 + 2 * MCX_N_FAM), abl((size_t)MCX_N_FAM * MCX_LEN_BINS);

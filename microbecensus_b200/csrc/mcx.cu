@@ -66,10 +66,8 @@ struct DevDB {
     const int32_t *off;
     const uint8_t *res;
     const uint8_t *fam;
-    const uint32_t *hkey[N_PAT];   // open-addressing tables, 0xffffffff = empty
-    const uint32_t *hval[N_PAT];   // first posting of the word
-    uint32_t hmask[N_PAT];
-    int hshift[N_PAT];
+    const uint2 *htab;             // N_PAT open-addressing tables of 2^hbits slots, one after the other: x = word code
+    int hbits;                     // (0xffffffff = empty), y = 25-bit posting start | 7-bit (count - 1)
     const uint32_t *post;          // (subject << 11 | position), bit 31 = last posting of the word
     const uint32_t *bloom;         // 2^28-bit presence filter over (pattern, word): absorbs ~97 % of the probes in L2
 };
@@ -616,6 +614,9 @@ __device__ __forceinline__ int warp_scan_add(int v, int lane) {
 // compacted into a per-warp list and resolved by as many lanes in parallel: table slot, posting list, then ONE
 // reservation for the warp and a cooperative, coalesced copy of all postings into the candidate queue.  (First
 // version resolved hits inside the per-lane loop: ~1.3 lanes active on four dependent memory round trips per hit.)
+// (Tried and measured slower, 5.9 -> 8.8 ms: letting the filter passes wait in a per-warp ring until 32 of them can do
+// their table lookups together.  The kernel as it stands issues at 66 % of peak; the ring version executes 27 % fewer
+// instructions but stalls on the MIO pipe (shuffles, shared-memory traffic of the ring) and issues at 24 %.)
 template <int NT>
 __global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -685,12 +686,14 @@ __global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
                     const uint32_t c = qcode[t];
                     meta = qmeta[t];
                     const int p = meta & 7;
-                    const uint32_t *__restrict__ hk = A.db.hkey[p];
-                    uint32_t sl = (c * 2654435761u) >> A.db.hshift[p];
-                    uint32_t k = __ldg(hk + sl);
-                    while (k != 0xffffffffu && k != c) { sl = (sl + 1) & A.db.hmask[p]; k = __ldg(hk + sl); }
-                    if (k == c) {
-                        const uint32_t v = __ldg(A.db.hval[p] + sl);
+                    // key and value share an 8-byte slot: one load per probe, no second round trip for the value
+                    const uint2 *__restrict__ tb = A.db.htab + ((size_t)p << A.db.hbits);
+                    const uint32_t hmask = (1u << A.db.hbits) - 1u;
+                    uint32_t sl = (c * 2654435761u) >> (32 - A.db.hbits);
+                    uint2 kv = __ldg(tb + sl);
+                    while (kv.x != 0xffffffffu && kv.x != c) { sl = (sl + 1) & hmask; kv = __ldg(tb + sl); }
+                    if (kv.x == c) {
+                        const uint32_t v = kv.y;
                         pi = v & 0x1ffffffu;                              // 25-bit start, 7-bit (count - 1)
                         cnt = (v >> 25) + 1;
                         if ((v >> 25) == 127) { cnt = __ldg(A.db.post + pi); ++pi; }   // longer lists start with their length
@@ -744,6 +747,10 @@ struct ExtArgs {
     unsigned long long cap_surv;
 };
 
+// (Tried and measured slower -- 5.1 -> 5.4 ms at 100 bp, 9.4 -> 19.3 ms at 150 bp: copying the frame row and the subject
+// residues on the candidate's diagonal into shared memory up front, with all word loads in flight together.  Three in
+// four candidates are rejected after looking at a dozen residues; staging whole rows for all of them costs more
+// than the dependent byte loads of the few that walk far.)
 template <int NT>
 __global__ void __launch_bounds__(NT) k_extend(ExtArgs A) {
     __shared__ __align__(4) int8_t s_bl[21 * 32];
@@ -938,7 +945,7 @@ struct GapArgs {
     const uint8_t *frames;         // frame store of the chunk the survivors came from
     const uint4 *surv;             // survivors [first, first + n_surv) of the global list
     int64_t first, n_surv;
-    uint32_t *items;               // work list: (survivor - first) << 1 | direction
+    unsigned long long *items;     // work list: sort key << 32 | (survivor - first) << 1 | direction
     unsigned long long *n_items;
     GExtRec *ext;                  // [2 * (survivor - first) + direction], zeroed before the launch
     mcx_hit *hsp;
@@ -952,6 +959,7 @@ struct GapArgs {
 __global__ void k_gap_list(GapArgs A) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool f = false, b = false;
+    uint32_t kf = 0, kb = 0;
     if (g < A.n_surv) {
         const Surv v = surv_unpack(A.surv[A.first + g]);
         if (v.score >= 49) {
@@ -960,6 +968,10 @@ __global__ void k_gap_list(GapArgs A) {
             const int t1 = v.t0 + (v.q1 - v.q0);
             f = (m - (v.q1 + 1) > 2) && (n - (t1 + 1) > 2);
             b = (v.q0 > 2) && (v.t0 > 2);
+            // sort key: longest remaining query stretch first (the rows the DP can run over); threads of a warp
+            // then finish at similar times
+            kf = 255u - (uint32_t)min(m - (v.q1 + 1), 255);
+            kb = 255u - (uint32_t)min((int)v.q0, 255);
         }
     }
     const int lane = threadIdx.x & 31;
@@ -970,8 +982,8 @@ __global__ void k_gap_list(GapArgs A) {
     if (lane == 0) base = atomicAdd(A.n_items, (unsigned long long)tot);
     base = __shfl_sync(0xffffffffu, base, 0);
     const uint32_t lt = (1u << lane) - 1;
-    if (f) A.items[base + __popc(mf & lt)] = (uint32_t)(g << 1);
-    if (b) A.items[base + __popc(mf) + __popc(mb & lt)] = (uint32_t)(g << 1) | 1u;
+    if (f) A.items[base + __popc(mf & lt)] = ((unsigned long long)kf << 32) | (uint32_t)(g << 1);
+    if (b) A.items[base + __popc(mf) + __popc(mb & lt)] = ((unsigned long long)kb << 32) | (uint32_t)(g << 1) | 1u;
 }
 
 // K3b: one thread per gapped extension, DP rows in local memory.  (Tried and measured slower on 2M x 100 bp: rows in
@@ -980,13 +992,13 @@ __global__ void k_gap_list(GapArgs A) {
 // First a score-only pass over all of them (two DP rows); only the ~20 % that
 // gain anything are queued for the second pass, which repeats the same DP carrying the alignment statistics.
 template <int NT, int GROW, bool STATS>
-__global__ void __launch_bounds__(NT) k_gap_dir(GapArgs A, const uint32_t *__restrict__ items, int64_t n_items,
-                                                uint32_t *__restrict__ items2, unsigned long long *n_items2) {
+__global__ void __launch_bounds__(NT) k_gap_dir(GapArgs A, const unsigned long long *__restrict__ items, int64_t n_items,
+                                                unsigned long long *__restrict__ items2, unsigned long long *n_items2) {
     const int64_t w = (int64_t)blockIdx.x * NT + threadIdx.x;
     bool again = false;
-    uint32_t item = 0;
+    uint32_t item = 0, cells_key = 0;
     if (w < n_items) {
-        item = items[w];
+        item = (uint32_t)items[w];
         const int64_t g = item >> 1;
         const int dir = item & 1;
         const Surv v = surv_unpack(A.surv[A.first + g]);
@@ -997,19 +1009,28 @@ __global__ void __launch_bounds__(NT) k_gap_dir(GapArgs A, const uint32_t *__res
         const uint8_t *t = A.db.res + o;
         const int q0 = v.q0, q1 = v.q1, t0 = v.t0, t1 = v.t0 + (v.q1 - v.q0);
         GExt e;
+        // the statistics pass stops with the row of the best cell found by the score pass: the DP is identical up to
+        // there, and the rows the X-drop explores past the best cell cannot change its statistics
+        int row_limit = 1 << 30;
+        if (STATS) row_limit = A.ext[2 * g + dir].eq;
         if (dir == 0) {
             int ql = m - (q1 + 1), tl = n - (t1 + 1);
             if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
-            gapped_xdrop<GROW, STATS>(fr, q1 + 1, 1, t + t1 + 1, 1, ql, tl, e);
+            gapped_xdrop<GROW, STATS>(fr, q1 + 1, 1, t + t1 + 1, 1, min(ql, row_limit), tl, e);
         } else {
             int ql = q0, tl = t0;
             if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
-            gapped_xdrop<GROW, STATS>(fr, q0 - 1, -1, t + t0 - 1, -1, ql, tl, e);
+            gapped_xdrop<GROW, STATS>(fr, q0 - 1, -1, t + t0 - 1, -1, min(ql, row_limit), tl, e);
         }
-        GExtRec r;
-        r.gain = e.gain; r.eq = (uint16_t)e.eq; r.et = (uint16_t)e.et; r.st = e.st; r.cells = (uint32_t)e.cells;
-        A.ext[2 * g + dir] = r;
+        if (STATS) {
+            A.ext[2 * g + dir].st = e.st;
+        } else {
+            GExtRec r;
+            r.gain = e.gain; r.eq = (uint16_t)e.eq; r.et = (uint16_t)e.et; r.st = e.st; r.cells = (uint32_t)e.cells;
+            A.ext[2 * g + dir] = r;
+        }
         again = !STATS && e.gain > 0;
+        cells_key = 65535u - (uint32_t)min(e.cells, 65535);      // the statistics pass repeats this DP: most cells first
     }
     if (!STATS) {
         const int lane = threadIdx.x & 31;
@@ -1018,7 +1039,7 @@ __global__ void __launch_bounds__(NT) k_gap_dir(GapArgs A, const uint32_t *__res
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(n_items2, (unsigned long long)__popc(ma));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (again) items2[base + __popc(ma & ((1u << lane) - 1))] = item;
+            if (again) items2[base + __popc(ma & ((1u << lane) - 1))] = ((unsigned long long)cells_key << 32) | item;
         }
     }
 }
@@ -1307,7 +1328,8 @@ struct mcx_ctx {
     // search buffers
     uint4 *d_surv = nullptr;
     uint8_t *d_frames = nullptr;
-    uint32_t *d_segq = nullptr, *d_gitems = nullptr;
+    uint32_t *d_segq = nullptr;
+    unsigned long long *d_gitems = nullptr;   // gapped work lists: three regions of 2 * survivors entries
     GExtRec *d_gext = nullptr;
     int64_t cap_gitems = 0, cap_gext = 0;
     int64_t cap_segq = 0, n_segq_last = 0;
@@ -1407,9 +1429,10 @@ static int build_index(mcx_ctx *ctx, const mcx_db *db) {
     for (int64_t g = 0; g < nres; ++g) red[(size_t)g] = db->res[g] < 20 ? MURPHY10[db->res[g]] : 10;
     std::vector<uint32_t> post_all, bloom((size_t)1 << BLOOM_WORD_BITS, 0u);
     post_all.reserve((size_t)nres * N_PAT);
+    std::vector<unsigned long long> ent[N_PAT];
+    size_t max_distinct = 0;
     for (int p = 0; p < N_PAT; ++p) {
-        std::vector<unsigned long long> ent;
-        ent.reserve((size_t)nres);
+        ent[p].reserve((size_t)nres);
         for (int s = 0; s < ns; ++s) {
             const int n = db->off[s + 1] - db->off[s];
             if (n >= 2048) return fail(ctx, MCX_EINVAL, "subject longer than 2047 residues");
@@ -1421,35 +1444,42 @@ static int build_index(mcx_ctx *ctx, const mcx_db *db) {
                     if (r[j + k] >= 10) { ok = false; break; }
                     c = c * 10 + r[j + k];
                 }
-                if (ok) ent.push_back(((unsigned long long)c << 32) | ((uint32_t)s << 11) | (uint32_t)j);
+                if (ok) ent[p].push_back(((unsigned long long)c << 32) | ((uint32_t)s << 11) | (uint32_t)j);
             }
         }
-        std::sort(ent.begin(), ent.end());
+        std::sort(ent[p].begin(), ent[p].end());
         size_t distinct = 0;
-        for (size_t k = 0; k < ent.size(); ++k) distinct += (k == 0 || (ent[k] >> 32) != (ent[k - 1] >> 32));
-        uint32_t size = 1024; int bits = 10;
-        while (size < distinct * 2) { size <<= 1; ++bits; }
-        std::vector<uint32_t> hk(size, 0xffffffffu), hv(size, 0);
-        for (size_t k = 0; k < ent.size();) {
-            const uint32_t code = (uint32_t)(ent[k] >> 32);
+        for (size_t k = 0; k < ent[p].size(); ++k) distinct += (k == 0 || (ent[p][k] >> 32) != (ent[p][k - 1] >> 32));
+        max_distinct = std::max(max_distinct, distinct);
+    }
+    // one table size for all patterns (load factor <= 0.5 for the fullest), slots of (key, value)
+    uint32_t size = 1024; int bits = 10;
+    while (size < max_distinct * 2) { size <<= 1; ++bits; }
+    std::vector<uint2> tab((size_t)N_PAT << bits, make_uint2(0xffffffffu, 0u));
+    for (int p = 0; p < N_PAT; ++p) {
+        uint2 *ht = tab.data() + ((size_t)p << bits);
+        const std::vector<unsigned long long> &en = ent[p];
+        for (size_t k = 0; k < en.size();) {
+            const uint32_t code = (uint32_t)(en[k] >> 32);
             size_t e = k;
-            while (e + 1 < ent.size() && (ent[e + 1] >> 32) == code) ++e;
+            while (e + 1 < en.size() && (en[e + 1] >> 32) == code) ++e;
             const uint32_t cnt = (uint32_t)(e - k + 1);
             const uint32_t h = bloom_hash(p, code);
             bloom[bloom_word(h)] |= bloom_mask(h);
             uint32_t slot = (code * 2654435761u) >> (32 - bits);
-            while (hk[slot] != 0xffffffffu) slot = (slot + 1) & (size - 1);
-            hk[slot] = code; hv[slot] = (uint32_t)post_all.size() | ((cnt > 127 ? 127u : cnt - 1) << 25);
+            while (ht[slot].x != 0xffffffffu) slot = (slot + 1) & (size - 1);
+            ht[slot] = make_uint2(code, (uint32_t)post_all.size() | ((cnt > 127 ? 127u : cnt - 1) << 25));
             if (cnt > 127) post_all.push_back(cnt);          // lists too long for the 7-bit field start with their length
-            for (size_t q = k; q <= e; ++q) post_all.push_back((uint32_t)(ent[q] & 0x7fffffffu) | (q == e ? 0x80000000u : 0u));
+            for (size_t q = k; q <= e; ++q) post_all.push_back((uint32_t)(en[q] & 0x7fffffffu) | (q == e ? 0x80000000u : 0u));
             k = e + 1;
         }
-        uint32_t *dk = nullptr, *dv = nullptr;
-        CK(dev_alloc(&dk, size)); ctx->db_allocs.push_back(dk);
-        CK(dev_alloc(&dv, size)); ctx->db_allocs.push_back(dv);
-        CK(cudaMemcpy(dk, hk.data(), size * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(dv, hv.data(), size * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        ctx->db.hkey[p] = dk; ctx->db.hval[p] = dv; ctx->db.hmask[p] = size - 1; ctx->db.hshift[p] = 32 - bits;
+        std::vector<unsigned long long>().swap(ent[p]);
+    }
+    {
+        uint2 *dt = nullptr;
+        CK(dev_alloc(&dt, tab.size())); ctx->db_allocs.push_back(dt);
+        CK(cudaMemcpy(dt, tab.data(), tab.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+        ctx->db.htab = dt; ctx->db.hbits = bits;
     }
     if (post_all.size() >= (1u << 25)) return fail(ctx, MCX_EINVAL, "seed index too large for 25-bit posting offsets");
     uint32_t *dp = nullptr;
@@ -1912,7 +1942,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             G.L = P.read_length; G.fstride = fstride; G.db = ctx->db; G.frames = ctx->d_frames; G.surv = ctx->d_surv;
             G.first = (int64_t)surv_before; G.n_surv = (int64_t)(n_surv - surv_before);
             G.hsp = ctx->d_hsp; G.keys = ctx->d_keys; G.idx = ctx->d_idx; G.counters = ctx->d_cnt + 10;
-            if ((rc = ensure(ctx, &ctx->d_gitems, &ctx->cap_gitems, 4 * G.n_surv)) != MCX_OK) return rc;
+            if ((rc = ensure(ctx, &ctx->d_gitems, &ctx->cap_gitems, 6 * G.n_surv)) != MCX_OK) return rc;
             if ((rc = ensure(ctx, &ctx->d_gext, &ctx->cap_gext, 2 * G.n_surv)) != MCX_OK) return rc;
             G.items = ctx->d_gitems; G.ext = ctx->d_gext; G.n_items = ctx->d_cnt + 13;
             CK(cudaMemsetAsync(ctx->d_gext, 0, (size_t)(2 * G.n_surv) * sizeof(GExtRec), st));
@@ -1922,23 +1952,35 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             CK(cudaMemcpyAsync(&n_items, ctx->d_cnt + 13, sizeof n_items, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             if (n_items > 0) {
-                uint32_t *items2 = ctx->d_gitems + G.n_surv * 2;     // second half of the work-list buffer
+                // work lists sorted by expected size (cub radix sort on the key byte / half-word above the item)
+                unsigned long long *list1 = ctx->d_gitems + G.n_surv * 2, *items2 = ctx->d_gitems + G.n_surv * 4, *list2 = ctx->d_gitems;
+                {
+                    size_t tb = 0;
+                    cub::DeviceRadixSort::SortKeys(nullptr, tb, G.items, list1, (int)n_items, 32, 40, st);
+                    if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
+                    cub::DeviceRadixSort::SortKeys(ctx->d_temp, tb, G.items, list1, (int)n_items, 32, 40, st);
+                }
                 CK(cudaMemsetAsync(ctx->d_cnt + 14, 0, sizeof(unsigned long long), st));
                 const unsigned gb = (unsigned)((n_items + 127) / 128);
                 const int grow = maxm + GAP_SLACK + 2;
-                if (grow <= 104) k_gap_dir<128, 104, false><<<gb, 128, 0, st>>>(G, G.items, (int64_t)n_items, items2, ctx->d_cnt + 14);
-                else if (grow <= 152) k_gap_dir<128, 152, false><<<gb, 128, 0, st>>>(G, G.items, (int64_t)n_items, items2, ctx->d_cnt + 14);
-                else k_gap_dir<128, MAX_FRAME + GAP_SLACK + 2, false><<<gb, 128, 0, st>>>(G, G.items, (int64_t)n_items, items2, ctx->d_cnt + 14);
+                if (grow <= 104) k_gap_dir<128, 104, false><<<gb, 128, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + 14);
+                else if (grow <= 152) k_gap_dir<128, 152, false><<<gb, 128, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + 14);
+                else k_gap_dir<128, MAX_FRAME + GAP_SLACK + 2, false><<<gb, 128, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + 14);
                 unsigned long long n2 = 0;
                 CK(cudaMemcpyAsync(&n2, ctx->d_cnt + 14, sizeof n2, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
                 if (n2 > 0) {
+                    size_t tb = 0;
+                    cub::DeviceRadixSort::SortKeys(nullptr, tb, items2, list2, (int)n2, 32, 48, st);
+                    if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
+                    cub::DeviceRadixSort::SortKeys(ctx->d_temp, tb, items2, list2, (int)n2, 32, 48, st);
                     const unsigned gb2 = (unsigned)((n2 + 127) / 128);
-                    if (grow <= 104) k_gap_dir<128, 104, true><<<gb2, 128, 0, st>>>(G, items2, (int64_t)n2, nullptr, nullptr);
-                    else if (grow <= 152) k_gap_dir<128, 152, true><<<gb2, 128, 0, st>>>(G, items2, (int64_t)n2, nullptr, nullptr);
-                    else k_gap_dir<128, MAX_FRAME + GAP_SLACK + 2, true><<<gb2, 128, 0, st>>>(G, items2, (int64_t)n2, nullptr, nullptr);
-                    ++ctx->launches;
+                    if (grow <= 104) k_gap_dir<128, 104, true><<<gb2, 128, 0, st>>>(G, list2, (int64_t)n2, nullptr, nullptr);
+                    else if (grow <= 152) k_gap_dir<128, 152, true><<<gb2, 128, 0, st>>>(G, list2, (int64_t)n2, nullptr, nullptr);
+                    else k_gap_dir<128, MAX_FRAME + GAP_SLACK + 2, true><<<gb2, 128, 0, st>>>(G, list2, (int64_t)n2, nullptr, nullptr);
+                    ctx->launches += 3;
                 }
+                ctx->launches += 2;
                 n_gapped_total += n_items;
             }
             k_gap_finish<<<(unsigned)((G.n_surv + 255) / 256), 256, 0, st>>>(G);

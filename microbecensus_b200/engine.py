@@ -226,14 +226,15 @@ def dna_coords(L, frame, q0, q1):
 
 
 def format_m8(hits, markers, read_length, read_names=None):
-    """m8 lines (RAPsearch2 layout, -b 0 subject coordinates; log10 E is not computed and printed as 0)."""
-    from .markers import bits_printed
+    """m8 lines in RAPsearch2's layout (the file search_seqs leaves for parse_rapsearch, mc.py:391-398): -b 0
+    subject coordinates, identity with six significant digits, log10 E and bit score with two decimals."""
+    from .markers import bits_printed, log10_evalue_printed
     lines = []
     for h in hits:
         d = dict(zip(HIT_FIELDS, (int(x) for x in h)))
         qs, qe = dna_coords(read_length, d["frame"], d["q0"], d["q1"])
         name = str(d["read"]) if read_names is None else read_names[d["read"]]
-        lines.append("%s\t%s\t%g\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%s\t%.2f" % (
+        lines.append("%s\t%s\t%g\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%s\t%s" % (
             name, markers.names[d["subject"]], 100.0 * d["ident"] / d["aln"], d["aln"], d["mism"], d["gapo"],
-            qs, qe, d["t0"], d["t1"], "0", bits_printed(d["score"])))
+            qs, qe, d["t0"], d["t1"], "%g" % log10_evalue_printed(d["score"], read_length), "%g" % bits_printed(d["score"])))
     return lines

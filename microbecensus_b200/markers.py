@@ -21,6 +21,31 @@ STAT_NAMES = ("hits", "cov", "aln")
 # The floor only decides which HSPs count as "reported"; every family cutoff of pars.map lies at or above it.
 _REPORT_FLOOR = {50: 47, 60: 48, 400: 50, 450: 51, 500: 52}
 
+# log10(K * search space) of RAPsearch2's E-values by read length: log10 E = LOG10_KN[L] - 0.267 S log10(e).
+# Fitted from the binary's own output (tools/blackbox/evalue_space.py): every m8 line bounds the constant to an
+# interval 0.01 wide, a few thousand lines pin it to ~1e-4.  The search space is not the textbook (m - l)(n - N l);
+# it is flat (~1.01e8) from 80 to 350 bp and the same for all six frames of a read.  The floors above follow from it:
+# smallest S with log10 E <= 1.
+LOG10_KN = {50: 6.42177, 60: 6.51877, 70: 6.57940, 80: 6.61364, 90: 6.60555, 100: 6.61851, 110: 6.61234, 120: 6.62247,
+            130: 6.61617, 140: 6.60965, 150: 6.61891, 175: 6.61844, 200: 6.61687, 225: 6.61174, 250: 6.60781,
+            300: 6.60900, 350: 6.62083, 400: 6.75603, 450: 6.85623, 500: 6.93852}
+
+
+def log10_evalue(raw, read_length):
+    """log10 of the E-value RAPsearch2 assigns to a single HSP of raw score `raw` at this read length."""
+    return LOG10_KN[int(read_length)] - 0.267 * raw * math.log10(math.e)
+
+
+def log10_evalue_printed(raw, read_length):
+    """... as its m8 shows it: two decimals, rounded away from zero, except that values between -0.01 and 0 print as 0
+    (observed on ~200,000 lines at all 20 lengths: positive values are rounded up, negative ones down, and the three
+    (length, score) pairs with -0.01 < log10 E < 0 -- S = 57 at 90, 250 and 300 bp -- print "0")."""
+    h = log10_evalue(raw, read_length) * 100.0
+    if h > 0:
+        return math.ceil(h - 1e-9) / 100.0
+    t = math.trunc(h + 1e-9)
+    return (t - 1) / 100.0 if t < 0 else 0.0
+
 
 def bits_printed(raw):
     """Bit score as RAPsearch2 prints it: (0.267 S + ln(1/0.041)) / ln 2 with two decimals."""

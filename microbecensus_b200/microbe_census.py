@@ -261,6 +261,22 @@ def concat_batches(batches):
     return ReadBatch(bases, np.concatenate(offs), quals)
 
 
+def _dump_m8(eng, fh, read_length, first_id):
+    """Append the reported HSPs of the last search to `fh` in RAPsearch2's m8 layout (the <tmp>.m8 of mc.py:375 that
+    parse_rapsearch reads): queries are named by their running index among the sampled reads, as process_seqfile
+    names them (mc.py:352), lines grouped by query in input order, best score first."""
+    from .engine import format_m8
+    hits = eng.hits()
+    if len(hits) == 0:
+        return
+    codes, _ = eng.qc_export(False)
+    rank = np.cumsum(codes == 0) - 1 + first_id
+    order = np.lexsort((hits[:, 1], -hits[:, 3], hits[:, 0]))
+    names = {int(r): str(int(rank[r])) for r in np.unique(hits[:, 0])}
+    for line in format_m8(hits[order], eng.markers, read_length, names):
+        fh.write(line + "\n")
+
+
 # ------------------------------------------------------------------------------------------------ the GPU seam
 def sample_and_search(args, engine=None):
     """process_seqfile + search_seqs + classify_reads + aggregate_hits (mc.py:611-620) on the GPU.
@@ -294,6 +310,11 @@ def sample_and_search(args, engine=None):
         return batch if fastq else ReadBatch(batch.bases, batch.offsets, None)
 
     want_total = args.get("no_equivs") is False      # the CLI will ask count_bases() next: finish the files in this pass
+    # optional m8-compatible dump of the reported HSPs (args["m8_out"] or $MCX_M8_OUT; single-GPU runs)
+    m8_path = args.get("m8_out") or os.environ.get("MCX_M8_OUT")
+    m8 = open(m8_path, "w") if m8_path and world == 1 else None
+    if m8:
+        m8.write("# Fields: Query\tSubject\tidentity\taln-len\tmismatch\tgap-openings\tq.start\tq.end\ts.start\ts.end\tlog(e-value)\tbit-score\n")
     if world > 1 or args.get("filter_dups"):
         # -d and the sharded run need the whole read stream at once (duplicates are decided over all reads)
         batch = checked(concat_batches([load_reads(f) for f in args["seqfiles"]]))
@@ -306,6 +327,8 @@ def sample_and_search(args, engine=None):
         else:
             eng.push(batch)
             res = eng.search(-1 if nreads is None else nreads)
+            if m8:
+                _dump_m8(eng, m8, L, 0)
     else:
         # stream: batches of records go to the GPU as they are parsed; reading stops with the read that fills -n
         # (mc.py:356) and the additive results of the batches are summed
@@ -321,6 +344,8 @@ def sample_and_search(args, engine=None):
                         break
                     eng.push(batch)
                     part = eng.search(-1 if remaining is None else remaining)
+                    if m8:
+                        _dump_m8(eng, m8, L, 0 if res is None else res.sampled_reads)
                     if remaining is not None:
                         remaining -= part.sampled_reads
                     if res is None:
@@ -334,6 +359,8 @@ def sample_and_search(args, engine=None):
         if res is None:
             eng.push(ReadBatch(np.zeros(0, np.uint8), np.zeros(1, np.int64), None if not fastq else np.zeros(0, np.uint8)))
             res = eng.search(-1)
+    if m8:
+        m8.close()
     if res.sampled_reads == 0:
         sys.exit("\nError! No reads remaining after filtering!")
     args["sampled_reads"] = res.sampled_reads

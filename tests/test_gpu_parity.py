@@ -209,3 +209,44 @@ def test_verdict_export_import_roundtrip(eng, oracle, markers):
     assert qc["kept"] == sampled and qc["dups"] == cnt["dups"]
     res = eng.search(-1)
     assert (res.sampled_reads, res.dups, res.low_qual, res.too_short) == (sampled, cnt["dups"], cnt["low_qual"], cnt["too_short"])
+
+
+@pytest.mark.gpu
+def test_streamed_batches_equal_one_push(eng, markers, tmp_path, monkeypatch):
+    """run_pipeline reads the files through libmcxio in batches; the sums of the batches, the -n cut across batch and
+    file boundaries and count_bases are those of a single push of everything."""
+    seqs = golden_io.read_fasta("meta.fa.gz")
+    a, b = tmp_path / "a.fa", tmp_path / "b.fa.gz"
+    a.write_text("".join(">r%d\n%s\n" % (i, s) for i, s in enumerate(seqs[:300])))
+    import gzip
+    with gzip.open(b, "wt") as fh:
+        fh.write("".join(">r%d x\n%s\n%s\n" % (i, s[:60], s[60:]) for i, s in enumerate(seqs[300:])))
+    results = []
+    for per_batch, nreads in (("1000000", None), ("64", None), ("64", 411), ("7", 411)):
+        monkeypatch.setenv("MCX_BATCH_READS", per_batch)
+        args = {"seqfiles": [str(a), str(b)], "verbose": False, "nreads": nreads, "read_length": 100, "no_equivs": False}
+        est, out = mcb.run_pipeline(args)
+        results.append((nreads, est, out["sampled_reads"], mcb.count_bases(out)))
+    assert results[0][1:] == results[1][1:] and results[2][1:] == results[3][1:]
+    assert results[0][2] == len(seqs) and results[2][2] == 411
+    assert results[0][3] == sum(len(s) for s in seqs)
+    one = ReadBatch.from_strings(seqs)
+    eng.set_params(100)
+    eng.push(one)
+    res = eng.search(411)
+    assert mcb.estimate_average_genome_size({"read_length": 100, "sampled_reads": 411, "verbose": False}, None, res.agg_hits()) == results[2][1]
+
+
+@pytest.mark.gpu
+def test_m8_dump_matches_rapsearch_lines(eng, markers, tmp_path):
+    """args['m8_out']: the m8-compatible dump.  On the reference's own reads >= 99 % of RAPsearch2's
+    single-HSP lines appear in it character for character, under the query ids process_seqfile assigns."""
+    import gzip
+    path = os.path.join(golden_io.GOLD, "meta.fa.gz")
+    out = tmp_path / "hits.m8"
+    mcb.run_pipeline({"seqfiles": [path], "verbose": False, "nreads": None, "read_length": 100, "m8_out": str(out)})
+    ours = set(l.rstrip("\n") for l in open(out) if l[0] != "#")
+    ref = [l.rstrip("\n") for l in gzip.open(os.path.join(golden_io.GOLD, "meta.L100.m8.gz"), "rt") if l[0] != "#"]
+    single = [l for l in ref if len(l.split("\t")[10].split(".")[-1]) <= 2]
+    same = sum(l in ours for l in single)
+    assert same >= 0.99 * len(single), (same, len(single))

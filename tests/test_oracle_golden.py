@@ -155,3 +155,27 @@ def test_alignment_coverage_matches_reference_formula(oracle):
         aln = int(rng.integers(5, 70))
         got = oracle.lib.oc_alignment_coverage(float(L), float(a), float(b), float(t0), float(t1), float(aln), float(tlen))
         assert got == ref_cov(L, float(a), float(b), float(t0), float(t1), float(aln), float(tlen))
+
+
+@pytest.mark.parametrize("fname,name,L", SETS)
+def test_m8_text_matches_rapsearch_character_for_character(oracle, markers, fname, name, L):
+    """engine.format_m8 (the m8-compatible dump) on the oracle's HSPs: every line whose alignment
+    RAPsearch2 also printed is the same TEXT -- identity with six significant digits, log10 E with two decimals
+    rounded away from zero from the fitted search space (markers.LOG10_KN), bit score with two decimals."""
+    import gzip, os
+    from microbecensus_b200.engine import format_m8, HIT_FIELDS
+    seqs = load_seqs(fname, L)
+    hits, _, _ = oracle_lines(oracle, markers, seqs, L)
+    col = [OC_HIT_FIELDS.index(k) for k in HIT_FIELDS]
+    ours = set(format_m8(hits[:, col], markers, L))
+    ref_lines = [l.rstrip("\n") for l in gzip.open(os.path.join(golden_io.GOLD, "%s.L%d.m8.gz" % (name, L)), "rt") if l[0] != "#"]
+    # single-HSP lines print log10 E with two decimals; sum-statistics lines (six digits) are not produced here
+    single = [l for l in ref_lines if len(l.split("\t")[10].split(".")[-1]) <= 2]
+    same = sum(l in ours for l in single)
+    assert same >= 0.99 * len(single), (same, len(single))
+    # and wherever the alignment is the same, so is every printed number
+    key = lambda l: tuple(l.split("\t")[i] for i in (0, 1, 3, 6, 7, 8, 9))
+    ours_by_key = {key(l): l for l in ours}
+    for l in single:
+        if key(l) in ours_by_key and ours_by_key[key(l)].split("\t")[11] == l.split("\t")[11]:
+            assert ours_by_key[key(l)] == l

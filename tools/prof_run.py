@@ -3,7 +3,9 @@
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from microbecensus_b200 import synth
+from microbecensus_b200 import synth, _lib
+if os.environ.get("MCX_LIB"):                 # A/B runs against another build of the library
+    _lib.LIB_PATH = os.environ["MCX_LIB"]
 from microbecensus_b200.engine import MarkerSearch
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 100

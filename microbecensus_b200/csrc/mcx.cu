@@ -745,6 +745,9 @@ struct ExtArgs {
     uint4 *surv;
     unsigned long long *n_surv;
     unsigned long long cap_surv;
+    unsigned long long *seen;      // open-addressing set of the HSP keys appended in this launch, ~0 = empty
+    unsigned long long seen_mask;
+    int seen_shift;
 };
 
 // (Tried and measured slower -- 5.1 -> 5.4 ms at 100 bp, 9.4 -> 19.3 ms at 150 bp: copying the frame row and the subject
@@ -823,6 +826,19 @@ __global__ void __launch_bounds__(NT) k_extend(ExtArgs A) {
     }
     const int total = score0 + gf + gb;
     if (total < A.thr_report) return;
+    const int hq0 = qb - be, hq1 = qb + len + fe - 1, ht0 = sb - be;
+    {   // An HSP is found once from every seed it contains; only its first copy goes on (the gapped extensions of
+        // the copies would be identical).  64-bit key: frame row, subject, (q0, q1) as a triangular index, t0.
+        const unsigned long long key = ((unsigned long long)c.gframe << 40) | ((unsigned long long)s << 25) |
+                                       ((unsigned long long)(hq1 * (hq1 + 1) / 2 + hq0) << 11) | (unsigned long long)ht0;
+        unsigned long long slot = (key * 0x9E3779B97F4A7C15ull) >> A.seen_shift;
+        for (int probe = 0; probe < 4096; ++probe) {
+            const unsigned long long old = atomicCAS(A.seen + slot, ~0ull, key);
+            if (old == ~0ull) break;
+            if (old == key) return;
+            slot = (slot + 1) & A.seen_mask;
+        }
+    }
     const uint32_t mask = __activemask();
     const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
     unsigned long long base = 0;
@@ -832,8 +848,8 @@ __global__ void __launch_bounds__(NT) k_extend(ExtArgs A) {
     if (idx >= A.cap_surv) return;
     Surv v;
     v.read = A.kept[A.first + c.gframe / 6u]; v.subject = s; v.frame = frame;
-    v.q0 = qb - be; v.q1 = qb + len + fe - 1;
-    v.ident = id0 + fid + bid; v.t0 = sb - be;
+    v.q0 = hq0; v.q1 = hq1;
+    v.ident = id0 + fid + bid; v.t0 = ht0;
     v.score = total;
     v.gframe = c.gframe;
     A.surv[idx] = surv_pack(v);
@@ -1329,6 +1345,8 @@ struct mcx_ctx {
     uint4 *d_surv = nullptr;
     uint8_t *d_frames = nullptr;
     uint32_t *d_segq = nullptr;
+    unsigned long long *d_seen = nullptr;     // k_extend's duplicate filter
+    int64_t cap_seen = 0;
     unsigned long long *d_gitems = nullptr;   // gapped work lists: three regions of 2 * survivors entries
     GExtRec *d_gext = nullptr;
     int64_t cap_gitems = 0, cap_gext = 0;
@@ -1611,7 +1629,7 @@ extern "C" void mcx_destroy(mcx_ctx *ctx) {
     if (ctx->own_reads) { cudaFree(ctx->d_bases); cudaFree(ctx->d_quals); cudaFree(ctx->d_offs); }
     void *bufs[] = {ctx->d_code, ctx->d_flag, ctx->d_pos, ctx->d_kept, ctx->d_surv, ctx->d_hsp, ctx->d_hits_out,
                     ctx->d_keys, ctx->d_idx, ctx->d_best, ctx->d_hflag, ctx->d_hpos, ctx->d_keep, ctx->d_cnt,
-                    ctx->d_acc, ctx->d_abl, ctx->d_temp, ctx->d_frames, ctx->d_cand, ctx->d_segq, ctx->d_qcnt, ctx->d_fp, ctx->d_gitems, ctx->d_gext, ctx->d_nrep, ctx->d_bestkey};
+                    ctx->d_acc, ctx->d_abl, ctx->d_temp, ctx->d_frames, ctx->d_cand, ctx->d_segq, ctx->d_qcnt, ctx->d_fp, ctx->d_gitems, ctx->d_gext, ctx->d_nrep, ctx->d_bestkey, ctx->d_seen};
     for (void *p : bufs) if (p) cudaFree(p);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -1925,6 +1943,13 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             E.qstart[0] = 0;
             for (int q = 0; q < NQ; ++q) E.qstart[q + 1] = E.qstart[q] + qfill[q];
             E.n_surv = ctx->d_cnt + 8; E.cap_surv = (unsigned long long)ctx->cap_surv;
+            {   // duplicate filter: at least two slots per survivor the list can take
+                int bits = 16;
+                while ((1ll << bits) < 2 * ctx->cap_surv) ++bits;
+                if ((rc = ensure(ctx, &ctx->d_seen, &ctx->cap_seen, 1ll << bits)) != MCX_OK) return rc;
+                CK(cudaMemsetAsync(ctx->d_seen, 0xff, (size_t)(1ll << bits) * sizeof(unsigned long long), st));
+                E.seen = ctx->d_seen; E.seen_mask = (1ull << bits) - 1; E.seen_shift = 64 - bits;
+            }
             k_extend<256><<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(E);
             ++ctx->launches;
             CK(cudaMemcpyAsync(&n_surv, ctx->d_cnt + 8, sizeof n_surv, cudaMemcpyDeviceToHost, st));

@@ -329,7 +329,7 @@ def main():
                 "peak_source": peak_src, "algorithmic_bytes_per_read": bytes_per_read, "kernel_ms": k_ms,
                 "kernel_timing": "CUDA events around the k_probe launch on the library's stream (mcx_timings[2])",
                 "kernel_share_of_step": k_ms / (t_dev * 1e3)}
-    prof = os.path.join(ROOT, "profiles", "r01_k_seed_traffic.json")
+    prof = os.path.join(ROOT, "profiles", "r01_k_probe_traffic.json")
     if os.path.exists(prof):
         try:
             roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")

@@ -134,8 +134,8 @@ int  mcx_get_hits(mcx_ctx *ctx, mcx_hit *out, int64_t cap, int64_t *n);
 int  mcx_get_classified(mcx_ctx *ctx, int32_t *best_subject, int64_t n);
 
 /* device time (ms, CUDA events on the context's stream) of the stages of the last push/search:
- * [0] h2d copy, [1] k_qc + compaction, [2] k_probe, [3] k_gapped, [4] sort, [5] k_classify, [6] d2h, [7] k_extend,
- * [8] k_frames, [9] k_seg; and the number of kernel launches */
+ * [0] h2d copy, [1] k_qc + compaction, [2] k_probe, [3] gapped stage (k_gap_*), [4] sort, [5] classifier (k_cls_*),
+ * [6] d2h, [7] k_seed + k_walk, [8] k_frames, [9] k_seg; and the number of kernel launches */
 int  mcx_timings(mcx_ctx *ctx, float ms[10], int64_t *launches);
 
 const char *mcx_last_error(mcx_ctx *ctx);

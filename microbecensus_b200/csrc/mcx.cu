@@ -1,17 +1,20 @@
 // mcx.cu -- libmcx.so: translated marker-gene search of MicrobeCensus on one B200 (sm_100a).
 //
-// One context = one GPU.  The hot path is five hand-written kernels (no CPU fallback anywhere):
+// One context = one GPU.  The hot path is a chain of hand-written kernels with compaction between every two stages
+// whose per-item work varies (no CPU fallback anywhere):
 //
-//   k_qc        read QC                      mc.py:265-279, 342-356      one warp per read, HBM-bound
-//   k_probe     6-frame translation + SEG + murphy10 seed-word lookup (RAPsearch2 BuildQHash / Searching /
-//               FindSeeds): one thread per (read, frame), frames staged in shared memory and written to a
-//               global frame store, word hits queued as candidates
-//   k_extend    seed growth, acceptance and ungapped X-drop extension (ExtendSeq2Set / AlignFwd / AlignBwd):
-//               one thread per candidate, survivors appended to the HSP list
-//   k_gapped    gapped X-drop extension with alignment statistics carried forward
-//               (RAPsearch2 AlignSeqs / AlignGapped / CalRes)   one thread per surviving HSP
-//   k_classify  HSP de-duplication per (read, subject), the three cutoffs, best hit per read and the
-//               per-family integer sums       mc.py:400-472              one thread per read segment
+//   k_qc          read QC                    mc.py:265-279, 342-356     one warp per read, HBM-bound
+//   k_frames      6-frame translation (RAPsearch2 BuildQHash) + "does any 12-window reach SEG's low cut?"
+//                 one thread per (read, frame); frames go to a global frame store
+//   k_seg         full SEG (Seg::segseq / Seg::trim) for the ~19 % of frames with such a window, one warp per frame
+//   k_probe       murphy10 seed-word lookup (Searching / FindSeeds): Bloom filter + hash tables, every posting of a
+//                 word hit queued as a candidate
+//   k_seed        seed growth and acceptance (ExtendSeq2Set), one thread per candidate
+//   k_walk        ungapped X-drop walks (AlignFwd / AlignBwd), one thread per accepted seed; duplicate HSPs dropped
+//   k_gap_list / k_gap_dir x2 / k_gap_finish   gapped X-drop extension (AlignSeqs / AlignGapped / CalRes): work list
+//                 sorted by size, score pass, statistics pass for the extensions that gained, HSP records + sort keys
+//   k_cls_groups / _cap / _cap_apply / _filter / _sum   HSP de-duplication per (read, subject), the 500-line cap, the
+//                 three cutoffs, best hit per read and the per-family integer sums    mc.py:400-472
 // plus CUB scans/sorts for compaction and ordering.  mc.py = /root/reference/microbe_census/
 // microbe_census.py; RAPsearch2 = the v2.15 binary it runs at mc.py:375 (behaviour pinned in DESIGN.md
 // and restated independently by oracle/mc_oracle.c, against which tests/ check every stage bit for bit).
@@ -745,6 +748,8 @@ struct ExtArgs {
     uint4 *surv;
     unsigned long long *n_surv;
     unsigned long long cap_surv;
+    uint4 *seedq;                  // accepted seeds (k_seed -> k_walk), at most n_cand
+    unsigned long long *n_seedq;
     unsigned long long *seen;      // open-addressing set of the HSP keys appended in this launch, ~0 = empty
     unsigned long long seen_mask;
     int seen_shift;
@@ -754,8 +759,19 @@ struct ExtArgs {
 // residues on the candidate's diagonal into shared memory up front, with all word loads in flight together.  Three in
 // four candidates are rejected after looking at a dozen residues; staging whole rows for all of them costs more
 // than the dependent byte loads of the few that walk far.)
+// Two kernels with a compacted queue between them: three in four candidates are rejected by k_seed, and the walks of
+// the rest are the long part -- in one kernel they ran with 8 of 32 lanes active.
+// accepted seed, 16 bytes: x frame row | y subject(15) sb(11) | z qb(8) len(8) score0(16) | w id0
+__device__ __forceinline__ uint4 seed_pack(uint32_t gframe, int s, int sb, int qb, int len, int score0, int id0) {
+    return make_uint4(gframe, (uint32_t)s | ((uint32_t)sb << 15), (uint32_t)qb | ((uint32_t)len << 8) | ((uint32_t)score0 << 16), (uint32_t)id0);
+}
+
+// (No duplicate filter here: the left-maximal rule for exact words and the one-window-per-position rule for the
+// substitution words already make every accepted stretch unique -- 74,491,397 of 74,491,397 at 2M x 150 bp.)
+// K2c: one thread per candidate: the cheap rejections, growth of the word to the maximal murphy10-identical stretch
+// and the seed acceptance test (ExtendSeq2Set 0x413fc4-0x414073); accepted seeds are queued for k_walk.
 template <int NT>
-__global__ void __launch_bounds__(NT) k_extend(ExtArgs A) {
+__global__ void __launch_bounds__(NT) k_seed(ExtArgs A) {
     __shared__ __align__(4) int8_t s_bl[21 * 32];
     for (int k = threadIdx.x; k < 21 * 32 / 4; k += NT) reinterpret_cast<uint32_t *>(s_bl)[k] = reinterpret_cast<const uint32_t *>(g_blosum)[k];
     __syncthreads();
@@ -789,6 +805,33 @@ __global__ void __launch_bounds__(NT) k_extend(ExtArgs A) {
         id0 += (a == b && a < 20);
     }
     if (score0 < SEED_MIN_SCORE || id0 < SEED_MIN_IDENT) return;
+    const uint32_t mask = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(A.n_seedq, (unsigned long long)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    A.seedq[base + __popc(mask & ((1u << lane) - 1))] = seed_pack(c.gframe, s, sb, qb, len, score0, id0);
+}
+
+// K2d: one thread per accepted seed: the ungapped X-drop walks both ways (AlignFwd / AlignBwd); HSPs reaching the
+// report floor are appended to the survivor list.
+template <int NT>
+__global__ void __launch_bounds__(NT) k_walk(ExtArgs A, int64_t n_seeds) {
+    __shared__ __align__(4) int8_t s_bl[21 * 32];
+    for (int k = threadIdx.x; k < 21 * 32 / 4; k += NT) reinterpret_cast<uint32_t *>(s_bl)[k] = reinterpret_cast<const uint32_t *>(g_blosum)[k];
+    __syncthreads();
+    const int64_t g = (int64_t)blockIdx.x * NT + threadIdx.x;
+    if (g >= n_seeds) return;
+    const uint4 sd = A.seedq[g];
+    const uint32_t gframe = sd.x;
+    const int s = (int)(sd.y & 0x7fffu), sb = (int)(sd.y >> 15), qb = (int)(sd.z & 0xffu), len = (int)((sd.z >> 8) & 0xffu);
+    const int score0 = (int)(sd.z >> 16), id0 = (int)sd.w;
+    const int frame = (int)(gframe % 6u);
+    const int m = (A.L - frame % 3) / 3;
+    const uint8_t *__restrict__ fr = A.frames + (int64_t)gframe * A.fstride;
+    const int32_t o = __ldg(A.db.off + s);
+    const int n = __ldg(A.db.off + s + 1) - o;
+    const uint8_t *__restrict__ t = A.db.res + o;
     // both walks start from the seed score; stop after a residue that leaves the running score below -20 or
     // at least 9 (> 8.94) under the best so far
     int fe = 0, fid = 0, gf = 0, be = 0, bid = 0, gb = 0;
@@ -829,7 +872,7 @@ __global__ void __launch_bounds__(NT) k_extend(ExtArgs A) {
     const int hq0 = qb - be, hq1 = qb + len + fe - 1, ht0 = sb - be;
     {   // An HSP is found once from every seed it contains; only its first copy goes on (the gapped extensions of
         // the copies would be identical).  64-bit key: frame row, subject, (q0, q1) as a triangular index, t0.
-        const unsigned long long key = ((unsigned long long)c.gframe << 40) | ((unsigned long long)s << 25) |
+        const unsigned long long key = ((unsigned long long)gframe << 40) | ((unsigned long long)s << 25) |
                                        ((unsigned long long)(hq1 * (hq1 + 1) / 2 + hq0) << 11) | (unsigned long long)ht0;
         unsigned long long slot = (key * 0x9E3779B97F4A7C15ull) >> A.seen_shift;
         for (int probe = 0; probe < 4096; ++probe) {
@@ -847,11 +890,11 @@ __global__ void __launch_bounds__(NT) k_extend(ExtArgs A) {
     const unsigned long long idx = base + __popc(mask & ((1u << lane) - 1));
     if (idx >= A.cap_surv) return;
     Surv v;
-    v.read = A.kept[A.first + c.gframe / 6u]; v.subject = s; v.frame = frame;
+    v.read = A.kept[A.first + gframe / 6u]; v.subject = s; v.frame = frame;
     v.q0 = hq0; v.q1 = hq1;
     v.ident = id0 + fid + bid; v.t0 = ht0;
     v.score = total;
-    v.gframe = c.gframe;
+    v.gframe = gframe;
     A.surv[idx] = surv_pack(v);
 }
 
@@ -1345,8 +1388,9 @@ struct mcx_ctx {
     uint4 *d_surv = nullptr;
     uint8_t *d_frames = nullptr;
     uint32_t *d_segq = nullptr;
-    unsigned long long *d_seen = nullptr;     // k_extend's duplicate filter
-    int64_t cap_seen = 0;
+    unsigned long long *d_seen = nullptr;     // k_walk's duplicate filter
+    uint4 *d_seedq = nullptr;                 // accepted seeds between k_seed and k_walk
+    int64_t cap_seen = 0, cap_seedq = 0;
     unsigned long long *d_gitems = nullptr;   // gapped work lists: three regions of 2 * survivors entries
     GExtRec *d_gext = nullptr;
     int64_t cap_gitems = 0, cap_gext = 0;
@@ -1629,7 +1673,7 @@ extern "C" void mcx_destroy(mcx_ctx *ctx) {
     if (ctx->own_reads) { cudaFree(ctx->d_bases); cudaFree(ctx->d_quals); cudaFree(ctx->d_offs); }
     void *bufs[] = {ctx->d_code, ctx->d_flag, ctx->d_pos, ctx->d_kept, ctx->d_surv, ctx->d_hsp, ctx->d_hits_out,
                     ctx->d_keys, ctx->d_idx, ctx->d_best, ctx->d_hflag, ctx->d_hpos, ctx->d_keep, ctx->d_cnt,
-                    ctx->d_acc, ctx->d_abl, ctx->d_temp, ctx->d_frames, ctx->d_cand, ctx->d_segq, ctx->d_qcnt, ctx->d_fp, ctx->d_gitems, ctx->d_gext, ctx->d_nrep, ctx->d_bestkey, ctx->d_seen};
+                    ctx->d_acc, ctx->d_abl, ctx->d_temp, ctx->d_frames, ctx->d_cand, ctx->d_segq, ctx->d_qcnt, ctx->d_fp, ctx->d_gitems, ctx->d_gext, ctx->d_nrep, ctx->d_bestkey, ctx->d_seen, ctx->d_seedq};
     for (void *p : bufs) if (p) cudaFree(p);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -1880,7 +1924,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         if ((rc = ensure(ctx, &ctx->d_segq, &ctx->cap_segq, chunk * 6 + 512)) != MCX_OK) return rc;
     }
     float ms_frames = 0, ms_seg = 0, ms_probe = 0, ms_ext = 0, ms_gap = 0;
-    unsigned long long n_surv = 0, n_cand_total = 0, n_gapped_total = 0;
+    unsigned long long n_surv = 0, n_cand_total = 0, n_gapped_total = 0, n_seeds_total = 0;
     for (int64_t first = 0; first < n_search; first += chunk) {
         const int64_t nr = std::min(chunk, n_search - first);
         CK(cudaMemsetAsync(ctx->d_qcnt, 0, NQ * sizeof(unsigned long long), st));
@@ -1935,14 +1979,28 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         }
         n_cand_total += n_cand;
         const unsigned long long surv_before = n_surv;
-        for (int attempt = 0; n_cand > 0; ++attempt) {
-            ExtArgs E;
-            E.kept = ctx->d_kept; E.first = first; E.L = P.read_length; E.fstride = fstride; E.thr_report = thr; E.db = ctx->db;
-            E.frames = ctx->d_frames; E.cand = ctx->d_cand; E.n_cand = (int64_t)n_cand; E.surv = ctx->d_surv;
-            E.cap_cand = (unsigned long long)(ctx->cap_cand / NQ);
-            E.qstart[0] = 0;
-            for (int q = 0; q < NQ; ++q) E.qstart[q + 1] = E.qstart[q] + qfill[q];
-            E.n_surv = ctx->d_cnt + 8; E.cap_surv = (unsigned long long)ctx->cap_surv;
+        ExtArgs E;
+        E.kept = ctx->d_kept; E.first = first; E.L = P.read_length; E.fstride = fstride; E.thr_report = thr; E.db = ctx->db;
+        E.frames = ctx->d_frames; E.cand = ctx->d_cand; E.n_cand = (int64_t)n_cand; E.surv = ctx->d_surv;
+        E.cap_cand = (unsigned long long)(ctx->cap_cand / NQ);
+        E.qstart[0] = 0;
+        for (int q = 0; q < NQ; ++q) E.qstart[q + 1] = E.qstart[q] + qfill[q];
+        E.n_surv = ctx->d_cnt + 8;
+        E.n_seedq = ctx->d_cnt + 9;
+        unsigned long long n_seeds = 0;
+        if (n_cand > 0) {
+            if ((rc = ensure(ctx, &ctx->d_seedq, &ctx->cap_seedq, (int64_t)n_cand)) != MCX_OK) return rc;
+            E.seedq = ctx->d_seedq;
+            CK(cudaMemsetAsync(ctx->d_cnt + 9, 0, sizeof(unsigned long long), st));
+            k_seed<256><<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(E);
+            ++ctx->launches;
+            CK(cudaMemcpyAsync(&n_seeds, ctx->d_cnt + 9, sizeof n_seeds, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+        }
+        n_seeds_total += n_seeds;
+        for (int attempt = 0; n_seeds > 0; ++attempt) {
+            E.surv = ctx->d_surv; E.cap_surv = (unsigned long long)ctx->cap_surv;
             {   // duplicate filter: at least two slots per survivor the list can take
                 int bits = 16;
                 while ((1ll << bits) < 2 * ctx->cap_surv) ++bits;
@@ -1950,7 +2008,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
                 CK(cudaMemsetAsync(ctx->d_seen, 0xff, (size_t)(1ll << bits) * sizeof(unsigned long long), st));
                 E.seen = ctx->d_seen; E.seen_mask = (1ull << bits) - 1; E.seen_shift = 64 - bits;
             }
-            k_extend<256><<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(E);
+            k_walk<256><<<(unsigned)((n_seeds + 255) / 256), 256, 0, st>>>(E, (int64_t)n_seeds);
             ++ctx->launches;
             CK(cudaMemcpyAsync(&n_surv, ctx->d_cnt + 8, sizeof n_surv, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -2058,7 +2116,8 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     CK(cudaGetLastError());
     R.reads_with_hits = (int64_t)acc[0]; R.reads_classified = (int64_t)acc[1]; R.n_hsp = (int64_t)acc[2];
     R.n_gapped = (int64_t)n_gapped_total; R.gapped_cells = (int64_t)gc[1];
-    if (getenv("MCX_DEBUG")) fprintf(stderr, "[mcx] gapped extensions %llu, with gain > 0: %llu, cells %llu\n", n_gapped_total, gc[0], gc[1]);
+    if (getenv("MCX_DEBUG")) fprintf(stderr, "[mcx] candidates %llu, accepted seeds %llu, ungapped HSPs %llu; gapped extensions %llu, with gain > 0: %llu, cells %llu\n",
+                                     n_cand_total, n_seeds_total, n_surv, n_gapped_total, gc[0], gc[1]);
     for (int f = 0; f < MCX_N_FAM; ++f) { R.fam_hits[f] = (int64_t)acc[3 + f]; R.fam_aln[f] = (int64_t)acc[3 + MCX_N_FAM + f]; }
     for (size_t k = 0; k < abl.size(); ++k) R.aln_by_len[k] = (int64_t)abl[k];
     ctx->ms[2] = ms_probe; ctx->ms[7] = ms_ext; ctx->ms[3] = ms_gap; ctx->ms[8] = ms_frames; ctx->ms[9] = ms_seg;

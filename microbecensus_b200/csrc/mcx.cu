@@ -427,6 +427,12 @@ __device__ __forceinline__ int prev_clear_bit(const uint32_t *m, int from, int d
     }
 }
 
+// doubles -> unsigned integers of the same order (no NaNs here)
+__device__ __forceinline__ unsigned long long dkey(double x) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(x);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
 __host__ __device__ inline int seg_warp_bytes(int fstride, int maxm) {   // shared memory of one warp of k_seg
     return 18 * 4 + fstride + (((maxm + 1) * 20 + 3) & ~3) + (maxm + 2) * 32;
 }
@@ -442,7 +448,7 @@ __device__ void coop_trim(const uint8_t *fr, int off, int tl, uint8_t *P, uint8_
     __syncwarp();
     int lend = 0, rend = tl - 1, minlen = 1;
     if (tl - SEG_MAXTRIM > minlen) minlen = tl - SEG_MAXTRIM;
-    double minprob = 1.0;
+    unsigned long long minkey = dkey(1.0);             // seg.c: minprob = 1.0, strict <
     // windows in seg.c's scan order: length tl, tl-1, ... minlen+1, starts left to right; row d = tl - len holds
     // d + 1 windows, so window number w sits in row d with d(d+1)/2 <= w < (d+1)(d+2)/2.  32 windows per round.
     const int D = tl - minlen, NW = D * (D + 1) / 2;
@@ -481,16 +487,16 @@ __device__ void coop_trim(const uint8_t *fr, int off, int tl, uint8_t *P, uint8_
                 prob = seg_getprob(nc, maxc, len, lnfac, ln20);
             }
         }
-        double best = prob;
-        int bl = lane;
-#pragma unroll
-        for (int dd = 16; dd; dd >>= 1) {
-            const double o = __shfl_xor_sync(0xffffffffu, best, dd);
-            const int ol = __shfl_xor_sync(0xffffffffu, bl, dd);
-            if (o < best || (o == best && ol < bl)) { best = o; bl = ol; }
-        }
-        if (best < minprob) {
-            minprob = best;
+        // warp argmin with seg.c's tie-break (first window in scan order = lowest lane): the doubles are mapped to
+        // integers of the same order and reduced with three redux / ballot steps instead of five shuffle rounds
+        const unsigned long long key = dkey(prob);
+        const uint32_t khi = (uint32_t)(key >> 32), klo = (uint32_t)key;
+        const uint32_t mh = __reduce_min_sync(0xffffffffu, khi);
+        const uint32_t ml = __reduce_min_sync(0xffffffffu, khi == mh ? klo : 0xffffffffu);
+        const int bl = __ffs(__ballot_sync(0xffffffffu, khi == mh && klo == ml)) - 1;
+        const unsigned long long best = ((unsigned long long)mh << 32) | ml;
+        if (best < minkey) {
+            minkey = best;
             lend = __shfl_sync(0xffffffffu, st, bl);
             rend = __shfl_sync(0xffffffffu, len, bl) + lend - 1;
         }
@@ -519,12 +525,32 @@ __global__ void __launch_bounds__(WARPS * 32) k_seg(uint8_t *frames, int fstride
     const uint32_t *lom = s_m, *him = s_m + 6;
     uint32_t *mask = s_m + 12;
     // blocks stride over the queue so that the tables above are staged once per block, not once per four frames
-    for (int64_t g = (int64_t)blockIdx.x * WARPS + warp; g < n; g += (int64_t)gridDim.x * WARPS) {
-        const uint32_t row = segq[g];
+    // the next frame's row is fetched into registers while the current one is processed (up to two words per lane)
+    const int64_t gstep = (int64_t)gridDim.x * WARPS;
+    const int fw = fstride / 4;
+    uint32_t nrow = 0, nw0 = 0, nw1 = 0;
+    {
+        const int64_t g0 = (int64_t)blockIdx.x * WARPS + warp;
+        if (g0 < n) {
+            nrow = segq[g0];
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(frames + (int64_t)nrow * fstride);
+            if (lane < fw) nw0 = src[lane];
+            if (lane + 32 < fw) nw1 = src[lane + 32];
+        }
+    }
+    for (int64_t g = (int64_t)blockIdx.x * WARPS + warp; g < n; g += gstep) {
+        const uint32_t row = nrow;
         uint8_t *gfr = frames + (int64_t)row * fstride;
         const int m = (L - (int)(row % 6u) % 3) / 3;
         __syncwarp();
-        for (int k = lane; k < fstride / 4; k += 32) reinterpret_cast<uint32_t *>(fr)[k] = reinterpret_cast<const uint32_t *>(gfr)[k];
+        if (lane < fw) reinterpret_cast<uint32_t *>(fr)[lane] = nw0;
+        if (lane + 32 < fw) reinterpret_cast<uint32_t *>(fr)[lane + 32] = nw1;
+        if (g + gstep < n) {
+            nrow = segq[g + gstep];
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(frames + (int64_t)nrow * fstride);
+            if (lane < fw) nw0 = src[lane];
+            if (lane + 32 < fw) nw1 = src[lane + 32];
+        }
         __syncwarp();
         // entropy of every 12-window against the two cut-offs, one window per lane
         for (int r = 0; r < 6; ++r) {

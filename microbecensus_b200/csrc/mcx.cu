@@ -187,21 +187,27 @@ __device__ double seg_getprob(uint8_t *nc, int maxc, int len, const double *lnfa
     if (nz > 0 && nz < 20) lnass -= lnfac[20 - nz];
     return lnass + lnperm - ln20[len];
 }
-// the same from a register histogram, one nibble per count value 1..15 (windows of at most 15 residues: neither a
-// count nor the number of letters sharing it can exceed 15)
-__device__ __forceinline__ double seg_getprob_packed(unsigned long long h, int len, const double *lnfac, const double *ln20) {
-    double lnperm = lnfac[len], lnass = lnfac[20];
-    int nz = 0;
-    while (h) {                                              // highest count first
-        const int c = (63 - __clzll((long long)h)) >> 2;
-        const int n = (int)((h >> (4 * c)) & 15);
-        if (c > 1) { const double lf = lnfac[c]; for (int r = 0; r < n; ++r) lnperm -= lf; }
-        if (n > 1) lnass -= lnfac[n];
-        nz += n;
-        h &= ~(15ull << (4 * c));
+// Windows of at most 15 residues: getprob() depends only on (window length, multiset of letter counts), and there are
+// only 2,454 such classes.  upload_tables() evaluates every one of them on the host with the floating-point sequence
+// above and stores the results in an open-addressing table keyed by (length, signature), signature = sum over the
+// letters of z[count] with 16 fixed pseudo-random words (checked to be unique per class).  A window then costs one
+// table value per letter present and one lookup instead of the histogram and ~20 dependent FP64 subtractions.
+constexpr int SEGP_MAXLEN = 15;
+constexpr int SEGP_SLOTS = 1 << 14;
+struct SegProbSlot { unsigned long long key; double prob; };     // key = len << 32 | signature; ~0 = empty
+__device__ SegProbSlot g_segprob[SEGP_SLOTS];
+__device__ uint32_t g_segz[16];
+__host__ __device__ __forceinline__ uint32_t segp_slot(unsigned long long key) {
+    return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 50) & (SEGP_SLOTS - 1);
+}
+__device__ __forceinline__ double seg_prob_lookup(uint32_t sig, int len) {
+    const unsigned long long key = ((unsigned long long)len << 32) | sig;
+    uint32_t sl = segp_slot(key);
+    for (;;) {
+        const SegProbSlot e = g_segprob[sl];
+        if (e.key == key) return e.prob;
+        sl = (sl + 1) & (SEGP_SLOTS - 1);
     }
-    if (nz > 0 && nz < 20) lnass -= lnfac[20 - nz];
-    return lnass + lnperm - ln20[len];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -438,7 +444,7 @@ __host__ __device__ inline int seg_warp_bytes(int fstride, int maxm) {   // shar
 }
 
 __device__ void coop_trim(const uint8_t *fr, int off, int tl, uint8_t *P, uint8_t *nc, int lane, const double *lnfac,
-                          const double *ln20, int &leftend, int &rightend) {
+                          const double *ln20, const uint32_t *zt, int &leftend, int &rightend) {
     __syncwarp();
     if (lane < 20) {                       // P[k][a] = occurrences of letter a among the first k residues
         int acc = 0;
@@ -466,17 +472,14 @@ __device__ void coop_trim(const uint8_t *fr, int off, int tl, uint8_t *P, uint8_
             uint32_t cw[5];
 #pragma unroll
             for (int q = 0; q < 5; ++q) cw[q] = w1[q] - w0[q];      // no borrow: every byte of w1 >= that of w0
-            if (len <= 15) {
-                unsigned long long h = 0;
+            if (len <= SEGP_MAXLEN) {
+                uint32_t sig = 0;
 #pragma unroll
                 for (int q = 0; q < 5; ++q) {
                     const uint32_t x = cw[q];
-                    if (x) {
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) { const uint32_t c = (x >> (8 * b)) & 0xffu; if (c) h += 1ull << (4 * c); }
-                    }
+                    if (x) sig += zt[x & 0xffu] + zt[(x >> 8) & 0xffu] + zt[(x >> 16) & 0xffu] + zt[x >> 24];
                 }
-                prob = seg_getprob_packed(h, len, lnfac, ln20);
+                prob = seg_prob_lookup(sig, len);
             } else {
                 int maxc = 0;
 #pragma unroll
@@ -512,8 +515,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_seg(uint8_t *frames, int fstride
     double *s_lnfac = reinterpret_cast<double *>(smem);        // [SEG_TAB] ln(i!)
     double *s_ln20 = s_lnfac + SEG_TAB;                         // [SEG_TAB] i ln 20
     SegTab *s_tab = reinterpret_cast<SegTab *>(s_ln20 + SEG_TAB);
+    uint32_t *s_z = reinterpret_cast<uint32_t *>(s_tab + 1);   // [16] signature words
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t *wbase = smem + 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + (size_t)warp * seg_warp_bytes(fstride, maxm);
+    uint8_t *wbase = smem + 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + 64 + (size_t)warp * seg_warp_bytes(fstride, maxm);
+    if (threadIdx.x < 16) s_z[threadIdx.x] = g_segz[threadIdx.x];
     uint32_t *s_m = reinterpret_cast<uint32_t *>(wbase);       // [0..5] lo, [6..11] hi, [12..17] result mask
     uint8_t *fr = wbase + 18 * 4;
     uint8_t *P = fr + fstride;                                 // [maxm + 1][20] prefix counts of the segment being trimmed
@@ -596,7 +601,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_seg(uint8_t *frames, int fstride
                     if (k >= 0) hii = k - off - 1;
                 }
                 int leftend = loi, rightend = hii;
-                coop_trim(fr, off + leftend, rightend - leftend + 1, P, nc, lane, s_lnfac, s_ln20, leftend, rightend);
+                coop_trim(fr, off + leftend, rightend - leftend + 1, P, nc, lane, s_lnfac, s_ln20, s_z, leftend, rightend);
                 if (i < leftend && nwl < 12) { wl_off[nwl] = off + loi; wl_len[nwl] = leftend - loi; ++nwl; }
                 if (lane < 6) {                    // mask[off + leftend .. off + rightend], one word per lane
                     const int b0 = max(off + leftend, lane * 32), b1 = min(off + rightend, lane * 32 + 31);
@@ -1631,6 +1636,65 @@ static int upload_tables(mcx_ctx *ctx) {
         }
         CK(cudaMemcpyToSymbol(g_segtab, &T, sizeof T));
     }
+    // getprob() of every (window length <= 15, multiset of letter counts), see g_segprob
+    {
+        uint32_t z[16];
+        std::vector<SegProbSlot> tab;
+        for (unsigned long long seed = 0x243F6A8885A308D3ull;; seed += 0x9E3779B97F4A7C15ull) {
+            unsigned long long x = seed;
+            z[0] = 0;
+            for (int c = 1; c < 16; ++c) {                   // splitmix64
+                x += 0x9E3779B97F4A7C15ull;
+                unsigned long long t = x;
+                t = (t ^ (t >> 30)) * 0xBF58476D1CE4E5B9ull; t = (t ^ (t >> 27)) * 0x94D049BB133111EBull; t ^= t >> 31;
+                z[c] = (uint32_t)t;
+            }
+            tab.assign(SEGP_SLOTS, SegProbSlot{~0ull, 0.0});
+            bool unique = true;
+            size_t classes = 0;
+            int part[20];
+            for (int len = 1; len <= SEGP_MAXLEN && unique; ++len)
+                for (int tot = 0; tot <= len && unique; ++tot) {
+                    auto rec = [&](auto &&self, int left, int maxpart, int np) -> void {
+                        if (!unique) return;
+                        if (left == 0) {
+                            // seg.c getprob() on the counts, largest first (same operations as seg_getprob above)
+                            double lnperm = lnfac[len], lnass = lnfac[20];
+                            uint32_t sig = 0;
+                            int nz = 0;
+                            for (int k = 0; k < np;) {
+                                int e = k;
+                                while (e + 1 < np && part[e + 1] == part[k]) ++e;
+                                const int c = part[k], n = e - k + 1;
+                                if (c > 1) for (int r = 0; r < n; ++r) lnperm -= lnfac[c];
+                                if (n > 1) lnass -= lnfac[n];
+                                nz += n;
+                                sig += (uint32_t)n * z[c];
+                                k = e + 1;
+                            }
+                            if (nz > 0 && nz < 20) lnass -= lnfac[20 - nz];
+                            const double prob = lnass + lnperm - ln20[len];
+                            const unsigned long long key = ((unsigned long long)len << 32) | sig;
+                            uint32_t sl = segp_slot(key);
+                            while (tab[sl].key != ~0ull) {
+                                if (tab[sl].key == key) { unique = false; return; }
+                                sl = (sl + 1) & (SEGP_SLOTS - 1);
+                            }
+                            tab[sl] = SegProbSlot{key, prob};
+                            ++classes;
+                            return;
+                        }
+                        if (np == 20) return;
+                        for (int k = std::min(left, maxpart); k >= 1; --k) { part[np] = k; self(self, left - k, k, np + 1); }
+                    };
+                    rec(rec, tot, tot, 0);
+                }
+            if (unique && classes * 2 <= (size_t)SEGP_SLOTS) break;
+            if (classes * 2 > (size_t)SEGP_SLOTS) return fail(ctx, MCX_EINVAL, "internal: SEG probability table too small");
+        }
+        CK(cudaMemcpyToSymbol(g_segz, z, sizeof z));
+        CK(cudaMemcpyToSymbol(g_segprob, tab.data(), sizeof(SegProbSlot) * SEGP_SLOTS));
+    }
     {
         uint8_t lut[256];
         memset(lut, AA_STOP, sizeof lut);
@@ -1973,7 +2037,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         CK(cudaGetLastError());
         if (n_segq > 0) {
             constexpr int SW = 4;
-            const size_t smem = 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + (size_t)SW * seg_warp_bytes(fstride, maxm);
+            const size_t smem = 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + 64 + (size_t)SW * seg_warp_bytes(fstride, maxm);
             CK(cudaFuncSetAttribute(k_seg<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_seg<SW><<<(unsigned)std::min<unsigned long long>((n_segq + SW - 1) / SW, 148ull * 16), SW * 32, smem, st>>>(ctx->d_frames, fstride, P.read_length, ctx->d_segq,
                                                                            (int64_t)n_segq, maxm);

@@ -187,18 +187,18 @@ __device__ double seg_getprob(uint8_t *nc, int maxc, int len, const double *lnfa
     if (nz > 0 && nz < 20) lnass -= lnfac[20 - nz];
     return lnass + lnperm - ln20[len];
 }
-// Windows of at most 15 residues: getprob() depends only on (window length, multiset of letter counts), and there are
-// only 2,454 such classes.  upload_tables() evaluates every one of them on the host with the floating-point sequence
+// Windows of at most 20 residues: getprob() depends only on (window length, multiset of letter counts), and there are
+// only 10,979 such classes.  upload_tables() evaluates every one of them on the host with the floating-point sequence
 // above and stores the results in an open-addressing table keyed by (length, signature), signature = sum over the
-// letters of z[count] with 16 fixed pseudo-random words (checked to be unique per class).  A window then costs one
+// letters of z[count] with 21 fixed pseudo-random words (checked to be unique per class).  A window then costs one
 // table value per letter present and one lookup instead of the histogram and ~20 dependent FP64 subtractions.
-constexpr int SEGP_MAXLEN = 15;
-constexpr int SEGP_SLOTS = 1 << 14;
+constexpr int SEGP_MAXLEN = 20;
+constexpr int SEGP_SLOTS = 1 << 15;
 struct SegProbSlot { unsigned long long key; double prob; };     // key = len << 32 | signature; ~0 = empty
 __device__ SegProbSlot g_segprob[SEGP_SLOTS];
-__device__ uint32_t g_segz[16];
+__device__ uint32_t g_segz[32];
 __host__ __device__ __forceinline__ uint32_t segp_slot(unsigned long long key) {
-    return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 50) & (SEGP_SLOTS - 1);
+    return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 49) & (SEGP_SLOTS - 1);
 }
 __device__ __forceinline__ double seg_prob_lookup(uint32_t sig, int len) {
     const unsigned long long key = ((unsigned long long)len << 32) | sig;
@@ -515,10 +515,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_seg(uint8_t *frames, int fstride
     double *s_lnfac = reinterpret_cast<double *>(smem);        // [SEG_TAB] ln(i!)
     double *s_ln20 = s_lnfac + SEG_TAB;                         // [SEG_TAB] i ln 20
     SegTab *s_tab = reinterpret_cast<SegTab *>(s_ln20 + SEG_TAB);
-    uint32_t *s_z = reinterpret_cast<uint32_t *>(s_tab + 1);   // [16] signature words
+    uint32_t *s_z = reinterpret_cast<uint32_t *>(s_tab + 1);   // [32] signature words
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t *wbase = smem + 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + 64 + (size_t)warp * seg_warp_bytes(fstride, maxm);
-    if (threadIdx.x < 16) s_z[threadIdx.x] = g_segz[threadIdx.x];
+    uint8_t *wbase = smem + 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + 128 + (size_t)warp * seg_warp_bytes(fstride, maxm);
+    if (threadIdx.x < 32) s_z[threadIdx.x] = g_segz[threadIdx.x];
     uint32_t *s_m = reinterpret_cast<uint32_t *>(wbase);       // [0..5] lo, [6..11] hi, [12..17] result mask
     uint8_t *fr = wbase + 18 * 4;
     uint8_t *P = fr + fstride;                                 // [maxm + 1][20] prefix counts of the segment being trimmed
@@ -1636,14 +1636,14 @@ static int upload_tables(mcx_ctx *ctx) {
         }
         CK(cudaMemcpyToSymbol(g_segtab, &T, sizeof T));
     }
-    // getprob() of every (window length <= 15, multiset of letter counts), see g_segprob
+    // getprob() of every (window length <= 20, multiset of letter counts), see g_segprob
     {
-        uint32_t z[16];
+        uint32_t z[32] = {0};
         std::vector<SegProbSlot> tab;
         for (unsigned long long seed = 0x243F6A8885A308D3ull;; seed += 0x9E3779B97F4A7C15ull) {
             unsigned long long x = seed;
             z[0] = 0;
-            for (int c = 1; c < 16; ++c) {                   // splitmix64
+            for (int c = 1; c <= SEGP_MAXLEN; ++c) {         // splitmix64
                 x += 0x9E3779B97F4A7C15ull;
                 unsigned long long t = x;
                 t = (t ^ (t >> 30)) * 0xBF58476D1CE4E5B9ull; t = (t ^ (t >> 27)) * 0x94D049BB133111EBull; t ^= t >> 31;
@@ -2037,7 +2037,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         CK(cudaGetLastError());
         if (n_segq > 0) {
             constexpr int SW = 4;
-            const size_t smem = 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + 64 + (size_t)SW * seg_warp_bytes(fstride, maxm);
+            const size_t smem = 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + 128 + (size_t)SW * seg_warp_bytes(fstride, maxm);
             CK(cudaFuncSetAttribute(k_seg<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_seg<SW><<<(unsigned)std::min<unsigned long long>((n_segq + SW - 1) / SW, 148ull * 16), SW * 32, smem, st>>>(ctx->d_frames, fstride, P.read_length, ctx->d_segq,
                                                                            (int64_t)n_segq, maxm);

@@ -799,19 +799,26 @@ __device__ __forceinline__ uint4 seed_pack(uint32_t gframe, int s, int sb, int q
 
 // (No duplicate filter here: the left-maximal rule for exact words and the one-window-per-position rule for the
 // substitution words already make every accepted stretch unique -- 74,491,397 of 74,491,397 at 2M x 150 bp.)
+#define SAME(a, b) ((s_same[(a)] >> (b)) & 1u)   /* red_eq() from the shared-memory masks */
 // K2c: one thread per candidate: the cheap rejections, growth of the word to the maximal murphy10-identical stretch
 // and the seed acceptance test (ExtendSeq2Set 0x413fc4-0x414073); accepted seeds are queued for k_walk.
 template <int NT>
 __global__ void __launch_bounds__(NT) k_seed(ExtArgs A) {
     __shared__ __align__(4) int8_t s_bl[21 * 32];
+    __shared__ uint32_t s_same[32];                 // bit b of s_same[a]: residues a and b share a murphy10 letter
     for (int k = threadIdx.x; k < 21 * 32 / 4; k += NT) reinterpret_cast<uint32_t *>(s_bl)[k] = reinterpret_cast<const uint32_t *>(g_blosum)[k];
+    if (threadIdx.x < 32) {
+        uint32_t mk = 0;
+        const int a = threadIdx.x;
+        if (a < 20) for (int b = 0; b < 20; ++b) mk |= (uint32_t)(red_of(a) == red_of(b)) << b;
+        s_same[a] = mk;
+    }
     __syncthreads();
-    const int64_t g = (int64_t)blockIdx.x * NT + threadIdx.x;
-    if (g >= A.n_cand) return;
-    int sq = 0;
-#pragma unroll
-    for (int step = NQ / 2; step; step >>= 1) if ((unsigned long long)g >= A.qstart[sq + step]) sq += step;
-    const Cand c = A.cand[(unsigned long long)sq * A.cap_cand + ((unsigned long long)g - A.qstart[sq])];
+    // grid.y = candidate sub-queue, grid.x covers the fullest one
+    const int sq = blockIdx.y;
+    const unsigned long long k = (unsigned long long)blockIdx.x * NT + threadIdx.x;
+    if (k >= A.qstart[sq + 1] - A.qstart[sq]) return;
+    const Cand c = A.cand[(unsigned long long)sq * A.cap_cand + k];
     const int frame = (int)(c.gframe % 6u);
     const int m = (A.L - frame % 3) / 3;
     const uint8_t *__restrict__ fr = A.frames + (int64_t)c.gframe * A.fstride;
@@ -820,15 +827,15 @@ __global__ void __launch_bounds__(NT) k_seed(ExtArgs A) {
     const int n = __ldg(A.db.off + s + 1) - o;
     const uint8_t *__restrict__ t = A.db.res + o;
     if (p == 0) {                  // exact words: left-maximal only (ExtendSeq2Set 0x4140c0-0x414113)
-        if (i > 0 && j > 0 && red_eq(fr[i - 1], t[j - 1])) return;
+        if (i > 0 && j > 0 && SAME(fr[i - 1], t[j - 1])) return;
     } else {                       // one-substitution words: the replaced letter differs by construction;
         const int w = p + 2;       // keep one window per substituted position (all windows give the same seed)
         if (red_of(fr[i + w]) == red_of(t[j + w])) return;
-        if (w >= 4 && i + 10 < m && j + 10 < n && red_eq(fr[i + 10], t[j + 10])) return;
+        if (w >= 4 && i + 10 < m && j + 10 < n && SAME(fr[i + 10], t[j + 10])) return;
     }
     int qb = i, sb = j, len = p == 0 ? 9 : 10;
-    while (qb + len < m && sb + len < n && red_eq(fr[qb + len], t[sb + len])) ++len;
-    while (qb > 0 && sb > 0 && red_eq(fr[qb - 1], t[sb - 1])) { --qb; --sb; ++len; }
+    while (qb + len < m && sb + len < n && SAME(fr[qb + len], t[sb + len])) ++len;
+    while (qb > 0 && sb > 0 && SAME(fr[qb - 1], t[sb - 1])) { --qb; --sb; ++len; }
     int score0 = 0, id0 = 0;
     for (int k = 0; k < len; ++k) {
         const int a = fr[qb + k], b = t[sb + k];
@@ -844,6 +851,7 @@ __global__ void __launch_bounds__(NT) k_seed(ExtArgs A) {
     A.seedq[base + __popc(mask & ((1u << lane) - 1))] = seed_pack(c.gframe, s, sb, qb, len, score0, id0);
 }
 
+#undef SAME
 // K2d: one thread per accepted seed: the ungapped X-drop walks both ways (AlignFwd / AlignBwd); HSPs reaching the
 // report floor are appended to the survivor list.
 template <int NT>
@@ -2082,7 +2090,11 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             if ((rc = ensure(ctx, &ctx->d_seedq, &ctx->cap_seedq, (int64_t)n_cand)) != MCX_OK) return rc;
             E.seedq = ctx->d_seedq;
             CK(cudaMemsetAsync(ctx->d_cnt + 9, 0, sizeof(unsigned long long), st));
-            k_seed<256><<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(E);
+            {
+                unsigned long long worst = 0;
+                for (int q = 0; q < NQ; ++q) worst = std::max(worst, qfill[q]);
+                k_seed<256><<<dim3((unsigned)((worst + 255) / 256), NQ), 256, 0, st>>>(E);
+            }
             ++ctx->launches;
             CK(cudaMemcpyAsync(&n_seeds, ctx->d_cnt + 9, sizeof n_seeds, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));

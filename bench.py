@@ -336,6 +336,11 @@ def main():
         except Exception:
             pass
     gcups = res.gapped_cells / world / (stage_dev["gapped"] * 1e-3) / 1e9 if stage_dev.get("gapped") else None
+    # the DPX-bound cell rate = measured DPX issue rate / 3 DPX instructions per affine-gap cell
+    dpx = eng.dpx_peak()
+    gapped = {"gcups": gcups, "cells_per_step_per_gpu": res.gapped_cells / world, "stage_ms": stage_dev.get("gapped"),
+              "dpx_ginstr_per_s": dpx, "dpx_bound_gcups": dpx / 3.0, "frac_of_dpx_bound": (gcups / (dpx / 3.0)) if gcups else None,
+              "note": "X-drop extension with statistics carried per cell (DESIGN.md section 5): plain max/compare, one thread per extension"}
 
     line = {"metric": "reads/sec end-to-end AGS", "value": total_reads / t_dev, "unit": "reads/s", "n_gpus": world,
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": t_dev * 1e3, "higher_is_better": True,
@@ -346,7 +351,7 @@ def main():
                     "d2h_bytes_per_step": int(res.counts_vector().nbytes), "ms_per_step": t_e2e * 1e3},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "stages_ms": stage_dev, "stages_ms_e2e": stage_e2e,
-            "gapped_gcups": gcups, "ags": ags, "ags_e2e": ags2,
+            "gapped_gcups": gcups, "gapped": gapped, "ags": ags, "ags_e2e": ags2,
             "counts": {"sampled_reads": res.sampled_reads, "reads_with_hits": res.reads_with_hits,
                        "reads_classified": res.reads_classified, "n_hsp": res.n_hsp, "n_seed_hits": res.n_seed_hits,
                        "n_gapped": res.n_gapped, "gapped_cells": res.gapped_cells, "low_qual": res.low_qual, "dups": res.dups}}

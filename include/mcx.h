@@ -138,6 +138,11 @@ int  mcx_get_classified(mcx_ctx *ctx, int32_t *best_subject, int64_t n);
  * [6] d2h, [7] k_seed + k_walk, [8] k_frames, [9] k_seg; and the number of kernel launches */
 int  mcx_timings(mcx_ctx *ctx, float ms[10], int64_t *launches);
 
+/* Measurement aid: issue rate of the DPX instructions an affine-gap cell uses (viaddmax_s32 /
+ * vimax3_s32_relu, independent chains on every SM), in 1e9 thread-instructions per second.  The DPX-bound cell rate
+ * that the gapped stage's GCUPS is quoted against is this number / 3 (two viaddmax + one vimax3 per cell). */
+int  mcx_dpx_peak(mcx_ctx *ctx, double *gops_per_s);
+
 const char *mcx_last_error(mcx_ctx *ctx);
 const char *mcx_version(void);
 

@@ -54,7 +54,7 @@ class Hit(C.Structure):
 
 EXPORTS = ("mcx_create", "mcx_destroy", "mcx_set_params", "mcx_set_stream", "mcx_push_reads", "mcx_push_reads_dev",
            "mcx_qc_counts", "mcx_qc_export", "mcx_qc_import", "mcx_search", "mcx_result_get", "mcx_get_hits", "mcx_get_classified",
-           "mcx_timings", "mcx_last_error", "mcx_version")
+           "mcx_timings", "mcx_dpx_peak", "mcx_last_error", "mcx_version")
 
 _lib = None
 
@@ -84,6 +84,7 @@ def load():
     lib.mcx_get_hits.argtypes = [vp, vp, i64, C.POINTER(i64)]
     lib.mcx_get_classified.argtypes = [vp, vp, i64]
     lib.mcx_timings.argtypes = [vp, C.POINTER(C.c_float * 10), C.POINTER(i64)]
+    lib.mcx_dpx_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.mcx_last_error.argtypes = [vp]
     lib.mcx_last_error.restype = C.c_char_p
     lib.mcx_version.restype = C.c_char_p

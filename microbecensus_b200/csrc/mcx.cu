@@ -2271,6 +2271,52 @@ extern "C" int mcx_get_classified(mcx_ctx *ctx, int32_t *best_subject, int64_t n
     return MCX_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// DPX issue-rate microbenchmark (the denominator the north star asks for next to the gapped stage's
+// GCUPS).  Eight independent chains per thread of viaddmax / vimax3_relu, the two DPX forms an affine-gap cell uses.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dpx_bench(int iters, int seed, int *out) {
+    int a[8], b = seed + threadIdx.x, c = seed * 3 + blockIdx.x;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = seed + k * 17 + threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a[k] = __viaddmax_s32(a[k], b, c);            // max(a + b, c): the E / F update
+            a[k] = __vimax3_s32_relu(a[k], c, b);         // max(a, c, b, 0): the H update
+        }
+        b ^= it; c += it;
+    }
+    int r = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r ^= a[k];
+    if (r == 0x7fffffff) out[0] = r;                      // keeps the chains alive
+}
+
+extern "C" int mcx_dpx_peak(mcx_ctx *ctx, double *gops_per_s) {
+    if (!ctx || !gops_per_s) return fail(ctx, MCX_EINVAL, "mcx_dpx_peak: null argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    const int blocks = sms * 8, iters = 1 << 14;
+    int *d_out = reinterpret_cast<int *>(ctx->d_cnt);     // never written in practice
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(ctx->ev[12], st));
+        k_dpx_bench<<<blocks, 256, 0, st>>>(iters, 12345 + rep, d_out);
+        CK(cudaEventRecord(ctx->ev[13], st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[12], ctx->ev[13]));
+        const double ops = (double)blocks * 256.0 * (double)iters * 16.0;    // DPX thread-instructions
+        if (rep > 0) best = std::max(best, ops / (ms * 1e-3) / 1e9);
+    }
+    *gops_per_s = best;
+    return MCX_OK;
+}
+
 extern "C" int mcx_timings(mcx_ctx *ctx, float ms[10], int64_t *launches) {
     if (!ctx || !ms) return fail(ctx, MCX_EINVAL, "mcx_timings: null argument");
     memcpy(ms, ctx->ms, sizeof(float) * 10);

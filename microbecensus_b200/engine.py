@@ -205,6 +205,12 @@ class MarkerSearch:
         self._ck(self.lib.mcx_get_classified(self.ctx, _ptr(out), int(n)))
         return out
 
+    def dpx_peak(self):
+        """1e9 DPX thread-instructions per second this GPU issues (viaddmax_s32 / vimax3_s32_relu microbenchmark)."""
+        v = C.c_double(0.0)
+        self._ck(self.lib.mcx_dpx_peak(self.ctx, C.byref(v)))
+        return v.value
+
     def timings(self):
         ms = (C.c_float * 10)()
         launches = C.c_int64(0)

@@ -678,22 +678,24 @@ __global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
     for (int k = 0; k < 10; ++k) win |= (unsigned long long)(k < m ? red_of(fr[k]) : 15) << (4 * k);
     const int mmax = A.L / 3;
     for (int i = 0; i + 9 <= mmax; ++i) {
+        // word codes (base 10) of the 10-window d0..d9: the exact word d0..d8 and, for a wildcard at offset w = 3..6,
+        // the nine letters around it = (d0..d[w-1]) * 10^(9-w) + (d[w+1]..d9).  Prefixes and suffixes are shared
+        // between the patterns: 19 multiply-adds instead of 45.
         uint32_t code[N_PAT];
+        uint32_t d[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) d[k] = (uint32_t)(win >> (4 * k)) & 15;
         int bad9 = 0;
-        {
-            uint32_t c9 = 0;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) { uint32_t r = (uint32_t)(win >> (4 * k)) & 15; bad9 |= (r >= 10); c9 = c9 * 10 + r; }
-            code[0] = c9;
-        }
-        const int bad10 = bad9 | ((((uint32_t)(win >> 36)) & 15) >= 10);
-#pragma unroll
-        for (int p = 1; p < N_PAT; ++p) {
-            uint32_t c = 0;
-#pragma unroll
-            for (int k = 0; k < 10; ++k) if (k != p + 2) c = c * 10 + ((uint32_t)(win >> (4 * k)) & 15);
-            code[p] = c;
-        }
+        for (int k = 0; k < 9; ++k) bad9 |= (d[k] >= 10);
+        const int bad10 = bad9 | (d[9] >= 10);
+        const uint32_t h3 = (d[0] * 10 + d[1]) * 10 + d[2], h4 = h3 * 10 + d[3], h5 = h4 * 10 + d[4], h6 = h5 * 10 + d[5];
+        const uint32_t t6 = (d[7] * 10 + d[8]) * 10 + d[9], t5 = d[6] * 1000 + t6, t4 = d[5] * 10000 + t5, t3 = d[4] * 100000 + t4;
+        code[0] = h6 * 1000 + (d[6] * 10 + d[7]) * 10 + d[8];
+        code[1] = h3 * 1000000 + t3;
+        code[2] = h4 * 100000 + t4;
+        code[3] = h5 * 10000 + t5;
+        code[4] = h6 * 1000 + t6;
         // five filter words in flight together
         uint32_t bw[N_PAT], bh[N_PAT];
 #pragma unroll

@@ -31,6 +31,7 @@
 #include <climits>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace mcx;
@@ -1530,15 +1531,17 @@ static int build_index(mcx_ctx *ctx, const mcx_db *db) {
     const int64_t nres = db->off[ns];
     std::vector<uint8_t> red((size_t)nres);
     for (int64_t g = 0; g < nres; ++g) red[(size_t)g] = db->res[g] < 20 ? MURPHY10[db->res[g]] : 10;
-    std::vector<uint32_t> post_all, bloom((size_t)1 << BLOOM_WORD_BITS, 0u);
-    post_all.reserve((size_t)nres * N_PAT);
+    for (int s = 0; s < ns; ++s)
+        if (db->off[s + 1] - db->off[s] >= 2048) return fail(ctx, MCX_EINVAL, "subject longer than 2047 residues");
+    // the five patterns are independent: one host thread each (entries + sort, then table fill into its own region)
+    std::vector<uint32_t> bloom((size_t)1 << BLOOM_WORD_BITS, 0u);
     std::vector<unsigned long long> ent[N_PAT];
-    size_t max_distinct = 0;
-    for (int p = 0; p < N_PAT; ++p) {
-        ent[p].reserve((size_t)nres);
+    size_t distinct[N_PAT] = {0}, long_lists[N_PAT] = {0};
+    auto collect = [&](int p) {
+        std::vector<unsigned long long> &en = ent[p];
+        en.reserve((size_t)nres);
         for (int s = 0; s < ns; ++s) {
             const int n = db->off[s + 1] - db->off[s];
-            if (n >= 2048) return fail(ctx, MCX_EINVAL, "subject longer than 2047 residues");
             const uint8_t *r = red.data() + db->off[s];
             for (int j = 0; j + PAT_LEN[p] <= n; ++j) {
                 uint32_t c = 0; bool ok = true;
@@ -1547,36 +1550,59 @@ static int build_index(mcx_ctx *ctx, const mcx_db *db) {
                     if (r[j + k] >= 10) { ok = false; break; }
                     c = c * 10 + r[j + k];
                 }
-                if (ok) ent[p].push_back(((unsigned long long)c << 32) | ((uint32_t)s << 11) | (uint32_t)j);
+                if (ok) en.push_back(((unsigned long long)c << 32) | ((uint32_t)s << 11) | (uint32_t)j);
             }
         }
-        std::sort(ent[p].begin(), ent[p].end());
-        size_t distinct = 0;
-        for (size_t k = 0; k < ent[p].size(); ++k) distinct += (k == 0 || (ent[p][k] >> 32) != (ent[p][k - 1] >> 32));
-        max_distinct = std::max(max_distinct, distinct);
+        std::sort(en.begin(), en.end());
+        for (size_t k = 0; k < en.size();) {
+            size_t e = k;
+            while (e + 1 < en.size() && (en[e + 1] >> 32) == (en[k] >> 32)) ++e;
+            ++distinct[p];
+            long_lists[p] += (e - k + 1 > 127);
+            k = e + 1;
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int p = 0; p < N_PAT; ++p) th.emplace_back(collect, p);
+        for (auto &t : th) t.join();
     }
+    size_t max_distinct = 0, post_base[N_PAT + 1] = {0};
+    for (int p = 0; p < N_PAT; ++p) {
+        max_distinct = std::max(max_distinct, distinct[p]);
+        post_base[p + 1] = post_base[p] + ent[p].size() + long_lists[p];
+    }
+    if (post_base[N_PAT] >= (1u << 25)) return fail(ctx, MCX_EINVAL, "seed index too large for 25-bit posting offsets");
     // one table size for all patterns (load factor <= 0.5 for the fullest), slots of (key, value)
     uint32_t size = 1024; int bits = 10;
     while (size < max_distinct * 2) { size <<= 1; ++bits; }
-    std::vector<uint2> tab((size_t)N_PAT << bits, make_uint2(0xffffffffu, 0u));
-    for (int p = 0; p < N_PAT; ++p) {
+    std::vector<uint2> tab((size_t)N_PAT << bits);
+    std::vector<uint32_t> post_all(post_base[N_PAT]);
+    auto fill = [&](int p) {
         uint2 *ht = tab.data() + ((size_t)p << bits);
+        for (size_t k = 0; k < size; ++k) ht[k] = make_uint2(0xffffffffu, 0u);
         const std::vector<unsigned long long> &en = ent[p];
+        size_t w = post_base[p];
         for (size_t k = 0; k < en.size();) {
             const uint32_t code = (uint32_t)(en[k] >> 32);
             size_t e = k;
             while (e + 1 < en.size() && (en[e + 1] >> 32) == code) ++e;
             const uint32_t cnt = (uint32_t)(e - k + 1);
             const uint32_t h = bloom_hash(p, code);
-            bloom[bloom_word(h)] |= bloom_mask(h);
+            __atomic_fetch_or(&bloom[bloom_word(h)], bloom_mask(h), __ATOMIC_RELAXED);
             uint32_t slot = (code * 2654435761u) >> (32 - bits);
             while (ht[slot].x != 0xffffffffu) slot = (slot + 1) & (size - 1);
-            ht[slot] = make_uint2(code, (uint32_t)post_all.size() | ((cnt > 127 ? 127u : cnt - 1) << 25));
-            if (cnt > 127) post_all.push_back(cnt);          // lists too long for the 7-bit field start with their length
-            for (size_t q = k; q <= e; ++q) post_all.push_back((uint32_t)(en[q] & 0x7fffffffu) | (q == e ? 0x80000000u : 0u));
+            ht[slot] = make_uint2(code, (uint32_t)w | ((cnt > 127 ? 127u : cnt - 1) << 25));
+            if (cnt > 127) post_all[w++] = cnt;              // lists too long for the 7-bit field start with their length
+            for (size_t q = k; q <= e; ++q) post_all[w++] = (uint32_t)(en[q] & 0x7fffffffu) | (q == e ? 0x80000000u : 0u);
             k = e + 1;
         }
         std::vector<unsigned long long>().swap(ent[p]);
+    };
+    {
+        std::vector<std::thread> th;
+        for (int p = 0; p < N_PAT; ++p) th.emplace_back(fill, p);
+        for (auto &t : th) t.join();
     }
     {
         uint2 *dt = nullptr;
@@ -1584,7 +1610,6 @@ static int build_index(mcx_ctx *ctx, const mcx_db *db) {
         CK(cudaMemcpy(dt, tab.data(), tab.size() * sizeof(uint2), cudaMemcpyHostToDevice));
         ctx->db.htab = dt; ctx->db.hbits = bits;
     }
-    if (post_all.size() >= (1u << 25)) return fail(ctx, MCX_EINVAL, "seed index too large for 25-bit posting offsets");
     uint32_t *dp = nullptr;
     CK(dev_alloc(&dp, post_all.size())); ctx->db_allocs.push_back(dp);
     CK(cudaMemcpy(dp, post_all.data(), post_all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));

@@ -297,12 +297,14 @@ def sample_and_search(args, engine=None):
     # under torchrun every rank parses the input and searches its contiguous block of the read stream; -n, -d and
     # the sums are made global by microbecensus_b200.distributed (one all-reduce + two small all-gathers)
     world, rank = 1, 0
-    try:
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            world, rank = dist.get_world_size(), dist.get_rank()
-    except ImportError:
-        pass
+    if "torch" in sys.modules or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # (a plain single-GPU run never imports torch: the import alone costs more than searching a million reads)
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                world, rank = dist.get_world_size(), dist.get_rank()
+        except ImportError:
+            pass
 
     def checked(batch):
         if fastq and batch.quals is None and batch.n:

@@ -264,3 +264,10 @@ def test_sharded_quota_and_duplicates_equal_the_whole(oracle):
         assert tot == {"sampled": sampled, "too_short": cnt["too_short"], "low_qual": cnt["low_qual"], "dups": cnt["dups"]}, (nreads, tot, cnt)
         searched = np.concatenate(resolved)
         assert np.array_equal(np.flatnonzero(searched == 0)[:sampled], np.flatnonzero(code == 0))
+
+
+def test_host_module_does_not_import_torch():
+    """A single-GPU run goes numpy + ctypes only: importing torch costs more than searching a million reads."""
+    out = subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0, %r); import microbecensus_b200.microbe_census; "
+                          "print('torch' in sys.modules)" % ROOT], capture_output=True, text=True)
+    assert out.stdout.strip() == "False", out.stdout + out.stderr

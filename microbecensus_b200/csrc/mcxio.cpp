@@ -7,6 +7,7 @@
 
 #include <zlib.h>
 
+#include <algorithm>
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
@@ -299,6 +300,16 @@ extern "C" int mcxio_open(mcxio_file **out, const char *path) {
     f->src->fp = fp;
     f->src->gz = got >= 2 && magic[0] == 0x1f && magic[1] == 0x8b;
     f->offs.push_back(0);
+    {   // size the batch buffers once instead of doubling them while parsing (plain text: at most the file size;
+        // gzip: about four times the compressed size), capped so that a huge file does not reserve it all
+        fseek(fp, 0, SEEK_END);
+        const long fsz = ftell(fp);
+        rewind(fp);
+        if (fsz > 0) {
+            const size_t want = std::min<size_t>((size_t)fsz * (f->src->gz ? 4 : 1), (size_t)2 << 30);
+            try { f->bases.reserve(want / 2 + 64); f->quals.reserve(want / 2 + 64); f->offs.reserve(want / 200 + 16); } catch (const std::bad_alloc &) {}
+        }
+    }
     f->src->start();
     *out = f;
     return MCXIO_OK;

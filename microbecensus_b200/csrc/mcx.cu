@@ -806,7 +806,7 @@ __device__ __forceinline__ uint4 seed_pack(uint32_t gframe, int s, int sb, int q
 // K2c: one thread per candidate: the cheap rejections, growth of the word to the maximal murphy10-identical stretch
 // and the seed acceptance test (ExtendSeq2Set 0x413fc4-0x414073); accepted seeds are queued for k_walk.
 template <int NT>
-__global__ void __launch_bounds__(NT, 2048 / NT) k_seed(ExtArgs A) {
+__global__ void __launch_bounds__(NT) k_seed(ExtArgs A) {
     __shared__ __align__(4) int8_t s_bl[21 * 32];
     __shared__ uint32_t s_same[32];                 // bit b of s_same[a]: residues a and b share a murphy10 letter
     for (int k = threadIdx.x; k < 21 * 32 / 4; k += NT) reinterpret_cast<uint32_t *>(s_bl)[k] = reinterpret_cast<const uint32_t *>(g_blosum)[k];
@@ -2039,7 +2039,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     // K2a/K2b/K3 run per chunk of reads so that the frame store and the candidate queue stay bounded
     const int fstride = frame_stride(maxm);
     int64_t chunk = 2000000, cand_per_read = 96;
-    chunk = std::min<int64_t>(chunk, std::max<int64_t>(250000, 200000000 / P.read_length));   // queues scale with bases, not reads
+    chunk = std::min<int64_t>(chunk, std::max<int64_t>(250000, 300000000 / P.read_length));   // queues scale with bases, not reads
     if (const char *e = getenv("MCX_CHUNK_READS")) chunk = std::min(2700000, std::max(1, atoi(e)));   // frame rows < 2^24
     if (const char *e = getenv("MCX_CAND_PER_READ")) cand_per_read = std::max(1, atoi(e));
     chunk = std::min<int64_t>(chunk, std::max<int64_t>(n_search, 1));

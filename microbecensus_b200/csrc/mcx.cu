@@ -802,6 +802,7 @@ __device__ __forceinline__ uint4 seed_pack(uint32_t gframe, int s, int sb, int q
 
 // (No duplicate filter here: the left-maximal rule for exact words and the one-window-per-position rule for the
 // substitution words already make every accepted stretch unique -- 74,491,397 of 74,491,397 at 2M x 150 bp.)
+constexpr int SEED_NT = 128;       // threads per block of k_seed / k_walk
 #define SAME(a, b) ((s_same[(a)] >> (b)) & 1u)   /* red_eq() from the shared-memory masks */
 // K2c: one thread per candidate: the cheap rejections, growth of the word to the maximal murphy10-identical stretch
 // and the seed acceptance test (ExtendSeq2Set 0x413fc4-0x414073); accepted seeds are queued for k_walk.
@@ -2121,7 +2122,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             {
                 unsigned long long worst = 0;
                 for (int q = 0; q < NQ; ++q) worst = std::max(worst, qfill[q]);
-                k_seed<256><<<dim3((unsigned)((worst + 255) / 256), NQ), 256, 0, st>>>(E);
+                k_seed<SEED_NT><<<dim3((unsigned)((worst + SEED_NT - 1) / SEED_NT), NQ), SEED_NT, 0, st>>>(E);
             }
             ++ctx->launches;
             CK(cudaMemcpyAsync(&n_seeds, ctx->d_cnt + 9, sizeof n_seeds, cudaMemcpyDeviceToHost, st));
@@ -2138,7 +2139,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
                 CK(cudaMemsetAsync(ctx->d_seen, 0xff, (size_t)(1ll << bits) * sizeof(unsigned long long), st));
                 E.seen = ctx->d_seen; E.seen_mask = (1ull << bits) - 1; E.seen_shift = 64 - bits;
             }
-            k_walk<256><<<(unsigned)((n_seeds + 255) / 256), 256, 0, st>>>(E, (int64_t)n_seeds);
+            k_walk<SEED_NT><<<(unsigned)((n_seeds + SEED_NT - 1) / SEED_NT), SEED_NT, 0, st>>>(E, (int64_t)n_seeds);
             ++ctx->launches;
             CK(cudaMemcpyAsync(&n_surv, ctx->d_cnt + 8, sizeof n_surv, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));

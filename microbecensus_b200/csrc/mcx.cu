@@ -109,7 +109,7 @@ __device__ __forceinline__ Surv surv_unpack(const uint4 p) {
     return v;
 }
 
-struct __align__(16) SortKey {     // (read, subject, score desc, frame, q0 | q1, t0, t1, aln, ident)
+struct __align__(16) SortKey {     // (read, subject, score desc, frame, q0 | q1, t0, t1, aln, ungapped q0, ident)
     unsigned long long k1, k2;
 };
 struct SortKeyLess {
@@ -1185,8 +1185,10 @@ __global__ void k_gap_finish(GapArgs A) {
     SortKey k;
     k.k1 = ((unsigned long long)(uint32_t)v.read << 37) | ((unsigned long long)v.subject << 22) |
            ((unsigned long long)(2047 - score) << 11) | ((unsigned long long)v.frame << 8) | (unsigned long long)q0;
+    // after the alignment itself: the start of the ungapped HSP it grew from (different seeds can reach the same score and
+    // ends with another gap placement; RAPsearch2 reports the one it finds first, scanning the frame left to right)
     k.k2 = ((unsigned long long)q1 << 48) | ((unsigned long long)t0 << 37) | ((unsigned long long)t1 << 26) |
-           ((unsigned long long)aln << 17) | ((unsigned long long)ident << 8);
+           ((unsigned long long)aln << 17) | ((unsigned long long)v.q0 << 9) | (unsigned long long)ident;
     A.keys[g] = k;
     A.idx[g] = (int32_t)g;
 }
@@ -1226,7 +1228,7 @@ __device__ __forceinline__ KeyHit key_decode(const SortKey &k) {
     h.read = (int)(k.k1 >> 37); h.subject = (int)(k.k1 >> 22) & 0x7fff; h.score = 2047 - ((int)(k.k1 >> 11) & 0x7ff);
     h.frame = (int)(k.k1 >> 8) & 7; h.q0 = (int)k.k1 & 0xff;
     h.q1 = (int)(k.k2 >> 48); h.t0 = (int)(k.k2 >> 37) & 0x7ff; h.t1 = (int)(k.k2 >> 26) & 0x7ff;
-    h.aln = (int)(k.k2 >> 17) & 0x1ff; h.ident = (int)(k.k2 >> 8) & 0x1ff;
+    h.aln = (int)(k.k2 >> 17) & 0x1ff; h.ident = (int)k.k2 & 0x1ff;
     return h;
 }
 

@@ -37,7 +37,7 @@ typedef struct {
     int32_t read;      /* read index within the call */
     int32_t subject;   /* subject index in the marker DB */
     int32_t frame;     /* 0..2 forward offset, 3..5 reverse-complement offset */
-    int32_t diag;      /* seed diagonal: subject_pos - query_aa_pos */
+    int32_t diag;      /* first aa (on the frame) of the ungapped HSP the alignment grew from: tie-break, see cmp_hit */
     int32_t score;     /* raw Smith-Waterman score */
     int32_t aln;       /* alignment columns (incl. gap columns) */
     int32_t ident;     /* identical residue pairs */

@@ -109,7 +109,7 @@ __device__ __forceinline__ Surv surv_unpack(const uint4 p) {
     return v;
 }
 
-struct __align__(16) SortKey {     // (read, subject, score desc, frame, q0 | q1, t0, t1, aln, ungapped q0, ident)
+struct __align__(16) SortKey {     // (read, subject, score desc, aln desc | ungapped q0, frame, q0, q1, t0, t1, ident)
     unsigned long long k1, k2;
 };
 struct SortKeyLess {
@@ -1182,13 +1182,15 @@ __global__ void k_gap_finish(GapArgs A) {
         dst[1] = make_uint4((uint32_t)h.aln, (uint32_t)h.ident, (uint32_t)h.mism, (uint32_t)h.gapo);
         dst[2] = make_uint4((uint32_t)h.q0, (uint32_t)h.q1, (uint32_t)h.t0, (uint32_t)h.t1);
     }
+    // Sort key = every field the classifier needs, in the order that decides which of several overlapping HSPs of a
+    // (read, subject) pair is printed: score, then -- for alignments of equal score grown from different seeds --
+    // the longest, then the one from the leftmost ungapped HSP (RAPsearch2's choice, tools/blackbox/tie_rule.py).
     SortKey k;
     k.k1 = ((unsigned long long)(uint32_t)v.read << 37) | ((unsigned long long)v.subject << 22) |
-           ((unsigned long long)(2047 - score) << 11) | ((unsigned long long)v.frame << 8) | (unsigned long long)q0;
-    // after the alignment itself: the start of the ungapped HSP it grew from (different seeds can reach the same score and
-    // ends with another gap placement; RAPsearch2 reports the one it finds first, scanning the frame left to right)
-    k.k2 = ((unsigned long long)q1 << 48) | ((unsigned long long)t0 << 37) | ((unsigned long long)t1 << 26) |
-           ((unsigned long long)aln << 17) | ((unsigned long long)v.q0 << 9) | (unsigned long long)ident;
+           ((unsigned long long)(2047 - score) << 11) | ((unsigned long long)(511 - aln) << 2);
+    k.k2 = ((unsigned long long)v.q0 << 56) | ((unsigned long long)v.frame << 53) | ((unsigned long long)q0 << 45) |
+           ((unsigned long long)q1 << 37) | ((unsigned long long)t0 << 26) | ((unsigned long long)t1 << 15) |
+           ((unsigned long long)ident << 6);
     A.keys[g] = k;
     A.idx[g] = (int32_t)g;
 }
@@ -1226,9 +1228,9 @@ struct KeyHit { int read, subject, score, frame, q0, q1, t0, t1, aln, ident; };
 __device__ __forceinline__ KeyHit key_decode(const SortKey &k) {
     KeyHit h;
     h.read = (int)(k.k1 >> 37); h.subject = (int)(k.k1 >> 22) & 0x7fff; h.score = 2047 - ((int)(k.k1 >> 11) & 0x7ff);
-    h.frame = (int)(k.k1 >> 8) & 7; h.q0 = (int)k.k1 & 0xff;
-    h.q1 = (int)(k.k2 >> 48); h.t0 = (int)(k.k2 >> 37) & 0x7ff; h.t1 = (int)(k.k2 >> 26) & 0x7ff;
-    h.aln = (int)(k.k2 >> 17) & 0x1ff; h.ident = (int)k.k2 & 0x1ff;
+    h.aln = 511 - ((int)(k.k1 >> 2) & 0x1ff);
+    h.frame = (int)(k.k2 >> 53) & 7; h.q0 = (int)(k.k2 >> 45) & 0xff; h.q1 = (int)(k.k2 >> 37) & 0xff;
+    h.t0 = (int)(k.k2 >> 26) & 0x7ff; h.t1 = (int)(k.k2 >> 15) & 0x7ff; h.ident = (int)(k.k2 >> 6) & 0x1ff;
     return h;
 }
 

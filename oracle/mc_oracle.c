@@ -603,6 +603,8 @@ static void gapped_xdrop(const uint8_t *q, const uint8_t *t, int step, int nQ, i
 /* RS2 AlignSeqs (0x413370): seed -> ungapped X-drop both ways (both walks start from the seed score) ->
  * if the ungapped total reaches 48.2 raw, gapped X-drop extensions from both HSP ends when more than
  * two residues are left on both sequences.  Fills h (score, aln, ident, mism, gapo, ranges). */
+/* OC_DEBUG_ALN=1: every extended seed on stderr (tools/blackbox/tie_rule.py reads them) */
+static long g_dbg_read = -1; static int g_dbg_subj = -1, g_dbg_frame = -1;
 static void extend_seed(const uint8_t *q, int m, const uint8_t *t, int n, int qb, int sb, int len, oc_hit *h) {
     int score0 = 0, id0 = 0;
     for (int k = 0; k < len; ++k) { score0 += oc_blosum(q[qb + k], t[sb + k]); id0 += (q[qb + k] == t[sb + k] && q[qb + k] < 20); }
@@ -632,6 +634,9 @@ static void extend_seed(const uint8_t *q, int m, const uint8_t *t, int n, int qb
         }
     }
     h->mism = h->aln - h->ident - gapcols;
+    if (getenv("OC_DEBUG_ALN"))
+        fprintf(stderr, "HIT read %ld subj %d frame %d score %d q %d-%d t %d-%d aln %d ident %d gapo %d seed qb %d sb %d len %d\n", g_dbg_read,
+                g_dbg_subj, g_dbg_frame, h->score, h->q0, h->q1, h->t0, h->t1, h->aln, h->ident, h->gapo, qb, sb, len);
 }
 
 /* exported for tests: extension of one seed */
@@ -702,17 +707,18 @@ static int cmp_hit(const void *a, const void *b) {
     const oc_hit *x = (const oc_hit *)a, *y = (const oc_hit *)b;
     if (x->subject != y->subject) return x->subject < y->subject ? -1 : 1;
     if (x->score != y->score) return x->score > y->score ? -1 : 1;
+    /* Different seeds can grow into alignments of one (query, subject) pair with the same score: another end (a tail
+     * of net score zero), or the same ends with another gap placement and identity count.  Which one RAPsearch2
+     * prints was read off its output (tools/blackbox/tie_rule.py: 71 such pairs on the reference's own inputs at 100,
+     * 150 and 500 bp): the longest alignment, then the one grown from the leftmost seed -- 70 of 71; "highest
+     * identity" explains 40, "leftmost seed" alone 41. */
+    if (x->aln != y->aln) return x->aln > y->aln ? -1 : 1;
+    if (x->diag != y->diag) return x->diag < y->diag ? -1 : 1;
     if (x->frame != y->frame) return x->frame < y->frame ? -1 : 1;
     if (x->q0 != y->q0) return x->q0 < y->q0 ? -1 : 1;
     if (x->q1 != y->q1) return x->q1 < y->q1 ? -1 : 1;
     if (x->t0 != y->t0) return x->t0 < y->t0 ? -1 : 1;
     if (x->t1 != y->t1) return x->t1 < y->t1 ? -1 : 1;
-    if (x->aln != y->aln) return x->aln < y->aln ? -1 : 1;
-    /* Different seeds can grow into alignments with the same score and ends but another gap placement (and so another
-     * identity count).  RAPsearch2 reports the one it finds first, scanning the frame left to right: on the reference's
-     * example.fa.gz at 500 bp all 24 lines that differed from ours only in identity are the alignment grown from the
-     * leftmost ungapped HSP. */
-    if (x->diag != y->diag) return x->diag < y->diag ? -1 : 1;
     if (x->ident != y->ident) return x->ident < y->ident ? -1 : 1;
     return 0;
 }
@@ -731,6 +737,7 @@ int oc_search_read(const oc_index *ix, const uint8_t *read, int L, int W, int us
         int n = db->off[s + 1] - db->off[s];
         const uint8_t *t = db->res + db->off[s];
         oc_hit h; memset(&h, 0, sizeof h);
+        g_dbg_subj = s; g_dbg_frame = f;
         extend_seed(aa[f], m[f], t, n, tk[k].qb, tk[k].sb, tk[k].len, &h);
         if (h.score < min_raw) continue;
         h.read = 0; h.subject = s; h.frame = f;
@@ -858,6 +865,7 @@ int64_t oc_search_batch(const oc_index *ix, const uint8_t *bases, const int64_t 
     oc_hit *buf = (oc_hit *)malloc(sizeof(oc_hit) * PER);
     for (int64_t r = 0; r < n; ++r) {
         if (offs[r + 1] - offs[r] < L) continue;
+        g_dbg_read = (long)r;
         int k = oc_search_read(ix, bases + offs[r], L, 0, use_seg, min_raw, buf, PER, n_seeds, NULL);
         for (int i = 0; i < k && nh < cap; ++i) { buf[i].read = (int32_t)r; out[nh++] = buf[i]; }
     }

@@ -40,7 +40,7 @@ def gpu_vs_oracle(eng, oracle, markers, batch, L, quota=-1):
 
 
 @pytest.mark.parametrize("fname,L", [("meta.fa.gz", 100), ("meta50.fa.gz", 50), ("long.fa.gz", 500), ("long.fa.gz", 250),
-                                     ("long.fa.gz", 150), ("long.fa.gz", 60), ("long.fa.gz", 300)])
+                                     ("long.fa.gz", 150), ("long.fa.gz", 60), ("long.fa.gz", 300), ("ties.fa.gz", 500)])
 def test_golden_reads_bit_exact(eng, oracle, markers, fname, L):
     gpu_vs_oracle(eng, oracle, markers, ReadBatch.from_strings(golden_io.read_fasta(fname)), L)
 

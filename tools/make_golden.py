@@ -56,7 +56,22 @@ def write_set(name, seqs, L, tmp):
     print(name, L, "reads", len(seqs), "lines", exp["m8_lines"], "classified", len(exp["classified"]), "AGS", exp["ags"])
 
 
+def make_ties():
+    """G5: reads of example.fa.gz whose alignments to some subjects can be grown from several seeds into alignments of
+    the same score and ends but different gap placement / identity (reads 645, 1077, 1202 at 500 bp): RAPsearch2 reports
+    the one from the leftmost seed.  `python tools/make_golden.py ties` writes only this fixture."""
+    recs = [r.seq for r in mc.parse_seqs(mc.open_file(os.path.join(REF, "microbe_census", "example", "example.fa.gz")))]
+    pick = [640, 645, 646, 1077, 1202, 1203]
+    seqs = [recs[i] for i in pick]
+    with tempfile.TemporaryDirectory() as tmp:
+        with gzip.GzipFile(os.path.join(GOLD, "ties.fa.gz"), "wb", mtime=0) as fh:
+            fh.write("".join(">e%d\n%s\n" % (i, s) for i, s in zip(pick, seqs)).encode())
+        write_set("ties", seqs, 500, tmp)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "ties":
+        return make_ties()
     os.makedirs(GOLD, exist_ok=True)
     rnd = random.Random(20260101)
     with tempfile.TemporaryDirectory() as tmp:
@@ -119,6 +134,7 @@ def main():
         json.dump(qc_cases, open(os.path.join(GOLD, "short.qc.json"), "w"), indent=1, sort_keys=True)
         kept = [s for (_, s, _) in fq if len(s) >= 100]
         write_set("short", kept, 100, tmp)
+    make_ties()
     print("done")
 
 

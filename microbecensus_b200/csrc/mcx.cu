@@ -652,14 +652,39 @@ __device__ __forceinline__ int warp_scan_add(int v, int lane) {
 // (Tried and measured slower, 5.9 -> 8.8 ms: letting the filter passes wait in a per-warp ring until 32 of them can do
 // their table lookups together.  The kernel as it stands issues at 66 % of peak; the ring version executes 27 % fewer
 // instructions but stalls on the MIO pipe (shuffles, shared-memory traffic of the ring) and issues at 24 %.)
+// word codes (base 10) of the 10-window d0..d9 held as nibbles in `win`: the exact word d0..d8 and, for a wildcard at
+// offset w = 3..6, the nine letters around it = (d0..d[w-1]) * 10^(9-w) + (d[w+1]..d9); prefixes and suffixes shared
+__device__ __forceinline__ void window_codes(unsigned long long win, uint32_t *code, bool &ok9, bool &ok10) {
+    uint32_t d[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) d[k] = (uint32_t)(win >> (4 * k)) & 15;
+    int bad9 = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) bad9 |= (d[k] >= 10);
+    ok9 = !bad9; ok10 = !(bad9 | (d[9] >= 10));
+    const uint32_t h3 = (d[0] * 10 + d[1]) * 10 + d[2], h4 = h3 * 10 + d[3], h5 = h4 * 10 + d[4], h6 = h5 * 10 + d[5];
+    const uint32_t t6 = (d[7] * 10 + d[8]) * 10 + d[9], t5 = d[6] * 1000 + t6, t4 = d[5] * 10000 + t5, t3 = d[4] * 100000 + t4;
+    code[0] = h6 * 1000 + (d[6] * 10 + d[7]) * 10 + d[8];
+    code[1] = h3 * 1000000 + t3;
+    code[2] = h4 * 100000 + t4;
+    code[3] = h5 * 10000 + t5;
+    code[4] = h6 * 1000 + t6;
+}
+
+#ifndef MCX_PROBE_POS
+#define MCX_PROBE_POS 2
+#endif
+constexpr int PROBE_POS = MCX_PROBE_POS;   // window positions per loop iteration (2: one compaction round for 10 filter probes)
+constexpr int PROBE_Q = 32 * N_PAT * PROBE_POS;
+
 template <int NT>
 __global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int NW = NT / 32;
-    uint32_t *s_qcode = reinterpret_cast<uint32_t *>(smem);            // [NW][160] words that passed the filter
-    uint32_t *s_x = s_qcode + NW * 160;                                // [NW][4][32] incl. prefix, posting start, gframe, ip
-    uint8_t *s_qmeta = reinterpret_cast<uint8_t *>(s_x + NW * 128);    // [NW][160] lane << 3 | pattern
-    uint8_t *s_aa = s_qmeta + NW * 160;
+    uint32_t *s_qcode = reinterpret_cast<uint32_t *>(smem);            // [NW][PROBE_Q] words that passed the filter
+    uint32_t *s_x = s_qcode + NW * PROBE_Q;                            // [NW][4][32] incl. prefix, posting start, gframe, ip
+    uint16_t *s_qmeta = reinterpret_cast<uint16_t *>(s_x + NW * 128);  // [NW][PROBE_Q] lane | pattern << 5 | position offset << 8
+    uint8_t *s_aa = reinterpret_cast<uint8_t *>(s_qmeta + NW * PROBE_Q);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {   // each warp stages its 32 rows
         const int64_t row0 = (int64_t)blockIdx.x * NT + (tid - lane);
@@ -668,8 +693,8 @@ __global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
         for (int k = lane; k < 32 * fstride / 4; k += 32) dst[k] = src[k];
     }
     __syncwarp();
-    uint32_t *qcode = s_qcode + warp * 160, *xs = s_x + warp * 128;
-    uint8_t *qmeta = s_qmeta + warp * 160;
+    uint32_t *qcode = s_qcode + warp * PROBE_Q, *xs = s_x + warp * 128;
+    uint16_t *qmeta = s_qmeta + warp * PROBE_Q;
     const int64_t g = (int64_t)blockIdx.x * NT + tid;
     const uint8_t *fr = s_aa + tid * fstride;
     const int m = g < A.n_frames ? (A.L - (int)(g % 6) % 3) / 3 : 0;
@@ -678,43 +703,35 @@ __global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
     unsigned long long win = 0;
     for (int k = 0; k < 10; ++k) win |= (unsigned long long)(k < m ? red_of(fr[k]) : 15) << (4 * k);
     const int mmax = A.L / 3;
-    for (int i = 0; i + 9 <= mmax; ++i) {
-        // word codes (base 10) of the 10-window d0..d9: the exact word d0..d8 and, for a wildcard at offset w = 3..6,
-        // the nine letters around it = (d0..d[w-1]) * 10^(9-w) + (d[w+1]..d9).  Prefixes and suffixes are shared
-        // between the patterns: 19 multiply-adds instead of 45.
-        uint32_t code[N_PAT];
-        uint32_t d[10];
+    for (int i = 0; i + 9 <= mmax; i += PROBE_POS) {
+        uint32_t code[N_PAT * PROBE_POS];
+        bool ok9[PROBE_POS], ok10[PROBE_POS];
 #pragma unroll
-        for (int k = 0; k < 10; ++k) d[k] = (uint32_t)(win >> (4 * k)) & 15;
-        int bad9 = 0;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) bad9 |= (d[k] >= 10);
-        const int bad10 = bad9 | (d[9] >= 10);
-        const uint32_t h3 = (d[0] * 10 + d[1]) * 10 + d[2], h4 = h3 * 10 + d[3], h5 = h4 * 10 + d[4], h6 = h5 * 10 + d[5];
-        const uint32_t t6 = (d[7] * 10 + d[8]) * 10 + d[9], t5 = d[6] * 1000 + t6, t4 = d[5] * 10000 + t5, t3 = d[4] * 100000 + t4;
-        code[0] = h6 * 1000 + (d[6] * 10 + d[7]) * 10 + d[8];
-        code[1] = h3 * 1000000 + t3;
-        code[2] = h4 * 100000 + t4;
-        code[3] = h5 * 10000 + t5;
-        code[4] = h6 * 1000 + t6;
-        // five filter words in flight together
-        uint32_t bw[N_PAT], bh[N_PAT];
-#pragma unroll
-        for (int p = 0; p < N_PAT; ++p) {
-            bh[p] = bloom_hash(p, code[p]);
-            bw[p] = (p == 0 ? !bad9 : !bad10) ? __ldg(A.db.bloom + bloom_word(bh[p])) : 0u;
+        for (int h = 0; h < PROBE_POS; ++h) {
+            window_codes(win, code + N_PAT * h, ok9[h], ok10[h]);
+            if (i + h + 9 > mmax) { ok9[h] = false; ok10[h] = false; }      // past the last window of the longest frame
+            const int nx = i + h + 10;
+            win = (win >> 4) | ((unsigned long long)(nx < m ? red_of(fr[nx]) : 15) << 36);
         }
-        bool pass[N_PAT];
+        // all filter words of the iteration in flight together
+        uint32_t bw[N_PAT * PROBE_POS], bh[N_PAT * PROBE_POS];
+#pragma unroll
+        for (int q = 0; q < N_PAT * PROBE_POS; ++q) {
+            const int p = q % N_PAT, h = q / N_PAT;
+            bh[q] = bloom_hash(p, code[q]);
+            bw[q] = (p == 0 ? ok9[h] : ok10[h]) ? __ldg(A.db.bloom + bloom_word(bh[q])) : 0u;
+        }
+        bool pass[N_PAT * PROBE_POS];
         int npass = 0;
 #pragma unroll
-        for (int p = 0; p < N_PAT; ++p) { const uint32_t mk = bloom_mask(bh[p]); pass[p] = (bw[p] & mk) == mk; npass += pass[p]; }
+        for (int q = 0; q < N_PAT * PROBE_POS; ++q) { const uint32_t mk = bloom_mask(bh[q]); pass[q] = (bw[q] & mk) == mk; npass += pass[q]; }
         const int incl = warp_scan_add(npass, lane);
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         if (total > 0) {
             int o = incl - npass;
 #pragma unroll
-            for (int p = 0; p < N_PAT; ++p)
-                if (pass[p]) { qcode[o] = code[p]; qmeta[o] = (uint8_t)((lane << 3) | p); ++o; }
+            for (int q = 0; q < N_PAT * PROBE_POS; ++q)
+                if (pass[q]) { qcode[o] = code[q]; qmeta[o] = (uint16_t)(lane | ((q % N_PAT) << 5) | ((q / N_PAT) << 8)); ++o; }
             __syncwarp();
             for (int base = 0; base < total; base += 32) {
                 const int t = base + lane;
@@ -722,7 +739,7 @@ __global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
                 if (t < total) {
                     const uint32_t c = qcode[t];
                     meta = qmeta[t];
-                    const int p = meta & 7;
+                    const int p = (meta >> 5) & 7;
                     // key and value share an 8-byte slot: one load per probe, no second round trip for the value
                     const uint2 *__restrict__ tb = A.db.htab + ((size_t)p << A.db.hbits);
                     const uint32_t hmask = (1u << A.db.hbits) - 1u;
@@ -743,7 +760,7 @@ __global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
                 if (lane == 0) basepos = atomicAdd(A.n_cand + sq, (unsigned long long)tot2);
                 basepos = __shfl_sync(0xffffffffu, basepos, 0);
                 xs[lane] = (uint32_t)inc2; xs[32 + lane] = pi;
-                xs[64 + lane] = (uint32_t)(g - lane + (meta >> 3)); xs[96 + lane] = ((uint32_t)i << 8) | (meta & 7);
+                xs[64 + lane] = (uint32_t)(g - lane + (meta & 31)); xs[96 + lane] = ((uint32_t)(i + (int)(meta >> 8)) << 8) | ((meta >> 5) & 7);
                 __syncwarp();
                 if (basepos + (unsigned long long)tot2 <= A.cap_cand) {
                     Cand *dst = A.cand + (unsigned long long)sq * A.cap_cand + basepos;
@@ -760,8 +777,6 @@ __global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
             }
             __syncwarp();
         }
-        const int nx = i + 10;
-        win = (win >> 4) | ((unsigned long long)(nx < m ? red_of(fr[nx]) : 15) << 36);
     }
 }
 
@@ -2091,7 +2106,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             ProbeArgs A;
             A.n_frames = nr * 6; A.L = P.read_length; A.db = ctx->db; A.frames = ctx->d_frames; A.cand = ctx->d_cand;
             A.n_cand = ctx->d_qcnt; A.cap_cand = (unsigned long long)(ctx->cap_cand / NQ);
-            const size_t smem = (size_t)(NTF / 32) * (160 * 4 + 128 * 4 + 160) + (size_t)fstride * NTF;
+            const size_t smem = (size_t)(NTF / 32) * (PROBE_Q * 4 + 128 * 4 + PROBE_Q * 2) + (size_t)fstride * NTF;
             CK(cudaFuncSetAttribute(k_probe<NTF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_probe<NTF><<<(unsigned)((nr * 6 + NTF - 1) / NTF), NTF, smem, st>>>(A, fstride);
             ++ctx->launches;

@@ -125,6 +125,12 @@ int  mcx_qc_counts(mcx_ctx *ctx, mcx_qc *out);
  * mcx_qc_import replaces the verdicts (e.g. duplicates decided across GPUs, mc.py:345) and rebuilds the kept list. */
 int  mcx_qc_export(mcx_ctx *ctx, uint8_t *code, uint64_t *fingerprints);
 int  mcx_qc_import(mcx_ctx *ctx, const uint8_t *code);
+/* The same without leaving the device: *d_code = the n verdict bytes, *d_fingerprints (optional) = n records of 24 bytes
+ * {uint64 a, uint64 b, uint32 read index, uint32 0}, both in HBM and owned by the context.  The caller may rewrite the
+ * verdicts in place (on the context's stream or after synchronising) and then calls mcx_qc_refresh to rebuild the kept
+ * list.  Used by the cross-GPU duplicate exchange, which never brings fingerprints to the host. */
+int  mcx_qc_device(mcx_ctx *ctx, void **d_code, void **d_fingerprints, int64_t *n);
+int  mcx_qc_refresh(mcx_ctx *ctx);
 /* search the first `quota` kept reads (quota < 0: all of them) */
 int  mcx_search(mcx_ctx *ctx, int64_t quota);
 int  mcx_result_get(mcx_ctx *ctx, mcx_result *out);

@@ -2003,6 +2003,36 @@ extern "C" int mcx_qc_import(mcx_ctx *ctx, const uint8_t *code) {
     return refresh_kept(ctx);
 }
 
+// Device-side access to the verdicts for the cross-GPU duplicate exchange (microbecensus_b200/distributed.py): the
+// per-read codes and the fingerprint records (a, b, read index) stay in HBM, the caller's framework wraps the pointers,
+// rewrites codes in place and calls mcx_qc_refresh.
+extern "C" int mcx_qc_device(mcx_ctx *ctx, void **d_code, void **d_fingerprints, int64_t *n) {
+    if (!ctx || !d_code || !n) return fail(ctx, MCX_EINVAL, "mcx_qc_device: null argument");
+    if (!ctx->pushed) return fail(ctx, MCX_ESTATE, "mcx_qc_device: no reads pushed");
+    CK(cudaSetDevice(ctx->device));
+    *n = ctx->n_reads;
+    *d_code = ctx->d_code;
+    if (d_fingerprints) {
+        int rc;
+        if ((rc = ensure(ctx, &ctx->d_fp, &ctx->cap_fp, std::max<int64_t>(ctx->n_reads, 1))) != MCX_OK) return rc;
+        if (ctx->n_reads > 0) {
+            k_fingerprint<<<(unsigned)((ctx->n_reads + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_bases, ctx->d_offs, ctx->n_reads, ctx->d_fp);
+            ++ctx->launches;
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaGetLastError());
+        *d_fingerprints = ctx->d_fp;
+    }
+    return MCX_OK;
+}
+
+extern "C" int mcx_qc_refresh(mcx_ctx *ctx) {
+    if (!ctx) return fail(ctx, MCX_EINVAL, "mcx_qc_refresh: null context");
+    if (!ctx->pushed) return fail(ctx, MCX_ESTATE, "mcx_qc_refresh: no reads pushed");
+    CK(cudaSetDevice(ctx->device));
+    return refresh_kept(ctx);
+}
+
 extern "C" int mcx_qc_counts(mcx_ctx *ctx, mcx_qc *out) {
     if (!ctx || !out) return fail(ctx, MCX_EINVAL, "mcx_qc_counts: null argument");
     if (!ctx->pushed) return fail(ctx, MCX_ESTATE, "mcx_qc_counts: no reads pushed");

@@ -5,9 +5,10 @@ semantics are order-dependent over the whole input (microbe_census.py:328-367) a
 
 * ``-n``: the first `nreads` KEPT reads in file order are searched, and the too-short / low-quality / duplicate
   counters stop at the read that filled the quota -> all-gather of per-shard kept counts, then `shard_quota`;
-* ``-d``: a read is a duplicate if an earlier kept read has the same sequence (either strand) -> all-gather of the
-  fingerprints of the QC-passing reads, then `resolve_duplicates` (the first passing read of a fingerprint group is
-  kept, every later long-enough read of the group is a duplicate);
+* ``-d``: a read is a duplicate if an earlier kept read has the same sequence (either strand) -> `exchange_duplicates`:
+  one all-to-all of (fingerprint, global index, passed-QC) routed by fingerprint, the owner marks every record behind
+  the first passing read of its group, a second all-to-all returns the marks (`resolve_duplicates` is the same rule on
+  one host with all passing fingerprints gathered: kept as the reference the exchange is tested against);
 * the additive results (counters, per-family sums) -> one all-reduce of `SearchResult.counts_vector()`.
 
 Shards are contiguous blocks of the read stream in rank order.  The pure functions below are tested on CPU against
@@ -60,6 +61,93 @@ def resolve_duplicates(codes, fps, first_index, passing_fps, passing_index):
     return codes
 
 
+def _exchange_marks(a, b, gp, group):
+    """Core of the -d exchange on tensors of one device: a, b = fingerprint halves (int64), gp = global index << 1 | passed-QC
+    of this rank's long-enough reads.  Returns an int64 tensor, 1 where the read is a duplicate."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    dev = a.device
+    owner = torch.remainder(a & 0x7FFFFFFFFFFFFFFF, world)
+    order = torch.argsort(owner, stable=True)
+    counts = torch.bincount(owner, minlength=world)
+    send = torch.stack([a[order], b[order], gp[order]], dim=1).contiguous()
+    recv_counts = torch.empty_like(counts)
+    dist.all_to_all_single(recv_counts, counts, group=group)
+    in_split, out_split = [int(x) for x in counts.tolist()], [int(x) for x in recv_counts.tolist()]
+    recv = torch.empty((sum(out_split), 3), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv, send, output_split_sizes=out_split, input_split_sizes=in_split, group=group)
+    # owner: order by (a, b, index) with three stable sorts, then the smallest passing index of every group
+    ra, rb, rgp = recv[:, 0], recv[:, 1], recv[:, 2]
+    perm = torch.argsort(rgp, stable=True)
+    perm = perm[torch.argsort(rb[perm], stable=True)]
+    perm = perm[torch.argsort(ra[perm], stable=True)]
+    sa, sb, sgp = ra[perm], rb[perm], rgp[perm]
+    n = sa.numel()
+    dup_sorted = torch.zeros(n, dtype=torch.int64, device=dev)
+    if n:
+        new = torch.ones(n, dtype=torch.bool, device=dev)
+        new[1:] = (sa[1:] != sa[:-1]) | (sb[1:] != sb[:-1])
+        gid = torch.cumsum(new.to(torch.int64), 0) - 1
+        big = torch.iinfo(torch.int64).max
+        first_pass = torch.full((int(gid[-1]) + 1,), big, dtype=torch.int64, device=dev)
+        first_pass.scatter_reduce_(0, gid, torch.where((sgp & 1) == 1, sgp >> 1, torch.full_like(sgp, big)), reduce="amin")
+        dup_sorted = ((sgp >> 1) > first_pass[gid]).to(torch.int64)
+    marks = torch.empty(n, dtype=torch.int64, device=dev)
+    marks[perm] = dup_sorted
+    back = torch.empty(a.numel(), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(back, marks, output_split_sizes=in_split, input_split_sizes=out_split, group=group)
+    dup = torch.empty(a.numel(), dtype=torch.int64, device=dev)
+    dup[order] = back
+    return dup
+
+
+def exchange_duplicates(codes, fps, first_index, group=None, device=None):
+    """`-d` across ranks without any rank seeing all reads: every long-enough read sends (fingerprint, global
+    index, passed-QC flag) to the rank that owns its fingerprint (a mod world) with ONE all-to-all, the owner sorts its
+    records by (fingerprint, index) on its device and marks every record behind the first QC-passing one of its group,
+    and the marks travel back with a second all-to-all.  Same verdicts as `resolve_duplicates`, 1 / world of its work per
+    rank and no host-side sort.  Host arrays in, a copy of `codes` with 3 where the read is a duplicate out."""
+    import torch
+    dev = device or torch.device("cpu")
+    codes = np.array(codes, dtype=np.uint8, copy=True)
+    sel = np.flatnonzero(codes != 1)                                   # too short is decided before the duplicate test
+    fp = np.ascontiguousarray(fps, dtype=np.uint64)[sel].view(np.int64).reshape(-1, 2)
+    a = torch.from_numpy(fp[:, 0].copy()).to(dev)
+    b = torch.from_numpy(fp[:, 1].copy()).to(dev)
+    gp = torch.from_numpy(((first_index + sel.astype(np.int64)) << 1) | (codes[sel] == 0)).to(dev)    # index << 1 | passed
+    dup = _exchange_marks(a, b, gp, group)
+    codes[sel[dup.cpu().numpy() == 1]] = 3
+    return codes
+
+
+class _CudaView:
+    """raw device pointer -> object torch.as_tensor() wraps without a copy"""
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def exchange_duplicates_device(engine, first_index, group=None, device=None):
+    """The same on the verdicts and fingerprints as they sit in the engine's device memory (mcx_qc_device): nothing but
+    the two all-to-alls leaves the GPU.  Rewrites the verdicts in place and returns the refreshed QC counters."""
+    import torch
+    dc, df, n = engine.qc_device(True)
+    if n == 0:
+        dev = device or torch.device("cuda", torch.cuda.current_device())
+        z = torch.zeros(0, dtype=torch.int64, device=dev)
+        _exchange_marks(z, z, z, group)
+        return engine.qc_refresh()
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    codes = torch.as_tensor(_CudaView(dc, (n,), "|u1"), device=dev)
+    fp = torch.as_tensor(_CudaView(df, (n, 3), "<i8"), device=dev)
+    sel = torch.nonzero(codes != 1).squeeze(1)
+    gp = ((first_index + sel) << 1) | (codes[sel] == 0).to(torch.int64)
+    dup = _exchange_marks(fp[sel, 0].contiguous(), fp[sel, 1].contiguous(), gp, group)
+    codes[sel[dup == 1]] = 3
+    torch.cuda.current_stream(dev).synchronize()
+    return engine.qc_refresh()
+
+
 def sharded_search(engine, batch, first_index, nreads=None, filter_dups=False, group=None, device=None, push=None):
     """Search this rank's block of reads (already `set_params`-ed engine) and return the all-reduced SearchResult.
 
@@ -74,20 +162,11 @@ def sharded_search(engine, batch, first_index, nreads=None, filter_dups=False, g
         return engine.search(-1 if nreads is None else nreads)
     dev = device or (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu"))
     if filter_dups:
-        codes, fps = engine.qc_export(True)
-        ok = codes == 0
-        mine = torch.from_numpy(np.concatenate([fps[ok].view(np.int64).reshape(-1, 2),
-                                                (first_index + np.flatnonzero(ok)).astype(np.int64)[:, None]], axis=1)).to(dev)
-        sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(sizes, torch.tensor([mine.shape[0]], dtype=torch.int64, device=dev), group=group)
-        cap = int(max(int(s) for s in sizes))
-        padded = torch.zeros((cap, 3), dtype=torch.int64, device=dev)
-        padded[:mine.shape[0]] = mine
-        parts = [torch.zeros((cap, 3), dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(parts, padded, group=group)
-        allp = np.concatenate([p[:int(s)].cpu().numpy() for p, s in zip(parts, sizes)])
-        codes = resolve_duplicates(codes, fps, first_index, allp[:, :2].view(np.uint64), allp[:, 2])
-        qc = engine.qc_import(codes)
+        if dev.type == "cuda":
+            qc = exchange_duplicates_device(engine, first_index, group=group, device=dev)
+        else:
+            codes, fps = engine.qc_export(True)
+            qc = engine.qc_import(exchange_duplicates(codes, fps, first_index, group=group, device=dev))
     kept = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(kept, torch.tensor([qc["kept"]], dtype=torch.int64, device=dev), group=group)
     quota = shard_quota([int(k) for k in kept], nreads, rank)

@@ -182,6 +182,17 @@ class MarkerSearch:
         self._ck(self.lib.mcx_qc_export(self.ctx, _ptr(code), _ptr(fp)))
         return code[:n], (None if fp is None else fp[:n])
 
+    def qc_device(self, with_fingerprints=True):
+        """(pointer to the n verdict bytes, pointer to the n 24-byte fingerprint records or 0, n) in device memory"""
+        dc, df, n = C.c_void_p(0), C.c_void_p(0), C.c_int64(0)
+        self._ck(self.lib.mcx_qc_device(self.ctx, C.byref(dc), C.byref(df) if with_fingerprints else None, C.byref(n)))
+        return dc.value or 0, df.value or 0, n.value
+
+    def qc_refresh(self):
+        """rebuild the kept list after the verdicts were rewritten in device memory"""
+        self._ck(self.lib.mcx_qc_refresh(self.ctx))
+        return self.qc()
+
     def qc_import(self, code):
         code = np.ascontiguousarray(code, np.uint8)
         self._ck(self.lib.mcx_qc_import(self.ctx, _ptr(code)))

@@ -271,3 +271,34 @@ def test_host_module_does_not_import_torch():
     out = subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0, %r); import microbecensus_b200.microbe_census; "
                           "print('torch' in sys.modules)" % ROOT], capture_output=True, text=True)
     assert out.stdout.strip() == "False", out.stdout + out.stderr
+
+
+def test_exchange_duplicates_two_ranks_gloo(tmp_path):
+    """-d across ranks (all-to-all routed by fingerprint, owner-side sort and marks, all-to-all back) on two and three
+    gloo ranks on CPU: every rank ends with the verdicts `resolve_duplicates` gives with all passing fingerprints in hand."""
+    script = tmp_path / "w.py"
+    script.write_text('''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from microbecensus_b200.distributed import exchange_duplicates, resolve_duplicates
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(7)
+n = 6000
+fp = rng.integers(0, 2**63, size=(n, 2), dtype=np.int64).astype(np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 2)).astype(np.uint64)
+for i in rng.choice(np.arange(50, n), 900, replace=False):      # duplicates of earlier reads, some of them chains
+    fp[i] = fp[rng.integers(0, i)]
+codes = rng.choice(np.array([0, 0, 0, 0, 1, 2], np.uint8), n)
+ok = np.flatnonzero(codes == 0)
+bounds = [k * n // w for k in range(w + 1)]
+lo, hi = bounds[r], bounds[r + 1]
+got = exchange_duplicates(codes[lo:hi], fp[lo:hi], lo)
+want = resolve_duplicates(codes[lo:hi], fp[lo:hi], lo, fp[ok], ok)
+assert np.array_equal(got, want), (r, int((got != want).sum()))
+assert (want == 3).sum() > 50
+empty = exchange_duplicates(codes[:0], fp[:0], 0) if r == 0 else exchange_duplicates(codes[lo:hi], fp[lo:hi], lo)
+dist.destroy_process_group()
+''' % ROOT)
+    for nproc, port in ((2, "29518"), (3, "29519")):
+        subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nproc, "--master-addr", "127.0.0.1",
+                               "--master-port", port, str(script)], stdout=subprocess.DEVNULL, timeout=600)

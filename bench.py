@@ -194,6 +194,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the search has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"            # keeps NCCL's version banner out of stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     n = a.reads_per_gpu or (wl["reads"] // 2 if a.workload == "c3" else wl["reads"])

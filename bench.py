@@ -193,6 +193,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the search has no CPU path")
     torch.cuda.set_device(local)
+    numa_node = None
+    if world > 1:                                # host buffers next to the GPU that reads them (first touch after binding)
+        from microbecensus_b200.affinity import bind_to_gpu_numa_node
+        numa_node = bind_to_gpu_numa_node(int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local]) if os.environ.get("CUDA_VISIBLE_DEVICES", "").replace(",", "").isdigit() else local)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"            # keeps NCCL's version banner out of stdout (one JSON line only)
@@ -348,7 +352,7 @@ def main():
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": t_dev * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": wl["name"], "reads_per_gpu": n, "read_length": L, "parallelism": "reads sharded x%d, marker index replicated" % world,
-                       "l2": "inputs (%d MB per GPU) larger than L2, no flush needed" % (h2d_bytes >> 20)},
+                       "l2": "inputs (%d MB per GPU) larger than L2, no flush needed" % (h2d_bytes >> 20), "rank0_numa_node": numa_node},
             "e2e": {"value": total_reads / t_e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": int(res.counts_vector().nbytes), "ms_per_step": t_e2e * 1e3},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,

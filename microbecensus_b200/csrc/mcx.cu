@@ -674,6 +674,9 @@ __device__ __forceinline__ void window_codes(unsigned long long win, uint32_t *c
 #ifndef MCX_PROBE_POS
 #define MCX_PROBE_POS 2
 #endif
+#ifndef MCX_PROBE_NT
+#define MCX_PROBE_NT 64               /* threads per block of k_probe: small blocks retire early (measured 64 / 96 / 128 / 160 / 192 / 256: 5.17 / 5.19 / 5.30 / 5.41 / 5.71 / 6.18 ms at 100 bp) */
+#endif
 constexpr int PROBE_POS = MCX_PROBE_POS;   // window positions per loop iteration (2: one compaction round for 10 filter probes)
 constexpr int PROBE_Q = 32 * N_PAT * PROBE_POS;
 
@@ -2136,9 +2139,10 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             ProbeArgs A;
             A.n_frames = nr * 6; A.L = P.read_length; A.db = ctx->db; A.frames = ctx->d_frames; A.cand = ctx->d_cand;
             A.n_cand = ctx->d_qcnt; A.cap_cand = (unsigned long long)(ctx->cap_cand / NQ);
-            const size_t smem = (size_t)(NTF / 32) * (PROBE_Q * 4 + 128 * 4 + PROBE_Q * 2) + (size_t)fstride * NTF;
-            CK(cudaFuncSetAttribute(k_probe<NTF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_probe<NTF><<<(unsigned)((nr * 6 + NTF - 1) / NTF), NTF, smem, st>>>(A, fstride);
+            constexpr int NTP = MCX_PROBE_NT;
+            const size_t smem = (size_t)(NTP / 32) * (PROBE_Q * 4 + 128 * 4 + PROBE_Q * 2) + (size_t)fstride * NTP;
+            CK(cudaFuncSetAttribute(k_probe<NTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_probe<NTP><<<(unsigned)((nr * 6 + NTP - 1) / NTP), NTP, smem, st>>>(A, fstride);
             ++ctx->launches;
             CK(cudaMemcpyAsync(qfill, ctx->d_qcnt, sizeof qfill, cudaMemcpyDeviceToHost, st));
             if (attempt == 0) CK(cudaEventRecord(ctx->ev[3], st));

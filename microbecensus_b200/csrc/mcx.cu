@@ -820,7 +820,14 @@ __device__ __forceinline__ uint4 seed_pack(uint32_t gframe, int s, int sb, int q
 
 // (No duplicate filter here: the left-maximal rule for exact words and the one-window-per-position rule for the
 // substitution words already make every accepted stretch unique -- 74,491,397 of 74,491,397 at 2M x 150 bp.)
-constexpr int SEED_NT = 128;       // threads per block of k_seed / k_walk
+#ifndef MCX_SEED_NT
+#define MCX_SEED_NT 128
+#endif
+#ifndef MCX_GAP_NT
+#define MCX_GAP_NT 128
+#endif
+constexpr int SEED_NT = MCX_SEED_NT;   // threads per block of k_seed / k_walk
+constexpr int GAP_NT = MCX_GAP_NT;     // threads per block of k_gap_dir
 #define SAME(a, b) ((s_same[(a)] >> (b)) & 1u)   /* red_eq() from the shared-memory masks */
 // K2c: one thread per candidate: the cheap rejections, growth of the word to the maximal murphy10-identical stretch
 // and the seed acceptance test (ExtendSeq2Set 0x413fc4-0x414073); accepted seeds are queued for k_walk.
@@ -2228,11 +2235,11 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
                     cub::DeviceRadixSort::SortKeys(ctx->d_temp, tb, G.items, list1, (int)n_items, 32, 40, st);
                 }
                 CK(cudaMemsetAsync(ctx->d_cnt + 14, 0, sizeof(unsigned long long), st));
-                const unsigned gb = (unsigned)((n_items + 127) / 128);
+                const unsigned gb = (unsigned)((n_items + GAP_NT - 1) / GAP_NT);
                 const int grow = maxm + GAP_SLACK + 2;
-                if (grow <= 104) k_gap_dir<128, 104, false><<<gb, 128, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + 14);
-                else if (grow <= 152) k_gap_dir<128, 152, false><<<gb, 128, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + 14);
-                else k_gap_dir<128, MAX_FRAME + GAP_SLACK + 2, false><<<gb, 128, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + 14);
+                if (grow <= 104) k_gap_dir<GAP_NT, 104, false><<<gb, GAP_NT, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + 14);
+                else if (grow <= 152) k_gap_dir<GAP_NT, 152, false><<<gb, GAP_NT, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + 14);
+                else k_gap_dir<GAP_NT, MAX_FRAME + GAP_SLACK + 2, false><<<gb, GAP_NT, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + 14);
                 unsigned long long n2 = 0;
                 CK(cudaMemcpyAsync(&n2, ctx->d_cnt + 14, sizeof n2, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
@@ -2241,10 +2248,10 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
                     cub::DeviceRadixSort::SortKeys(nullptr, tb, items2, list2, (int)n2, 32, 48, st);
                     if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
                     cub::DeviceRadixSort::SortKeys(ctx->d_temp, tb, items2, list2, (int)n2, 32, 48, st);
-                    const unsigned gb2 = (unsigned)((n2 + 127) / 128);
-                    if (grow <= 104) k_gap_dir<128, 104, true><<<gb2, 128, 0, st>>>(G, list2, (int64_t)n2, nullptr, nullptr);
-                    else if (grow <= 152) k_gap_dir<128, 152, true><<<gb2, 128, 0, st>>>(G, list2, (int64_t)n2, nullptr, nullptr);
-                    else k_gap_dir<128, MAX_FRAME + GAP_SLACK + 2, true><<<gb2, 128, 0, st>>>(G, list2, (int64_t)n2, nullptr, nullptr);
+                    const unsigned gb2 = (unsigned)((n2 + GAP_NT - 1) / GAP_NT);
+                    if (grow <= 104) k_gap_dir<GAP_NT, 104, true><<<gb2, GAP_NT, 0, st>>>(G, list2, (int64_t)n2, nullptr, nullptr);
+                    else if (grow <= 152) k_gap_dir<GAP_NT, 152, true><<<gb2, GAP_NT, 0, st>>>(G, list2, (int64_t)n2, nullptr, nullptr);
+                    else k_gap_dir<GAP_NT, MAX_FRAME + GAP_SLACK + 2, true><<<gb2, GAP_NT, 0, st>>>(G, list2, (int64_t)n2, nullptr, nullptr);
                     ctx->launches += 3;
                 }
                 ctx->launches += 2;

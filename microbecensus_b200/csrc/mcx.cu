@@ -511,7 +511,7 @@ __device__ void coop_trim(const uint8_t *fr, int off, int tl, uint8_t *P, uint8_
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_seg(uint8_t *frames, int fstride, int L, const uint32_t *__restrict__ segq,
-                                                    int64_t n, int maxm) {
+                                                    int64_t n, int maxm, unsigned int *work) {
     extern __shared__ __align__(16) uint8_t smem[];
     double *s_lnfac = reinterpret_cast<double *>(smem);        // [SEG_TAB] ln(i!)
     double *s_ln20 = s_lnfac + SEG_TAB;                         // [SEG_TAB] i ln 20
@@ -530,29 +530,34 @@ __global__ void __launch_bounds__(WARPS * 32) k_seg(uint8_t *frames, int fstride
     for (int k = 0; k < maxm + 2; ++k) nc[k * 32] = 0;
     const uint32_t *lom = s_m, *him = s_m + 6;
     uint32_t *mask = s_m + 12;
-    // blocks stride over the queue so that the tables above are staged once per block, not once per four frames
-    // the next frame's row is fetched into registers while the current one is processed (up to two words per lane)
-    const int64_t gstep = (int64_t)gridDim.x * WARPS;
+    // resident blocks (the tables above are staged once per block) whose warps draw frames from the queue through a
+    // shared counter: the cost of a frame varies with the number and length of its low-complexity segments, and a
+    // fixed stride left the slowest warp running long after the others.  The next frame's row is fetched into
+    // registers while the current one is processed (up to two words per lane)
+    const int64_t gfirst = (int64_t)gridDim.x * WARPS;        // entries below it are the warps' first frames
     const int fw = fstride / 4;
     uint32_t nrow = 0, nw0 = 0, nw1 = 0;
-    {
-        const int64_t g0 = (int64_t)blockIdx.x * WARPS + warp;
-        if (g0 < n) {
-            nrow = segq[g0];
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(frames + (int64_t)nrow * fstride);
-            if (lane < fw) nw0 = src[lane];
-            if (lane + 32 < fw) nw1 = src[lane + 32];
-        }
+    int64_t g = (int64_t)blockIdx.x * WARPS + warp;
+    if (g < n) {
+        nrow = segq[g];
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(frames + (int64_t)nrow * fstride);
+        if (lane < fw) nw0 = src[lane];
+        if (lane + 32 < fw) nw1 = src[lane + 32];
     }
-    for (int64_t g = (int64_t)blockIdx.x * WARPS + warp; g < n; g += gstep) {
+    for (int64_t gn; g < n; g = gn) {
         const uint32_t row = nrow;
         uint8_t *gfr = frames + (int64_t)row * fstride;
         const int m = (L - (int)(row % 6u) % 3) / 3;
         __syncwarp();
         if (lane < fw) reinterpret_cast<uint32_t *>(fr)[lane] = nw0;
         if (lane + 32 < fw) reinterpret_cast<uint32_t *>(fr)[lane + 32] = nw1;
-        if (g + gstep < n) {
-            nrow = segq[g + gstep];
+        {
+            unsigned int t = 0;
+            if (lane == 0) t = atomicAdd(work, 1u);
+            gn = gfirst + __shfl_sync(0xffffffffu, t, 0);
+        }
+        if (gn < n) {
+            nrow = segq[gn];
             const uint32_t *src = reinterpret_cast<const uint32_t *>(frames + (int64_t)nrow * fstride);
             if (lane < fw) nw0 = src[lane];
             if (lane + 32 < fw) nw1 = src[lane + 32];
@@ -826,7 +831,17 @@ __device__ __forceinline__ uint4 seed_pack(uint32_t gframe, int s, int sb, int q
 #ifndef MCX_GAP_NT
 #define MCX_GAP_NT 128
 #endif
-constexpr int SEED_NT = MCX_SEED_NT;   // threads per block of k_seed / k_walk
+#ifndef MCX_WALK_NT
+#define MCX_WALK_NT MCX_SEED_NT
+#endif
+#ifndef MCX_SEG_W
+#define MCX_SEG_W 4
+#endif
+#ifndef MCX_FRAMES_NT
+#define MCX_FRAMES_NT 192
+#endif
+constexpr int SEED_NT = MCX_SEED_NT;   // threads per block of k_seed
+constexpr int WALK_NT = MCX_WALK_NT;   // threads per block of k_walk
 constexpr int GAP_NT = MCX_GAP_NT;     // threads per block of k_gap_dir
 #define SAME(a, b) ((s_same[(a)] >> (b)) & 1u)   /* red_eq() from the shared-memory masks */
 // K2c: one thread per candidate: the cheap rejections, growth of the word to the maximal murphy10-identical stretch
@@ -1477,6 +1492,7 @@ struct mcx_ctx {
     unsigned long long *d_bestkey = nullptr;
     int64_t cap_surv = 0, cap_best = 0, cap_nrep = 0, cap_bestkey = 0;
     unsigned long long *d_cnt = nullptr;     // 16 scalar counters
+    int n_sm = 148;                          // multiprocessors of the device (sizes the resident grids)
     unsigned long long *d_qcnt = nullptr;    // NQ candidate sub-queue fills
     unsigned long long *d_acc = nullptr;     // 3 + 60
     unsigned long long *d_abl = nullptr;     // 30 * 1280
@@ -1794,6 +1810,7 @@ extern "C" int mcx_create(mcx_ctx **out, const mcx_db *db, int device) {
     int rc = MCX_OK;
     auto body = [&]() -> int {
         CK(cudaSetDevice(device));
+        CK(cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device));
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         for (auto &ev : ctx->ev) CK(cudaEventCreate(&ev));
         const int ns = db->n_subj;
@@ -2114,9 +2131,9 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     for (int64_t first = 0; first < n_search; first += chunk) {
         const int64_t nr = std::min(chunk, n_search - first);
         CK(cudaMemsetAsync(ctx->d_qcnt, 0, NQ * sizeof(unsigned long long), st));
-        CK(cudaMemsetAsync(ctx->d_cnt + 12, 0, sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(ctx->d_cnt + 12, 0, 2 * sizeof(unsigned long long), st));   // [12] SEG queue length, [13] k_seg's work counter (then k_gap_list's)
         CK(cudaEventRecord(ctx->ev[2], st));
-        constexpr int NTF = 192;
+        constexpr int NTF = MCX_FRAMES_NT;      // a multiple of 6: whole reads per block
         {
             FrameArgs F;
             F.bases = ctx->d_bases; F.offs = ctx->d_offs; F.kept = ctx->d_kept; F.first = first; F.n_search = nr;
@@ -2132,11 +2149,14 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
         if (n_segq > 0) {
-            constexpr int SW = 4;
+            constexpr int SW = MCX_SEG_W;
             const size_t smem = 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + 128 + (size_t)SW * seg_warp_bytes(fstride, maxm);
             CK(cudaFuncSetAttribute(k_seg<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_seg<SW><<<(unsigned)std::min<unsigned long long>((n_segq + SW - 1) / SW, 148ull * 16), SW * 32, smem, st>>>(ctx->d_frames, fstride, P.read_length, ctx->d_segq,
-                                                                           (int64_t)n_segq, maxm);
+            int per_sm = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seg<SW>, SW * 32, smem));
+            const unsigned long long resident = (unsigned long long)std::max(per_sm, 1) * (unsigned long long)ctx->n_sm;
+            k_seg<SW><<<(unsigned)std::min<unsigned long long>((n_segq + SW - 1) / SW, resident), SW * 32, smem, st>>>(
+                ctx->d_frames, fstride, P.read_length, ctx->d_segq, (int64_t)n_segq, maxm, reinterpret_cast<unsigned int *>(ctx->d_cnt + 13));
             ++ctx->launches;
         }
         ctx->n_segq_last = (int64_t)n_segq;
@@ -2199,7 +2219,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
                 CK(cudaMemsetAsync(ctx->d_seen, 0xff, (size_t)(1ll << bits) * sizeof(unsigned long long), st));
                 E.seen = ctx->d_seen; E.seen_mask = (1ull << bits) - 1; E.seen_shift = 64 - bits;
             }
-            k_walk<SEED_NT><<<(unsigned)((n_seeds + SEED_NT - 1) / SEED_NT), SEED_NT, 0, st>>>(E, (int64_t)n_seeds);
+            k_walk<WALK_NT><<<(unsigned)((n_seeds + WALK_NT - 1) / WALK_NT), WALK_NT, 0, st>>>(E, (int64_t)n_seeds);
             ++ctx->launches;
             CK(cudaMemcpyAsync(&n_surv, ctx->d_cnt + 8, sizeof n_surv, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));

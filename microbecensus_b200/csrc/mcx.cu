@@ -40,7 +40,6 @@ using namespace mcx;
 // device-side constants
 // ------------------------------------------------------------------------------------------------
 __constant__ mcx_cutoff c_cut[MCX_N_FAM];
-__constant__ int8_t c_blosum[21 * 32];
 // Look-up tables live in global memory and are staged in shared memory by the blocks that index them per lane:
 // constant-bank reads with a per-lane index are serialised (k_extend once spent 11 % of its time filling its
 // BLOSUM62 copy from a __constant__ array, k_frames 11 % on the codon table).
@@ -993,92 +992,6 @@ __global__ void __launch_bounds__(NT) k_walk(ExtArgs A, int64_t n_seeds) {
 #define ST_ALN 0x100u
 #define ST_GAPCOL 0x20000u
 #define ST_GAPRUN 0x4000000u
-struct GExt { int gain, eq, et; uint32_t st; int cells; };
-
-template <int GROW, bool STATS>    // GROW = row capacity (longest frame + GAP_SLACK + 2); STATS = carry the alignment statistics
-__device__ void gapped_xdrop(const uint8_t *fr, int q_first, int qstep, const uint8_t *__restrict__ t,
-                             int tstep, int nQ, int nD, GExt &g) {
-    g.gain = 0; g.eq = 0; g.et = 0; g.st = 0; g.cells = 0;
-    const int GI = GAP_OPEN, GE = GAP_EXT, GIE = GAP_OPEN + GAP_EXT;
-    const int limit = 15;                      // (int)((26.98 - 11) / 1)
-    int H[GROW], F[GROW];
-    uint32_t HS[STATS ? GROW : 1], FS[STATS ? GROW : 1];
-    H[0] = 0; F[0] = -GI;
-    if (STATS) { HS[0] = 0; FS[0] = 0; }
-    {
-        int r = -GI;
-        for (int j = 1; j <= limit && j <= nD; ++j) {
-            r -= GE; H[j] = r; F[j] = r - GI;
-            if (STATS) { HS[j] = (uint32_t)j * (ST_ALN + ST_GAPCOL) + ST_GAPRUN; FS[j] = HS[j]; }
-        }
-    }
-    int cs = 1, ce = limit, best = 0, bcol = 0, brow = 0, cells = 0;
-    uint32_t bst = 0;
-    for (int i = 1; i <= nQ; ++i) {
-        int diag = H[cs - 1];
-        uint32_t dst = 0, bs = 0;
-        if (STATS) {
-            dst = HS[cs - 1];
-            // boundary cell (i, cs-1): value max(H-12, F-1), always traced as a vertical gap column
-            bs = (i == 1 ? HS[cs - 1] + ST_GAPRUN : FS[cs - 1]) + ST_ALN + ST_GAPCOL;
-        }
-        int v = H[cs - 1] - GIE, f1 = F[cs - 1] - GE;
-        if (v < f1) v = f1;
-        F[cs - 1] = v; H[cs - 1] = v;
-        if (STATS) { HS[cs - 1] = bs; FS[cs - 1] = bs; }
-        int E = v - GI, hl = v, j = cs;
-        uint32_t ES = bs, hls = bs;
-        bool skip_tail = false;
-        const int qa = fr[q_first + (i - 1) * qstep];
-        if (!(cs > ce || cs > nD)) {
-            for (;;) {
-                ++cells;
-                int a = hl - GIE, b = E - GE;
-                if (a >= b) { E = a; if (STATS) ES = hls + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { E = b; if (STATS) ES += ST_ALN + ST_GAPCOL; }
-                int c = H[j] - GIE, d = F[j] - GE, Fv;
-                uint32_t FSv = 0;
-                if (c >= d) { Fv = c; if (STATS) FSv = HS[j] + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { Fv = d; if (STATS) FSv = FS[j] + ST_ALN + ST_GAPCOL; }
-                const int tb = t[(j - 1) * tstep];
-                int h = diag + c_blosum[qa * 32 + tb];
-                uint32_t hs = 0;
-                if (STATS) hs = dst + ST_ALN + (uint32_t)(qa == tb && qa < 20);
-                if (E > h) { h = E; hs = ES; }
-                if (h < Fv) { h = Fv; hs = FSv; }
-                diag = H[j];
-                if (STATS) dst = HS[j];
-                H[j] = h; F[j] = Fv; hl = h;
-                if (STATS) { HS[j] = hs; FS[j] = FSv; hls = hs; }
-                if (h > best) { best = h; bcol = j; brow = i; bst = hs; }
-                else if (h <= best - 27 && j > bcol) {       // h < best - 26.98
-                    if (j >= ce) { ce = j; break; }
-                    ce = j; skip_tail = true; break;
-                }
-                ++j;
-                if (j > nD || j > ce) break;
-            }
-        }
-        if (!skip_tail) {
-            for (int jj = ce + 1; jj <= nD; ++jj) {          // run on along the row by horizontal gaps
-                ++cells;
-                int a = hl - GIE, b = E - GE;
-                if (a > b) { E = a; if (STATS) ES = hls + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { E = b; if (STATS) ES += ST_ALN + ST_GAPCOL; }
-                H[jj] = E; F[jj] = E - GI; hl = E;
-                if (STATS) { HS[jj] = ES; FS[jj] = ES; hls = ES; }
-                if (E > best) { best = E; bcol = jj; brow = i; bst = ES; }
-                else if (E <= best - 27) { ce = jj; break; }
-            }
-            if (cs <= bcol) {                                // drop dead cells on the left
-                int thr = best - 27;
-                if (H[bcol] <= thr) cs = bcol;
-                else for (int c = bcol - 1; c >= cs; --c) if (H[c] <= thr) { cs = c; break; }
-            }
-        }
-        if (!(cs < ce)) break;
-    }
-    g.cells = cells;
-    if (best > 0) { g.gain = best; g.eq = brow; g.et = bcol; g.st = bst; }
-}
-
 struct __align__(16) GExtRec { int32_t gain; uint16_t eq, et; uint32_t st; uint32_t cells; };   // result of one direction
 
 struct GapArgs {
@@ -1128,60 +1041,169 @@ __global__ void k_gap_list(GapArgs A) {
     if (b) A.items[base + __popc(mf) + __popc(mb & lt)] = ((unsigned long long)kb << 32) | (uint32_t)(g << 1) | 1u;
 }
 
-// K3b: one thread per gapped extension, DP rows in local memory.  (Tried and measured slower on 2M x 100 bp: rows in
-// shared memory, column-major and conflict-free -- 6.8 ms instead of 4.9, the 53-80 KB per block leave too few warps
-// to hide the serial dependency of the cells; packed (H, F) cells with the next cell prefetched -- no change.)
-// First a score-only pass over all of them (two DP rows); only the ~20 % that
-// gain anything are queued for the second pass, which repeats the same DP carrying the alignment statistics.
+// K3b: the DP itself, one LANE per gapped extension (one direction of one survivor), rows in local memory; a lane that
+// finishes its extension draws the next one from the work list instead of idling until the longest extension of its
+// warp is done -- the X-drop decides the size of an extension and nothing known beforehand predicts it (the first
+// version, one thread per list entry, ran at 9-10 of 32 lanes: 2.72 -> 2.08 ms at 100 bp, 6.12 -> 4.80 at 150 bp).
+// Resident blocks; every trip of the warp loop advances each busy lane by ONE row of its own extension; idle lanes are
+// refilled together once MCX_GAP_REFILL of them wait (a refill is three dependent loads plus row 0, issued for the whole
+// warp whatever the number of lanes that need it; measured 1 / 4 / 8 / 16 / 24 / 28: 5.69 / 5.50 / 5.28 / 5.19 / 4.80 /
+// 4.80 ms at 150 bp, flat at 100 bp).
+// First a score-only pass over all extensions (two DP rows); only the ~16 % that gain anything are queued for the
+// second pass, which repeats the same DP carrying the alignment statistics and stops at the row of the best cell.
+// (Tried and measured slower on 2M x 100 bp: rows in shared memory, column-major and conflict-free -- 6.8 ms instead
+// of 4.9, the 53-80 KB per block leave too few warps to hide the serial dependency of the cells; packed (H, F) cells
+// with the next cell prefetched -- no change; rows as a 64-column ring -- slower at every length.)
+#ifndef MCX_GAP_REFILL
+#define MCX_GAP_REFILL 24
+#endif
 template <int NT, int GROW, bool STATS>
 __global__ void __launch_bounds__(NT) k_gap_dir(GapArgs A, const unsigned long long *__restrict__ items, int64_t n_items,
-                                                unsigned long long *__restrict__ items2, unsigned long long *n_items2) {
-    const int64_t w = (int64_t)blockIdx.x * NT + threadIdx.x;
-    bool again = false;
-    uint32_t item = 0, cells_key = 0;
-    if (w < n_items) {
-        item = (uint32_t)items[w];
-        const int64_t g = item >> 1;
-        const int dir = item & 1;
-        const Surv v = surv_unpack(A.surv[A.first + g]);
-        const uint8_t *__restrict__ fr = A.frames + (int64_t)v.gframe * A.fstride;
-        const int m = (A.L - v.frame % 3) / 3;
-        const int32_t o = A.db.off[v.subject];
-        const int n = A.db.off[v.subject + 1] - o;
-        const uint8_t *t = A.db.res + o;
-        const int q0 = v.q0, q1 = v.q1, t0 = v.t0, t1 = v.t0 + (v.q1 - v.q0);
-        GExt e;
-        // the statistics pass stops with the row of the best cell found by the score pass: the DP is identical up to
-        // there, and the rows the X-drop explores past the best cell cannot change its statistics
-        int row_limit = 1 << 30;
-        if (STATS) row_limit = A.ext[2 * g + dir].eq;
-        if (dir == 0) {
-            int ql = m - (q1 + 1), tl = n - (t1 + 1);
-            if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
-            gapped_xdrop<GROW, STATS>(fr, q1 + 1, 1, t + t1 + 1, 1, min(ql, row_limit), tl, e);
-        } else {
-            int ql = q0, tl = t0;
-            if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
-            gapped_xdrop<GROW, STATS>(fr, q0 - 1, -1, t + t0 - 1, -1, min(ql, row_limit), tl, e);
-        }
-        if (STATS) {
-            A.ext[2 * g + dir].st = e.st;
-        } else {
-            GExtRec r;
-            r.gain = e.gain; r.eq = (uint16_t)e.eq; r.et = (uint16_t)e.et; r.st = e.st; r.cells = (uint32_t)e.cells;
-            A.ext[2 * g + dir] = r;
-        }
-        again = !STATS && e.gain > 0;
-        cells_key = 65535u - (uint32_t)min(e.cells, 65535);      // the statistics pass repeats this DP: most cells first
-    }
-    if (!STATS) {
-        const int lane = threadIdx.x & 31;
-        const uint32_t ma = __ballot_sync(0xffffffffu, again);
-        if (ma) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(n_items2, (unsigned long long)__popc(ma));
+                                                unsigned long long *__restrict__ items2, unsigned long long *n_items2,
+                                                unsigned int *work) {
+    __shared__ __align__(16) int8_t s_bl[21 * 32];
+    for (int k = threadIdx.x; k < 21 * 32 / 4; k += NT) reinterpret_cast<uint32_t *>(s_bl)[k] = reinterpret_cast<const uint32_t *>(g_blosum)[k];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1;
+    const int GI = GAP_OPEN, GE = GAP_EXT, GIE = GAP_OPEN + GAP_EXT;
+    const int limit = 15;                      // (int)((26.98 - 11) / 1)
+    int H[GROW], F[GROW];
+    uint32_t HS[STATS ? GROW : 1], FS[STATS ? GROW : 1];
+    bool busy = false, dry = false;            // dry: the work list has nothing left for this lane
+    uint32_t item = 0;
+    const uint8_t *qp = nullptr, *t = nullptr; // residue of row i is qp[(i - 1) * step], of column j is t[(j - 1) * step]
+    int step = 1, nQ = 0, nD = 0;
+    int i = 1, cs = 1, ce = limit, best = 0, bcol = 0, brow = 0, cells = 0;
+    uint32_t bst = 0;
+    for (;;) {
+        const uint32_t idle = __ballot_sync(0xffffffffu, !busy && !dry);
+        const uint32_t live = __ballot_sync(0xffffffffu, busy);
+        if (idle && (live == 0 || __popc(idle) >= MCX_GAP_REFILL)) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(work, (unsigned int)__popc(idle));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (again) items2[base + __popc(ma & ((1u << lane) - 1))] = ((unsigned long long)cells_key << 32) | item;
+            if (!busy && !dry) {
+                const int64_t w = (int64_t)base + __popc(idle & lt);
+                if (w >= n_items) dry = true;
+                else {
+                    item = (uint32_t)items[w];
+                    const int64_t g = item >> 1;
+                    const Surv v = surv_unpack(A.surv[A.first + g]);
+                    const uint8_t *fr = A.frames + (int64_t)v.gframe * A.fstride;
+                    const int m = (A.L - v.frame % 3) / 3;
+                    const int32_t o = A.db.off[v.subject];
+                    const int n = A.db.off[v.subject + 1] - o;
+                    const int q0 = v.q0, q1 = v.q1, t0 = v.t0, t1 = v.t0 + (v.q1 - v.q0);
+                    // the statistics pass stops with the row of the best cell found by the score pass
+                    int row_limit = 1 << 30;
+                    if (STATS) row_limit = A.ext[item].eq;
+                    int ql, tl;
+                    if ((item & 1) == 0) { ql = m - (q1 + 1); tl = n - (t1 + 1); qp = fr + q1 + 1; t = A.db.res + o + t1 + 1; step = 1; }
+                    else { ql = q0; tl = t0; qp = fr + q0 - 1; t = A.db.res + o + t0 - 1; step = -1; }
+                    if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
+                    nQ = min(ql, row_limit); nD = tl;
+                    H[0] = 0; F[0] = -GI;
+                    if (STATS) { HS[0] = 0; FS[0] = 0; }
+                    // row 0: the binary fills min(limit, nD) cells of it; the ones past nD are never read
+#pragma unroll
+                    for (int j = 1; j <= limit; ++j) {
+                        H[j] = -GI - j * GE; F[j] = -GI - j * GE - GI;
+                        if (STATS) { HS[j] = (uint32_t)j * (ST_ALN + ST_GAPCOL) + ST_GAPRUN; FS[j] = HS[j]; }
+                    }
+                    i = 1; cs = 1; ce = limit; best = 0; bcol = 0; brow = 0; cells = 0; bst = 0;
+                    busy = true;
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, !busy && dry)) break;
+        bool again = false;
+        if (busy) {
+            bool fin = true;
+            if (i <= nQ) {
+                int diag = H[cs - 1];
+                uint32_t dst = 0, bs = 0;
+                if (STATS) {
+                    dst = HS[cs - 1];
+                    bs = (i == 1 ? HS[cs - 1] + ST_GAPRUN : FS[cs - 1]) + ST_ALN + ST_GAPCOL;
+                }
+                int v = H[cs - 1] - GIE, f1 = F[cs - 1] - GE;
+                if (v < f1) v = f1;
+                F[cs - 1] = v; H[cs - 1] = v;
+                if (STATS) { HS[cs - 1] = bs; FS[cs - 1] = bs; }
+                int E = v - GI, hl = v, j = cs;
+                uint32_t ES = bs, hls = bs;
+                bool skip_tail = false;
+                const int qa = qp[(i - 1) * step];
+                const int8_t *brow_q = s_bl + qa * 32;
+                if (!(cs > ce || cs > nD)) {
+                    for (;;) {
+                        ++cells;
+                        int a = hl - GIE, b = E - GE;
+                        if (a >= b) { E = a; if (STATS) ES = hls + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { E = b; if (STATS) ES += ST_ALN + ST_GAPCOL; }
+                        int c = H[j] - GIE, d = F[j] - GE, Fv;
+                        uint32_t FSv = 0;
+                        if (c >= d) { Fv = c; if (STATS) FSv = HS[j] + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { Fv = d; if (STATS) FSv = FS[j] + ST_ALN + ST_GAPCOL; }
+                        const int tb = t[(j - 1) * step];
+                        int h = diag + brow_q[tb];
+                        uint32_t hs = 0;
+                        if (STATS) hs = dst + ST_ALN + (uint32_t)(qa == tb && qa < 20);
+                        if (E > h) { h = E; hs = ES; }
+                        if (h < Fv) { h = Fv; hs = FSv; }
+                        diag = H[j];
+                        if (STATS) dst = HS[j];
+                        H[j] = h; F[j] = Fv; hl = h;
+                        if (STATS) { HS[j] = hs; FS[j] = FSv; hls = hs; }
+                        if (h > best) { best = h; bcol = j; brow = i; bst = hs; }
+                        else if (h <= best - 27 && j > bcol) {       // h < best - 26.98
+                            if (j >= ce) { ce = j; break; }
+                            ce = j; skip_tail = true; break;
+                        }
+                        ++j;
+                        if (j > nD || j > ce) break;
+                    }
+                }
+                if (!skip_tail) {
+                    for (int jj = ce + 1; jj <= nD; ++jj) {          // run on along the row by horizontal gaps
+                        ++cells;
+                        int a = hl - GIE, b = E - GE;
+                        if (a > b) { E = a; if (STATS) ES = hls + ST_ALN + ST_GAPCOL + ST_GAPRUN; } else { E = b; if (STATS) ES += ST_ALN + ST_GAPCOL; }
+                        H[jj] = E; F[jj] = E - GI; hl = E;
+                        if (STATS) { HS[jj] = ES; FS[jj] = ES; hls = ES; }
+                        if (E > best) { best = E; bcol = jj; brow = i; bst = ES; }
+                        else if (E <= best - 27) { ce = jj; break; }
+                    }
+                    if (cs <= bcol) {                                // drop dead cells on the left
+                        int thr = best - 27;
+                        if (H[bcol] <= thr) cs = bcol;
+                        else for (int c = bcol - 1; c >= cs; --c) if (H[c] <= thr) { cs = c; break; }
+                    }
+                }
+                fin = !(cs < ce) || i >= nQ;
+                ++i;
+            }
+            if (fin) {
+                if (STATS) {
+                    A.ext[item].st = best > 0 ? bst : 0u;
+                } else {
+                    GExtRec r;
+                    r.gain = 0; r.eq = 0; r.et = 0; r.st = 0; r.cells = (uint32_t)cells;
+                    if (best > 0) { r.gain = best; r.eq = (uint16_t)brow; r.et = (uint16_t)bcol; }
+                    A.ext[item] = r;
+                    again = best > 0;
+                }
+                busy = false;
+            }
+        }
+        if (!STATS) {
+            const uint32_t ma = __ballot_sync(0xffffffffu, again);
+            if (ma) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(n_items2, (unsigned long long)__popc(ma));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                // the statistics pass repeats this DP: most cells first
+                if (again) items2[base + __popc(ma & lt)] = ((unsigned long long)(65535u - (uint32_t)min(cells, 65535)) << 32) | item;
+            }
         }
     }
 }
@@ -1491,7 +1513,7 @@ struct mcx_ctx {
     int32_t *d_nrep = nullptr;
     unsigned long long *d_bestkey = nullptr;
     int64_t cap_surv = 0, cap_best = 0, cap_nrep = 0, cap_bestkey = 0;
-    unsigned long long *d_cnt = nullptr;     // 16 scalar counters
+    unsigned long long *d_cnt = nullptr;     // 32 scalar counters ([16], [17]: work counters of the two gapped passes)
     int n_sm = 148;                          // multiprocessors of the device (sizes the resident grids)
     unsigned long long *d_qcnt = nullptr;    // NQ candidate sub-queue fills
     unsigned long long *d_acc = nullptr;     // 3 + 60
@@ -1790,7 +1812,6 @@ static int upload_tables(mcx_ctx *ctx) {
         CK(cudaMemcpyToSymbol(g_codon_lut, lut, sizeof lut));
     }
     CK(cudaMemcpyToSymbol(g_blosum, bl, sizeof bl));
-    CK(cudaMemcpyToSymbol(c_blosum, bl, sizeof bl));
     CK(cudaMemcpyToSymbol(g_lnfac, lnfac, sizeof lnfac));
     CK(cudaMemcpyToSymbol(g_ln20, ln20, sizeof ln20));
     return MCX_OK;
@@ -1826,7 +1847,7 @@ extern "C" int mcx_create(mcx_ctx **out, const mcx_db *db, int device) {
         ctx->n_subj = ns;
         int r = upload_tables(ctx); if (r) return r;
         r = build_index(ctx, db); if (r) return r;
-        CK(dev_alloc(&ctx->d_cnt, 16));
+        CK(dev_alloc(&ctx->d_cnt, 32));
         CK(dev_alloc(&ctx->d_qcnt, NQ));
         CK(dev_alloc(&ctx->d_acc, 3 + 2 * MCX_N_FAM));
         CK(dev_alloc(&ctx->d_abl, (size_t)MCX_N_FAM * MCX_LEN_BINS));
@@ -2255,11 +2276,18 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
                     cub::DeviceRadixSort::SortKeys(ctx->d_temp, tb, G.items, list1, (int)n_items, 32, 40, st);
                 }
                 CK(cudaMemsetAsync(ctx->d_cnt + 14, 0, sizeof(unsigned long long), st));
+                CK(cudaMemsetAsync(ctx->d_cnt + 16, 0, 2 * sizeof(unsigned long long), st));
+                unsigned int *work1 = reinterpret_cast<unsigned int *>(ctx->d_cnt + 16), *work2 = reinterpret_cast<unsigned int *>(ctx->d_cnt + 17);
                 const unsigned gb = (unsigned)((n_items + GAP_NT - 1) / GAP_NT);
                 const int grow = maxm + GAP_SLACK + 2;
-                if (grow <= 104) k_gap_dir<GAP_NT, 104, false><<<gb, GAP_NT, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + 14);
-                else if (grow <= 152) k_gap_dir<GAP_NT, 152, false><<<gb, GAP_NT, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + 14);
-                else k_gap_dir<GAP_NT, MAX_FRAME + GAP_SLACK + 2, false><<<gb, GAP_NT, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + 14);
+                auto resident = [&](auto kernel, unsigned want) -> unsigned {      // blocks of a grid that is resident at once
+                    int per_sm = 0;
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, GAP_NT, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+                    return std::min(want, (unsigned)(per_sm * ctx->n_sm));
+                };
+                if (grow <= 104) k_gap_dir<GAP_NT, 104, false><<<resident(k_gap_dir<GAP_NT, 104, false>, gb), GAP_NT, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + 14, work1);
+                else if (grow <= 152) k_gap_dir<GAP_NT, 152, false><<<resident(k_gap_dir<GAP_NT, 152, false>, gb), GAP_NT, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + 14, work1);
+                else k_gap_dir<GAP_NT, MAX_FRAME + GAP_SLACK + 2, false><<<resident(k_gap_dir<GAP_NT, MAX_FRAME + GAP_SLACK + 2, false>, gb), GAP_NT, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + 14, work1);
                 unsigned long long n2 = 0;
                 CK(cudaMemcpyAsync(&n2, ctx->d_cnt + 14, sizeof n2, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
@@ -2269,9 +2297,9 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
                     if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
                     cub::DeviceRadixSort::SortKeys(ctx->d_temp, tb, items2, list2, (int)n2, 32, 48, st);
                     const unsigned gb2 = (unsigned)((n2 + GAP_NT - 1) / GAP_NT);
-                    if (grow <= 104) k_gap_dir<GAP_NT, 104, true><<<gb2, GAP_NT, 0, st>>>(G, list2, (int64_t)n2, nullptr, nullptr);
-                    else if (grow <= 152) k_gap_dir<GAP_NT, 152, true><<<gb2, GAP_NT, 0, st>>>(G, list2, (int64_t)n2, nullptr, nullptr);
-                    else k_gap_dir<GAP_NT, MAX_FRAME + GAP_SLACK + 2, true><<<gb2, GAP_NT, 0, st>>>(G, list2, (int64_t)n2, nullptr, nullptr);
+                    if (grow <= 104) k_gap_dir<GAP_NT, 104, true><<<resident(k_gap_dir<GAP_NT, 104, true>, gb2), GAP_NT, 0, st>>>(G, list2, (int64_t)n2, nullptr, nullptr, work2);
+                    else if (grow <= 152) k_gap_dir<GAP_NT, 152, true><<<resident(k_gap_dir<GAP_NT, 152, true>, gb2), GAP_NT, 0, st>>>(G, list2, (int64_t)n2, nullptr, nullptr, work2);
+                    else k_gap_dir<GAP_NT, MAX_FRAME + GAP_SLACK + 2, true><<<resident(k_gap_dir<GAP_NT, MAX_FRAME + GAP_SLACK + 2, true>, gb2), GAP_NT, 0, st>>>(G, list2, (int64_t)n2, nullptr, nullptr, work2);
                     ctx->launches += 3;
                 }
                 ctx->launches += 2;

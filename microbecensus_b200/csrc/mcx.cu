@@ -6,13 +6,15 @@
 //   k_qc          read QC                    mc.py:265-279, 342-356     one warp per read, HBM-bound
 //   k_frames      6-frame translation (RAPsearch2 BuildQHash) + "does any 12-window reach SEG's low cut?"
 //                 one thread per (read, frame); frames go to a global frame store
-//   k_seg         full SEG (Seg::segseq / Seg::trim) for the ~19 % of frames with such a window, one warp per frame
+//   k_seg         full SEG (Seg::segseq / Seg::trim) for the ~19 % of frames with such a window, one warp per frame,
+//                 frames drawn from the queue by resident blocks
 //   k_probe       murphy10 seed-word lookup (Searching / FindSeeds): Bloom filter + hash tables, every posting of a
 //                 word hit queued as a candidate
 //   k_seed        seed growth and acceptance (ExtendSeq2Set), one thread per candidate
 //   k_walk        ungapped X-drop walks (AlignFwd / AlignBwd), one thread per accepted seed; duplicate HSPs dropped
 //   k_gap_list / k_gap_dir x2 / k_gap_finish   gapped X-drop extension (AlignSeqs / AlignGapped / CalRes): work list
-//                 sorted by size, score pass, statistics pass for the extensions that gained, HSP records + sort keys
+//                 sorted by size, score pass, statistics pass for the extensions that gained (one lane per extension,
+//                 refilled from the work list as extensions end), HSP records + sort keys
 //   k_cls_groups / _cap / _cap_apply / _filter / _sum   HSP de-duplication per (read, subject), the 500-line cap, the
 //                 three cutoffs, best hit per read and the per-family integer sums    mc.py:400-472
 // plus CUB scans/sorts for compaction and ordering.  mc.py = /root/reference/microbe_census/

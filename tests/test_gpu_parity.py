@@ -51,6 +51,14 @@ def test_seeded_synthetic_reads_bit_exact(eng, oracle, markers, L, n):
     assert res.reads_classified > 0
 
 
+@pytest.mark.parametrize("n", [1, 2, 7, 33])
+def test_small_batches_bit_exact(eng, oracle, markers, n):
+    """Fewer gapped extensions than lanes of a warp: the work-list refill of k_gap_dir / k_seg with lanes that never get work."""
+    seqs = golden_io.read_fasta("long.fa.gz")[:n]
+    res = gpu_vs_oracle(eng, oracle, markers, ReadBatch.from_strings(seqs), 150)
+    assert res.sampled_reads == n
+
+
 def test_classification_against_reference_golden(eng, markers):
     """GPU classification vs what the reference's classify_reads made of RAPsearch2's own output."""
     for fname, name, L in (("meta.fa.gz", "meta", 100), ("meta50.fa.gz", "meta50", 50)):

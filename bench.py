@@ -1,15 +1,17 @@
 #!/usr/bin/env python3
 """Benchmark of the MicrobeCensus hot path on B200: reads/s end-to-end AGS (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4] [--impl ours|reference]
 
 One step = one pass of the whole hot path over one batch of synthetic reads: read QC -> 6-frame
 translation + SEG + seeding + ungapped X-drop -> gapped X-drop -> per-read classification -> per-family
 sums (-> NCCL all-reduce for N > 1) -> weighted AGS estimate on the host.
 
-workloads (BASELINE.json configs):  c2 = 2,000,000 synthetic 100 bp single-end reads, -l 100 (default);
-c3 = 150 bp paired files with -q 5 -m 20 -u 5 (5M + 5M reads); c4 = 150 bp with -d, 12.5M reads per GPU.  Per-GPU work is fixed (weak scaling): rank r
-owns reads [r*n, (r+1)*n) of the deterministic stream (microbecensus_b200/synth.py).
+workloads (BASELINE.json configs):  c3 (default, the configuration the metric is quoted on: "reads/sec end-to-end AGS
+at 150 bp") = 150 bp paired FASTQ files with -q 5 -m 20 -u 5, 5M reads per GPU (R1 block then R2 block, as the reference
+processes paired files one after the other); c2 = 2,000,000 synthetic 100 bp single-end reads, -l 100; c4 = 150 bp with
+-d, 12.5M reads per GPU.  Per-GPU work is fixed (weak scaling): rank r owns its block of the deterministic stream
+(microbecensus_b200/synth.py).
 
 `value`  = reads/s with the reads resident in HBM when the clock starts (device path only);
 `e2e`    = the same through the public host API: pinned host buffers -> libmcx (H2D inside) -> results on host;
@@ -30,6 +32,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SEED_DUPS = 20260104
+# what the reference's auto_detect_quality_offset (mc.py:174-187) returns for Phred+33 files such as the synthetic FASTQ:
+# it subtracts 32, not 33, and the drop-in does the same (run_pipeline detects it per file; the bench states it)
+QUAL_OFFSET = 32
 
 WORKLOADS = {
     "c2": dict(name="2M synthetic 100 bp single-end reads, -l 100", config_id=2, reads=2_000_000, L=100, fastq=False,
@@ -48,7 +53,7 @@ def parse():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    p.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     p.add_argument("--reads-per-gpu", type=int, default=None)
     p.add_argument("--ref-sample", type=int, default=20000, help="reads per step of the CPU reference arm")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -95,19 +100,35 @@ def reference_available():
     return all(os.path.exists(os.path.join(ref, p)) for p in ("microbe_census.py", "bin/rapsearch_Linux_2.15", "data/rapdb_2.15"))
 
 
-def run_reference_once(batch, wl, threads, tmpdir):
-    """The unmodified reference's hot path (mc.py:611-626) on `batch`: process_seqfile -> search_seqs
-    (rapsearch child, -z threads) -> classify_reads -> aggregate_hits -> estimate.  Returns (seconds, AGS, sampled)."""
+def sample_batches(wl, sample_reads):
+    """The bounded sample both arms see: the first reads of the workload stream, as the list of files the
+    workload names (c3: R1 and R2 of the first sample_reads/2 pairs; otherwise one file)."""
+    from microbecensus_b200 import synth
+    if wl["config_id"] == 3:
+        return list(synth.paired_reads(wl["config_id"], 0, sample_reads // 2, wl["L"]))
+    return [synth.reads(wl["config_id"], 0, sample_reads, wl["L"], with_quals=wl["fastq"])]
+
+
+def run_reference_once(batches, wl, threads, tmpdir):
+    """The unmodified reference's hot path (mc.py:611-626) on the sample files: process_seqfile -> search_seqs
+    (rapsearch child, -z threads) -> classify_reads -> aggregate_hits -> estimate.
+    Returns (seconds, AGS, sampled, agg_hits, best_hits)."""
     import warnings
     warnings.filterwarnings("ignore")
     sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
     from microbe_census import microbe_census as mc
     from microbecensus_b200 import synth
-    path = os.path.join(tmpdir, "sample.fq" if wl["fastq"] else "sample.fa")
-    (synth.write_fastq if wl["fastq"] else synth.write_fasta)(batch, path)
+    paths_in = []
+    for k, batch in enumerate(batches):
+        path = os.path.join(tmpdir, "sample_%d.%s" % (k + 1, "fq" if wl["fastq"] else "fa"))
+        if not os.path.exists(path):
+            (synth.write_fastq if wl["fastq"] else synth.write_fasta)(batch, path)
+        paths_in.append(path)
     os.chmod(os.path.join(ROOT, "baseline", "_ref", "microbe_census", "bin", "rapsearch_Linux_2.15"), 0o755)
-    args = {"seqfiles": [path], "verbose": False, "nreads": batch.n, "threads": threads, "read_length": wl["L"]}
+    args = {"seqfiles": paths_in, "verbose": False, "nreads": sum(b.n for b in batches), "threads": threads, "read_length": wl["L"]}
     args.update(wl["qc"])
+    if wl.get("dups"):
+        args["filter_dups"] = True
     t0 = time.perf_counter()
     paths = mc.get_relative_paths(args)
     mc.impute_missing_args(args)
@@ -117,15 +138,17 @@ def run_reference_once(batch, wl, threads, tmpdir):
     agg = mc.aggregate_hits(args, paths, best)
     mc.clean_up(paths)
     ags = mc.estimate_average_genome_size(args, paths, agg)
-    return time.perf_counter() - t0, ags, args["sampled_reads"]
+    return time.perf_counter() - t0, ags, args["sampled_reads"], agg, best
 
 
-def run_oracle_port_once(batch, wl, threads, tmpdir):
+def run_oracle_port_once(batches, wl, threads, tmpdir):
     """CPU oracle port (oracle/oracle_cli, pthreads over reads) when the reference install is absent."""
     from microbecensus_b200 import synth
+    from microbecensus_b200 import microbe_census as mcb
     import gzip
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "oracle_cli"], stdout=subprocess.DEVNULL)
     fa = os.path.join(tmpdir, "sample.fa")
+    batch = mcb.concat_batches(batches)
     synth.write_fasta(batch, fa)
     db = os.path.join(tmpdir, "markers.mcxdb")
     if not os.path.exists(db):
@@ -134,30 +157,79 @@ def run_oracle_port_once(batch, wl, threads, tmpdir):
     t0 = time.perf_counter()
     subprocess.check_call([os.path.join(ROOT, "oracle", "oracle_cli"), db, fa, str(wl["L"]), "16", "1", "49", os.path.join(tmpdir, "o.m8")],
                           env=env, stderr=subprocess.DEVNULL)
-    return time.perf_counter() - t0, None, batch.n
+    return time.perf_counter() - t0, None, batch.n, None, None
 
 
 def cpu_baseline(wl, sample_reads, steps=1, warmup=0):
-    from microbecensus_b200 import synth
     cores = os.cpu_count() or 1
-    if wl["fastq"]:
-        batch = synth.reads(wl["config_id"], 0, sample_reads, wl["L"], with_quals=True)
-    else:
-        batch = synth.reads(wl["config_id"], 0, sample_reads, wl["L"])
+    batches = sample_batches(wl, sample_reads)
     kind = "reference" if reference_available() else "port"
     fn = run_reference_once if kind == "reference" else run_oracle_port_once
-    times, ags, sampled = [], None, sample_reads
+    times, ags, sampled, agg, best = [], None, sample_reads, None, None
     with tempfile.TemporaryDirectory() as tmp:
         for i in range(warmup + steps):
-            dt, ags, sampled = fn(batch, wl, cores, tmp)
+            dt, ags, sampled, agg, best = fn(batches, wl, cores, tmp)
             if i >= warmup:
                 times.append(dt)
     sec = sum(times) / len(times)
+    files = "%d file%s" % (len(batches), "s (R1, R2)" if len(batches) == 2 else "")
     return {"value": sampled / sec, "unit": "reads/s", "cores": cores, "kind": kind,
-            "sample": "first %d reads of the workload stream; whole reference hot path (process_seqfile, rapsearch -z %d, "
-                      "classify_reads, aggregate_hits, estimate)" % (sample_reads, cores) if kind == "reference" else
+            "sample": "first %d reads of the workload stream in %s; whole reference hot path (process_seqfile, rapsearch -z %d, "
+                      "classify_reads, aggregate_hits, estimate)" % (sample_reads, files, cores) if kind == "reference" else
                       "first %d reads; CPU oracle port, %d pthreads" % (sample_reads, cores),
-            "seconds_per_step": sec, "ags": ags}
+            "seconds_per_step": sec, "ags": ags, "sampled": sampled, "agg_hits": agg, "best_hits": best}
+
+
+def parity_block(eng, markers, wl, sample_reads, cb):
+    """SURVEY 8d "parity reported with every perf run": the GPU arm on the SAME bounded sample the reference arm just
+    processed -- per-family agg_hits, per-read classification (discrepant sampled-read ids with the reason) and the AGS
+    relative difference (bar: <= 1 %)."""
+    import numpy as np
+    from microbecensus_b200 import microbe_census as mcb
+    L = wl["L"]
+    batch = mcb.concat_batches(sample_batches(wl, sample_reads))
+    eng.set_params(L, quality_offset=QUAL_OFFSET if wl["fastq"] else None, filter_dups=bool(wl.get("dups")), **wl["qc"])
+    eng.push(batch)
+    res = eng.search(-1)
+    agg = res.agg_hits()
+    ags = mcb.estimate_average_genome_size({"read_length": L, "sampled_reads": res.sampled_reads, "verbose": False}, None, agg)
+    out = {"sample": "first %d reads of the workload stream (the reference arm's sample)" % sample_reads,
+           "sampled_reads": {"gpu": res.sampled_reads, "reference": cb.get("sampled")},
+           "ags": {"gpu": ags, "reference": cb.get("ags")}, "ags_rel_diff": None, "ags_within_1pct": None}
+    if cb.get("ags"):
+        out["ags_rel_diff"] = float(abs(ags - cb["ags"]) / cb["ags"])
+        out["ags_within_1pct"] = bool(out["ags_rel_diff"] <= 0.01)
+    ref_agg, ref_best = cb.get("agg_hits"), cb.get("best_hits")
+    if ref_agg is not None:
+        fams = sorted(set(agg) | set(ref_agg))
+        diff = {f: [agg.get(f, 0.0), ref_agg.get(f, 0.0)] for f in fams
+                if abs(agg.get(f, 0.0) - ref_agg.get(f, 0.0)) > 1e-9 * max(1.0, abs(ref_agg.get(f, 0.0)))}
+        out["families_compared"] = len(fams)
+        out["families_equal"] = len(fams) - len(diff)
+        out["families_differing"] = diff          # family: [gpu, reference]
+    if ref_best is not None:
+        codes, _ = eng.qc_export(False)
+        best = eng.classified(batch.n)
+        rank = np.cumsum(codes == 0) - 1          # running index among the sampled reads = the reference's read ids
+        ours = {int(rank[i]): (markers.fam_names[markers.fam[s]], int(s)) for i, s in enumerate(best) if s >= 0}
+        theirs = {int(k): v for k, v in ref_best.items()}
+        disc = []
+        for rid in sorted(set(ours) | set(theirs)):
+            if rid not in theirs:
+                disc.append([rid, "gpu-only", ours[rid][0]])
+            elif rid not in ours:
+                disc.append([rid, "reference-only", theirs[rid][0]])
+            elif ours[rid][0] != theirs[rid][0]:
+                disc.append([rid, "family", ours[rid][0], theirs[rid][0]])
+            else:
+                slen = float(markers.subj_len[ours[rid][1]])
+                t = theirs[rid]               # [fam, aln, aln/target_len, score]
+                if abs(float(t[1]) / float(t[2]) - slen) > 0.5:
+                    disc.append([rid, "tie: same family, equal-score subject of another length", ours[rid][0]])
+        out["reads_classified"] = {"gpu": len(ours), "reference": len(theirs), "common": len(set(ours) & set(theirs))}
+        out["discrepant_reads"] = disc[:50]
+        out["n_discrepant_reads"] = len(disc)
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- main
@@ -178,7 +250,7 @@ def main():
                 "config": {"workload": wl["name"], "sample_reads_per_step": a.ref_sample, "read_length": wl["L"]},
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0, "ags": cb["ags"]}
+                "gpu_launches": 0, "ags": cb["ags"], "sampled_reads": cb["sampled"]}
         print(json.dumps(line))
         return 0
 
@@ -210,7 +282,7 @@ def main():
     eng = MarkerSearch(markers, local)
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
     dups = bool(wl.get("dups"))
-    eng.set_params(L, quality_offset=33 if wl["fastq"] else None, filter_dups=dups and world == 1, **wl["qc"])
+    eng.set_params(L, quality_offset=QUAL_OFFSET if wl["fastq"] else None, filter_dups=dups and world == 1, **wl["qc"])
 
     # ---- synthetic shard, generated on the host (untimed), staged in pinned memory
     if a.workload == "c3":
@@ -366,9 +438,10 @@ def main():
             cb = cpu_baseline(wl, a.ref_sample)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["cpu_baseline"]["ags_on_sample"] = cb["ags"]
+            line["parity"] = parity_block(eng, markers, wl, a.ref_sample, cb)
         except Exception as exc:      # the baseline is reporting only; never lose the GPU line over it
             line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(exc)[:200]}
-    print(json.dumps(line))
+    print(json.dumps(line, default=lambda o: o.item() if hasattr(o, "item") else str(o)))
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -10,7 +10,7 @@
  *   mcx_set_params               args['read_length'|'quality_offset'|'min_quality'|'mean_quality'|
  *                                'max_unknown'|'filter_dups'] (mc.py:189-224) and the per-family cutoff
  *                                rows find_opt_pars() returns (mc.py:61-72)
- *   mcx_push_reads[_dev]         process_seqfile()'s per-read filter chain (mc.py:328-356) and
+ *   mcx_push_reads[_packed][_dev] process_seqfile()'s per-read filter chain (mc.py:328-356) and
  *                                quality_filter() (mc.py:265-279); the reads are what the reference
  *                                writes to its FASTA tempfile (mc.py:352)
  *   mcx_qc_counts                the too_short / low_qual / dups / read_id counters (mc.py:336, 363-367)
@@ -28,6 +28,7 @@
  */
 #ifndef MCX_H
 #define MCX_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -88,6 +89,7 @@ typedef struct {
     int64_t n_seed_hits;     /* seeds whose ungapped extension reached the report floor */
     int64_t n_gapped;        /* gapped X-drop extensions run */
     int64_t gapped_cells;    /* DP cells evaluated by them */
+    int64_t n_capped_reads;  /* reads with more than 500 reportable lines (RAPsearch2 -v 500: the lowest were dropped) */
     int64_t fam_hits[MCX_N_FAM];          /* classified reads per family */
     int64_t fam_aln[MCX_N_FAM];           /* sum of aln-len per family */
     int64_t aln_by_len[MCX_N_FAM * MCX_LEN_BINS]; /* sum of aln-len per (family, subject length) */
@@ -111,14 +113,36 @@ int  mcx_set_params(mcx_ctx *ctx, const mcx_params *p);
  * the context's own; lets the caller bracket calls with its own CUDA events */
 int  mcx_set_stream(mcx_ctx *ctx, void *cuda_stream);
 
+/* Reads as 2-bit bases + mask in bit-planes of 32 bases -- the layout the reads have in HBM and the one the host
+ * reader (libmcxio) and the synthetic generator produce.  Read i of lengths[i] bases owns 3 G words, G =
+ * ceil(lengths[i] / 32), stored back to back in read order: lo[G], hi[G], mask[G].  Bit k of lo / hi = low / high bit of
+ * the code of base k (T 0, C 1, A 2, G 3); a mask bit marks a base that is not an upper-case A, C, G or T, and under it
+ * lo = 0 means 'N' (the character mc.py:269 counts), lo = 1 anything else (hi = 0); bits past the length are zero.
+ * quals (NULL for FASTA) holds one byte per base, all reads back to back; n_words / n_bases are the sizes of the two
+ * arrays (= sum of 3 G / sum of lengths).  Host pointers; pinned memory (mcx_host_alloc) makes the call asynchronous: it
+ * returns once the copies are queued on the context's copy stream, and mcx_search consumes the reads chunk by chunk as
+ * they arrive, so the copy of later reads overlaps the search of earlier ones.  The buffers must stay valid and
+ * unchanged until the next call that waits for them (mcx_search, or any mcx_qc_* call).  Replaces any reads pushed before. */
+int  mcx_push_reads_packed(mcx_ctx *ctx, const uint32_t *packed, int64_t n_words, const uint32_t *lengths,
+                           const uint8_t *quals, int64_t n_bases, int64_t n);
+/* same with device-resident buffers (no copy; d_quals 16-byte aligned; the buffers stay the caller's) */
+int  mcx_push_reads_packed_dev(mcx_ctx *ctx, const uint32_t *d_packed, int64_t n_words, const uint32_t *d_lengths,
+                               const uint8_t *d_quals, int64_t n_bases, int64_t n);
 /* Reads as ASCII bytes, read i = bases[offsets[i] .. offsets[i+1]); quals may be NULL (FASTA) and
- * otherwise shares the offsets.  Host pointers (pinned or pageable).  Replaces any reads pushed before. */
+ * otherwise shares the offsets.  Host pointers (pinned or pageable).  The device packs them into the layout above
+ * (k_pack_ascii).  Replaces any reads pushed before. */
 int  mcx_push_reads(mcx_ctx *ctx, const uint8_t *bases, const uint8_t *quals,
                     const int64_t *offsets, int64_t n);
-/* same with device-resident buffers (no host->device copy) */
+/* same with device-resident buffers (no host->device copy; d_quals 16-byte aligned) */
 int  mcx_push_reads_dev(mcx_ctx *ctx, const uint8_t *d_bases, const uint8_t *d_quals,
                         const int64_t *d_offsets, int64_t n, int64_t total_bytes);
+/* page-locked host memory for the push buffers (cudaHostAlloc, portable across the GPUs of the box) */
+int  mcx_host_alloc(void **out, size_t bytes);
+void mcx_host_free(void *p);
 
+/* verdict counts over ALL pushed reads.  Forces the QC of every pushed read (and so waits for every copy of the
+ * push): a caller that does not need them before the search should not ask -- mcx_result carries the counts the
+ * reference prints (up to the read that filled -n). */
 int  mcx_qc_counts(mcx_ctx *ctx, mcx_qc *out);
 /* Per-read verdicts of the pushed reads (0 keep, 1 too short, 2 low quality, 3 duplicate) and, optionally,
  * the 128-bit strand-canonical fingerprints of the untrimmed reads (2 x uint64 per read) to host memory;

@@ -43,7 +43,7 @@ class Result(C.Structure):
     _fields_ = [("sampled_reads", C.c_int64), ("too_short", C.c_int64), ("low_qual", C.c_int64),
                 ("dups", C.c_int64), ("reads_with_hits", C.c_int64), ("reads_classified", C.c_int64),
                 ("n_hsp", C.c_int64), ("n_seed_hits", C.c_int64), ("n_gapped", C.c_int64),
-                ("gapped_cells", C.c_int64), ("fam_hits", C.c_int64 * N_FAM), ("fam_aln", C.c_int64 * N_FAM),
+                ("gapped_cells", C.c_int64), ("n_capped_reads", C.c_int64), ("fam_hits", C.c_int64 * N_FAM), ("fam_aln", C.c_int64 * N_FAM),
                 ("aln_by_len", C.c_int64 * (N_FAM * LEN_BINS))]
 
 
@@ -53,6 +53,7 @@ class Hit(C.Structure):
 
 
 EXPORTS = ("mcx_create", "mcx_destroy", "mcx_set_params", "mcx_set_stream", "mcx_push_reads", "mcx_push_reads_dev",
+           "mcx_push_reads_packed", "mcx_push_reads_packed_dev", "mcx_host_alloc", "mcx_host_free",
            "mcx_qc_counts", "mcx_qc_export", "mcx_qc_import", "mcx_qc_device", "mcx_qc_refresh", "mcx_search", "mcx_result_get", "mcx_get_hits", "mcx_get_classified",
            "mcx_timings", "mcx_dpx_peak", "mcx_last_error", "mcx_version")
 
@@ -76,6 +77,11 @@ def load():
     lib.mcx_set_stream.argtypes = [vp, vp]
     lib.mcx_push_reads.argtypes = [vp, vp, vp, vp, i64]
     lib.mcx_push_reads_dev.argtypes = [vp, vp, vp, vp, i64, i64]
+    lib.mcx_push_reads_packed.argtypes = [vp, vp, i64, vp, vp, i64, i64]
+    lib.mcx_push_reads_packed_dev.argtypes = [vp, vp, i64, vp, vp, i64, i64]
+    lib.mcx_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    lib.mcx_host_free.argtypes = [vp]
+    lib.mcx_host_free.restype = None
     lib.mcx_qc_counts.argtypes = [vp, C.POINTER(Qc)]
     lib.mcx_qc_export.argtypes = [vp, vp, vp]
     lib.mcx_qc_import.argtypes = [vp, vp]
@@ -91,7 +97,7 @@ def load():
     lib.mcx_last_error.restype = C.c_char_p
     lib.mcx_version.restype = C.c_char_p
     for name in EXPORTS:
-        if name not in ("mcx_destroy", "mcx_last_error", "mcx_version"):
+        if name not in ("mcx_destroy", "mcx_last_error", "mcx_version", "mcx_host_free"):
             getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

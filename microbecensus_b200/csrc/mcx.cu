@@ -25,6 +25,8 @@
 
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include <algorithm>
 #include <cmath>
@@ -213,35 +215,142 @@ __device__ __forceinline__ double seg_prob_lookup(uint32_t sig, int len) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: read QC (mc.py:342 too short on the untrimmed length; mc.py:265-279 on seq[:L], qual[:L]).
-// One warp per read, byte loads strided by lane (each warp request = consecutive bytes).
-// The reference's float comparisons are exact in integers (see oracle oc_read_qc).
-// codes: 0 keep, 1 too short, 2 low quality
+// Read store.  Reads live in HBM as 2-bit bases + a mask, in bit-planes of 32 bases: the record of a read of `len`
+// bases is 3 G words, G = ceil(len / 32): lo[G], hi[G], mask[G].  Base code T C A G = 0..3 (bit k of lo / hi = low /
+// high bit of base k's code; complement = hi flipped); a mask bit marks a base that is not an upper-case ACGT, and under
+// it lo = 0 means 'N' (what mc.py:269 counts), lo = 1 any other character.  Bits past `len` are zero in all planes.
+// 60 bytes per 150 bp read instead of 150 (57 B of bases + mask); qualities stay bytes (only read when
+// -q / -m are active).  Host buffers arrive in this layout through mcx_push_reads_packed; ASCII pushes are packed on
+// the device by k_pack_ascii, so every kernel below has one input format.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_qc(const uint8_t *__restrict__ bases, const uint8_t *__restrict__ quals,
-                     const int64_t *__restrict__ offs, int64_t n, int L, int qoff, int minq, int meanq,
-                     int maxunk, uint8_t *__restrict__ code) {
-    int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
+struct ReadStore {
+    const uint32_t *pk;            // records
+    const int64_t *woff;           // n + 1 word offsets of the records
+    const uint32_t *len;           // n lengths
+    const uint8_t *quals;          // qualities of all reads, one byte per base, or nullptr
+    const int64_t *qoff;           // n + 1 byte offsets into quals (prefix sums of len)
+    int64_t qbytes;                // bytes readable at quals
+};
+
+struct GroupsOf { __host__ __device__ __forceinline__ int64_t operator()(uint32_t len) const { return 3 * (int64_t)((len + 31u) >> 5); } };
+struct LenOf { __host__ __device__ __forceinline__ int64_t operator()(uint32_t len) const { return (int64_t)len; } };
+
+__global__ void k_lens_from_offsets(const int64_t *__restrict__ offs, int64_t n, uint32_t *__restrict__ len) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) len[i] = (uint32_t)(offs[i + 1] - offs[i]);
+    else if (i == n) len[i] = 0;
+}
+
+// ASCII -> bit-planes, one warp per read, one base per lane and three ballots per 32 bases (compatibility path of
+// mcx_push_reads / mcx_push_reads_dev; the packed pushes skip it)
+__global__ void k_pack_ascii(const uint8_t *__restrict__ bases, const int64_t *__restrict__ offs, int64_t n,
+                             const int64_t *__restrict__ woff, uint32_t *__restrict__ pk) {
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (r >= n) return;
-    int64_t b = offs[r];
-    int len = (int)(offs[r + 1] - b);
-    if (len < L) { if (lane == 0) code[r] = 1; return; }
-    int nN = 0, sum = 0, mn = 1 << 30;
-    for (int i = lane; i < L; i += 32) {
-        nN += (bases[b + i] == 'N');
-        if (quals) { int q = (int)quals[b + i] - qoff; sum += q; mn = q < mn ? q : mn; }
+    const int64_t b = offs[r];
+    const int len = (int)(offs[r + 1] - b);
+    const int G = (len + 31) >> 5;
+    uint32_t *rec = pk + woff[r];
+    for (int g = 0; g < G; ++g) {
+        const int k = 32 * g + lane;
+        int lo = 0, hi = 0, mk = 0;
+        if (k < len) {
+            const uint8_t c = bases[b + k];
+            const int code = base_code(c);
+            if (code < 4) { lo = code & 1; hi = code >> 1; }
+            else { mk = 1; lo = (c != 'N'); }
+        }
+        const uint32_t wl = __ballot_sync(0xffffffffu, lo), wh = __ballot_sync(0xffffffffu, hi), wm = __ballot_sync(0xffffffffu, mk);
+        if (lane == 0) { rec[g] = wl; rec[G + g] = wh; rec[2 * G + g] = wm; }
     }
-    for (int s = 16; s; s >>= 1) {
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: read QC (mc.py:342 too short on the untrimmed length; mc.py:265-279 on seq[:L], qual[:L]).
+// Eight lanes per read.  Unknown bases: popcount of mask & ~lo & ~hi over the first L bases.  Qualities: the L bytes
+// of a read are fetched as aligned 128-bit pieces (a warp request = the contiguous qualities of its four reads), summed
+// with dp4a and minimised with the per-byte SIMD minimum; the bytes of a piece outside [start, start + L) are blanked.
+// HBM-bound: 4 ceil(L/32) * 3 + L (+ 20 of lengths / offsets) bytes per read, one code byte written.
+// The reference's float comparisons are exact in integers (see oracle oc_read_qc).
+// codes: 0 keep, 1 too short, 2 low quality (3 duplicate: k_mark_dups; 4 = not examined)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t byte_range_mask(int lo, int hi) {      // bytes [lo, hi) of a word as 0xff, 0 <= lo, hi <= 4
+    if (hi <= lo) return 0u;
+    const uint32_t up = hi >= 4 ? 0xffffffffu : ((1u << (8 * hi)) - 1u);
+    const uint32_t dn = lo <= 0 ? 0u : ((1u << (8 * lo)) - 1u);
+    return up & ~dn;
+}
+__global__ void __launch_bounds__(256) k_qc(ReadStore S, int64_t r0, int64_t r1, int L, int qoff, int minq, int meanq,
+                                            int maxunk, uint8_t *__restrict__ code) {
+    const int64_t r = r0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3);
+    const int sub = threadIdx.x & 7;
+    const bool live = r < r1;
+    const int len = live ? (int)S.len[r] : 0;
+    const bool ok = live && len >= L;
+    int nN = 0;
+    uint32_t sum = 0, mn = 0xffffffffu;
+    if (ok) {
+        const int G = (len + 31) >> 5, GL = (L + 31) >> 5;
+        const uint32_t *__restrict__ rec = S.pk + S.woff[r];
+        for (int g = sub; g < GL; g += 8) {
+            uint32_t m = __ldg(rec + 2 * G + g);
+            if (m) {
+                if (32 * g + 32 > L) m &= (1u << (L - 32 * g)) - 1u;
+                nN += __popc(m & ~__ldg(rec + g) & ~__ldg(rec + G + g));
+            }
+        }
+        if (S.quals) {
+            const int64_t start = S.qoff[r], end = start + L;
+            for (int64_t p = (start & ~15ll) + 16 * sub; p < end; p += 128) {
+                if (p >= start && p + 16 <= end) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(S.quals + p));
+                    sum = __dp4a(v.x, 0x01010101u, sum); sum = __dp4a(v.y, 0x01010101u, sum);
+                    sum = __dp4a(v.z, 0x01010101u, sum); sum = __dp4a(v.w, 0x01010101u, sum);
+                    mn = __vminu4(mn, __vminu4(__vminu4(v.x, v.y), __vminu4(v.z, v.w)));
+                } else {
+                    uint32_t w[4];
+                    if (p >= 0 && p + 16 <= S.qbytes) {
+                        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(S.quals + p));
+                        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+                    } else {                                   // the piece sticks out of the buffer: bytes
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            w[q] = 0;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const int64_t a = p + 4 * q + c;
+                                if (a >= start && a < end) w[q] |= (uint32_t)S.quals[a] << (8 * c);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int64_t a = p + 4 * q;
+                        const uint32_t vm = byte_range_mask((int)max(start - a, (int64_t)0), (int)min(end - a, (int64_t)4));
+                        sum = __dp4a(w[q] & vm, 0x01010101u, sum);
+                        mn = __vminu4(mn, w[q] | ~vm);
+                    }
+                }
+            }
+        }
+    }
+    // the eight lanes of a read are neighbours: three butterfly steps
+#pragma unroll
+    for (int s = 1; s < 8; s <<= 1) {
         nN += __shfl_xor_sync(0xffffffffu, nN, s);
         sum += __shfl_xor_sync(0xffffffffu, sum, s);
-        int o = __shfl_xor_sync(0xffffffffu, mn, s);
-        mn = o < mn ? o : mn;
+        mn = __vminu4(mn, __shfl_xor_sync(0xffffffffu, mn, s));
     }
-    if (lane == 0) {
+    if (live && sub == 0) {
         int c = 0;
-        if (100 * nN > maxunk * L) c = 2;
-        else if (quals && (sum < meanq * L || mn < minq)) c = 2;
+        if (!ok) c = 1;
+        else if (100 * nN > maxunk * L) c = 2;
+        else if (S.quals) {
+            const uint32_t m2 = __vminu4(mn, mn >> 16);
+            const int minb = (int)(__vminu4(m2, m2 >> 8) & 0xffu);
+            if ((int)sum - qoff * L < meanq * L || minb - qoff < minq) c = 2;
+        }
         code[r] = (uint8_t)c;
     }
 }
@@ -252,29 +361,66 @@ __global__ void k_qc(const uint8_t *__restrict__ bases, const uint8_t *__restric
 // duplicate iff an earlier KEPT read has the same fingerprint.  Per fingerprint group in index order: everything
 // after the first kept read is a duplicate; reads before it keep their QC verdict.
 struct FpKey { unsigned long long a, b; uint32_t idx; uint32_t pad; };
-struct FpLess {
-    __device__ __forceinline__ bool operator()(const FpKey &x, const FpKey &y) const {
-        return x.a < y.a || (x.a == y.a && (x.b < y.b || (x.b == y.b && x.idx < y.idx)));
-    }
-};
 #define FP_B1 0x9E3779B97F4A7C15ull
 #define FP_B2 0xC2B2AE3D27D4EB4Full
 #define FP_LEN 0xD6E8FEB86659FD93ull
-__device__ __forceinline__ unsigned long long fp_code(uint8_t c) {
-    return c == 'A' ? 1 : c == 'C' ? 2 : c == 'G' ? 3 : c == 'T' ? 4 : c == 'N' ? 5 : 6 + (c & 0x7f);
+// character codes of the fingerprint: A 1, C 2, G 3, T 4 (complement = 5 - c), N 5, other 6 + (c & 0x7f).  The packed
+// store does not keep which "other" character a base was; under -d the reference raises KeyError on them
+// (mc.py:288), so every character that can reach the duplicate test is one of ACGTN.  Others hash as 6.
+__host__ __device__ __forceinline__ unsigned long long fp_of_code(int code2, int masked, int lo) {   // base code T C A G = 0..3
+    if (masked) return lo ? 6ull : 5ull;
+    return code2 == 0 ? 4ull : code2 == 1 ? 2ull : code2 == 2 ? 1ull : 3ull;
 }
-__global__ void k_fingerprint(const uint8_t *__restrict__ bases, const int64_t *__restrict__ offs, int64_t n,
-                              FpKey *__restrict__ keys) {
+__host__ __device__ __forceinline__ unsigned long long fp_comp(unsigned long long c) { return (c >= 1 && c <= 4) ? 5 - c : c; }
+// Four bases at a time: the forward hash is a Horner scheme from the left, f = f B^4 + TF[nibbles], the hash of the
+// reverse complement a Horner scheme from the right, r = r B^4 + TR[nibbles]; TF / TR hold the contribution of every
+// combination of four unmasked bases, indexed by (hi nibble << 4 | lo nibble).  One thread per read; groups with a
+// masked base and the ragged last nibble go base by base.
+struct FpTab { unsigned long long f1[256], f2[256], r1[256], r2[256]; };
+__device__ FpTab g_fptab;
+__global__ void __launch_bounds__(128) k_fingerprint(ReadStore S, int64_t n, FpKey *__restrict__ keys) {
+    __shared__ FpTab T;
+    for (int k = threadIdx.x; k < (int)(sizeof(FpTab) / 8); k += 128) reinterpret_cast<unsigned long long *>(&T)[k] = reinterpret_cast<const unsigned long long *>(&g_fptab)[k];
+    __syncthreads();
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
-    const int64_t b = offs[r];
-    const int len = (int)(offs[r + 1] - b);
-    unsigned long long f1 = 0, f2 = 0, r1 = 0, r2 = 0, p1 = 1, p2 = 1;
-    for (int i = 0; i < len; ++i) {
-        const unsigned long long c = fp_code(bases[b + i]);
-        const unsigned long long rc = (c >= 1 && c <= 4) ? 5 - c : c;
-        f1 = f1 * FP_B1 + c; f2 = f2 * FP_B2 + c;
-        r1 += rc * p1; r2 += rc * p2; p1 *= FP_B1; p2 *= FP_B2;
+    const int len = (int)S.len[r];
+    const int G = (len + 31) >> 5;
+    const uint32_t *__restrict__ rec = S.pk + S.woff[r];
+    constexpr unsigned long long B1_4 = FP_B1 * FP_B1 * FP_B1 * FP_B1, B2_4 = FP_B2 * FP_B2 * FP_B2 * FP_B2;
+    unsigned long long f1 = 0, f2 = 0, r1 = 0, r2 = 0;
+    for (int g = 0; g < G; ++g) {                               // forward
+        const uint32_t lo = __ldg(rec + g), hi = __ldg(rec + G + g), m = __ldg(rec + 2 * G + g);
+        const int nb = min(32, len - 32 * g);
+        int k = 0;
+        if (m == 0)
+            for (; k + 4 <= nb; k += 4) {
+                const uint32_t ix = (((hi >> k) & 15u) << 4) | ((lo >> k) & 15u);
+                f1 = f1 * B1_4 + T.f1[ix]; f2 = f2 * B2_4 + T.f2[ix];
+            }
+        for (; k < nb; ++k) {
+            const unsigned long long c = fp_of_code((int)(((hi >> k) & 1u) << 1 | ((lo >> k) & 1u)), (int)((m >> k) & 1u), (int)((lo >> k) & 1u));
+            f1 = f1 * FP_B1 + c; f2 = f2 * FP_B2 + c;
+        }
+    }
+    for (int g = G - 1; g >= 0; --g) {                          // reverse complement, from the last base down
+        const uint32_t lo = __ldg(rec + g), hi = __ldg(rec + G + g), m = __ldg(rec + 2 * G + g);
+        const int nb = min(32, len - 32 * g);
+        int k = nb;
+        if (m == 0) {
+            for (; k & 3; --k) {
+                const unsigned long long c = fp_comp(fp_of_code((int)(((hi >> (k - 1)) & 1u) << 1 | ((lo >> (k - 1)) & 1u)), 0, 0));
+                r1 = r1 * FP_B1 + c; r2 = r2 * FP_B2 + c;
+            }
+            for (; k >= 4; k -= 4) {
+                const uint32_t ix = (((hi >> (k - 4)) & 15u) << 4) | ((lo >> (k - 4)) & 15u);
+                r1 = r1 * B1_4 + T.r1[ix]; r2 = r2 * B2_4 + T.r2[ix];
+            }
+        } else
+            for (; k > 0; --k) {
+                const unsigned long long c = fp_comp(fp_of_code((int)(((hi >> (k - 1)) & 1u) << 1 | ((lo >> (k - 1)) & 1u)), (int)((m >> (k - 1)) & 1u), (int)((lo >> (k - 1)) & 1u)));
+                r1 = r1 * FP_B1 + c; r2 = r2 * FP_B2 + c;
+            }
     }
     f1 += (unsigned long long)len * FP_LEN; r1 += (unsigned long long)len * FP_LEN;
     FpKey k;
@@ -282,31 +428,47 @@ __global__ void k_fingerprint(const uint8_t *__restrict__ bases, const int64_t *
     k.idx = (uint32_t)r; k.pad = 0;
     keys[r] = k;
 }
-__global__ void k_mark_dups(const FpKey *__restrict__ keys, int64_t n, uint8_t *__restrict__ code) {
+// sort input of the duplicate test: (a, read index) of the reads that are long enough; too-short reads are decided
+// before the duplicate test and stay out
+__global__ void k_fp_keys(const FpKey *__restrict__ fp, const uint8_t *__restrict__ code, int64_t n,
+                          unsigned long long *__restrict__ ka, uint32_t *__restrict__ vi, unsigned long long *n_out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool take = r < n && code[r] != 1;
+    const uint32_t bm = __ballot_sync(0xffffffffu, take);
+    if (!bm) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(n_out, (unsigned long long)__popc(bm));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (take) { const unsigned long long o = base + __popc(bm & ((1u << lane) - 1)); ka[o] = fp[r].a; vi[o] = (uint32_t)r; }
+}
+// One thread per run of equal `a` in the sorted (a, index) list (the sort is stable, so indices ascend inside a run).
+// Runs are fingerprint groups except when two fingerprints share `a` (never expected; handled all the same: the
+// thread walks the run once per distinct `b` it meets).
+__global__ void k_mark_dups(const unsigned long long *__restrict__ ka, const uint32_t *__restrict__ vi,
+                            const FpKey *__restrict__ fp, int64_t n, uint8_t *__restrict__ code) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    const FpKey k = keys[p];
-    if (p > 0 && keys[p - 1].a == k.a && keys[p - 1].b == k.b) return;   // not the first of its group
-    bool seen_kept = false;
-    for (int64_t e = p; e < n; ++e) {
-        const FpKey q = keys[e];
-        if (q.a != k.a || q.b != k.b) break;
-        const uint8_t c = code[q.idx];
-        if (c == 1) continue;                  // too short is decided before the duplicate test
-        if (seen_kept) code[q.idx] = 3;
-        else if (c == 0) seen_kept = true;
+    const unsigned long long a = ka[p];
+    if (p > 0 && ka[p - 1] == a) return;                      // not the first of its run
+    int64_t e = p + 1;
+    while (e < n && ka[e] == a) ++e;
+    if (e == p + 1) return;
+    for (int64_t s = p; s < e; ++s) {
+        const unsigned long long b = fp[vi[s]].b;
+        bool first_of_b = true;
+        for (int64_t q = p; q < s; ++q) if (fp[vi[q]].b == b) { first_of_b = false; break; }
+        if (!first_of_b) continue;
+        bool seen_kept = false;
+        for (int64_t q = s; q < e; ++q) {
+            const uint32_t i = vi[q];
+            if (q > s && fp[i].b != b) continue;
+            if (seen_kept) code[i] = 3;
+            else if (code[i] == 0) seen_kept = true;
+        }
     }
 }
 
-__global__ void k_keep_flags(const uint8_t *__restrict__ code, int64_t n, int32_t *__restrict__ flag) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flag[i] = code[i] == 0;
-}
-__global__ void k_scatter_kept(const uint8_t *__restrict__ code, const int32_t *__restrict__ pos, int64_t n,
-                               int32_t *__restrict__ kept) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && code[i] == 0) kept[pos[i]] = (int32_t)i;
-}
 // counts of codes 0..3 among reads [0, upto)
 __global__ void k_count_codes(const uint8_t *__restrict__ code, int64_t upto, unsigned long long *__restrict__ cnt) {
     __shared__ unsigned int s[4];
@@ -325,10 +487,10 @@ __global__ void k_count_codes(const uint8_t *__restrict__ code, int64_t upto, un
 // frame to the global frame store (each warp copies its 32 rows as words).  Frames holding a low-entropy window
 // (a few per cent) are queued for k_seg instead of running the irregular SEG code with one lane alive.
 struct FrameArgs {
-    const uint8_t *bases;
-    const int64_t *offs;
+    ReadStore S;
     const int32_t *kept;
-    int64_t first, n_search;       // kept reads [first, first + n_search) in this launch
+    int64_t first;                 // kept[first ...] are the reads of this launch
+    const unsigned long long *n_search;   // how many (device counter: the launch is sized for the largest possible chunk)
     int L;
     uint8_t *frames;               // rows of fstride bytes, one per (read, frame)
     uint32_t *segq;                // frames that need the full SEG
@@ -355,17 +517,25 @@ __global__ void __launch_bounds__(NT) k_frames(FrameArgs A, int fstride) {
     for (int k = tid; k < 64; k += NT) reinterpret_cast<uint32_t *>(s_lut)[k] = reinterpret_cast<const uint32_t *>(g_codon_lut)[k];
     for (int k = tid; k < NT * fstride / 4; k += NT) reinterpret_cast<uint32_t *>(s_aa)[k] = 0x14141414u;  // AA_STOP
     const int64_t read0 = (int64_t)blockIdx.x * RPB;
+    const int64_t n_search = (int64_t)*A.n_search;
+    if (read0 >= n_search) return;
     for (int r = warp; r < RPB; r += NT / 32) {
-        if (read0 + r >= A.n_search) break;
-        const uint8_t *__restrict__ rd = A.bases + A.offs[A.kept[A.first + read0 + r]];
-        for (int k = lane; k < L; k += 32) s_code[r * L + k] = (uint8_t)base_code(rd[k]);
+        if (read0 + r >= n_search) break;
+        const int64_t rd = A.kept[A.first + read0 + r];
+        const int G = (int)((A.S.len[rd] + 31u) >> 5);
+        const uint32_t *__restrict__ rec = A.S.pk + A.S.woff[rd];
+        for (int k = lane; k < L; k += 32) {                   // the three plane words of a group are the same for the warp
+            const int g = k >> 5;
+            const uint32_t lo = __ldg(rec + g) >> lane, hi = __ldg(rec + G + g) >> lane, mk = __ldg(rec + 2 * G + g) >> lane;
+            s_code[r * L + k] = (mk & 1u) ? (uint8_t)4 : (uint8_t)(((hi & 1u) << 1) | (lo & 1u));
+        }
     }
     __syncthreads();
     const int64_t g = (int64_t)blockIdx.x * NT + tid;          // frame row within this launch
     const int r = tid / 6, frame = tid - r * 6;
     uint8_t *fr = s_aa + tid * fstride;
     bool trig = false;
-    if (read0 + r < A.n_search) {
+    if (read0 + r < n_search) {
         const int o = frame % 3, m = (L - o) / 3;
         const bool rev = frame >= 3;
         const int step = rev ? -1 : 1;
@@ -512,7 +682,9 @@ __device__ void coop_trim(const uint8_t *fr, int off, int tl, uint8_t *P, uint8_
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_seg(uint8_t *frames, int fstride, int L, const uint32_t *__restrict__ segq,
-                                                    int64_t n, int maxm, unsigned int *work) {
+                                                    const unsigned long long *n_queued, int maxm, unsigned int *work) {
+    const int64_t n = (int64_t)*n_queued;      // device-side count: no host round trip between k_frames and this launch
+    if ((int64_t)blockIdx.x * WARPS >= n) return;
     extern __shared__ __align__(16) uint8_t smem[];
     double *s_lnfac = reinterpret_cast<double *>(smem);        // [SEG_TAB] ln(i!)
     double *s_ln20 = s_lnfac + SEG_TAB;                         // [SEG_TAB] i ln 20
@@ -635,7 +807,7 @@ struct Cand {                      // 12 bytes
 };
 
 struct ProbeArgs {
-    int64_t n_frames;
+    const unsigned long long *n_reads;   // reads of this chunk (device counter); frames = 6 per read
     int L;
     DevDB db;
     const uint8_t *frames;
@@ -690,6 +862,8 @@ template <int NT>
 __global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int NW = NT / 32;
+    const int64_t n_frames = 6 * (int64_t)*A.n_reads;
+    if ((int64_t)blockIdx.x * NT >= n_frames) return;
     uint32_t *s_qcode = reinterpret_cast<uint32_t *>(smem);            // [NW][PROBE_Q] words that passed the filter
     uint32_t *s_x = s_qcode + NW * PROBE_Q;                            // [NW][4][32] incl. prefix, posting start, gframe, ip
     uint16_t *s_qmeta = reinterpret_cast<uint16_t *>(s_x + NW * 128);  // [NW][PROBE_Q] lane | pattern << 5 | position offset << 8
@@ -706,7 +880,7 @@ __global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
     uint16_t *qmeta = s_qmeta + warp * PROBE_Q;
     const int64_t g = (int64_t)blockIdx.x * NT + tid;
     const uint8_t *fr = s_aa + tid * fstride;
-    const int m = g < A.n_frames ? (A.L - (int)(g % 6) % 3) / 3 : 0;
+    const int m = g < n_frames ? (A.L - (int)(g % 6) % 3) / 3 : 0;
     const int sq = blockIdx.x & (NQ - 1);
     // reduced letters of the 10-window [i, i+10) as nibbles (letter k at bits 4k); 15 past the end
     unsigned long long win = 0;
@@ -800,14 +974,14 @@ struct ExtArgs {
     DevDB db;
     const uint8_t *frames;
     const Cand *cand;
-    int64_t n_cand;                // total over the sub-queues
+    const unsigned long long *qfill;     // NQ sub-queue fills (device counters)
     unsigned long long cap_cand;   // per sub-queue
-    unsigned long long qstart[NQ + 1];   // exclusive prefix of the sub-queue fills
     uint4 *surv;
     unsigned long long *n_surv;
     unsigned long long cap_surv;
-    uint4 *seedq;                  // accepted seeds (k_seed -> k_walk), at most n_cand
+    uint4 *seedq;                  // accepted seeds (k_seed -> k_walk)
     unsigned long long *n_seedq;
+    unsigned long long cap_seedq;
     unsigned long long *seen;      // open-addressing set of the HSP keys appended in this launch, ~0 = empty
     unsigned long long seen_mask;
     int seen_shift;
@@ -859,10 +1033,10 @@ __global__ void __launch_bounds__(NT) k_seed(ExtArgs A) {
         s_same[a] = mk;
     }
     __syncthreads();
-    // grid.y = candidate sub-queue, grid.x covers the fullest one
+    // grid.y = candidate sub-queue, grid.x covers a full one; the fills are read on the device
     const int sq = blockIdx.y;
     const unsigned long long k = (unsigned long long)blockIdx.x * NT + threadIdx.x;
-    if (k >= A.qstart[sq + 1] - A.qstart[sq]) return;
+    if (k >= min(A.qfill[sq], A.cap_cand)) return;
     const Cand c = A.cand[(unsigned long long)sq * A.cap_cand + k];
     const int frame = (int)(c.gframe % 6u);
     const int m = (A.L - frame % 3) / 3;
@@ -893,19 +1067,14 @@ __global__ void __launch_bounds__(NT) k_seed(ExtArgs A) {
     unsigned long long base = 0;
     if (lane == leader) base = atomicAdd(A.n_seedq, (unsigned long long)__popc(mask));
     base = __shfl_sync(mask, base, leader);
-    A.seedq[base + __popc(mask & ((1u << lane) - 1))] = seed_pack(c.gframe, s, sb, qb, len, score0, id0);
+    const unsigned long long at = base + __popc(mask & ((1u << lane) - 1));
+    if (at < A.cap_seedq) A.seedq[at] = seed_pack(c.gframe, s, sb, qb, len, score0, id0);
 }
 
 #undef SAME
 // K2d: one thread per accepted seed: the ungapped X-drop walks both ways (AlignFwd / AlignBwd); HSPs reaching the
 // report floor are appended to the survivor list.
-template <int NT>
-__global__ void __launch_bounds__(NT) k_walk(ExtArgs A, int64_t n_seeds) {
-    __shared__ __align__(4) int8_t s_bl[21 * 32];
-    for (int k = threadIdx.x; k < 21 * 32 / 4; k += NT) reinterpret_cast<uint32_t *>(s_bl)[k] = reinterpret_cast<const uint32_t *>(g_blosum)[k];
-    __syncthreads();
-    const int64_t g = (int64_t)blockIdx.x * NT + threadIdx.x;
-    if (g >= n_seeds) return;
+__device__ __forceinline__ void walk_one(const ExtArgs &A, const int8_t *s_bl, int64_t g) {
     const uint4 sd = A.seedq[g];
     const uint32_t gframe = sd.x;
     const int s = (int)(sd.y & 0x7fffu), sb = (int)(sd.y >> 15), qb = (int)(sd.z & 0xffu), len = (int)((sd.z >> 8) & 0xffu);
@@ -980,6 +1149,15 @@ __global__ void __launch_bounds__(NT) k_walk(ExtArgs A, int64_t n_seeds) {
     v.score = total;
     v.gframe = gframe;
     A.surv[idx] = surv_pack(v);
+}
+// grid-stride over the seed queue, whose length is read on the device (no host round trip after k_seed)
+template <int NT>
+__global__ void __launch_bounds__(NT) k_walk(ExtArgs A) {
+    __shared__ __align__(4) int8_t s_bl[21 * 32];
+    for (int k = threadIdx.x; k < 21 * 32 / 4; k += NT) reinterpret_cast<uint32_t *>(s_bl)[k] = reinterpret_cast<const uint32_t *>(g_blosum)[k];
+    __syncthreads();
+    const int64_t n_seeds = (int64_t)min(*A.n_seedq, A.cap_seedq);
+    for (int64_t g = (int64_t)blockIdx.x * NT + threadIdx.x; g < n_seeds; g += (int64_t)gridDim.x * NT) walk_one(A, s_bl, g);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1470,9 +1648,11 @@ __global__ void k_keep_sorted(const uint8_t *__restrict__ keep, int64_t n, int32
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+constexpr int MAX_COPY_STEPS = 64;             // host->device copies of a push are cut into at most this many steps
 struct mcx_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;             // kernels
+    cudaStream_t copy_stream = nullptr;        // host -> device copies of pushed reads (overlap the search of earlier chunks)
     bool own_stream = true;
     std::string err;
     mcx_params par{};
@@ -1481,18 +1661,34 @@ struct mcx_ctx {
     DevDB db{};
     std::vector<void *> db_allocs;
     int n_subj = 0;
-    // reads
-    int64_t n_reads = 0, total_bytes = 0;
-    uint8_t *d_bases = nullptr, *d_quals = nullptr;
-    int64_t *d_offs = nullptr;
-    bool own_reads = false;
-    int64_t cap_bases = 0, cap_quals = 0, cap_offs = 0;
+    // read store (see ReadStore)
+    int64_t n_reads = 0, n_words = 0, n_bases = 0;
+    uint32_t *d_pk = nullptr, *d_len = nullptr;
+    int64_t *d_woff = nullptr, *d_qoff = nullptr;
+    uint8_t *d_quals = nullptr;
+    bool have_quals = false;
+    bool ext_pk = false, ext_len = false, ext_quals = false;   // buffers owned by the caller (mcx_push_reads*_dev)
+    int64_t cap_pk = 0, cap_len = 0, cap_woff = 0, cap_qoff = 0, cap_quals = 0;
+    // ASCII staging of mcx_push_reads / mcx_push_reads_dev
+    uint8_t *d_ascii = nullptr;
+    int64_t *d_aoffs = nullptr;
+    int64_t cap_ascii = 0, cap_aoffs = 0;
+    // progress of the host -> device copies: step k covers packed words [k * step_words, ...) and quality bytes
+    // [k * step_qbytes, ...); ev_copy[k] is recorded behind it on the copy stream
+    int n_steps = 0;                           // 0: nothing to wait for (device-resident push, or everything already waited on)
+    int steps_waited = 0;
+    int64_t step_words = 0, step_qbytes = 0;
+    cudaEvent_t ev_copy[MAX_COPY_STEPS] = {nullptr}, ev_len = nullptr, ev_h2d0 = nullptr;
+    // QC state
     uint8_t *d_code = nullptr;
     FpKey *d_fp = nullptr;
-    int64_t cap_fp = 0;
-    int32_t *d_flag = nullptr, *d_pos = nullptr, *d_kept = nullptr;
-    int64_t cap_reads = 0, cap_flag = 0, cap_pos = 0, cap_kept = 0;
-    int64_t kept = 0;
+    unsigned long long *d_fpa = nullptr, *d_fpa2 = nullptr;
+    uint32_t *d_fpi = nullptr, *d_fpi2 = nullptr;
+    int64_t cap_fp = 0, cap_fpa = 0, cap_fpa2 = 0, cap_fpi = 0, cap_fpi2 = 0;
+    int32_t *d_kept = nullptr;
+    int64_t cap_code = 0, cap_kept = 0;
+    int64_t qc_upto = 0;                       // reads [0, qc_upto) have their verdict
+    bool dedup_done = false, fp_done = false, counts_valid = false;
     mcx_qc qc{};
     bool pushed = false, searched = false;
     // search buffers
@@ -1505,7 +1701,7 @@ struct mcx_ctx {
     unsigned long long *d_gitems = nullptr;   // gapped work lists: three regions of 2 * survivors entries
     GExtRec *d_gext = nullptr;
     int64_t cap_gitems = 0, cap_gext = 0;
-    int64_t cap_segq = 0, n_segq_last = 0;
+    int64_t cap_segq = 0;
     Cand *d_cand = nullptr;
     int64_t cap_frames = 0, cap_cand = 0, n_cand_last = 0;
     mcx_hit *d_hsp = nullptr, *d_hits_out = nullptr;
@@ -1515,19 +1711,24 @@ struct mcx_ctx {
     int32_t *d_nrep = nullptr;
     unsigned long long *d_bestkey = nullptr;
     int64_t cap_surv = 0, cap_best = 0, cap_nrep = 0, cap_bestkey = 0;
-    unsigned long long *d_cnt = nullptr;     // 32 scalar counters ([16], [17]: work counters of the two gapped passes)
+    unsigned long long *d_cnt = nullptr;     // 64 scalar counters (layout: enum Cnt)
     int n_sm = 148;                          // multiprocessors of the device (sizes the resident grids)
     unsigned long long *d_qcnt = nullptr;    // NQ candidate sub-queue fills
     unsigned long long *d_acc = nullptr;     // 3 + 60
     unsigned long long *d_abl = nullptr;     // 30 * 1280
+    unsigned long long *h_cnt = nullptr;     // pinned mirror for counter read-backs (64 + NQ)
     void *d_temp = nullptr;
     size_t temp_bytes = 0;
     int64_t n_hsp_sorted = 0;
     mcx_result res{};
     float ms[12] = {0};
-    int64_t launches = 0;
-    cudaEvent_t ev[16] = {nullptr};
+    int64_t launches = 0, host_syncs = 0;
+    cudaEvent_t ev[20] = {nullptr};
 };
+// slots of d_cnt
+enum Cnt { C_QC0 = 0 /* ..3: verdict counts of the search */, C_QCALL = 4 /* ..7: verdict counts over all pushed reads */,
+           C_SURV = 8, C_SEEDQ = 9, C_GAPPED = 10, C_CELLS = 11, C_SEGQ = 12, C_WORK = 13, C_ITEMS2 = 14, C_NCAP = 15,
+           C_WORK1 = 16, C_WORK2 = 17, C_ITEMS = 18, C_NKEPT = 20, C_NFP = 21, C_TOTW = 22, C_TOTQ = 23, C_N = 64 };
 
 static thread_local std::string g_err;
 
@@ -1813,6 +2014,19 @@ static int upload_tables(mcx_ctx *ctx) {
                     }
         CK(cudaMemcpyToSymbol(g_codon_lut, lut, sizeof lut));
     }
+    {   // fingerprint contributions of four unmasked bases at a time (k_fingerprint)
+        static FpTab T;
+        for (int ix = 0; ix < 256; ++ix) {
+            unsigned long long f1 = 0, f2 = 0, r1 = 0, r2 = 0, p1 = 1, p2 = 1;
+            for (int k = 0; k < 4; ++k) {
+                const unsigned long long c = fp_of_code((((ix >> 4) >> k) & 1) << 1 | ((ix >> k) & 1), 0, 0);
+                f1 = f1 * FP_B1 + c; f2 = f2 * FP_B2 + c;
+                r1 += fp_comp(c) * p1; r2 += fp_comp(c) * p2; p1 *= FP_B1; p2 *= FP_B2;
+            }
+            T.f1[ix] = f1; T.f2[ix] = f2; T.r1[ix] = r1; T.r2[ix] = r2;
+        }
+        CK(cudaMemcpyToSymbol(g_fptab, &T, sizeof T));
+    }
     CK(cudaMemcpyToSymbol(g_blosum, bl, sizeof bl));
     CK(cudaMemcpyToSymbol(g_lnfac, lnfac, sizeof lnfac));
     CK(cudaMemcpyToSymbol(g_ln20, ln20, sizeof ln20));
@@ -1835,7 +2049,12 @@ extern "C" int mcx_create(mcx_ctx **out, const mcx_db *db, int device) {
         CK(cudaSetDevice(device));
         CK(cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device));
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         for (auto &ev : ctx->ev) CK(cudaEventCreate(&ev));
+        for (auto &ev : ctx->ev_copy) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_len, cudaEventDisableTiming));
+        CK(cudaEventCreate(&ctx->ev_h2d0));
+        CK(cudaHostAlloc((void **)&ctx->h_cnt, (C_N + NQ) * sizeof(unsigned long long), cudaHostAllocDefault));
         const int ns = db->n_subj;
         const int64_t nres = db->off[ns];
         int32_t *doff = nullptr; uint8_t *dres = nullptr, *dfam = nullptr;
@@ -1849,7 +2068,7 @@ extern "C" int mcx_create(mcx_ctx **out, const mcx_db *db, int device) {
         ctx->n_subj = ns;
         int r = upload_tables(ctx); if (r) return r;
         r = build_index(ctx, db); if (r) return r;
-        CK(dev_alloc(&ctx->d_cnt, 32));
+        CK(dev_alloc(&ctx->d_cnt, C_N));
         CK(dev_alloc(&ctx->d_qcnt, NQ));
         CK(dev_alloc(&ctx->d_acc, 3 + 2 * MCX_N_FAM));
         CK(dev_alloc(&ctx->d_abl, (size_t)MCX_N_FAM * MCX_LEN_BINS));
@@ -1864,13 +2083,22 @@ extern "C" int mcx_create(mcx_ctx **out, const mcx_db *db, int device) {
 extern "C" void mcx_destroy(mcx_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
     for (void *p : ctx->db_allocs) cudaFree(p);
-    if (ctx->own_reads) { cudaFree(ctx->d_bases); cudaFree(ctx->d_quals); cudaFree(ctx->d_offs); }
-    void *bufs[] = {ctx->d_code, ctx->d_flag, ctx->d_pos, ctx->d_kept, ctx->d_surv, ctx->d_hsp, ctx->d_hits_out,
-                    ctx->d_keys, ctx->d_idx, ctx->d_best, ctx->d_hflag, ctx->d_hpos, ctx->d_keep, ctx->d_cnt,
-                    ctx->d_acc, ctx->d_abl, ctx->d_temp, ctx->d_frames, ctx->d_cand, ctx->d_segq, ctx->d_qcnt, ctx->d_fp, ctx->d_gitems, ctx->d_gext, ctx->d_nrep, ctx->d_bestkey, ctx->d_seen, ctx->d_seedq};
+    if (!ctx->ext_pk) cudaFree(ctx->d_pk);
+    if (!ctx->ext_len) cudaFree(ctx->d_len);
+    if (!ctx->ext_quals) cudaFree(ctx->d_quals);
+    void *bufs[] = {ctx->d_woff, ctx->d_qoff, ctx->d_ascii, ctx->d_aoffs, ctx->d_code, ctx->d_fp, ctx->d_fpa, ctx->d_fpa2, ctx->d_fpi, ctx->d_fpi2,
+                    ctx->d_kept, ctx->d_surv, ctx->d_hsp, ctx->d_hits_out, ctx->d_keys, ctx->d_idx, ctx->d_best, ctx->d_hflag,
+                    ctx->d_hpos, ctx->d_keep, ctx->d_cnt, ctx->d_acc, ctx->d_abl, ctx->d_temp, ctx->d_frames, ctx->d_cand,
+                    ctx->d_segq, ctx->d_qcnt, ctx->d_gitems, ctx->d_gext, ctx->d_nrep, ctx->d_bestkey, ctx->d_seen, ctx->d_seedq};
     for (void *p : bufs) if (p) cudaFree(p);
+    if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->ev_copy) if (ev) cudaEventDestroy(ev);
+    if (ctx->ev_len) cudaEventDestroy(ctx->ev_len);
+    if (ctx->ev_h2d0) cudaEventDestroy(ctx->ev_h2d0);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1897,127 +2125,284 @@ extern "C" int mcx_set_params(mcx_ctx *ctx, const mcx_params *p) {
     return MCX_OK;
 }
 
-static int run_qc(mcx_ctx *ctx) {
+// ------------------------------------------------------------------------------------------------
+// pushes: the four entry points end in the same read store (ReadStore); nothing here waits for the GPU
+// ------------------------------------------------------------------------------------------------
+static ReadStore read_store(const mcx_ctx *ctx) {
+    ReadStore S;
+    S.pk = ctx->d_pk; S.woff = ctx->d_woff; S.len = ctx->d_len;
+    S.quals = (ctx->have_quals && ctx->par.has_quality) ? ctx->d_quals : nullptr;
+    S.qoff = ctx->d_qoff; S.qbytes = ctx->n_bases;
+    return S;
+}
+
+static void release_external(mcx_ctx *ctx) {      // forget caller-owned buffers of an earlier *_dev push
+    if (ctx->ext_pk) { ctx->d_pk = nullptr; ctx->cap_pk = 0; ctx->ext_pk = false; }
+    if (ctx->ext_len) { ctx->d_len = nullptr; ctx->cap_len = 0; ctx->ext_len = false; }
+    if (ctx->ext_quals) { ctx->d_quals = nullptr; ctx->cap_quals = 0; ctx->ext_quals = false; }
+}
+
+// offsets of the records and of the qualities from the lengths (two scans over n + 1 items: slot n receives the total)
+static int scan_offsets(mcx_ctx *ctx, bool with_quals) {
     const int64_t n = ctx->n_reads;
-    const mcx_params &P = ctx->par;
     cudaStream_t st = ctx->stream;
     int rc;
-    if ((rc = ensure(ctx, &ctx->d_code, &ctx->cap_reads, n)) != MCX_OK) return rc;
-    if ((rc = ensure(ctx, &ctx->d_flag, &ctx->cap_flag, n + 1)) != MCX_OK) return rc;
-    if ((rc = ensure(ctx, &ctx->d_pos, &ctx->cap_pos, n + 1)) != MCX_OK) return rc;
-    if ((rc = ensure(ctx, &ctx->d_kept, &ctx->cap_kept, n + 1)) != MCX_OK) return rc;
-    CK(cudaEventRecord(ctx->ev[1], st));
-    if (n > 0) {
-        const int NT = 256;
-        int64_t blocks = (n * 32 + NT - 1) / NT;
-        k_qc<<<(unsigned)blocks, NT, 0, st>>>(ctx->d_bases, P.has_quality ? ctx->d_quals : nullptr, ctx->d_offs, n,
-                                             P.read_length, P.quality_offset, P.min_quality, P.mean_quality,
-                                             P.max_unknown, ctx->d_code);
-        if (P.filter_dups) {
-            if ((rc = ensure(ctx, &ctx->d_fp, &ctx->cap_fp, n)) != MCX_OK) return rc;
-            k_fingerprint<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->d_bases, ctx->d_offs, n, ctx->d_fp);
-            size_t tbs = 0;
-            cub::DeviceMergeSort::SortKeys(nullptr, tbs, ctx->d_fp, n, FpLess(), st);
-            if ((rc = ensure_temp(ctx, tbs)) != MCX_OK) return rc;
-            cub::DeviceMergeSort::SortKeys(ctx->d_temp, tbs, ctx->d_fp, n, FpLess(), st);
-            k_mark_dups<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_fp, n, ctx->d_code);
-            ctx->launches += 5;
+    if ((rc = ensure(ctx, &ctx->d_woff, &ctx->cap_woff, n + 1)) != MCX_OK) return rc;
+    if (with_quals && (rc = ensure(ctx, &ctx->d_qoff, &ctx->cap_qoff, n + 1)) != MCX_OK) return rc;
+    auto gw = thrust::make_transform_iterator(static_cast<const uint32_t *>(ctx->d_len), GroupsOf());
+    auto gl = thrust::make_transform_iterator(static_cast<const uint32_t *>(ctx->d_len), LenOf());
+    size_t tb = 0, tb2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, gw, ctx->d_woff, (int)(n + 1), st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb2, gl, ctx->d_qoff, (int)(n + 1), st);
+    if ((rc = ensure_temp(ctx, std::max(tb, tb2))) != MCX_OK) return rc;
+    cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, gw, ctx->d_woff, (int)(n + 1), st);
+    ctx->launches += 2;
+    if (with_quals) { cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb2, gl, ctx->d_qoff, (int)(n + 1), st); ctx->launches += 2; }
+    return MCX_OK;
+}
+
+static int begin_push(mcx_ctx *ctx, const char *who, int64_t n, bool quals_given) {
+    if (!ctx->have_par) return fail(ctx, MCX_ESTATE, std::string(who) + ": call mcx_set_params first");
+    if (n >= (1ll << 27)) return fail(ctx, MCX_EINVAL, std::string(who) + ": at most 2^27 reads per call");
+    if (ctx->par.has_quality && !quals_given && n > 0) return fail(ctx, MCX_EINVAL, std::string(who) + ": FASTQ parameters but no qualities");
+    CK(cudaSetDevice(ctx->device));
+    release_external(ctx);
+    ctx->launches = 0; ctx->host_syncs = 0;
+    memset(ctx->ms, 0, sizeof ctx->ms);
+    ctx->n_steps = 0; ctx->steps_waited = 0;
+    ctx->qc_upto = 0; ctx->dedup_done = false; ctx->fp_done = false; ctx->counts_valid = false;
+    ctx->pushed = false; ctx->searched = false;
+    return MCX_OK;
+}
+
+static int end_push(mcx_ctx *ctx) {
+    int rc;
+    const int64_t n = ctx->n_reads;
+    if ((rc = ensure(ctx, &ctx->d_code, &ctx->cap_code, n + 1)) != MCX_OK) return rc;
+    CK(cudaMemsetAsync(ctx->d_code, 4, (size_t)(n + 1), ctx->stream));       // 4 = not examined
+    ctx->pushed = true;
+    return MCX_OK;
+}
+
+// how many copy steps a push of this size is cut into (~32 MB each)
+static int copy_steps(int64_t bytes) {
+    int64_t k = (bytes + (32ll << 20) - 1) / (32ll << 20);
+    if (const char *e = getenv("MCX_COPY_STEPS")) k = atoi(e);
+    return (int)std::max<int64_t>(1, std::min<int64_t>(k, MAX_COPY_STEPS));
+}
+
+extern "C" int mcx_push_reads_packed(mcx_ctx *ctx, const uint32_t *packed, int64_t n_words, const uint32_t *lengths,
+                                     const uint8_t *quals, int64_t n_bases, int64_t n) {
+    if (!ctx || n < 0 || n_words < 0 || n_bases < 0 || (n > 0 && (!packed || !lengths)))
+        return fail(ctx, MCX_EINVAL, "mcx_push_reads_packed: bad argument");
+    int rc;
+    if ((rc = begin_push(ctx, "mcx_push_reads_packed", n, quals != nullptr)) != MCX_OK) return rc;
+    ctx->n_reads = n; ctx->n_words = n_words; ctx->n_bases = n_bases; ctx->have_quals = quals != nullptr;
+    if ((rc = ensure(ctx, &ctx->d_pk, &ctx->cap_pk, n_words + 4)) != MCX_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_len, &ctx->cap_len, n + 1)) != MCX_OK) return rc;
+    if (quals && (rc = ensure(ctx, &ctx->d_quals, &ctx->cap_quals, n_bases + 32)) != MCX_OK) return rc;
+    cudaStream_t cs = ctx->copy_stream;
+    // the copies run on their own stream in steps, an event behind each; the search waits per chunk of reads for
+    // the steps that hold it, so the copy of later reads overlaps the kernels of earlier ones
+    CK(cudaEventRecord(ctx->ev_h2d0, cs));
+    if (n > 0) CK(cudaMemcpyAsync(ctx->d_len, lengths, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
+    CK(cudaMemsetAsync(ctx->d_len + n, 0, sizeof(uint32_t), cs));
+    CK(cudaEventRecord(ctx->ev_len, cs));
+    const int K = copy_steps(n_words * 4 + (quals ? n_bases : 0));
+    ctx->step_words = (n_words + K - 1) / K;
+    ctx->step_qbytes = (((n_bases + K - 1) / K) + 15) & ~15ll;
+    for (int k = 0; k < K; ++k) {
+        const int64_t w0 = std::min(n_words, k * ctx->step_words), w1 = std::min(n_words, (k + 1) * ctx->step_words);
+        if (w1 > w0) CK(cudaMemcpyAsync(ctx->d_pk + w0, packed + w0, (size_t)(w1 - w0) * 4, cudaMemcpyHostToDevice, cs));
+        if (quals) {
+            const int64_t q0 = std::min(n_bases, k * ctx->step_qbytes), q1 = std::min(n_bases, (k + 1) * ctx->step_qbytes);
+            if (q1 > q0) CK(cudaMemcpyAsync(ctx->d_quals + q0, quals + q0, (size_t)(q1 - q0), cudaMemcpyHostToDevice, cs));
         }
-        k_keep_flags<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_code, n, ctx->d_flag);
-        size_t tb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->d_flag, ctx->d_pos, (int)(n + 1), st);
-        if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
-        CK(cudaMemsetAsync(ctx->d_flag + n, 0, sizeof(int32_t), st));
-        cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, ctx->d_flag, ctx->d_pos, (int)(n + 1), st);
-        k_scatter_kept<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_code, ctx->d_pos, n, ctx->d_kept);
-        CK(cudaMemsetAsync(ctx->d_cnt, 0, 16 * sizeof(unsigned long long), st));
-        k_count_codes<<<592, 256, 0, st>>>(ctx->d_code, n, ctx->d_cnt);
-        ctx->launches += 6;
+        CK(cudaEventRecord(ctx->ev_copy[k], cs));
     }
-    CK(cudaEventRecord(ctx->ev[2], st));
-    unsigned long long cnt[4] = {0, 0, 0, 0};
-    if (n > 0) CK(cudaMemcpyAsync(cnt, ctx->d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
-    ctx->qc.n_reads = n; ctx->qc.kept = (int64_t)cnt[0]; ctx->qc.too_short = (int64_t)cnt[1];
-    ctx->qc.low_qual = (int64_t)cnt[2]; ctx->qc.dups = (int64_t)cnt[3];
-    ctx->kept = (int64_t)cnt[0];
-    CK(cudaEventElapsedTime(&ctx->ms[1], ctx->ev[1], ctx->ev[2]));
-    ctx->pushed = true; ctx->searched = false;
+    CK(cudaEventRecord(ctx->ev[19], cs));
+    ctx->n_steps = K;
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_len, 0));
+    if ((rc = scan_offsets(ctx, quals != nullptr)) != MCX_OK) return rc;
+    return end_push(ctx);
+}
+
+extern "C" int mcx_push_reads_packed_dev(mcx_ctx *ctx, const uint32_t *d_packed, int64_t n_words, const uint32_t *d_lengths,
+                                         const uint8_t *d_quals, int64_t n_bases, int64_t n) {
+    if (!ctx || n < 0 || n_words < 0 || n_bases < 0 || (n > 0 && (!d_packed || !d_lengths)))
+        return fail(ctx, MCX_EINVAL, "mcx_push_reads_packed_dev: bad argument");
+    if (d_quals && ((uintptr_t)d_quals & 15)) return fail(ctx, MCX_EINVAL, "mcx_push_reads_packed_dev: qualities must be 16-byte aligned");
+    int rc;
+    if ((rc = begin_push(ctx, "mcx_push_reads_packed_dev", n, d_quals != nullptr)) != MCX_OK) return rc;
+    ctx->n_reads = n; ctx->n_words = n_words; ctx->n_bases = n_bases; ctx->have_quals = d_quals != nullptr;
+    if (!ctx->ext_pk && ctx->d_pk) { CK(cudaFree(ctx->d_pk)); }
+    if (!ctx->ext_quals && ctx->d_quals) { CK(cudaFree(ctx->d_quals)); }
+    ctx->d_pk = const_cast<uint32_t *>(d_packed); ctx->ext_pk = true; ctx->cap_pk = 0;
+    ctx->d_quals = const_cast<uint8_t *>(d_quals); ctx->ext_quals = true; ctx->cap_quals = 0;
+    // the lengths are copied (n + 1 entries are scanned; the caller's array has n)
+    if ((rc = ensure(ctx, &ctx->d_len, &ctx->cap_len, n + 1)) != MCX_OK) return rc;
+    if (n > 0) CK(cudaMemcpyAsync(ctx->d_len, d_lengths, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_len + n, 0, sizeof(uint32_t), ctx->stream));
+    if ((rc = scan_offsets(ctx, d_quals != nullptr)) != MCX_OK) return rc;
+    return end_push(ctx);
+}
+
+// ASCII reads (device-resident by now): lengths, offsets, then the bit-planes
+static int pack_ascii(mcx_ctx *ctx, const uint8_t *d_bases, const int64_t *d_offsets, int64_t n, int64_t total, bool with_quals) {
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_len, &ctx->cap_len, n + 1)) != MCX_OK) return rc;
+    k_lens_from_offsets<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(d_offsets, n, ctx->d_len);
+    if ((rc = scan_offsets(ctx, false)) != MCX_OK) return rc;
+    // every read of l bases takes 3 ceil(l / 32) words: at most 3 (total / 32 + n)
+    const int64_t bound = 3 * (total / 32 + n) + 4;
+    if ((rc = ensure(ctx, &ctx->d_pk, &ctx->cap_pk, bound)) != MCX_OK) return rc;
+    if (n > 0) k_pack_ascii<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(d_bases, d_offsets, n, ctx->d_woff, ctx->d_pk);
+    ctx->launches += 2;
+    ctx->n_words = -1;            // not known on the host (and not needed: nothing waits on copy steps)
+    (void)with_quals;
     return MCX_OK;
 }
 
 extern "C" int mcx_push_reads(mcx_ctx *ctx, const uint8_t *bases, const uint8_t *quals, const int64_t *offsets,
                               int64_t n) {
     if (!ctx || !offsets || n < 0 || (n > 0 && !bases)) return fail(ctx, MCX_EINVAL, "mcx_push_reads: bad argument");
-    if (!ctx->have_par) return fail(ctx, MCX_ESTATE, "mcx_push_reads: call mcx_set_params first");
-    if (n >= (1ll << 27)) return fail(ctx, MCX_EINVAL, "mcx_push_reads: at most 2^27 reads per call");
-    if (ctx->par.has_quality && !quals && n > 0) return fail(ctx, MCX_EINVAL, "mcx_push_reads: FASTQ parameters but no qualities");
-    CK(cudaSetDevice(ctx->device));
-    if (!ctx->own_reads) { ctx->d_bases = nullptr; ctx->d_quals = nullptr; ctx->d_offs = nullptr; ctx->cap_bases = ctx->cap_quals = ctx->cap_offs = 0; }
-    ctx->own_reads = true;
-    const int64_t total = n > 0 ? offsets[n] : 0;
     int rc;
-    if ((rc = ensure(ctx, &ctx->d_bases, &ctx->cap_bases, total + 16)) != MCX_OK) return rc;
-    if (quals && (rc = ensure(ctx, &ctx->d_quals, &ctx->cap_quals, total + 16)) != MCX_OK) return rc;
-    if ((rc = ensure(ctx, &ctx->d_offs, &ctx->cap_offs, n + 1)) != MCX_OK) return rc;
-    ctx->launches = 0;
-    memset(ctx->ms, 0, sizeof ctx->ms);
-    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    if (total > 0) CK(cudaMemcpyAsync(ctx->d_bases, bases, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
-    if (quals && total > 0) CK(cudaMemcpyAsync(ctx->d_quals, quals, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_offs, offsets, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    ctx->n_reads = n; ctx->total_bytes = total;
-    rc = run_qc(ctx);
-    if (rc == MCX_OK) cudaEventElapsedTime(&ctx->ms[0], ctx->ev[0], ctx->ev[1]);
-    return rc;
+    if ((rc = begin_push(ctx, "mcx_push_reads", n, quals != nullptr)) != MCX_OK) return rc;
+    const int64_t total = n > 0 ? offsets[n] : 0;
+    ctx->n_reads = n; ctx->n_bases = total; ctx->have_quals = quals != nullptr;
+    if ((rc = ensure(ctx, &ctx->d_ascii, &ctx->cap_ascii, total + 16)) != MCX_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_aoffs, &ctx->cap_aoffs, n + 1)) != MCX_OK) return rc;
+    if (quals && (rc = ensure(ctx, &ctx->d_quals, &ctx->cap_quals, total + 32)) != MCX_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->ev_h2d0, st));
+    if (total > 0) CK(cudaMemcpyAsync(ctx->d_ascii, bases, (size_t)total, cudaMemcpyHostToDevice, st));
+    if (quals && total > 0) CK(cudaMemcpyAsync(ctx->d_quals, quals, (size_t)total, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_aoffs, offsets, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev[19], st));
+    if ((rc = pack_ascii(ctx, ctx->d_ascii, ctx->d_aoffs, n, total, quals != nullptr)) != MCX_OK) return rc;
+    // the qualities keep the caller's offsets (one byte per base, same offsets as the bases)
+    if (quals) {
+        if ((rc = ensure(ctx, &ctx->d_qoff, &ctx->cap_qoff, n + 1)) != MCX_OK) return rc;
+        CK(cudaMemcpyAsync(ctx->d_qoff, ctx->d_aoffs, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    }
+    return end_push(ctx);
 }
 
 extern "C" int mcx_push_reads_dev(mcx_ctx *ctx, const uint8_t *d_bases, const uint8_t *d_quals,
                                   const int64_t *d_offsets, int64_t n, int64_t total_bytes) {
     if (!ctx || !d_offsets || n < 0 || (n > 0 && !d_bases)) return fail(ctx, MCX_EINVAL, "mcx_push_reads_dev: bad argument");
-    if (!ctx->have_par) return fail(ctx, MCX_ESTATE, "mcx_push_reads_dev: call mcx_set_params first");
-    if (n >= (1ll << 27)) return fail(ctx, MCX_EINVAL, "mcx_push_reads_dev: at most 2^27 reads per call");
-    if (ctx->par.has_quality && !d_quals && n > 0) return fail(ctx, MCX_EINVAL, "mcx_push_reads_dev: FASTQ parameters but no qualities");
-    CK(cudaSetDevice(ctx->device));
-    if (ctx->own_reads) {
-        cudaFree(ctx->d_bases); cudaFree(ctx->d_quals); cudaFree(ctx->d_offs);
-        ctx->cap_bases = ctx->cap_quals = ctx->cap_offs = 0;
+    if (d_quals && ((uintptr_t)d_quals & 15)) return fail(ctx, MCX_EINVAL, "mcx_push_reads_dev: qualities must be 16-byte aligned");
+    int rc;
+    if ((rc = begin_push(ctx, "mcx_push_reads_dev", n, d_quals != nullptr)) != MCX_OK) return rc;
+    ctx->n_reads = n; ctx->n_bases = total_bytes; ctx->have_quals = d_quals != nullptr;
+    if (!ctx->ext_quals && ctx->d_quals) { CK(cudaFree(ctx->d_quals)); }
+    ctx->d_quals = const_cast<uint8_t *>(d_quals); ctx->ext_quals = true; ctx->cap_quals = 0;
+    if ((rc = pack_ascii(ctx, d_bases, d_offsets, n, total_bytes, d_quals != nullptr)) != MCX_OK) return rc;
+    if (d_quals) {
+        if ((rc = ensure(ctx, &ctx->d_qoff, &ctx->cap_qoff, n + 1)) != MCX_OK) return rc;
+        CK(cudaMemcpyAsync(ctx->d_qoff, d_offsets, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
     }
-    ctx->own_reads = false;
-    ctx->d_bases = const_cast<uint8_t *>(d_bases); ctx->d_quals = const_cast<uint8_t *>(d_quals);
-    ctx->d_offs = const_cast<int64_t *>(d_offsets);
-    ctx->n_reads = n; ctx->total_bytes = total_bytes;
-    ctx->launches = 0;
-    memset(ctx->ms, 0, sizeof ctx->ms);
-    return run_qc(ctx);
+    return end_push(ctx);
 }
 
-static int refresh_kept(mcx_ctx *ctx) {
+extern "C" int mcx_host_alloc(void **out, size_t bytes) {
+    if (!out) return fail(nullptr, MCX_EINVAL, "mcx_host_alloc: null argument");
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) return fail(nullptr, MCX_ECUDA, std::string("mcx_host_alloc: ") + cudaGetErrorString(e));
+    return MCX_OK;
+}
+extern "C" void mcx_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------------------------------------
+// QC
+// ------------------------------------------------------------------------------------------------
+// make the compute stream wait for the copy steps that hold packed words [0, words) and quality bytes [0, qbytes)
+static int wait_copies(mcx_ctx *ctx, int64_t words, int64_t qbytes) {
+    if (ctx->steps_waited >= ctx->n_steps) return MCX_OK;
+    int need = 0;
+    if (words < 0) need = ctx->n_steps;
+    else {
+        if (words > 0 && ctx->step_words > 0) need = (int)std::min<int64_t>(ctx->n_steps, (words + ctx->step_words - 1) / ctx->step_words);
+        if (ctx->have_quals && qbytes > 0 && ctx->step_qbytes > 0)
+            need = std::max(need, (int)std::min<int64_t>(ctx->n_steps, (qbytes + 15 + ctx->step_qbytes - 1) / ctx->step_qbytes));
+    }
+    for (int k = ctx->steps_waited; k < need; ++k) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[k], 0));
+    ctx->steps_waited = std::max(ctx->steps_waited, need);
+    return MCX_OK;
+}
+
+static int sync_stream(mcx_ctx *ctx) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    ++ctx->host_syncs;
+    return MCX_OK;
+}
+
+// verdicts of reads [qc_upto, upto) (the copies holding them must have been waited for)
+static int qc_range(mcx_ctx *ctx, int64_t upto) {
+    if (upto <= ctx->qc_upto) return MCX_OK;
+    const mcx_params &P = ctx->par;
+    const int64_t r0 = ctx->qc_upto, nr = upto - r0;
+    k_qc<<<(unsigned)((nr * 8 + 255) / 256), 256, 0, ctx->stream>>>(read_store(ctx), r0, upto, P.read_length, P.quality_offset,
+                                                                  P.min_quality, P.mean_quality, P.max_unknown, ctx->d_code);
+    ++ctx->launches;
+    ctx->qc_upto = upto;
+    return MCX_OK;
+}
+
+// everything decided over all pushed reads: verdicts and, with -d, the duplicates
+static int qc_all(mcx_ctx *ctx) {
     const int64_t n = ctx->n_reads;
     cudaStream_t st = ctx->stream;
     int rc;
-    if (n > 0) {
-        k_keep_flags<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_code, n, ctx->d_flag);
-        size_t tb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->d_flag, ctx->d_pos, (int)(n + 1), st);
-        if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
-        CK(cudaMemsetAsync(ctx->d_flag + n, 0, sizeof(int32_t), st));
-        cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, ctx->d_flag, ctx->d_pos, (int)(n + 1), st);
-        k_scatter_kept<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_code, ctx->d_pos, n, ctx->d_kept);
-        CK(cudaMemsetAsync(ctx->d_cnt, 0, 16 * sizeof(unsigned long long), st));
-        k_count_codes<<<592, 256, 0, st>>>(ctx->d_code, n, ctx->d_cnt);
-        ctx->launches += 5;
+    if ((rc = wait_copies(ctx, -1, -1)) != MCX_OK) return rc;
+    CK(cudaEventRecord(ctx->ev[14], st));
+    if ((rc = qc_range(ctx, n)) != MCX_OK) return rc;
+    if (ctx->par.filter_dups && !ctx->dedup_done && n > 0) {
+        if ((rc = ensure(ctx, &ctx->d_fp, &ctx->cap_fp, n)) != MCX_OK) return rc;
+        if ((rc = ensure(ctx, &ctx->d_fpa, &ctx->cap_fpa, n)) != MCX_OK) return rc;
+        if ((rc = ensure(ctx, &ctx->d_fpa2, &ctx->cap_fpa2, n)) != MCX_OK) return rc;
+        if ((rc = ensure(ctx, &ctx->d_fpi, &ctx->cap_fpi, n)) != MCX_OK) return rc;
+        if ((rc = ensure(ctx, &ctx->d_fpi2, &ctx->cap_fpi2, n)) != MCX_OK) return rc;
+        if (!ctx->fp_done) { k_fingerprint<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(read_store(ctx), n, ctx->d_fp); ++ctx->launches; ctx->fp_done = true; }
+        CK(cudaMemsetAsync(ctx->d_cnt + C_NFP, 0, sizeof(unsigned long long), st));
+        k_fp_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_fp, ctx->d_code, n, ctx->d_fpa, ctx->d_fpi, ctx->d_cnt + C_NFP);
+        CK(cudaMemcpyAsync(ctx->h_cnt + C_NFP, ctx->d_cnt + C_NFP, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
+        const int64_t nk = (int64_t)ctx->h_cnt[C_NFP];
+        if (nk > 1) {
+            // k_fp_keys appends warp by warp in no fixed order; the radix sort is stable, so the indices are sorted first
+            // (low 27 bits are enough) and then the fingerprints: equal fingerprints end up in index order
+            size_t tb = 0, tb2 = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_fpi, ctx->d_fpi2, ctx->d_fpa, ctx->d_fpa2, (int)nk, 0, 27, st);
+            cub::DeviceRadixSort::SortPairs(nullptr, tb2, ctx->d_fpa2, ctx->d_fpa, ctx->d_fpi2, ctx->d_fpi, (int)nk, 0, 64, st);
+            if ((rc = ensure_temp(ctx, std::max(tb, tb2))) != MCX_OK) return rc;
+            cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_fpi, ctx->d_fpi2, ctx->d_fpa, ctx->d_fpa2, (int)nk, 0, 27, st);
+            cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb2, ctx->d_fpa2, ctx->d_fpa, ctx->d_fpi2, ctx->d_fpi, (int)nk, 0, 64, st);
+            k_mark_dups<<<(unsigned)((nk + 255) / 256), 256, 0, st>>>(ctx->d_fpa, ctx->d_fpi, ctx->d_fp, nk, ctx->d_code);
+            ctx->launches += 12;
+        }
+        ctx->dedup_done = true;
     }
-    unsigned long long cnt[4] = {0, 0, 0, 0};
-    if (n > 0) CK(cudaMemcpyAsync(cnt, ctx->d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
-    ctx->qc.n_reads = n; ctx->qc.kept = (int64_t)cnt[0]; ctx->qc.too_short = (int64_t)cnt[1];
-    ctx->qc.low_qual = (int64_t)cnt[2]; ctx->qc.dups = (int64_t)cnt[3];
-    ctx->kept = (int64_t)cnt[0];
-    ctx->searched = false;
+    CK(cudaEventRecord(ctx->ev[15], st));
+    return MCX_OK;
+}
+
+static int qc_counts_all(mcx_ctx *ctx) {
+    if (ctx->counts_valid) return MCX_OK;
+    int rc;
+    if ((rc = qc_all(ctx)) != MCX_OK) return rc;
+    const int64_t n = ctx->n_reads;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemsetAsync(ctx->d_cnt + C_QCALL, 0, 4 * sizeof(unsigned long long), st));
+    if (n > 0) { k_count_codes<<<592, 256, 0, st>>>(ctx->d_code, n, ctx->d_cnt + C_QCALL); ++ctx->launches; }
+    CK(cudaMemcpyAsync(ctx->h_cnt + C_QCALL, ctx->d_cnt + C_QCALL, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
+    const unsigned long long *c = ctx->h_cnt + C_QCALL;
+    ctx->qc.n_reads = n; ctx->qc.kept = (int64_t)c[0]; ctx->qc.too_short = (int64_t)c[1];
+    ctx->qc.low_qual = (int64_t)c[2]; ctx->qc.dups = (int64_t)c[3];
+    ctx->counts_valid = true;
     return MCX_OK;
 }
 
@@ -2028,29 +2413,30 @@ extern "C" int mcx_qc_export(mcx_ctx *ctx, uint8_t *code, uint64_t *fingerprints
     const int64_t n = ctx->n_reads;
     cudaStream_t st = ctx->stream;
     if (n == 0) return MCX_OK;
+    int rc;
+    if ((rc = qc_all(ctx)) != MCX_OK) return rc;
     CK(cudaMemcpyAsync(code, ctx->d_code, (size_t)n, cudaMemcpyDeviceToHost, st));
     if (fingerprints) {
-        int rc;
         if ((rc = ensure(ctx, &ctx->d_fp, &ctx->cap_fp, n)) != MCX_OK) return rc;
-        k_fingerprint<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->d_bases, ctx->d_offs, n, ctx->d_fp);
-        ++ctx->launches;
+        if (!ctx->fp_done) { k_fingerprint<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(read_store(ctx), n, ctx->d_fp); ++ctx->launches; ctx->fp_done = true; }
         std::vector<FpKey> h((size_t)n);
         CK(cudaMemcpyAsync(h.data(), ctx->d_fp, (size_t)n * sizeof(FpKey), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
         for (int64_t i = 0; i < n; ++i) { fingerprints[2 * i] = h[(size_t)i].a; fingerprints[2 * i + 1] = h[(size_t)i].b; }
     }
-    CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
-    return MCX_OK;
+    return sync_stream(ctx);
 }
 
 extern "C" int mcx_qc_import(mcx_ctx *ctx, const uint8_t *code) {
     if (!ctx || !code) return fail(ctx, MCX_EINVAL, "mcx_qc_import: null argument");
     if (!ctx->pushed) return fail(ctx, MCX_ESTATE, "mcx_qc_import: no reads pushed");
     CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = qc_all(ctx)) != MCX_OK) return rc;
     if (ctx->n_reads > 0)
         CK(cudaMemcpyAsync(ctx->d_code, code, (size_t)ctx->n_reads, cudaMemcpyHostToDevice, ctx->stream));
-    return refresh_kept(ctx);
+    ctx->counts_valid = false; ctx->searched = false;
+    return qc_counts_all(ctx);
 }
 
 // Device-side access to the verdicts for the cross-GPU duplicate exchange (microbecensus_b200/distributed.py): the
@@ -2060,35 +2446,43 @@ extern "C" int mcx_qc_device(mcx_ctx *ctx, void **d_code, void **d_fingerprints,
     if (!ctx || !d_code || !n) return fail(ctx, MCX_EINVAL, "mcx_qc_device: null argument");
     if (!ctx->pushed) return fail(ctx, MCX_ESTATE, "mcx_qc_device: no reads pushed");
     CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = qc_all(ctx)) != MCX_OK) return rc;
     *n = ctx->n_reads;
     *d_code = ctx->d_code;
     if (d_fingerprints) {
-        int rc;
         if ((rc = ensure(ctx, &ctx->d_fp, &ctx->cap_fp, std::max<int64_t>(ctx->n_reads, 1))) != MCX_OK) return rc;
-        if (ctx->n_reads > 0) {
-            k_fingerprint<<<(unsigned)((ctx->n_reads + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_bases, ctx->d_offs, ctx->n_reads, ctx->d_fp);
-            ++ctx->launches;
+        if (ctx->n_reads > 0 && !ctx->fp_done) {
+            k_fingerprint<<<(unsigned)((ctx->n_reads + 127) / 128), 128, 0, ctx->stream>>>(read_store(ctx), ctx->n_reads, ctx->d_fp);
+            ++ctx->launches; ctx->fp_done = true;
         }
-        CK(cudaStreamSynchronize(ctx->stream));
-        CK(cudaGetLastError());
         *d_fingerprints = ctx->d_fp;
     }
-    return MCX_OK;
+    return sync_stream(ctx);
 }
 
 extern "C" int mcx_qc_refresh(mcx_ctx *ctx) {
     if (!ctx) return fail(ctx, MCX_EINVAL, "mcx_qc_refresh: null context");
     if (!ctx->pushed) return fail(ctx, MCX_ESTATE, "mcx_qc_refresh: no reads pushed");
     CK(cudaSetDevice(ctx->device));
-    return refresh_kept(ctx);
+    ctx->counts_valid = false; ctx->searched = false;
+    return qc_counts_all(ctx);
 }
 
 extern "C" int mcx_qc_counts(mcx_ctx *ctx, mcx_qc *out) {
     if (!ctx || !out) return fail(ctx, MCX_EINVAL, "mcx_qc_counts: null argument");
     if (!ctx->pushed) return fail(ctx, MCX_ESTATE, "mcx_qc_counts: no reads pushed");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = qc_counts_all(ctx)) != MCX_OK) return rc;
     *out = ctx->qc;
     return MCX_OK;
 }
+
+struct IsKept {
+    const uint8_t *code;
+    __device__ __forceinline__ bool operator()(const int32_t &i) const { return code[i] == 0; }
+};
 
 extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     if (!ctx) return fail(ctx, MCX_EINVAL, "mcx_search: null context");
@@ -2097,144 +2491,151 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     cudaStream_t st = ctx->stream;
     const mcx_params &P = ctx->par;
     const int64_t n = ctx->n_reads;
-    const int64_t n_search = (quota < 0 || quota > ctx->kept) ? ctx->kept : quota;
     int rc;
     mcx_result &R = ctx->res;
     memset(&R, 0, sizeof R);
-    R.sampled_reads = n_search;
-    // counters up to the read that filled the quota (mc.py:356 breaks out of the loop there); when the quota is
-    // not reached the loop runs to the end of the input and every rejected read counts
-    if (quota < 0 || quota > ctx->kept) {
-        R.too_short = ctx->qc.too_short; R.low_qual = ctx->qc.low_qual; R.dups = ctx->qc.dups;
-    } else if (n_search > 0) {
-        int32_t cut = 0;
-        CK(cudaMemcpyAsync(&cut, ctx->d_kept + (n_search - 1), sizeof cut, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        CK(cudaMemsetAsync(ctx->d_cnt, 0, 16 * sizeof(unsigned long long), st));
-        k_count_codes<<<592, 256, 0, st>>>(ctx->d_code, (int64_t)cut + 1, ctx->d_cnt);
-        ++ctx->launches;
-        unsigned long long cnt[4];
-        CK(cudaMemcpyAsync(cnt, ctx->d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        R.too_short = (int64_t)cnt[1]; R.low_qual = (int64_t)cnt[2]; R.dups = (int64_t)cnt[3];
-    }
+    unsigned long long *hc = ctx->h_cnt;
     // buffers
     int64_t per_read = 8;
     if (const char *e = getenv("MCX_SURV_PER_READ")) per_read = std::max(1, atoi(e));
-    const int64_t want = std::max<int64_t>(n_search * per_read, 1 << 16);
+    const int64_t want = std::max<int64_t>((quota >= 0 ? std::min(quota, n) : n) * per_read, 1 << 16);
     if (ctx->cap_surv < want && (rc = grow_survivors(ctx, 0, want)) != MCX_OK) return rc;
     if ((rc = ensure(ctx, &ctx->d_best, &ctx->cap_best, n + 1)) != MCX_OK) return rc;
     if ((rc = ensure(ctx, &ctx->d_nrep, &ctx->cap_nrep, n + 1)) != MCX_OK) return rc;
     if ((rc = ensure(ctx, &ctx->d_bestkey, &ctx->cap_bestkey, n + 1)) != MCX_OK) return rc;
-    CK(cudaMemsetAsync(ctx->d_nrep, 0, (size_t)(n + 1) * sizeof(int32_t), st));
-    CK(cudaMemsetAsync(ctx->d_bestkey, 0, (size_t)(n + 1) * sizeof(unsigned long long), st));
-    CK(cudaMemsetAsync(ctx->d_cnt, 0, 16 * sizeof(unsigned long long), st));
-    CK(cudaMemsetAsync(ctx->d_acc, 0, (3 + 2 * MCX_N_FAM) * sizeof(unsigned long long), st));
-    CK(cudaMemsetAsync(ctx->d_abl, 0, (size_t)MCX_N_FAM * MCX_LEN_BINS * sizeof(unsigned long long), st));
-    if (n > 0) { k_fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_best, n, -1); ++ctx->launches; }
     const int maxm = (P.read_length + 2) / 3;
     // an ungapped HSP of 49+ can still grow in the gapped stage, so it survives whatever the floor is
     const int thr = std::max(1, std::min(P.min_report_raw, 49));
-
-    // K2a/K2b/K3 run per chunk of reads so that the frame store and the candidate queue stay bounded
+    // the stages run per chunk of pushed reads so that the frame store and the queues stay bounded
     const int fstride = frame_stride(maxm);
     int64_t chunk = 2000000, cand_per_read = 96;
     chunk = std::min<int64_t>(chunk, std::max<int64_t>(250000, 300000000 / P.read_length));   // queues scale with bases, not reads
     if (const char *e = getenv("MCX_CHUNK_READS")) chunk = std::min(2700000, std::max(1, atoi(e)));   // frame rows < 2^24
     if (const char *e = getenv("MCX_CAND_PER_READ")) cand_per_read = std::max(1, atoi(e));
-    chunk = std::min<int64_t>(chunk, std::max<int64_t>(n_search, 1));
+    chunk = std::min<int64_t>(chunk, std::max<int64_t>(n, 1));
     {
         const int64_t need_fr = (chunk * 6 + 512) * fstride, need_cand = std::max<int64_t>(chunk * cand_per_read, 1 << 16);
         if ((rc = ensure(ctx, &ctx->d_frames, &ctx->cap_frames, need_fr)) != MCX_OK) return rc;
         if ((rc = ensure(ctx, &ctx->d_cand, &ctx->cap_cand, need_cand)) != MCX_OK) return rc;
+        if ((rc = ensure(ctx, &ctx->d_seedq, &ctx->cap_seedq, std::max<int64_t>(ctx->cap_cand / 2, 1 << 16))) != MCX_OK) return rc;
         if ((rc = ensure(ctx, &ctx->d_segq, &ctx->cap_segq, chunk * 6 + 512)) != MCX_OK) return rc;
+        if ((rc = ensure(ctx, &ctx->d_kept, &ctx->cap_kept, chunk + 1)) != MCX_OK) return rc;
     }
+    // chunk boundaries; while host -> device copies are in flight the first chunks are small, so that the search starts
+    // as soon as a few tens of megabytes have arrived
+    std::vector<int64_t> bounds(1, 0);
+    {
+        int64_t c = ctx->n_steps > 1 ? std::max<int64_t>(chunk / 8, 65536) : chunk;
+        while (bounds.back() < n) { bounds.push_back(std::min(n, bounds.back() + c)); c = std::min(chunk, c * 2); }
+    }
+    const int nb = (int)bounds.size() - 1;
+    std::vector<long long> bw((size_t)nb + 1, -1), bq((size_t)nb + 1, -1);
+    if (ctx->steps_waited < ctx->n_steps && !P.filter_dups) {
+        // where the chunks end in the packed words / quality bytes (the offsets were scanned on the device)
+        for (int c = 1; c <= nb; ++c) {
+            CK(cudaMemcpyAsync(&bw[(size_t)c], ctx->d_woff + bounds[(size_t)c], sizeof(long long), cudaMemcpyDeviceToHost, st));
+            if (ctx->have_quals) CK(cudaMemcpyAsync(&bq[(size_t)c], ctx->d_qoff + bounds[(size_t)c], sizeof(long long), cudaMemcpyDeviceToHost, st));
+        }
+        if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
+        if (nb > 0 && (bw[(size_t)nb] != ctx->n_words || (ctx->have_quals && bq[(size_t)nb] != ctx->n_bases)))
+            return fail(ctx, MCX_EINVAL, "mcx_search: the pushed lengths do not add up to the pushed words / bases");
+    }
+    CK(cudaMemsetAsync(ctx->d_nrep, 0, (size_t)(n + 1) * sizeof(int32_t), st));
+    CK(cudaMemsetAsync(ctx->d_bestkey, 0, (size_t)(n + 1) * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ctx->d_cnt, 0, 4 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ctx->d_cnt + C_SURV, 0, (C_N - C_SURV) * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ctx->d_acc, 0, (3 + 2 * MCX_N_FAM) * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ctx->d_abl, 0, (size_t)MCX_N_FAM * MCX_LEN_BINS * sizeof(unsigned long long), st));
+    if (n > 0) { k_fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_best, n, -1); ++ctx->launches; }
+    float ms_qc = 0;
+    if (P.filter_dups || ctx->counts_valid) {     // -d is decided over all reads before anything is searched
+        if ((rc = qc_all(ctx)) != MCX_OK) return rc;
+        if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
+        float t = 0; cudaEventElapsedTime(&t, ctx->ev[14], ctx->ev[15]); ms_qc += t;
+    }
+
     float ms_frames = 0, ms_seg = 0, ms_probe = 0, ms_ext = 0, ms_gap = 0;
     unsigned long long n_surv = 0, n_cand_total = 0, n_gapped_total = 0, n_seeds_total = 0;
-    for (int64_t first = 0; first < n_search; first += chunk) {
-        const int64_t nr = std::min(chunk, n_search - first);
-        CK(cudaMemsetAsync(ctx->d_qcnt, 0, NQ * sizeof(unsigned long long), st));
-        CK(cudaMemsetAsync(ctx->d_cnt + 12, 0, 2 * sizeof(unsigned long long), st));   // [12] SEG queue length, [13] k_seg's work counter (then k_gap_list's)
+    int64_t remaining = quota, sampled = 0;
+    for (int c = 0; c < nb && (quota < 0 || remaining > 0); ++c) {
+        const int64_t r0 = bounds[(size_t)c], r1 = bounds[(size_t)c + 1], nr_in = r1 - r0;
+        // ---- K1 on this chunk: verdicts, list of kept reads
+        if ((rc = wait_copies(ctx, bw[(size_t)c + 1], bq[(size_t)c + 1])) != MCX_OK) return rc;
+        CK(cudaEventRecord(ctx->ev[14], st));
+        if ((rc = qc_range(ctx, r1)) != MCX_OK) return rc;
+        {
+            size_t tb = 0;
+            thrust::counting_iterator<int32_t> it((int32_t)r0);
+            cub::DeviceSelect::If(nullptr, tb, it, ctx->d_kept, ctx->d_cnt + C_NKEPT, (int)nr_in, IsKept{ctx->d_code}, st);
+            if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
+            cub::DeviceSelect::If(ctx->d_temp, tb, it, ctx->d_kept, ctx->d_cnt + C_NKEPT, (int)nr_in, IsKept{ctx->d_code}, st);
+            ctx->launches += 2;
+        }
+        int64_t upto = r1;                      // verdicts counted up to here (mc.py:356 leaves the loop at the read that fills -n)
+        int64_t nr = -1;                        // kept reads of the chunk that are searched; -1: all of them, count on the device
+        if (quota >= 0) {
+            CK(cudaMemcpyAsync(hc + C_NKEPT, ctx->d_cnt + C_NKEPT, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
+            const int64_t kept_c = (int64_t)hc[C_NKEPT];
+            nr = std::min(kept_c, remaining);
+            if (nr == remaining && nr > 0) {    // the quota is filled inside this chunk: by its nr-th kept read
+                int32_t cut = 0;
+                CK(cudaMemcpyAsync(&cut, ctx->d_kept + (nr - 1), sizeof cut, cudaMemcpyDeviceToHost, st));
+                if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
+                upto = (int64_t)cut + 1;
+            }
+            if (nr < kept_c) { hc[C_NKEPT + 1] = (unsigned long long)nr; CK(cudaMemcpyAsync(ctx->d_cnt + C_NKEPT, hc + C_NKEPT + 1, sizeof(unsigned long long), cudaMemcpyHostToDevice, st)); }
+            remaining -= nr;
+        }
+        if (upto > r0) { k_count_codes<<<592, 256, 0, st>>>(ctx->d_code + r0, upto - r0, ctx->d_cnt + C_QC0); ++ctx->launches; }
+        if (nr == 0) continue;
+        const int64_t nr_max = nr < 0 ? nr_in : nr;        // launch bound; the kernels read the count on the device
+        CK(cudaMemsetAsync(ctx->d_cnt + C_SEGQ, 0, 2 * sizeof(unsigned long long), st));   // SEG queue length, k_seg's work counter
         CK(cudaEventRecord(ctx->ev[2], st));
         constexpr int NTF = MCX_FRAMES_NT;      // a multiple of 6: whole reads per block
         {
             FrameArgs F;
-            F.bases = ctx->d_bases; F.offs = ctx->d_offs; F.kept = ctx->d_kept; F.first = first; F.n_search = nr;
-            F.L = P.read_length; F.frames = ctx->d_frames; F.segq = ctx->d_segq; F.n_segq = ctx->d_cnt + 12;
+            F.S = read_store(ctx); F.kept = ctx->d_kept; F.first = 0; F.n_search = ctx->d_cnt + C_NKEPT;
+            F.L = P.read_length; F.frames = ctx->d_frames; F.segq = ctx->d_segq; F.n_segq = ctx->d_cnt + C_SEGQ;
             const size_t smem = sizeof(SegTab) + 256 + (size_t)fstride * NTF + (size_t)(NTF / 6) * P.read_length;
             CK(cudaFuncSetAttribute(k_frames<NTF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_frames<NTF><<<(unsigned)((nr * 6 + NTF - 1) / NTF), NTF, smem, st>>>(F, fstride);
+            k_frames<NTF><<<(unsigned)((nr_max * 6 + NTF - 1) / NTF), NTF, smem, st>>>(F, fstride);
             ++ctx->launches;
         }
         CK(cudaEventRecord(ctx->ev[10], st));
-        unsigned long long n_segq = 0;
-        CK(cudaMemcpyAsync(&n_segq, ctx->d_cnt + 12, sizeof n_segq, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        CK(cudaGetLastError());
-        if (n_segq > 0) {
+        {   // full SEG of the queued frames: resident blocks, queue length read on the device
             constexpr int SW = MCX_SEG_W;
             const size_t smem = 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + 128 + (size_t)SW * seg_warp_bytes(fstride, maxm);
             CK(cudaFuncSetAttribute(k_seg<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int per_sm = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seg<SW>, SW * 32, smem));
             const unsigned long long resident = (unsigned long long)std::max(per_sm, 1) * (unsigned long long)ctx->n_sm;
-            k_seg<SW><<<(unsigned)std::min<unsigned long long>((n_segq + SW - 1) / SW, resident), SW * 32, smem, st>>>(
-                ctx->d_frames, fstride, P.read_length, ctx->d_segq, (int64_t)n_segq, maxm, reinterpret_cast<unsigned int *>(ctx->d_cnt + 13));
+            k_seg<SW><<<(unsigned)std::min<unsigned long long>((nr_max * 6 + SW - 1) / SW, resident), SW * 32, smem, st>>>(
+                ctx->d_frames, fstride, P.read_length, ctx->d_segq, ctx->d_cnt + C_SEGQ, maxm, reinterpret_cast<unsigned int *>(ctx->d_cnt + C_WORK));
             ++ctx->launches;
         }
-        ctx->n_segq_last = (int64_t)n_segq;
         CK(cudaEventRecord(ctx->ev[11], st));
-        unsigned long long n_cand = 0, qfill[NQ];
+        const unsigned long long surv_before = n_surv;
+        unsigned long long n_cand = 0, n_seeds = 0;
         for (int attempt = 0;; ++attempt) {
+            // ---- K2: probe -> seed -> walk, queue lengths read on the device; one read-back behind the three
+            CK(cudaMemsetAsync(ctx->d_qcnt, 0, NQ * sizeof(unsigned long long), st));
+            CK(cudaMemsetAsync(ctx->d_cnt + C_SEEDQ, 0, sizeof(unsigned long long), st));
             ProbeArgs A;
-            A.n_frames = nr * 6; A.L = P.read_length; A.db = ctx->db; A.frames = ctx->d_frames; A.cand = ctx->d_cand;
+            A.n_reads = ctx->d_cnt + C_NKEPT; A.L = P.read_length; A.db = ctx->db; A.frames = ctx->d_frames; A.cand = ctx->d_cand;
             A.n_cand = ctx->d_qcnt; A.cap_cand = (unsigned long long)(ctx->cap_cand / NQ);
             constexpr int NTP = MCX_PROBE_NT;
             const size_t smem = (size_t)(NTP / 32) * (PROBE_Q * 4 + 128 * 4 + PROBE_Q * 2) + (size_t)fstride * NTP;
             CK(cudaFuncSetAttribute(k_probe<NTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_probe<NTP><<<(unsigned)((nr * 6 + NTP - 1) / NTP), NTP, smem, st>>>(A, fstride);
-            ++ctx->launches;
-            CK(cudaMemcpyAsync(qfill, ctx->d_qcnt, sizeof qfill, cudaMemcpyDeviceToHost, st));
+            k_probe<NTP><<<(unsigned)((nr_max * 6 + NTP - 1) / NTP), NTP, smem, st>>>(A, fstride);
             if (attempt == 0) CK(cudaEventRecord(ctx->ev[3], st));
-            CK(cudaStreamSynchronize(st));
-            CK(cudaGetLastError());
-            unsigned long long worst = 0;
-            n_cand = 0;
-            for (int q = 0; q < NQ; ++q) { n_cand += qfill[q]; worst = std::max(worst, qfill[q]); }
-            if ((int64_t)worst <= ctx->cap_cand / NQ) break;
-            if (attempt) return fail(ctx, MCX_ENOMEM, "mcx_search: candidate queue overflow after regrowth");
-            // the fills are exact: size every sub-queue for the fullest one and probe this chunk again
-            if ((rc = ensure(ctx, &ctx->d_cand, &ctx->cap_cand, (int64_t)(worst + worst / 16 + 1024) * NQ)) != MCX_OK) return rc;
-            CK(cudaMemsetAsync(ctx->d_qcnt, 0, NQ * sizeof(unsigned long long), st));
-        }
-        n_cand_total += n_cand;
-        const unsigned long long surv_before = n_surv;
-        ExtArgs E;
-        E.kept = ctx->d_kept; E.first = first; E.L = P.read_length; E.fstride = fstride; E.thr_report = thr; E.db = ctx->db;
-        E.frames = ctx->d_frames; E.cand = ctx->d_cand; E.n_cand = (int64_t)n_cand; E.surv = ctx->d_surv;
-        E.cap_cand = (unsigned long long)(ctx->cap_cand / NQ);
-        E.qstart[0] = 0;
-        for (int q = 0; q < NQ; ++q) E.qstart[q + 1] = E.qstart[q] + qfill[q];
-        E.n_surv = ctx->d_cnt + 8;
-        E.n_seedq = ctx->d_cnt + 9;
-        unsigned long long n_seeds = 0;
-        if (n_cand > 0) {
-            if ((rc = ensure(ctx, &ctx->d_seedq, &ctx->cap_seedq, (int64_t)n_cand)) != MCX_OK) return rc;
-            E.seedq = ctx->d_seedq;
-            CK(cudaMemsetAsync(ctx->d_cnt + 9, 0, sizeof(unsigned long long), st));
-            {
-                unsigned long long worst = 0;
-                for (int q = 0; q < NQ; ++q) worst = std::max(worst, qfill[q]);
-                k_seed<SEED_NT><<<dim3((unsigned)((worst + SEED_NT - 1) / SEED_NT), NQ), SEED_NT, 0, st>>>(E);
-            }
-            ++ctx->launches;
-            CK(cudaMemcpyAsync(&n_seeds, ctx->d_cnt + 9, sizeof n_seeds, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            CK(cudaGetLastError());
-        }
-        n_seeds_total += n_seeds;
-        for (int attempt = 0; n_seeds > 0; ++attempt) {
+            ExtArgs E;
+            E.kept = ctx->d_kept; E.first = 0; E.L = P.read_length; E.fstride = fstride; E.thr_report = thr; E.db = ctx->db;
+            E.frames = ctx->d_frames; E.cand = ctx->d_cand; E.qfill = ctx->d_qcnt;
+            E.cap_cand = (unsigned long long)(ctx->cap_cand / NQ);
             E.surv = ctx->d_surv; E.cap_surv = (unsigned long long)ctx->cap_surv;
+            E.n_surv = ctx->d_cnt + C_SURV; E.n_seedq = ctx->d_cnt + C_SEEDQ;
+            E.seedq = ctx->d_seedq; E.cap_seedq = (unsigned long long)ctx->cap_seedq;
             {   // duplicate filter: at least two slots per survivor the list can take
                 int bits = 16;
                 while ((1ll << bits) < 2 * ctx->cap_surv) ++bits;
@@ -2242,32 +2643,48 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
                 CK(cudaMemsetAsync(ctx->d_seen, 0xff, (size_t)(1ll << bits) * sizeof(unsigned long long), st));
                 E.seen = ctx->d_seen; E.seen_mask = (1ull << bits) - 1; E.seen_shift = 64 - bits;
             }
-            k_walk<WALK_NT><<<(unsigned)((n_seeds + WALK_NT - 1) / WALK_NT), WALK_NT, 0, st>>>(E, (int64_t)n_seeds);
-            ++ctx->launches;
-            CK(cudaMemcpyAsync(&n_surv, ctx->d_cnt + 8, sizeof n_surv, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            CK(cudaGetLastError());
-            if ((int64_t)n_surv <= ctx->cap_surv) break;
-            if (attempt) return fail(ctx, MCX_ENOMEM, "mcx_search: survivor buffer overflow after regrowth");
-            if ((rc = grow_survivors(ctx, (int64_t)surv_before, (int64_t)n_surv + (int64_t)n_surv / 4)) != MCX_OK) return rc;
-            CK(cudaMemcpyAsync(ctx->d_cnt + 8, &surv_before, sizeof surv_before, cudaMemcpyHostToDevice, st));
-            n_surv = surv_before;
+            k_seed<SEED_NT><<<dim3((unsigned)((E.cap_cand + SEED_NT - 1) / SEED_NT), NQ), SEED_NT, 0, st>>>(E);
+            {
+                int per_sm = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk<WALK_NT>, WALK_NT, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+                k_walk<WALK_NT><<<(unsigned)(per_sm * ctx->n_sm * 8), WALK_NT, 0, st>>>(E);
+            }
+            ctx->launches += 3;
+            CK(cudaEventRecord(ctx->ev[8], st));
+            CK(cudaMemcpyAsync(hc + C_N, ctx->d_qcnt, NQ * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(hc, ctx->d_cnt, C_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
+            unsigned long long worst = 0;
+            n_cand = 0;
+            for (int q = 0; q < NQ; ++q) { n_cand += hc[C_N + q]; worst = std::max(worst, hc[C_N + q]); }
+            n_seeds = hc[C_SEEDQ];
+            const bool over_cand = (int64_t)worst > ctx->cap_cand / NQ, over_seed = (int64_t)n_seeds > ctx->cap_seedq,
+                       over_surv = (int64_t)hc[C_SURV] > ctx->cap_surv;
+            if (!over_cand && !over_seed && !over_surv) { n_surv = hc[C_SURV]; break; }
+            if (attempt >= 3) return fail(ctx, MCX_ENOMEM, "mcx_search: a queue (candidates / seeds / survivors) overflowed after regrowth");
+            // the fills are exact: size the queue that overflowed for what was seen and run the chunk's seed stage again
+            if (over_cand && (rc = ensure(ctx, &ctx->d_cand, &ctx->cap_cand, (int64_t)(worst + worst / 16 + 1024) * NQ)) != MCX_OK) return rc;
+            if ((over_cand || over_seed) && (rc = ensure(ctx, &ctx->d_seedq, &ctx->cap_seedq, std::max<int64_t>((int64_t)(n_seeds + n_seeds / 8), ctx->cap_cand / 2))) != MCX_OK) return rc;
+            if (over_surv && (rc = grow_survivors(ctx, (int64_t)surv_before, (int64_t)hc[C_SURV] + (int64_t)hc[C_SURV] / 4)) != MCX_OK) return rc;
+            hc[C_SURV] = surv_before;
+            CK(cudaMemcpyAsync(ctx->d_cnt + C_SURV, hc + C_SURV, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
         }
-        CK(cudaEventRecord(ctx->ev[8], st));
+        n_cand_total += n_cand; n_seeds_total += n_seeds;
+        sampled += nr < 0 ? (int64_t)hc[C_NKEPT] : nr;
         if (n_surv > surv_before) {
             GapArgs G;
             G.L = P.read_length; G.fstride = fstride; G.db = ctx->db; G.frames = ctx->d_frames; G.surv = ctx->d_surv;
             G.first = (int64_t)surv_before; G.n_surv = (int64_t)(n_surv - surv_before);
-            G.hsp = ctx->d_hsp; G.keys = ctx->d_keys; G.idx = ctx->d_idx; G.counters = ctx->d_cnt + 10;
+            G.hsp = ctx->d_hsp; G.keys = ctx->d_keys; G.idx = ctx->d_idx; G.counters = ctx->d_cnt + C_GAPPED;
             if ((rc = ensure(ctx, &ctx->d_gitems, &ctx->cap_gitems, 6 * G.n_surv)) != MCX_OK) return rc;
             if ((rc = ensure(ctx, &ctx->d_gext, &ctx->cap_gext, 2 * G.n_surv)) != MCX_OK) return rc;
-            G.items = ctx->d_gitems; G.ext = ctx->d_gext; G.n_items = ctx->d_cnt + 13;
+            G.items = ctx->d_gitems; G.ext = ctx->d_gext; G.n_items = ctx->d_cnt + C_ITEMS;
             CK(cudaMemsetAsync(ctx->d_gext, 0, (size_t)(2 * G.n_surv) * sizeof(GExtRec), st));
-            CK(cudaMemsetAsync(ctx->d_cnt + 13, 0, sizeof(unsigned long long), st));
+            CK(cudaMemsetAsync(ctx->d_cnt + C_ITEMS, 0, sizeof(unsigned long long), st));
             k_gap_list<<<(unsigned)((G.n_surv + 255) / 256), 256, 0, st>>>(G);
-            unsigned long long n_items = 0;
-            CK(cudaMemcpyAsync(&n_items, ctx->d_cnt + 13, sizeof n_items, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
+            CK(cudaMemcpyAsync(hc + C_ITEMS, ctx->d_cnt + C_ITEMS, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
+            const unsigned long long n_items = hc[C_ITEMS];
             if (n_items > 0) {
                 // work lists sorted by expected size (cub radix sort on the key byte / half-word above the item)
                 unsigned long long *list1 = ctx->d_gitems + G.n_surv * 2, *items2 = ctx->d_gitems + G.n_surv * 4, *list2 = ctx->d_gitems;
@@ -2277,9 +2694,9 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
                     if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
                     cub::DeviceRadixSort::SortKeys(ctx->d_temp, tb, G.items, list1, (int)n_items, 32, 40, st);
                 }
-                CK(cudaMemsetAsync(ctx->d_cnt + 14, 0, sizeof(unsigned long long), st));
-                CK(cudaMemsetAsync(ctx->d_cnt + 16, 0, 2 * sizeof(unsigned long long), st));
-                unsigned int *work1 = reinterpret_cast<unsigned int *>(ctx->d_cnt + 16), *work2 = reinterpret_cast<unsigned int *>(ctx->d_cnt + 17);
+                CK(cudaMemsetAsync(ctx->d_cnt + C_ITEMS2, 0, sizeof(unsigned long long), st));
+                CK(cudaMemsetAsync(ctx->d_cnt + C_WORK1, 0, 2 * sizeof(unsigned long long), st));
+                unsigned int *work1 = reinterpret_cast<unsigned int *>(ctx->d_cnt + C_WORK1), *work2 = reinterpret_cast<unsigned int *>(ctx->d_cnt + C_WORK2);
                 const unsigned gb = (unsigned)((n_items + GAP_NT - 1) / GAP_NT);
                 const int grow = maxm + GAP_SLACK + 2;
                 auto resident = [&](auto kernel, unsigned want) -> unsigned {      // blocks of a grid that is resident at once
@@ -2287,12 +2704,12 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
                     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, GAP_NT, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
                     return std::min(want, (unsigned)(per_sm * ctx->n_sm));
                 };
-                if (grow <= 104) k_gap_dir<GAP_NT, 104, false><<<resident(k_gap_dir<GAP_NT, 104, false>, gb), GAP_NT, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + 14, work1);
-                else if (grow <= 152) k_gap_dir<GAP_NT, 152, false><<<resident(k_gap_dir<GAP_NT, 152, false>, gb), GAP_NT, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + 14, work1);
-                else k_gap_dir<GAP_NT, MAX_FRAME + GAP_SLACK + 2, false><<<resident(k_gap_dir<GAP_NT, MAX_FRAME + GAP_SLACK + 2, false>, gb), GAP_NT, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + 14, work1);
-                unsigned long long n2 = 0;
-                CK(cudaMemcpyAsync(&n2, ctx->d_cnt + 14, sizeof n2, cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
+                if (grow <= 104) k_gap_dir<GAP_NT, 104, false><<<resident(k_gap_dir<GAP_NT, 104, false>, gb), GAP_NT, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + C_ITEMS2, work1);
+                else if (grow <= 152) k_gap_dir<GAP_NT, 152, false><<<resident(k_gap_dir<GAP_NT, 152, false>, gb), GAP_NT, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + C_ITEMS2, work1);
+                else k_gap_dir<GAP_NT, MAX_FRAME + GAP_SLACK + 2, false><<<resident(k_gap_dir<GAP_NT, MAX_FRAME + GAP_SLACK + 2, false>, gb), GAP_NT, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + C_ITEMS2, work1);
+                CK(cudaMemcpyAsync(hc + C_ITEMS2, ctx->d_cnt + C_ITEMS2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
+                const unsigned long long n2 = hc[C_ITEMS2];
                 if (n2 > 0) {
                     size_t tb = 0;
                     cub::DeviceRadixSort::SortKeys(nullptr, tb, items2, list2, (int)n2, 32, 48, st);
@@ -2311,15 +2728,16 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             ctx->launches += 3;
         }
         CK(cudaEventRecord(ctx->ev[9], st));
-        CK(cudaStreamSynchronize(st));
-        CK(cudaGetLastError());
+        if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
         float t;
+        cudaEventElapsedTime(&t, ctx->ev[14], ctx->ev[2]); ms_qc += t;
         cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[10]); ms_frames += t;
         cudaEventElapsedTime(&t, ctx->ev[10], ctx->ev[11]); ms_seg += t;
         cudaEventElapsedTime(&t, ctx->ev[11], ctx->ev[3]); ms_probe += t;
         cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[8]); ms_ext += t;
         cudaEventElapsedTime(&t, ctx->ev[8], ctx->ev[9]); ms_gap += t;
     }
+    R.sampled_reads = sampled;
     R.n_seed_hits = (int64_t)n_surv;
     ctx->n_cand_last = (int64_t)n_cand_total;
     const int64_t ns = (int64_t)n_surv;
@@ -2337,7 +2755,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         C.keys = ctx->d_keys; C.n = ns; C.L = P.read_length; C.min_report = P.min_report_raw;
         C.db = ctx->db; C.keep = ctx->d_keep; C.nrep = ctx->d_nrep; C.bestkey = ctx->d_bestkey;
         C.best_subject = ctx->d_best; C.acc = ctx->d_acc; C.aln_by_len = ctx->d_abl;
-        C.caplist = ctx->d_hflag; C.n_cap = ctx->d_cnt + 15;
+        C.caplist = ctx->d_hflag; C.n_cap = ctx->d_cnt + C_NCAP;
         const unsigned cb = (unsigned)((ns + 255) / 256);
         k_cls_groups<<<cb, 256, 0, st>>>(C);
         k_cls_cap<<<cb, 256, 0, st>>>(C);
@@ -2348,23 +2766,24 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     }
     CK(cudaEventRecord(ctx->ev[6], st));
     std::vector<unsigned long long> acc(3 + 2 * MCX_N_FAM), abl((size_t)MCX_N_FAM * MCX_LEN_BINS);
-    unsigned long long gc[2] = {0, 0};
     CK(cudaMemcpyAsync(acc.data(), ctx->d_acc, acc.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(abl.data(), ctx->d_abl, abl.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(gc, ctx->d_cnt + 10, sizeof gc, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hc, ctx->d_cnt, C_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[7], st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
+    if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
+    R.too_short = (int64_t)hc[C_QC0 + 1]; R.low_qual = (int64_t)hc[C_QC0 + 2]; R.dups = (int64_t)hc[C_QC0 + 3];
     R.reads_with_hits = (int64_t)acc[0]; R.reads_classified = (int64_t)acc[1]; R.n_hsp = (int64_t)acc[2];
-    R.n_gapped = (int64_t)n_gapped_total; R.gapped_cells = (int64_t)gc[1];
-    if (getenv("MCX_DEBUG")) fprintf(stderr, "[mcx] candidates %llu, accepted seeds %llu, ungapped HSPs %llu; gapped extensions %llu, with gain > 0: %llu, cells %llu\n",
-                                     n_cand_total, n_seeds_total, n_surv, n_gapped_total, gc[0], gc[1]);
+    R.n_gapped = (int64_t)n_gapped_total; R.gapped_cells = (int64_t)hc[C_CELLS];
+    R.n_capped_reads = (int64_t)hc[C_NCAP];
+    if (getenv("MCX_DEBUG")) fprintf(stderr, "[mcx] candidates %llu, accepted seeds %llu, ungapped HSPs %llu; gapped extensions %llu, with gain > 0: %llu, cells %llu; host syncs %lld\n",
+                                     n_cand_total, n_seeds_total, n_surv, n_gapped_total, hc[C_GAPPED], hc[C_CELLS], (long long)ctx->host_syncs);
     for (int f = 0; f < MCX_N_FAM; ++f) { R.fam_hits[f] = (int64_t)acc[3 + f]; R.fam_aln[f] = (int64_t)acc[3 + MCX_N_FAM + f]; }
     for (size_t k = 0; k < abl.size(); ++k) R.aln_by_len[k] = (int64_t)abl[k];
-    ctx->ms[2] = ms_probe; ctx->ms[7] = ms_ext; ctx->ms[3] = ms_gap; ctx->ms[8] = ms_frames; ctx->ms[9] = ms_seg;
+    ctx->ms[1] = ms_qc; ctx->ms[2] = ms_probe; ctx->ms[7] = ms_ext; ctx->ms[3] = ms_gap; ctx->ms[8] = ms_frames; ctx->ms[9] = ms_seg;
     cudaEventElapsedTime(&ctx->ms[4], ctx->ev[4], ctx->ev[5]);
     cudaEventElapsedTime(&ctx->ms[5], ctx->ev[5], ctx->ev[6]);
     cudaEventElapsedTime(&ctx->ms[6], ctx->ev[6], ctx->ev[7]);
+    if (cudaEventQuery(ctx->ev[19]) == cudaSuccess && cudaEventQuery(ctx->ev_h2d0) == cudaSuccess) cudaEventElapsedTime(&ctx->ms[0], ctx->ev_h2d0, ctx->ev[19]);
     ctx->n_hsp_sorted = ns;
     ctx->searched = true;
     return MCX_OK;

@@ -131,6 +131,10 @@ def exchange_duplicates_device(engine, first_index, group=None, device=None):
     """The same on the verdicts and fingerprints as they sit in the engine's device memory (mcx_qc_device): nothing but
     the two all-to-alls leaves the GPU.  Rewrites the verdicts in place and returns the refreshed QC counters."""
     import torch
+    dev_idx = (device.index if device is not None and device.index is not None else torch.cuda.current_device())
+    if getattr(engine, "device", dev_idx) != dev_idx:
+        raise RuntimeError("exchange_duplicates_device: the engine lives on GPU %d but the exchange tensors on GPU %d "
+                           "(one process per GPU: create the engine on the rank's own device)" % (engine.device, dev_idx))
     dc, df, n = engine.qc_device(True)
     if n == 0:
         dev = device or torch.device("cuda", torch.cuda.current_device())
@@ -157,16 +161,22 @@ def sharded_search(engine, batch, first_index, nreads=None, filter_dups=False, g
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
-    qc = push() if push is not None else engine.push(batch)
+    if push is not None:
+        push()
+    else:
+        engine.push(batch)
     if world == 1:
         return engine.search(-1 if nreads is None else nreads)
     dev = device or (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu"))
+    qc = None
     if filter_dups:
         if dev.type == "cuda":
             qc = exchange_duplicates_device(engine, first_index, group=group, device=dev)
         else:
             codes, fps = engine.qc_export(True)
             qc = engine.qc_import(exchange_duplicates(codes, fps, first_index, group=group, device=dev))
+    if qc is None:
+        qc = engine.qc()
     kept = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(kept, torch.tensor([qc["kept"]], dtype=torch.int64, device=dev), group=group)
     quota = shard_quota([int(k) for k in kept], nreads, rank)

@@ -45,6 +45,100 @@ class ReadBatch:
         return self.bases.nbytes + self.offsets.nbytes + (0 if self.quals is None else self.quals.nbytes)
 
 
+_CODE_LUT = np.full(256, 5, np.uint8)        # T C A G = 0..3 (the codon table's order), N = 4, anything else = 5
+for _c, _v in ((84, 0), (67, 1), (65, 2), (71, 3), (78, 4)):
+    _CODE_LUT[_c] = _v
+
+
+def pinned_empty(n, dtype):
+    """numpy array of n items in page-locked memory from libmcx (mcx_host_alloc); the owner object frees it."""
+    lib = _lib.load()
+    dt = np.dtype(dtype)
+    ptr = C.c_void_p(0)
+    _lib.check(lib, None, lib.mcx_host_alloc(C.byref(ptr), max(int(n), 1) * dt.itemsize))
+    buf = (C.c_uint8 * (max(int(n), 1) * dt.itemsize)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dt, count=int(n))
+    return arr, _PinnedOwner(lib, ptr)
+
+
+class _PinnedOwner:
+    def __init__(self, lib, ptr):
+        self.lib, self.ptr = lib, ptr
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.mcx_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class PackedBatch:
+    """Reads in the layout they have in HBM (include/mcx.h, mcx_push_reads_packed): per read of l bases 3 * ceil(l / 32)
+    uint32 words -- lo[G], hi[G], mask[G] bit-planes of the 2-bit base codes -- plus the lengths and, for FASTQ, the
+    quality bytes of all reads back to back."""
+
+    def __init__(self, packed, lengths, quals=None, n_bases=None):
+        self.packed = np.ascontiguousarray(packed, dtype=np.uint32)
+        self.lengths = np.ascontiguousarray(lengths, dtype=np.uint32)
+        self.quals = None if quals is None else np.ascontiguousarray(quals, dtype=np.uint8)
+        self.n = len(self.lengths)
+        self.n_bases = int(self.lengths.sum(dtype=np.int64)) if n_bases is None else int(n_bases)
+        self._owners = []
+
+    @property
+    def nbytes(self):
+        return self.packed.nbytes + self.lengths.nbytes + (0 if self.quals is None else self.quals.nbytes)
+
+    @classmethod
+    def from_batch(cls, batch, pinned=False):
+        """Pack an ASCII ReadBatch (numpy; the C++ reader of libmcxio packs while it parses)."""
+        lens = np.diff(batch.offsets).astype(np.int64)
+        n = len(lens)
+        G = (lens + 31) // 32
+        woff = np.zeros(n + 1, np.int64)
+        np.cumsum(3 * G, out=woff[1:])
+        alloc = (lambda k, dt: pinned_empty(k, dt)) if pinned else (lambda k, dt: (np.empty(k, dt), None))
+        packed, o1 = alloc(int(woff[-1]), np.uint32)
+        lengths, o2 = alloc(n, np.uint32)
+        lengths[:] = lens
+        base0 = int(batch.offsets[0]) if n else 0
+        if n and (lens == lens[0]).all() and lens[0] > 0:
+            L, g = int(lens[0]), int(G[0])
+            out = packed.reshape(n, 3, g)
+            step = max(1, (1 << 24) // max(L, 1))
+            for lo_r in range(0, n, step):               # blocks keep the temporaries small
+                hi_r = min(n, lo_r + step)
+                code = _CODE_LUT[batch.bases[base0 + lo_r * L: base0 + hi_r * L]].reshape(hi_r - lo_r, L)
+                pad = np.zeros((hi_r - lo_r, g * 32), np.uint8)
+                for plane, bits in enumerate((((code & 1) & (code < 4)) | (code == 5), ((code >> 1) & 1) & (code < 4), code >= 4)):
+                    pad[:, :L] = bits
+                    out[lo_r:hi_r, plane, :] = np.packbits(pad.reshape(-1, g, 32), axis=-1, bitorder="little").view("<u4").reshape(-1, g)
+        elif n:
+            total = int(batch.offsets[-1]) - base0
+            code = _CODE_LUT[batch.bases[base0: base0 + total]]
+            rd = np.repeat(np.arange(n), lens)
+            pos = np.arange(total, dtype=np.int64) - np.repeat(batch.offsets[:-1] - base0, lens)
+            word, bit = woff[rd] + pos // 32, (pos % 32).astype(np.uint64)
+            g_rd = G[rd]
+            acc = np.zeros(int(woff[-1]), np.float64)
+            for plane, bits in enumerate((((code & 1) & (code < 4)) | (code == 5), ((code >> 1) & 1) & (code < 4), code >= 4)):
+                sel = bits.astype(bool)
+                acc += np.bincount(word[sel] + plane * g_rd[sel], weights=np.left_shift(np.uint64(1), bit[sel]).astype(np.float64),
+                                   minlength=len(acc))
+            packed[:] = acc.astype(np.uint64).astype(np.uint32)
+        quals = None
+        o3 = None
+        if batch.quals is not None:
+            nb = int(batch.offsets[-1]) - base0 if n else 0
+            quals, o3 = alloc(nb, np.uint8)
+            quals[:] = batch.quals[base0: base0 + nb]
+        pb = cls(packed, lengths, quals, n_bases=int(lens.sum()))
+        pb._owners = [o for o in (o1, o2, o3) if o is not None]
+        return pb
+
+
 class SearchResult:
     def __init__(self, raw, markers, read_length):
         self.sampled_reads = int(raw.sampled_reads)
@@ -57,6 +151,7 @@ class SearchResult:
         self.n_seed_hits = int(raw.n_seed_hits)
         self.n_gapped = int(raw.n_gapped)
         self.gapped_cells = int(raw.gapped_cells)
+        self.n_capped_reads = int(raw.n_capped_reads)
         self.fam_hits = np.array(raw.fam_hits, np.int64)
         self.fam_aln = np.array(raw.fam_aln, np.int64)
         self.aln_by_len = np.array(raw.aln_by_len, np.int64).reshape(_lib.N_FAM, _lib.LEN_BINS)
@@ -66,17 +161,18 @@ class SearchResult:
     def counts_vector(self):
         """Everything additive, as one int64 vector (what a multi-GPU run all-reduces)."""
         head = np.array([self.sampled_reads, self.too_short, self.low_qual, self.dups, self.reads_with_hits,
-                         self.reads_classified, self.n_hsp, self.n_seed_hits, self.n_gapped, self.gapped_cells], np.int64)
+                         self.reads_classified, self.n_hsp, self.n_seed_hits, self.n_gapped, self.gapped_cells,
+                         self.n_capped_reads], np.int64)
         return np.concatenate([head, self.fam_hits, self.fam_aln, self.aln_by_len.ravel()])
 
     def load_counts_vector(self, v):
         v = np.asarray(v, np.int64)
         (self.sampled_reads, self.too_short, self.low_qual, self.dups, self.reads_with_hits, self.reads_classified,
-         self.n_hsp, self.n_seed_hits, self.n_gapped, self.gapped_cells) = (int(x) for x in v[:10])
+         self.n_hsp, self.n_seed_hits, self.n_gapped, self.gapped_cells, self.n_capped_reads) = (int(x) for x in v[:11])
         nf = _lib.N_FAM
-        self.fam_hits = v[10:10 + nf].copy()
-        self.fam_aln = v[10 + nf:10 + 2 * nf].copy()
-        self.aln_by_len = v[10 + 2 * nf:].reshape(nf, _lib.LEN_BINS).copy()
+        self.fam_hits = v[11:11 + nf].copy()
+        self.fam_aln = v[11 + nf:11 + 2 * nf].copy()
+        self.aln_by_len = v[11 + 2 * nf:].reshape(nf, _lib.LEN_BINS).copy()
 
     def agg_hits(self):
         """{family id: weighted count} as aggregate_hits returns it (microbe_census.py:462-472).
@@ -112,6 +208,7 @@ class MarkerSearch:
         m = self.markers
         self._db = _lib.Db(m.n_subj, m.off.ctypes.data, m.res.ctypes.data, m.fam.ctypes.data)
         self.ctx = C.c_void_p(0)
+        self.device = int(device)
         rc = self.lib.mcx_create(C.byref(self.ctx), C.byref(self._db), int(device))
         if rc != 0:
             _lib.check(self.lib, None, rc)
@@ -159,15 +256,25 @@ class MarkerSearch:
         self._ck(self.lib.mcx_set_stream(self.ctx, C.c_void_p(int(cuda_stream))))
 
     def push(self, batch):
-        """Host -> device copy of the reads + QC kernel.  Returns the QC counters over all pushed reads."""
-        self._batch = batch  # keep the arrays alive
-        self._ck(self.lib.mcx_push_reads(self.ctx, _ptr(batch.bases), _ptr(batch.quals), _ptr(batch.offsets), batch.n))
-        return self.qc()
+        """Queue the host -> device copy of the reads (ReadBatch = ASCII, PackedBatch = the device layout).  Nothing is
+        waited for: the search consumes the reads as they arrive.  `qc()` gives the verdict counts over all pushed reads
+        (and waits for all of them)."""
+        self._batch = batch  # the copies are asynchronous: keep the arrays alive
+        if isinstance(batch, PackedBatch):
+            self._ck(self.lib.mcx_push_reads_packed(self.ctx, _ptr(batch.packed), int(batch.packed.size), _ptr(batch.lengths),
+                                                    _ptr(batch.quals), int(batch.n_bases), batch.n))
+        else:
+            self._ck(self.lib.mcx_push_reads(self.ctx, _ptr(batch.bases), _ptr(batch.quals), _ptr(batch.offsets), batch.n))
 
     def push_device(self, d_bases_ptr, d_quals_ptr, d_offsets_ptr, n, total_bytes):
+        """ASCII reads already in device memory"""
         self._ck(self.lib.mcx_push_reads_dev(self.ctx, C.c_void_p(d_bases_ptr), C.c_void_p(d_quals_ptr or 0),
                                              C.c_void_p(d_offsets_ptr), int(n), int(total_bytes)))
-        return self.qc()
+
+    def push_packed_device(self, d_packed_ptr, n_words, d_lengths_ptr, d_quals_ptr, n_bases, n):
+        """packed reads already in device memory (the buffers stay the caller's)"""
+        self._ck(self.lib.mcx_push_reads_packed_dev(self.ctx, C.c_void_p(d_packed_ptr), int(n_words), C.c_void_p(d_lengths_ptr),
+                                                    C.c_void_p(d_quals_ptr or 0), int(n_bases), int(n)))
 
     def qc(self):
         q = _lib.Qc()

@@ -40,8 +40,27 @@ def get_markers():
     return _markers
 
 
-def get_engine(device=0):
+def default_device():
+    """The GPU this process searches on: $MCX_DEVICE if set; under torchrun (one process per GPU) the rank's own GPU --
+    torch's current device once a process group is up, else $LOCAL_RANK; otherwise GPU 0."""
+    if os.environ.get("MCX_DEVICE"):
+        return int(os.environ["MCX_DEVICE"])
+    if "torch" in sys.modules:
+        try:
+            import torch
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl":
+                return int(torch.cuda.current_device()) if os.environ.get("LOCAL_RANK") is None else int(os.environ["LOCAL_RANK"])
+        except Exception:
+            pass
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("LOCAL_RANK") is not None:
+        return int(os.environ["LOCAL_RANK"])
+    return 0
+
+
+def get_engine(device=None):
     """One GPU context per device, created on first use (marker index upload ~ seconds) and reused."""
+    device = default_device() if device is None else int(device)
     if device not in _engines:
         _engines[device] = MarkerSearch(get_markers(), device)
     return _engines[device]
@@ -284,7 +303,7 @@ def sample_and_search(args, engine=None):
     Files are taken in order and concatenated (mc.py:337: paired files are processed one after the other);
     the device applies the filter chain too-short -> low-quality per read and the `-n` cut as "first nreads
     kept reads"; counters are those of the reference loop up to the read that filled the quota."""
-    eng = engine or get_engine(int(os.environ.get("MCX_DEVICE", "0")))
+    eng = engine or get_engine()
     if args["verbose"]:
         print("====Estimating Average Genome Size====")
         print("Sampling & trimming reads...")

@@ -54,7 +54,42 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.Cutoff) == 24
     assert ctypes.sizeof(_lib.Params) == 32 + 24 * 30
     assert ctypes.sizeof(_lib.Hit) == 48
-    assert ctypes.sizeof(_lib.Result) == 8 * (10 + 30 + 30 + 30 * 1280)
+    assert ctypes.sizeof(_lib.Result) == 8 * (11 + 30 + 30 + 30 * 1280)
+
+
+def _unpack(pb):
+    """PackedBatch -> strings ('x' for characters that are neither ACGT nor N), checking the padding bits"""
+    out, w = [], 0
+    for l in (int(x) for x in pb.lengths):
+        G = (l + 31) // 32
+        lo, hi, mk = (pb.packed[w + k * G: w + (k + 1) * G] for k in range(3))
+        w += 3 * G
+        chars = []
+        for k in range(l):
+            a, b, m = ((int(pl[k // 32]) >> (k % 32)) & 1 for pl in (lo, hi, mk))
+            chars.append(("N" if a == 0 else "x") if m else "TCAG"[a | (b << 1)])
+        if l % 32:
+            assert all(int(pl[-1]) >> (l % 32) == 0 for pl in (lo, hi, mk))
+        out.append("".join(chars))
+    assert w == pb.packed.size
+    return out
+
+
+def test_packed_read_layout_roundtrip():
+    """The 2-bit + mask bit-plane layout of include/mcx.h (mcx_push_reads_packed) as the numpy packer writes it:
+    fixed-length and ragged batches, N / lower-case / IUPAC characters, empty reads."""
+    from microbecensus_b200.engine import PackedBatch
+    rng = np.random.default_rng(5)
+    alpha = np.frombuffer(b"ACGTNacgtRY", np.uint8)
+    p = np.array([0.23] * 4 + [0.04] + [0.04 / 6] * 6); p /= p.sum()
+    for lengths in ([150] * 70, [32] * 5, [64] * 3, [int(x) for x in rng.integers(0, 200, size=150)], [0, 1, 31, 32, 33, 0], []):
+        seqs = [alpha[rng.choice(len(alpha), size=l, p=p)].tobytes().decode() for l in lengths]
+        quals = ["".join(chr(33 + int(q)) for q in rng.integers(0, 42, size=l)) for l in lengths]
+        pb = PackedBatch.from_batch(ReadBatch.from_strings(seqs, quals))
+        assert pb.n == len(seqs) and pb.n_bases == sum(lengths)
+        assert _unpack(pb) == ["".join(c if c in "ACGTN" else "x" for c in s) for s in seqs]
+        assert pb.quals.tobytes().decode() == "".join(quals)
+        assert pb.packed.size == sum(3 * ((l + 31) // 32) for l in lengths)
 
 
 def test_reader_matches_readfq_state_machine(tmp_path):
@@ -153,7 +188,7 @@ def counts(ss):
     h, _ = o.search(b, 100, report_floor(100)); c = o.classify(h, 100, m, b.n)
     class Raw: pass
     raw = Raw()
-    for k in ("too_short","low_qual","dups","n_seed_hits","n_gapped","gapped_cells"): setattr(raw, k, 0)
+    for k in ("too_short","low_qual","dups","n_seed_hits","n_gapped","gapped_cells","n_capped_reads"): setattr(raw, k, 0)
     raw.sampled_reads = b.n; raw.reads_classified = c["classified"]; raw.n_hsp = len(h); raw.reads_with_hits = len(set(h[:,0].tolist()))
     raw.fam_hits = c["fam_hits"]; raw.fam_aln = c["fam_aln"]; raw.aln_by_len = c["aln_by_len"].ravel()
     return SearchResult(raw, m, 100)

@@ -10,7 +10,8 @@ from microbecensus_b200 import microbe_census as mcb
 from oracle_lib import OC_HIT_FIELDS
 
 SETS = [("meta.fa.gz", "meta", 100), ("meta50.fa.gz", "meta50", 50), ("long.fa.gz", "long", 500),
-        ("long.fa.gz", "long", 250), ("long.fa.gz", "long", 150), ("short.fq.gz", "short", 100), ("ties.fa.gz", "ties", 500)]
+        ("long.fa.gz", "long", 250), ("long.fa.gz", "long", 150), ("short.fq.gz", "short", 100), ("ties.fa.gz", "ties", 500),
+        ("cap.fa.gz", "cap", 100)]
 
 
 def load_seqs(fname, L):
@@ -58,36 +59,61 @@ def test_oracle_reproduces_rapsearch_lines(oracle, markers, fname, name, L):
     assert len(ref_reads - ours_reads) <= max(2, 0.01 * len(ref_reads))
 
 
+# reads the oracle classifies and the reference does not: read 86 of the `cap` fixture has more than 500 reportable
+# subjects; RAPsearch2's 500 printed lines (its own E-value order among equal scores) leave out the one that passes
+EXTRA_CLASSIFIED = {("cap", 100): {86}}
+
+
 @pytest.mark.parametrize("fname,name,L", SETS)
 def test_oracle_classification_matches_reference(oracle, markers, fname, name, L):
-    """classify_reads / aggregate_hits of the reference on RAPsearch2's own m8 vs the oracle's search + classify:
-    same classified reads, same family for each; weighted sums differ only through equal-score ties
-    (m8 tie order is unspecified) and the -v 500 line cap."""
+    """classify_reads / aggregate_hits of the reference on RAPsearch2's own m8 vs the oracle's search + classify, read
+    by read: the same reads are classified (explicit allow-list above), into the same family, by a hit of the same
+    printed bit score; the alignment length of the winning hit is the same unless the read has several best-scoring
+    passing subjects (m8 order among equal E-values is RAPsearch2's own) -- then the reference's choice
+    must be one of them.  Per-family sums over the reads without such a tie are identical."""
     seqs = load_seqs(fname, L)
     hits, _, batch = oracle_lines(oracle, markers, seqs, L)
     res = oracle.classify(hits, L, markers, batch.n)
     exp = golden_io.read_json("%s.L%d.json" % (name, L))
-    ref_cls = {int(k): v["fam"] for k, v in exp["classified"].items()}
-    ours_cls = {int(i): markers.fam_names[markers.fam[s]] for i, s in enumerate(res["best_subject"]) if s >= 0}
-    common = set(ref_cls) & set(ours_cls)
-    assert len(common) >= 0.97 * max(len(ref_cls), len(ours_cls)), (len(ref_cls), len(ours_cls), len(common))
-    assert all(ref_cls[k] == ours_cls[k] for k in common)
-    # Weighted sums: `hits` families must be identical; `cov`/`aln` families may differ through equal-score ties
-    # (the tied subjects have different lengths).  These fixtures are small biased subsets (a handful of reads per
-    # family), so the tolerance is per family; the < 1 % AGS bar is checked on the full 70,623-read metagenome
-    # (DESIGN.md section 7: 0.28 %) because AGS on ~5 reads per family jumps with every tie.
-    if set(ref_cls) == set(ours_cls):
-        cut = markers.cutoffs(L)
-        for f, fam in enumerate(markers.fam_names):
-            ref_v = exp["agg_hits"].get(fam, 0.0)
-            if int(cut[f]["stat"]) == 0:
-                assert float(res["fam_hits"][f]) == ref_v, fam
-            elif int(cut[f]["stat"]) == 2:
-                assert abs(float(res["fam_aln"][f]) - ref_v) <= 0.15 * max(ref_v, 1.0), fam
-            else:
-                row = res["aln_by_len"][f]
-                got = sum(float(row[ln]) / float(ln) for ln in np.nonzero(row)[0])
-                assert abs(got - ref_v) <= 0.15 * max(ref_v, 1e-9), (fam, got, ref_v)
+    ref = {int(k): v for k, v in exp["classified"].items()}
+    ours = {int(i): int(s) for i, s in enumerate(res["best_subject"]) if s >= 0}
+    assert set(ref) <= set(ours)
+    assert set(ours) - set(ref) == EXTRA_CLASSIFIED.get((name, L), set())
+    col = {k: i for i, k in enumerate(OC_HIT_FIELDS)}
+    by_read = {}
+    for h in hits:
+        by_read.setdefault(int(h[col["read"]]), []).append(h)
+    cut = markers.cutoffs(L)
+    ties = set()
+    sums = {}
+    for rd, want in ref.items():
+        mine = [h for h in by_read[rd] if int(h[col["subject"]]) == ours[rd]]
+        best = max(mine, key=lambda h: h[col["score"]])
+        fam = markers.fam_names[markers.fam[ours[rd]]]
+        assert fam == want["fam"], rd
+        assert bits_printed(int(best[col["score"]])) == want["score"], rd
+        # a tie: other subjects of the family with the same score (their length, and with it aln / target_len, may differ)
+        alts = [h for h in by_read[rd] if h[col["score"]] == best[col["score"]] and int(h[col["subject"]]) != ours[rd]
+                and markers.fam_names[markers.fam[int(h[col["subject"]])]] == fam]
+        if float(best[col["aln"]]) != float(want["aln"]):
+            assert any(float(h[col["aln"]]) == float(want["aln"]) for h in alts), (rd, "alignment length differs without an equal-score alternative")
+        if alts:
+            ties.add(rd)
+            continue
+        f = markers.fam_names.index(fam)
+        stat = int(cut[f]["stat"])
+        slen = float(markers.subj_len[ours[rd]])
+        sums[fam] = sums.get(fam, 0.0) + (1.0 if stat == 0 else float(best[col["aln"]]) if stat == 2 else float(best[col["aln"]]) / slen)
+    # what the reference summed over the reads without a tie: its aggregate minus the tied reads' own contributions
+    # cannot be rebuilt from the fixture (it stores aln, not aln / target_len), so the sums are compared for the
+    # families no tied read fell into
+    tied_fams = {markers.fam_names[markers.fam[ours[rd]]] for rd in ties} | {markers.fam_names[markers.fam[ours[rd]]] for rd in set(ours) - set(ref)}
+    checked = 0
+    for fam, v in exp["agg_hits"].items():
+        if fam not in tied_fams:
+            assert abs(sums.get(fam, 0.0) - v) <= 1e-9 * max(1.0, v), fam
+            checked += 1
+    assert checked >= 1 or len(ref) < 10
 
 
 def test_bits_formula_and_cutoff_table(oracle):

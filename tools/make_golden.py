@@ -69,9 +69,65 @@ def make_ties():
         write_set("ties", seqs, 500, tmp)
 
 
+def make_full():
+    """G6: the reference's own inputs, whole, with what the unmodified reference makes of them (no m8: classification,
+    per-family sums, counters, AGS).  `python tools/make_golden.py full`.
+      full/metagenome.fa.gz  tests/data/metagenome.fa.gz, API defaults (tests/test_microbe_census.py:15-25)
+      full/example.fq.gz     BASELINE config 1: CLI defaults (-n 2000000)
+      full/example.fa.gz     -l 150 and -l 500
+    and G7 `cap`: the reads of the metagenome with the most m8 lines (RAPsearch2 prints at most 500 per read) plus the
+    classified reads the first fixtures left out (more than 60 lines), with RAPsearch2's own lines."""
+    import shutil
+    full = os.path.join(GOLD, "full")
+    os.makedirs(full, exist_ok=True)
+    srcs = {"metagenome.fa.gz": os.path.join(REF, "tests", "data", "metagenome.fa.gz"),
+            "example.fq.gz": os.path.join(REF, "microbe_census", "example", "example.fq.gz"),
+            "example.fa.gz": os.path.join(REF, "microbe_census", "example", "example.fa.gz")}
+    for name, src in srcs.items():
+        shutil.copyfile(src, os.path.join(full, name))
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for key, name, opts in (("metagenome", "metagenome.fa.gz", {}), ("example_fq", "example.fq.gz", {"nreads": 2000000}),
+                                ("example_fa_150", "example.fa.gz", {"read_length": 150}), ("example_fa_500", "example.fa.gz", {"read_length": 500})):
+            args = {"seqfiles": [os.path.join(full, name)], "verbose": False}
+            args.update(opts)
+            paths = mc.get_relative_paths(args)
+            mc.impute_missing_args(args)
+            mc.process_seqfile(args, paths)
+            mc.search_seqs(args, paths)
+            lines = [l for l in open(paths["tempfile"] + ".m8") if l[0] != "#"]
+            best = mc.classify_reads(args, paths)
+            agg = mc.aggregate_hits(args, paths, best)
+            if key == "metagenome":
+                shutil.copyfile(paths["tempfile"] + ".m8", os.path.join(tmp, "meta_full.m8"))
+            mc.clean_up(paths)
+            ags = mc.estimate_average_genome_size(args, paths, agg)
+            total = mc.count_bases(args)
+            out[key] = {"file": name, "opts": opts, "read_length": args["read_length"], "sampled_reads": args["sampled_reads"],
+                        "quality_offset": args.get("quality_offset"), "m8_lines": len(lines),
+                        "reads_with_hits": len(set(l.split("\t")[0] for l in lines)), "classified": {k: v[0] for k, v in best.items()},
+                        "agg_hits": agg, "ags": ags, "total_bases": total}
+            print(key, "sampled", args["sampled_reads"], "hits", out[key]["reads_with_hits"], "classified", len(best), "AGS", ags, "bases", total)
+        json.dump(out, open(os.path.join(full, "expected.json"), "w"), indent=1, sort_keys=True)
+        # ---- G7
+        recs = [r.seq for r in mc.parse_seqs(mc.open_file(srcs["metagenome.fa.gz"]))]
+        m8 = os.path.join(tmp, "meta_full.m8")
+        nl = collections.Counter(l.split("\t")[0] for l in open(m8) if l[0] != "#")
+        most = [int(k) for k, v in nl.most_common(40)]
+        left_out = [int(k) for k in out["metagenome"]["classified"] if nl[k] > 60]
+        pick = sorted(set(most + left_out))
+        seqs = [recs[i] for i in pick]
+        with gzip.GzipFile(os.path.join(GOLD, "cap.fa.gz"), "wb", mtime=0) as fh:
+            fh.write("".join(">r%d\n%s\n" % (i, s) for i, s in zip(pick, seqs)).encode())
+        write_set("cap", seqs, 100, tmp)
+        print("cap: lines per read", sorted(nl[str(i)] for i in pick)[-10:], "left-out classified", len(left_out))
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "ties":
         return make_ties()
+    if len(sys.argv) > 1 and sys.argv[1] == "full":
+        return make_full()
     os.makedirs(GOLD, exist_ok=True)
     rnd = random.Random(20260101)
     with tempfile.TemporaryDirectory() as tmp:

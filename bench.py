@@ -422,7 +422,7 @@ def main():
     dpx = eng.dpx_peak()
     gapped = {"gcups": gcups, "cells_per_step_per_gpu": res.gapped_cells / world, "stage_ms": stage_dev.get("gapped"),
               "dpx_ginstr_per_s": dpx, "dpx_bound_gcups": dpx / 3.0, "frac_of_dpx_bound": (gcups / (dpx / 3.0)) if gcups else None,
-              "note": "X-drop extension with statistics carried per cell (DESIGN.md section 5): plain max/compare, one lane per extension, refilled from the work list"}
+              "note": "X-drop extension (RAPsearch2 AlignGapped): k_gap_screen (all extensions until first gain or death, rows in shared memory, DPX viaddmax/vimax3) + k_gap_dp (complete DP of the gainers, direction nibbles) + k_gap_trace; cells = every DP cell once"}
 
     line = {"metric": "reads/sec end-to-end AGS", "value": total_reads / t_dev, "unit": "reads/s", "n_gpus": world,
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": t_dev * 1e3, "higher_is_better": True,

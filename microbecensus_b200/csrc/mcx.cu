@@ -1182,6 +1182,7 @@ struct GapArgs {
     int64_t first, n_surv;
     unsigned long long *items;     // work list: sort key << 32 | (survivor - first) << 1 | direction
     unsigned long long *n_items;
+    unsigned long long *n_items_total;   // running total over the chunks of a search
     GExtRec *ext;                  // [2 * (survivor - first) + direction], zeroed before the launch
     mcx_hit *hsp;
     SortKey *keys;
@@ -1214,14 +1215,431 @@ __global__ void k_gap_list(GapArgs A) {
     const int tot = __popc(mf) + __popc(mb);
     if (tot == 0) return;
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(A.n_items, (unsigned long long)tot);
+    if (lane == 0) { base = atomicAdd(A.n_items, (unsigned long long)tot); atomicAdd(A.n_items_total, (unsigned long long)tot); }
     base = __shfl_sync(0xffffffffu, base, 0);
     const uint32_t lt = (1u << lane) - 1;
     if (f) A.items[base + __popc(mf & lt)] = ((unsigned long long)kf << 32) | (uint32_t)(g << 1);
     if (b) A.items[base + __popc(mf) + __popc(mb & lt)] = ((unsigned long long)kb << 32) | (uint32_t)(g << 1) | 1u;
 }
 
-// K3b: the DP itself, one LANE per gapped extension (one direction of one survivor), rows in local memory; a lane that
+// K3b, new layout (round 2): two kernels, no local memory.
+//  * k_gap_screen: ALL extensions, one thread each, until the extension either dies without ever reaching a positive
+//    score (72-85 % of them: nothing to add to the HSP) or produces its first positive cell (then it is queued for
+//    k_gap_dp).  While the best score is still 0 the X-drop bookkeeping collapses: the threshold is the constant -27,
+//    the best column is 0, so the window always starts at column 1, the left side is never pruned and the boundary
+//    cell of row i is -11 - i in closed form.  The DP rows are one packed word per column (H and F as 16-bit halves)
+//    in shared memory, column-major with the thread as the fastest index (bank = lane: conflict-free whatever column
+//    each lane is at).  All lanes of a warp start row 1 together, so their windows have similar widths throughout.
+//    The recurrences use the DPX forms: E and F are max(a + b, c) = viaddmax, H is a three-way max = vimax3.
+//  * k_gap_dp + k_gap_trace: the extensions that gain.  k_gap_dp runs the complete X-drop DP (scores only) to its natural
+//    end with the rows in a 64-column ring of packed H|F words in shared memory, and records for every cell which way it
+//    came as a nibble in global memory (what the binary keeps in its three trace matrices); k_gap_trace walks back from
+//    the best cell like the binary's CalRes and counts identities, columns, gap columns and gap runs.  (Carrying those
+//    statistics through the DP, as round 1 did, needs two more words per column: 768 bytes of shared memory per
+//    extension, 9 warps per SM, 32 % of the issue slots used.)  The live window [cs - 1, ce] never came near 56 columns
+//    in 25 M extensions (widest: 43) -- an extension that would is handed to the local-memory kernel k_gap_dir below,
+//    which stays as that fallback.
+// The first version of this stage (k_gap_dir for everything: rows of GROW ints in local memory, 6 LDL + 14 STL sites in
+// the score pass, 1.09 GB of DRAM writes per 226 M cells) ran at 110 GCUPS at 100 bp and 85 at 150 bp.
+#ifndef MCX_GAP_REFILL
+#define MCX_GAP_REFILL 24
+#endif
+constexpr int SCR_COLS = 48;                   // columns of the screening pass (an extension that needs more goes to k_gap_dp)
+constexpr int RING = 64;                       // ring of k_gap_dp
+#ifndef MCX_SCR_NT
+#define MCX_SCR_NT 128
+#endif
+#ifndef MCX_FULL_NT
+#define MCX_FULL_NT 128
+#endif
+__device__ __forceinline__ uint32_t pack_hf(int h, int f) { return ((uint32_t)h & 0xffffu) | ((uint32_t)f << 16); }
+__device__ __forceinline__ int hf_h(uint32_t w) { return (int)(short)(w & 0xffffu); }
+__device__ __forceinline__ int hf_f(uint32_t w) { return (int)w >> 16; }
+
+constexpr int SCR_ROWS = 32;                   // rows of the screening pass (no extension without a gain came near: they die by row 28)
+// residues p[0], p[step], p[2 step], ... (at most 4 W of them, `have` exist) -> W words of four in a column of shared
+// memory with stride NT; aligned 32-bit loads, shifted into place (and byte-reversed for step = -1)
+template <int W, int NT>
+__device__ __forceinline__ void load_residues(const uint8_t *p, int step, int have, uint32_t *dst) {
+    const int nw = min(W, (have + 3) >> 2);
+    if (step > 0) {
+        const uint32_t *a = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+        const int sh = 8 * (int)(reinterpret_cast<uintptr_t>(p) & 3);
+        uint32_t lo = __ldg(a);
+        for (int k = 0; k < nw; ++k) { const uint32_t hi = __ldg(a + k + 1); dst[k * NT] = __funnelshift_r(lo, hi, sh); lo = hi; }
+    } else {
+        // bytes p[0], p[-1], ...: the word holding p[0] is the highest one
+        const uintptr_t top = reinterpret_cast<uintptr_t>(p) + 1;            // one past p[0]
+        const uint32_t *a = reinterpret_cast<const uint32_t *>((top + 3) & ~(uintptr_t)3);   // first aligned word boundary at or above top
+        const int sh = 8 * (int)((reinterpret_cast<uintptr_t>(a) - top) & 3);               // bytes of a[-1] above p[0]
+        uint32_t hi = __ldg(a - 1);
+        for (int k = 0; k < nw; ++k) {
+            const uint32_t lo = __ldg(a - 2 - k);
+            // four bytes ending at p[-4k]: (lo:hi) shifted left by sh bytes, upper word, then reversed
+            dst[k * NT] = __byte_perm(__funnelshift_l(lo, hi, sh), 0, 0x0123);
+            hi = lo;
+        }
+    }
+}
+struct ExtSetup { const uint8_t *qp, *t; int step, nQ, nD; };
+__device__ __forceinline__ ExtSetup ext_setup(const GapArgs &A, uint32_t item) {
+    const int64_t g = item >> 1;
+    const Surv v = surv_unpack(A.surv[A.first + g]);
+    const uint8_t *fr = A.frames + (int64_t)v.gframe * A.fstride;
+    const int m = (A.L - v.frame % 3) / 3;
+    const int32_t o = A.db.off[v.subject];
+    const int n = A.db.off[v.subject + 1] - o;
+    const int q0 = v.q0, q1 = v.q1, t0 = v.t0, t1 = v.t0 + (v.q1 - v.q0);
+    ExtSetup S;
+    int ql, tl;
+    if ((item & 1) == 0) { ql = m - (q1 + 1); tl = n - (t1 + 1); S.qp = fr + q1 + 1; S.t = A.db.res + o + t1 + 1; S.step = 1; }
+    else { ql = q0; tl = t0; S.qp = fr + q0 - 1; S.t = A.db.res + o + t0 - 1; S.step = -1; }
+    if (tl > ql + GAP_SLACK) tl = ql + GAP_SLACK;
+    S.nQ = ql; S.nD = tl;
+    return S;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_gap_screen(GapArgs A, const unsigned long long *__restrict__ items,
+                                                   unsigned long long *__restrict__ gainers, unsigned long long *n_gainers) {
+    __shared__ __align__(16) int8_t s_bl[21 * 32];
+    __shared__ uint32_t s_hf[SCR_COLS * NT];
+    __shared__ uint32_t s_tq[(SCR_COLS / 4 + SCR_ROWS / 4) * NT];    // subject residues of columns 1 .. 48 and query residues of rows 1 .. 32, four per word
+    for (int k = threadIdx.x; k < 21 * 32 / 4; k += NT) reinterpret_cast<uint32_t *>(s_bl)[k] = reinterpret_cast<const uint32_t *>(g_blosum)[k];
+    __syncthreads();
+    const int64_t n_items = (int64_t)*A.n_items;
+    uint32_t *tw = s_tq + threadIdx.x, *qw = tw + (SCR_COLS / 4) * NT;
+    const int lane = threadIdx.x & 31;
+    const int GI = GAP_OPEN, GE = GAP_EXT, GIE = GAP_OPEN + GAP_EXT;
+    constexpr int LIMIT = 15, DROP = 27;       // (int)((26.98 - 11) / 1); h < best - 26.98 <=> h <= best - 27
+    uint32_t *hf = s_hf + threadIdx.x;
+#define HF(j) hf[(j) * NT]
+    for (int64_t w = (int64_t)blockIdx.x * NT + threadIdx.x; w - lane < n_items; w += (int64_t)gridDim.x * NT) {
+        bool gain = false, busy = false;
+        uint32_t item = 0;
+        int nQ = 0, nD = 0, step = 1, ce = LIMIT, cells = 0, i = 1;
+        const uint8_t *__restrict__ qp = nullptr, *__restrict__ t = nullptr;
+        if (w < n_items) {
+            item = (uint32_t)items[w];
+            const ExtSetup S = ext_setup(A, item);
+            nQ = S.nQ; nD = S.nD; step = S.step; qp = S.qp; t = S.t;
+            // the residues this pass can touch go to shared memory once (with 25-34 KB of shared memory per block the L1
+            // left over does not hold the rows of a thousand threads: the per-cell byte loads missed it 97 % of the time)
+            load_residues<SCR_COLS / 4, NT>(t, step, nD, tw);
+            load_residues<SCR_ROWS / 4, NT>(qp, step, nQ, qw);
+            // row 0: H = -11 - j, F = H - 11 for j = 1 .. 15 (the cells past nD are never read)
+#pragma unroll
+            for (int j = 1; j <= LIMIT; ++j) HF(j) = pack_hf(-GI - j * GE, -GI - j * GE - GI);
+            busy = nQ >= 1;
+        }
+        // one row per trip for every lane that still runs: the vote at the top brings the warp back together each row
+        // (left to themselves the lanes drift apart and the warp issues their loops one after the other: 2 of 32 lanes
+        // per instruction in the first version of this kernel)
+        for (;;) {
+            const uint32_t bm = __ballot_sync(0xffffffffu, busy);
+            if (!bm) break;
+            if (busy) {
+                // boundary cell, column 0: H = F = -11 - i; the diagonal of column 1 is the boundary of the row before
+                const int v = -GI - i * GE;
+                int diag = i == 1 ? 0 : v + GE;
+                int E = v - GI, hl = v, j = 1;
+                bool skip_tail = false;
+                const int8_t *brow_q = s_bl + ((qw[((i - 1) >> 2) * NT] >> (8 * ((i - 1) & 3))) & 0xffu) * 32;
+                const int jend = min(ce, nD);
+                // four columns per word of subject residues; one test covers both ways a row can end early: h outside
+                // [-26, 0] (a positive cell = gain; h <= -27 = dead, and with the best column at 0 every column is right of
+                // it).  An exit leaves j = first column not computed.  (One copy of the cell code on purpose: a variant with
+                // a check-free copy for whole groups ran at 10.8 instead of 17.2 lanes per instruction -- lanes in different
+                // copies cannot issue together.)
+                int hx = 0;
+                bool stop = false, ended = false;
+                for (int jb = 0; jb < jend && !ended; jb += 4) {
+                    const uint32_t tword = tw[(jb >> 2) * NT];
+                    uint32_t *hp = hf + (jb + 1) * NT;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (jb + k + 1 > jend) { ended = true; break; }
+                        const uint32_t old = hp[k * NT];
+                        const int Ho = hf_h(old), Fo = hf_f(old);
+                        E = __viaddmax_s32(hl, -GIE, E - GE);
+                        const int Fv = __viaddmax_s32(Ho, -GIE, Fo - GE);
+                        const int h = __vimax3_s32(diag + brow_q[(tword >> (8 * k)) & 0xffu], E, Fv);
+                        diag = Ho;
+                        hp[k * NT] = pack_hf(h, Fv);
+                        hl = h;
+                        if ((unsigned)(h + (DROP - 1)) >= (unsigned)DROP) { j = jb + k + 2; hx = h; stop = true; ended = true; break; }
+                    }
+                }
+                if (!stop) j = jend + 1;
+                else if (hx > 0) gain = true;
+                else { skip_tail = j - 1 < ce; ce = j - 1; }
+                if (gain) busy = false;
+                else {
+                    cells += j - 1;
+                    if (!skip_tail) {                            // run on along the row by horizontal gaps
+                        for (int jj = ce + 1; jj <= nD; ++jj) {
+                            if (jj >= SCR_COLS) { gain = true; busy = false; break; }   // needs more columns than this pass has: the full pass takes it
+                            ++cells;
+                            E = __viaddmax_s32(hl, -GIE, E - GE);
+                            HF(jj) = pack_hf(E, E - GI);
+                            hl = E;
+                            if (E <= -DROP) { ce = jj; break; }
+                        }
+                    }
+                    if (!(1 < ce) || i >= nQ) busy = false;
+                    else if (i >= SCR_ROWS) { gain = true; busy = false; }   // more rows than this pass holds residues for
+                    ++i;
+                }
+            }
+        }
+        if (w < n_items && !gain) {
+            GExtRec r;
+            r.gain = 0; r.eq = 0; r.et = 0; r.st = 0; r.cells = (uint32_t)cells;
+            A.ext[item] = r;
+        }
+        const uint32_t mg = __ballot_sync(0xffffffffu, gain);
+        if (mg) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(n_gainers, (unsigned long long)__popc(mg));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (gain) gainers[base + __popc(mg & ((1u << lane) - 1))] = item;
+        }
+    }
+#undef HF
+}
+
+// complete score-only DP for the extensions that gain, recording per cell which way it came (for k_gap_trace); lanes draw
+// extensions from the list as they finish.  Directions: 9 words per row of an extension -- the row's cs, then a nibble
+// per column (ring-indexed like the DP row): bits 0-1 = 0 diagonal / 1 from E / 2 from F, bit 2 = E was opened from H
+// (rather than extended), bit 3 = F was opened.
+constexpr int DIR_ROW_WORDS = 1 + RING / 8;
+template <int NT>
+__global__ void __launch_bounds__(NT) k_gap_dp(GapArgs A, const unsigned long long *__restrict__ items, int64_t first, int64_t n_items,
+                                               uint32_t *__restrict__ dirs, int rows_per_ext,
+                                               unsigned long long *__restrict__ wide, unsigned long long *n_wide, unsigned int *work) {
+    __shared__ __align__(16) int8_t s_bl[21 * 32];
+    __shared__ uint32_t s_ring[RING * NT];
+    __shared__ uint32_t s_tr[(RING / 4) * NT];       // subject residues of the columns around the window, ring-indexed like the row
+    for (int k = threadIdx.x; k < 21 * 32 / 4; k += NT) reinterpret_cast<uint32_t *>(s_bl)[k] = reinterpret_cast<const uint32_t *>(g_blosum)[k];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1;
+    const int GI = GAP_OPEN, GE = GAP_EXT, GIE = GAP_OPEN + GAP_EXT;
+    constexpr int LIMIT = 15, DROP = 27;
+    uint32_t *hf = s_ring + threadIdx.x, *tr = s_tr + threadIdx.x;
+#define RI(j) (((j) & (RING - 1)) * NT)
+    bool busy = false, dry = false;
+    uint32_t item = 0;
+    const uint8_t *qp = nullptr, *t = nullptr;
+    uint32_t *drow = nullptr;                  // directions of the current row
+    int step = 1, nQ = 0, nD = 0;
+    int i = 1, cs = 1, ce = LIMIT, best = 0, bcol = 0, brow = 0, cells = 0;
+    int t_hi = 0, qa_next = 0;                 // columns 0 .. t_hi - 1 are (or were) in the residue ring; query residue of the next row
+    for (;;) {
+        const uint32_t idle = __ballot_sync(0xffffffffu, !busy && !dry);
+        const uint32_t live = __ballot_sync(0xffffffffu, busy);
+        if (idle && (live == 0 || __popc(idle) >= MCX_GAP_REFILL)) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(work, (unsigned int)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (!busy && !dry) {
+                const int64_t w = (int64_t)base + __popc(idle & lt);
+                if (w >= n_items) dry = true;
+                else {
+                    item = (uint32_t)items[first + w];
+                    const ExtSetup S = ext_setup(A, item);
+                    qp = S.qp; t = S.t; step = S.step; nQ = S.nQ; nD = S.nD;
+                    drow = dirs + (size_t)w * (size_t)rows_per_ext * DIR_ROW_WORDS;
+                    hf[0] = pack_hf(0, -GI);
+#pragma unroll
+                    for (int j = 1; j <= LIMIT; ++j) hf[j * NT] = pack_hf(-GI - j * GE, -GI - j * GE - GI);
+                    i = 1; cs = 1; ce = LIMIT; best = 0; bcol = 0; brow = 0; cells = 0;
+                    // the residue of column j sits in byte j & 63 of the ring (column 0 has none: whatever precedes the
+                    // extension is loaded in its place and never used)
+                    load_residues<RING / 4, NT>(t - step, step, nD + 1, tr);
+                    t_hi = RING;
+                    qa_next = qp[0];
+                    busy = true;
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, !busy && dry)) break;
+        if (busy) {
+            bool fin = true, over = false;
+            if (i <= nQ) {
+                // every column this row can touch must fit the ring next to column cs - 1 (8 columns to spare: a word of
+                // direction nibbles is written once per row)
+                if (min(ce, nD) - (cs - 1) >= RING - 8) over = true;
+                else {
+                    const int r0 = RI(cs - 1);
+                    const uint32_t w0 = hf[r0];
+                    int diag = hf_h(w0);
+                    const int v = __viaddmax_s32(hf_h(w0), -GIE, hf_f(w0) - GE);
+                    hf[r0] = pack_hf(v, v);
+                    int E = v - GI, hl = v;
+                    const int8_t *brow_q = s_bl + qa_next * 32;
+                    if (i < nQ) qa_next = qp[i * step];                   // a row ahead: its latency hides behind this row
+                    // residues of the columns this row can reach (the tail stops 55 columns right of cs - 1 at the latest)
+                    for (const int need = min(nD, cs + RING - 9); t_hi <= need; t_hi += 4) {
+                        const uint8_t *tp = t + (t_hi - 1) * step;
+                        tr[((t_hi & (RING - 1)) >> 2) * NT] = (uint32_t)tp[0] | ((uint32_t)tp[step] << 8) | ((uint32_t)tp[2 * step] << 16) | ((uint32_t)tp[3 * step] << 24);
+                    }
+                    uint32_t *dw = drow + (size_t)(i - 1) * DIR_ROW_WORDS;
+                    dw[0] = (uint32_t)cs;
+                    uint32_t acc = 0;
+                    int cur = (cs & (RING - 1)) >> 3;
+                    // main loop over columns cs .. min(ce, nD) in aligned groups of four (one word of residues, half a word of
+                    // direction nibbles).  dead = the row ended at a dead cell right of the best column (then `jx` is that
+                    // column); cand = rightmost dead cell at or left of the best column seen on the way (the left prune
+                    // below starts from it instead of walking back over the whole row); moved = the best cell moved in
+                    // this row.
+                    const int jend = min(ce, nD);
+                    int jx = 0, cand = cs - 1;
+                    bool dead = false, moved = false;
+                    if (cs <= jend) {
+                        int j = cs, ro = cs & (RING - 1);
+                        uint32_t tword = tr[(ro >> 2) * NT] >> (8 * (ro & 3));       // residue of the current column in the low byte
+                        for (;;) {
+                            const uint32_t old = hf[ro * NT];
+                            const int Ho = hf_h(old), Fo = hf_f(old);
+                            const int a = hl - GIE, b = E - GE;
+                            uint32_t nib = a >= b ? 4u : 0u;
+                            E = max(a, b);
+                            const int c = Ho - GIE, d = Fo - GE;
+                            nib |= c >= d ? 8u : 0u;
+                            const int Fv = max(c, d);
+                            int h = diag + brow_q[tword & 0xffu];
+                            if (E > h) { h = E; nib |= 1u; }
+                            if (h < Fv) { h = Fv; nib = (nib & 12u) | 2u; }
+                            diag = Ho;
+                            hf[ro * NT] = pack_hf(h, Fv);
+                            hl = h;
+                            const int wi = ro >> 3;
+                            if (wi != cur) { dw[1 + cur] = acc; acc = 0; cur = wi; }
+                            acc |= nib << (4 * (ro & 7));
+                            if (h > best) { best = h; bcol = j; brow = i; moved = true; }
+                            else if (h <= best - DROP) {
+                                if (j > bcol) { jx = j; dead = true; break; }
+                                cand = j;
+                            }
+                            ++j;
+                            if (j > jend) break;
+                            ro = (ro + 1) & (RING - 1);
+                            tword >>= 8;
+                            if ((ro & 3) == 0) tword = tr[(ro >> 2) * NT];
+                        }
+                    }
+                    bool skip_tail = false;
+                    if (dead) { cells += jx - cs + 1; skip_tail = jx < ce; ce = jx; }
+                    else if (cs <= jend) cells += jend - cs + 1;
+                    if (!skip_tail) {
+                        for (int jj = ce + 1; jj <= nD; ++jj) {          // run on along the row by horizontal gaps
+                            if (jj - (cs - 1) >= RING - 8) { over = true; break; }
+                            ++cells;
+                            const int a = hl - GIE, b = E - GE;
+                            const uint32_t nib = (a > b ? 4u : 0u) | 8u | 1u;
+                            E = max(a, b);
+                            hf[RI(jj)] = pack_hf(E, E - GI);
+                            hl = E;
+                            const int wi = (jj & (RING - 1)) >> 3;
+                            if (wi != cur) { dw[1 + cur] = acc; acc = 0; cur = wi; }
+                            acc |= nib << (4 * (jj & 7));
+                            if (E > best) { best = E; bcol = jj; brow = i; moved = true; }
+                            else if (E <= best - DROP) { ce = jj; break; }
+                        }
+                        if (!over && cs <= bcol) {                       // drop dead cells on the left: cs = rightmost dead column <= bcol
+                            // cells recorded in `cand` are dead under the final threshold as well (it only rises within a
+                            // row); cells between cand and a best cell that moved may have died with the higher threshold
+                            const int thr = best - DROP;
+                            int nc = cand;
+                            if (moved) for (int c = bcol - 1; c > cand; --c) if (hf_h(hf[RI(c)]) <= thr) { nc = c; break; }
+                            if (nc >= cs) cs = nc;
+                        }
+                    }
+                    dw[1 + cur] = acc;
+                    fin = !(cs < ce) || i >= nQ;
+                    ++i;
+                }
+            }
+            if (over) {                                                  // hand the extension to the wide-row fallback
+                const uint32_t am = __activemask();
+                unsigned long long base = 0;
+                const int leader = __ffs(am) - 1;
+                if (lane == leader) base = atomicAdd(n_wide, (unsigned long long)__popc(am));
+                base = __shfl_sync(am, base, leader);
+                wide[base + __popc(am & lt)] = item;
+                GExtRec r;
+                r.gain = 0; r.eq = 0; r.et = 0; r.st = 0; r.cells = 0;
+                A.ext[item] = r;
+                busy = false;
+            } else if (fin) {
+                GExtRec r;
+                r.gain = 0; r.eq = 0; r.et = 0; r.st = 0; r.cells = (uint32_t)cells;
+                if (best > 0) { r.gain = best; r.eq = (uint16_t)brow; r.et = (uint16_t)bcol; }
+                A.ext[item] = r;
+                busy = false;
+            }
+        }
+    }
+#undef RI
+}
+
+// K3b'': walk back from the best cell of every extension k_gap_dp finished with a gain (AlignGapped's traceback, CalRes):
+// identities, alignment columns, gap columns and gap runs.  One thread per extension; the steps are dependent loads
+// of the direction words (L2), a few dozen per extension.
+__global__ void k_gap_trace(GapArgs A, const unsigned long long *__restrict__ items, int64_t first, int64_t n_items,
+                            const uint32_t *__restrict__ dirs, int rows_per_ext) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_items) return;
+    const uint32_t item = (uint32_t)items[first + w];
+    const GExtRec r = A.ext[item];
+    if (r.gain <= 0) return;
+    const ExtSetup S = ext_setup(A, item);
+    const uint32_t *drow = dirs + (size_t)w * (size_t)rows_per_ext * DIR_ROW_WORDS;
+    enum { C_S = 0, C_E_OPEN, C_E_EXT, C_D_OPEN, C_D_EXT, C_ORIGIN };
+    // what the three trace matrices hold at (i, j): m = M, e = EM, f = FM of the oracle
+    auto cell = [&](int i, int j, int &m, int &e, int &f) {
+        if (i == 0) {
+            if (j == 0) { m = C_ORIGIN; e = C_ORIGIN; f = C_ORIGIN; return; }
+            m = e = (j == 1) ? C_E_OPEN : C_E_EXT; f = C_D_OPEN;
+            return;
+        }
+        const uint32_t *dw = drow + (size_t)(i - 1) * DIR_ROW_WORDS;
+        const int cs = (int)dw[0];
+        if (j == cs - 1) { m = f = (i == 1) ? C_D_OPEN : C_D_EXT; e = (i == 1) ? C_E_OPEN : C_E_EXT; return; }
+        const uint32_t nib = (dw[1 + ((j & (RING - 1)) >> 3)] >> (4 * (j & 7))) & 15u;
+        e = (nib & 4u) ? C_E_OPEN : C_E_EXT;
+        f = (nib & 8u) ? C_D_OPEN : C_D_EXT;
+        m = (nib & 3u) == 0 ? C_S : (nib & 3u) == 1 ? e : f;
+    };
+    int i = r.eq, j = r.et, c = C_S, prev = -1;
+    int ident = 0, aln = 0, gapcols = 0, gapruns = 0;
+    while (c != C_ORIGIN && aln < 1023) {
+        ++aln;
+        int m, e, f;
+        if (c == C_S) {
+            const int qa = S.qp[(i - 1) * S.step], tb = S.t[(j - 1) * S.step];
+            ident += (qa == tb && qa < 20);
+            --i; --j; prev = 0;
+            cell(i, j, m, e, f);
+            c = m;
+        } else if (c == C_D_OPEN || c == C_D_EXT) {
+            ++gapcols; gapruns += (prev != 1); prev = 1;
+            --i;
+            cell(i, j, m, e, f);
+            c = (c == C_D_OPEN) ? m : f;
+        } else {
+            ++gapcols; gapruns += (prev != 2); prev = 2;
+            --j;
+            cell(i, j, m, e, f);
+            c = (c == C_E_OPEN) ? m : e;
+        }
+    }
+    A.ext[item].st = (uint32_t)ident | ((uint32_t)aln << 8) | ((uint32_t)gapcols << 17) | ((uint32_t)gapruns << 26);
+}
+
+// K3b (fallback for extensions whose live window outgrows the ring of k_gap_dp; the first version of the stage): the DP
+// itself, one LANE per gapped extension (one direction of one survivor), rows in local memory; a lane that
 // finishes its extension draws the next one from the work list instead of idling until the longest extension of its
 // warp is done -- the X-drop decides the size of an extension and nothing known beforehand predicts it (the first
 // version, one thread per list entry, ran at 9-10 of 32 lanes: 2.72 -> 2.08 ms at 100 bp, 6.12 -> 4.80 at 150 bp).
@@ -1234,13 +1652,12 @@ __global__ void k_gap_list(GapArgs A) {
 // (Tried and measured slower on 2M x 100 bp: rows in shared memory, column-major and conflict-free -- 6.8 ms instead
 // of 4.9, the 53-80 KB per block leave too few warps to hide the serial dependency of the cells; packed (H, F) cells
 // with the next cell prefetched -- no change; rows as a 64-column ring -- slower at every length.)
-#ifndef MCX_GAP_REFILL
-#define MCX_GAP_REFILL 24
-#endif
 template <int NT, int GROW, bool STATS>
-__global__ void __launch_bounds__(NT) k_gap_dir(GapArgs A, const unsigned long long *__restrict__ items, int64_t n_items,
+__global__ void __launch_bounds__(NT) k_gap_dir(GapArgs A, const unsigned long long *__restrict__ items, const unsigned long long *n_items_dev,
                                                 unsigned long long *__restrict__ items2, unsigned long long *n_items2,
                                                 unsigned int *work) {
+    const int64_t n_items = (int64_t)*n_items_dev;
+    if (n_items == 0) return;
     __shared__ __align__(16) int8_t s_bl[21 * 32];
     for (int k = threadIdx.x; k < 21 * 32 / 4; k += NT) reinterpret_cast<uint32_t *>(s_bl)[k] = reinterpret_cast<const uint32_t *>(g_blosum)[k];
     __syncthreads();
@@ -1700,7 +2117,8 @@ struct mcx_ctx {
     int64_t cap_seen = 0, cap_seedq = 0;
     unsigned long long *d_gitems = nullptr;   // gapped work lists: three regions of 2 * survivors entries
     GExtRec *d_gext = nullptr;
-    int64_t cap_gitems = 0, cap_gext = 0;
+    uint32_t *d_dirs = nullptr;               // direction nibbles of k_gap_dp for k_gap_trace
+    int64_t cap_gitems = 0, cap_gext = 0, cap_dirs = 0;
     int64_t cap_segq = 0;
     Cand *d_cand = nullptr;
     int64_t cap_frames = 0, cap_cand = 0, n_cand_last = 0;
@@ -1728,7 +2146,7 @@ struct mcx_ctx {
 // slots of d_cnt
 enum Cnt { C_QC0 = 0 /* ..3: verdict counts of the search */, C_QCALL = 4 /* ..7: verdict counts over all pushed reads */,
            C_SURV = 8, C_SEEDQ = 9, C_GAPPED = 10, C_CELLS = 11, C_SEGQ = 12, C_WORK = 13, C_ITEMS2 = 14, C_NCAP = 15,
-           C_WORK1 = 16, C_WORK2 = 17, C_ITEMS = 18, C_NKEPT = 20, C_NFP = 21, C_TOTW = 22, C_TOTQ = 23, C_N = 64 };
+           C_WORK1 = 16, C_WORK2 = 17, C_ITEMS = 18, C_NKEPT = 20, C_NWIDE = 24 /* ..26 */, C_NGAPTOT = 27, C_NFP = 21, C_TOTW = 22, C_TOTQ = 23, C_N = 64 };
 
 static thread_local std::string g_err;
 
@@ -2059,7 +2477,9 @@ extern "C" int mcx_create(mcx_ctx **out, const mcx_db *db, int device) {
         const int64_t nres = db->off[ns];
         int32_t *doff = nullptr; uint8_t *dres = nullptr, *dfam = nullptr;
         CK(dev_alloc(&doff, (size_t)ns + 1)); ctx->db_allocs.push_back(doff);
-        CK(dev_alloc(&dres, (size_t)nres)); ctx->db_allocs.push_back(dres);
+        CK(dev_alloc(&dres, (size_t)nres + 64)); ctx->db_allocs.push_back(dres);
+        CK(cudaMemset(dres, AA_STOP, (size_t)nres + 64));
+        dres += 32;                                   // residues are also fetched as aligned words around a position (load_residues)
         CK(dev_alloc(&dfam, (size_t)ns)); ctx->db_allocs.push_back(dfam);
         CK(cudaMemcpy(doff, db->off, ((size_t)ns + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(dres, db->res, (size_t)nres, cudaMemcpyHostToDevice));
@@ -2091,7 +2511,7 @@ extern "C" void mcx_destroy(mcx_ctx *ctx) {
     void *bufs[] = {ctx->d_woff, ctx->d_qoff, ctx->d_ascii, ctx->d_aoffs, ctx->d_code, ctx->d_fp, ctx->d_fpa, ctx->d_fpa2, ctx->d_fpi, ctx->d_fpi2,
                     ctx->d_kept, ctx->d_surv, ctx->d_hsp, ctx->d_hits_out, ctx->d_keys, ctx->d_idx, ctx->d_best, ctx->d_hflag,
                     ctx->d_hpos, ctx->d_keep, ctx->d_cnt, ctx->d_acc, ctx->d_abl, ctx->d_temp, ctx->d_frames, ctx->d_cand,
-                    ctx->d_segq, ctx->d_qcnt, ctx->d_gitems, ctx->d_gext, ctx->d_nrep, ctx->d_bestkey, ctx->d_seen, ctx->d_seedq};
+                    ctx->d_segq, ctx->d_qcnt, ctx->d_gitems, ctx->d_gext, ctx->d_dirs, ctx->d_nrep, ctx->d_bestkey, ctx->d_seen, ctx->d_seedq};
     for (void *p : bufs) if (p) cudaFree(p);
     if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -2514,13 +2934,14 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     if (const char *e = getenv("MCX_CAND_PER_READ")) cand_per_read = std::max(1, atoi(e));
     chunk = std::min<int64_t>(chunk, std::max<int64_t>(n, 1));
     {
-        const int64_t need_fr = (chunk * 6 + 512) * fstride, need_cand = std::max<int64_t>(chunk * cand_per_read, 1 << 16);
+        const int64_t need_fr = (chunk * 6 + 512) * fstride + 128, need_cand = std::max<int64_t>(chunk * cand_per_read, 1 << 16);
         if ((rc = ensure(ctx, &ctx->d_frames, &ctx->cap_frames, need_fr)) != MCX_OK) return rc;
         if ((rc = ensure(ctx, &ctx->d_cand, &ctx->cap_cand, need_cand)) != MCX_OK) return rc;
         if ((rc = ensure(ctx, &ctx->d_seedq, &ctx->cap_seedq, std::max<int64_t>(ctx->cap_cand / 2, 1 << 16))) != MCX_OK) return rc;
         if ((rc = ensure(ctx, &ctx->d_segq, &ctx->cap_segq, chunk * 6 + 512)) != MCX_OK) return rc;
         if ((rc = ensure(ctx, &ctx->d_kept, &ctx->cap_kept, chunk + 1)) != MCX_OK) return rc;
     }
+    uint8_t *const frames = ctx->d_frames + 64;      // rows are also read as aligned words around a position (load_residues)
     // chunk boundaries; while host -> device copies are in flight the first chunks are small, so that the search starts
     // as soon as a few tens of megabytes have arrived
     std::vector<int64_t> bounds(1, 0);
@@ -2555,7 +2976,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     }
 
     float ms_frames = 0, ms_seg = 0, ms_probe = 0, ms_ext = 0, ms_gap = 0;
-    unsigned long long n_surv = 0, n_cand_total = 0, n_gapped_total = 0, n_seeds_total = 0;
+    unsigned long long n_surv = 0, n_cand_total = 0, n_seeds_total = 0;
     int64_t remaining = quota, sampled = 0;
     for (int c = 0; c < nb && (quota < 0 || remaining > 0); ++c) {
         const int64_t r0 = bounds[(size_t)c], r1 = bounds[(size_t)c + 1], nr_in = r1 - r0;
@@ -2596,7 +3017,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         {
             FrameArgs F;
             F.S = read_store(ctx); F.kept = ctx->d_kept; F.first = 0; F.n_search = ctx->d_cnt + C_NKEPT;
-            F.L = P.read_length; F.frames = ctx->d_frames; F.segq = ctx->d_segq; F.n_segq = ctx->d_cnt + C_SEGQ;
+            F.L = P.read_length; F.frames = frames; F.segq = ctx->d_segq; F.n_segq = ctx->d_cnt + C_SEGQ;
             const size_t smem = sizeof(SegTab) + 256 + (size_t)fstride * NTF + (size_t)(NTF / 6) * P.read_length;
             CK(cudaFuncSetAttribute(k_frames<NTF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_frames<NTF><<<(unsigned)((nr_max * 6 + NTF - 1) / NTF), NTF, smem, st>>>(F, fstride);
@@ -2611,7 +3032,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seg<SW>, SW * 32, smem));
             const unsigned long long resident = (unsigned long long)std::max(per_sm, 1) * (unsigned long long)ctx->n_sm;
             k_seg<SW><<<(unsigned)std::min<unsigned long long>((nr_max * 6 + SW - 1) / SW, resident), SW * 32, smem, st>>>(
-                ctx->d_frames, fstride, P.read_length, ctx->d_segq, ctx->d_cnt + C_SEGQ, maxm, reinterpret_cast<unsigned int *>(ctx->d_cnt + C_WORK));
+                frames, fstride, P.read_length, ctx->d_segq, ctx->d_cnt + C_SEGQ, maxm, reinterpret_cast<unsigned int *>(ctx->d_cnt + C_WORK));
             ++ctx->launches;
         }
         CK(cudaEventRecord(ctx->ev[11], st));
@@ -2622,7 +3043,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             CK(cudaMemsetAsync(ctx->d_qcnt, 0, NQ * sizeof(unsigned long long), st));
             CK(cudaMemsetAsync(ctx->d_cnt + C_SEEDQ, 0, sizeof(unsigned long long), st));
             ProbeArgs A;
-            A.n_reads = ctx->d_cnt + C_NKEPT; A.L = P.read_length; A.db = ctx->db; A.frames = ctx->d_frames; A.cand = ctx->d_cand;
+            A.n_reads = ctx->d_cnt + C_NKEPT; A.L = P.read_length; A.db = ctx->db; A.frames = frames; A.cand = ctx->d_cand;
             A.n_cand = ctx->d_qcnt; A.cap_cand = (unsigned long long)(ctx->cap_cand / NQ);
             constexpr int NTP = MCX_PROBE_NT;
             const size_t smem = (size_t)(NTP / 32) * (PROBE_Q * 4 + 128 * 4 + PROBE_Q * 2) + (size_t)fstride * NTP;
@@ -2631,7 +3052,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             if (attempt == 0) CK(cudaEventRecord(ctx->ev[3], st));
             ExtArgs E;
             E.kept = ctx->d_kept; E.first = 0; E.L = P.read_length; E.fstride = fstride; E.thr_report = thr; E.db = ctx->db;
-            E.frames = ctx->d_frames; E.cand = ctx->d_cand; E.qfill = ctx->d_qcnt;
+            E.frames = frames; E.cand = ctx->d_cand; E.qfill = ctx->d_qcnt;
             E.cap_cand = (unsigned long long)(ctx->cap_cand / NQ);
             E.surv = ctx->d_surv; E.cap_surv = (unsigned long long)ctx->cap_surv;
             E.n_surv = ctx->d_cnt + C_SURV; E.n_seedq = ctx->d_cnt + C_SEEDQ;
@@ -2673,57 +3094,63 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         sampled += nr < 0 ? (int64_t)hc[C_NKEPT] : nr;
         if (n_surv > surv_before) {
             GapArgs G;
-            G.L = P.read_length; G.fstride = fstride; G.db = ctx->db; G.frames = ctx->d_frames; G.surv = ctx->d_surv;
+            G.L = P.read_length; G.fstride = fstride; G.db = ctx->db; G.frames = frames; G.surv = ctx->d_surv;
             G.first = (int64_t)surv_before; G.n_surv = (int64_t)(n_surv - surv_before);
             G.hsp = ctx->d_hsp; G.keys = ctx->d_keys; G.idx = ctx->d_idx; G.counters = ctx->d_cnt + C_GAPPED;
             if ((rc = ensure(ctx, &ctx->d_gitems, &ctx->cap_gitems, 6 * G.n_surv)) != MCX_OK) return rc;
             if ((rc = ensure(ctx, &ctx->d_gext, &ctx->cap_gext, 2 * G.n_surv)) != MCX_OK) return rc;
-            G.items = ctx->d_gitems; G.ext = ctx->d_gext; G.n_items = ctx->d_cnt + C_ITEMS;
+            G.items = ctx->d_gitems; G.ext = ctx->d_gext; G.n_items = ctx->d_cnt + C_ITEMS; G.n_items_total = ctx->d_cnt + C_NGAPTOT;
             CK(cudaMemsetAsync(ctx->d_gext, 0, (size_t)(2 * G.n_surv) * sizeof(GExtRec), st));
             CK(cudaMemsetAsync(ctx->d_cnt + C_ITEMS, 0, sizeof(unsigned long long), st));
+            // work list (padded with all-ones keys up to its bound, so that it can be sorted without knowing its
+            // length on the host) -> sorted by remaining query length -> screening pass -> complete pass for the
+            // extensions that gain -> (never seen: wide-window fallback) ; no host round trip in between
+            unsigned long long *list1 = ctx->d_gitems + G.n_surv * 2, *gainers = ctx->d_gitems + G.n_surv * 4, *wide = ctx->d_gitems;
+            CK(cudaMemsetAsync(G.items, 0xff, (size_t)(2 * G.n_surv) * sizeof(unsigned long long), st));
             k_gap_list<<<(unsigned)((G.n_surv + 255) / 256), 256, 0, st>>>(G);
-            CK(cudaMemcpyAsync(hc + C_ITEMS, ctx->d_cnt + C_ITEMS, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-            if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
-            const unsigned long long n_items = hc[C_ITEMS];
-            if (n_items > 0) {
-                // work lists sorted by expected size (cub radix sort on the key byte / half-word above the item)
-                unsigned long long *list1 = ctx->d_gitems + G.n_surv * 2, *items2 = ctx->d_gitems + G.n_surv * 4, *list2 = ctx->d_gitems;
-                {
-                    size_t tb = 0;
-                    cub::DeviceRadixSort::SortKeys(nullptr, tb, G.items, list1, (int)n_items, 32, 40, st);
-                    if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
-                    cub::DeviceRadixSort::SortKeys(ctx->d_temp, tb, G.items, list1, (int)n_items, 32, 40, st);
-                }
-                CK(cudaMemsetAsync(ctx->d_cnt + C_ITEMS2, 0, sizeof(unsigned long long), st));
-                CK(cudaMemsetAsync(ctx->d_cnt + C_WORK1, 0, 2 * sizeof(unsigned long long), st));
-                unsigned int *work1 = reinterpret_cast<unsigned int *>(ctx->d_cnt + C_WORK1), *work2 = reinterpret_cast<unsigned int *>(ctx->d_cnt + C_WORK2);
-                const unsigned gb = (unsigned)((n_items + GAP_NT - 1) / GAP_NT);
-                const int grow = maxm + GAP_SLACK + 2;
-                auto resident = [&](auto kernel, unsigned want) -> unsigned {      // blocks of a grid that is resident at once
-                    int per_sm = 0;
-                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, GAP_NT, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-                    return std::min(want, (unsigned)(per_sm * ctx->n_sm));
-                };
-                if (grow <= 104) k_gap_dir<GAP_NT, 104, false><<<resident(k_gap_dir<GAP_NT, 104, false>, gb), GAP_NT, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + C_ITEMS2, work1);
-                else if (grow <= 152) k_gap_dir<GAP_NT, 152, false><<<resident(k_gap_dir<GAP_NT, 152, false>, gb), GAP_NT, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + C_ITEMS2, work1);
-                else k_gap_dir<GAP_NT, MAX_FRAME + GAP_SLACK + 2, false><<<resident(k_gap_dir<GAP_NT, MAX_FRAME + GAP_SLACK + 2, false>, gb), GAP_NT, 0, st>>>(G, list1, (int64_t)n_items, items2, ctx->d_cnt + C_ITEMS2, work1);
-                CK(cudaMemcpyAsync(hc + C_ITEMS2, ctx->d_cnt + C_ITEMS2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-                if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
-                const unsigned long long n2 = hc[C_ITEMS2];
-                if (n2 > 0) {
-                    size_t tb = 0;
-                    cub::DeviceRadixSort::SortKeys(nullptr, tb, items2, list2, (int)n2, 32, 48, st);
-                    if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
-                    cub::DeviceRadixSort::SortKeys(ctx->d_temp, tb, items2, list2, (int)n2, 32, 48, st);
-                    const unsigned gb2 = (unsigned)((n2 + GAP_NT - 1) / GAP_NT);
-                    if (grow <= 104) k_gap_dir<GAP_NT, 104, true><<<resident(k_gap_dir<GAP_NT, 104, true>, gb2), GAP_NT, 0, st>>>(G, list2, (int64_t)n2, nullptr, nullptr, work2);
-                    else if (grow <= 152) k_gap_dir<GAP_NT, 152, true><<<resident(k_gap_dir<GAP_NT, 152, true>, gb2), GAP_NT, 0, st>>>(G, list2, (int64_t)n2, nullptr, nullptr, work2);
-                    else k_gap_dir<GAP_NT, MAX_FRAME + GAP_SLACK + 2, true><<<resident(k_gap_dir<GAP_NT, MAX_FRAME + GAP_SLACK + 2, true>, gb2), GAP_NT, 0, st>>>(G, list2, (int64_t)n2, nullptr, nullptr, work2);
-                    ctx->launches += 3;
-                }
-                ctx->launches += 2;
-                n_gapped_total += n_items;
+            {
+                size_t tb = 0;
+                cub::DeviceRadixSort::SortKeys(nullptr, tb, G.items, list1, (int)(2 * G.n_surv), 32, 40, st);
+                if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
+                cub::DeviceRadixSort::SortKeys(ctx->d_temp, tb, G.items, list1, (int)(2 * G.n_surv), 32, 40, st);
             }
+            CK(cudaMemsetAsync(ctx->d_cnt + C_ITEMS2, 0, sizeof(unsigned long long), st));
+            CK(cudaMemsetAsync(ctx->d_cnt + C_WORK1, 0, 2 * sizeof(unsigned long long), st));
+            CK(cudaMemsetAsync(ctx->d_cnt + C_NWIDE, 0, 3 * sizeof(unsigned long long), st));
+            auto resident = [&](auto kernel, int nt, unsigned want) -> unsigned {      // blocks of a grid that is resident at once
+                int per_sm = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+                return std::max(1u, std::min(want, (unsigned)(per_sm * ctx->n_sm)));
+            };
+            constexpr int SNT = MCX_SCR_NT, FNT = MCX_FULL_NT;
+            const unsigned bound = (unsigned)(2 * G.n_surv);
+            k_gap_screen<SNT><<<resident(k_gap_screen<SNT>, SNT, (bound + SNT - 1) / SNT), SNT, 0, st>>>(G, list1, gainers, ctx->d_cnt + C_ITEMS2);
+            CK(cudaMemcpyAsync(hc + C_ITEMS2, ctx->d_cnt + C_ITEMS2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
+            const int64_t n_gain = (int64_t)hc[C_ITEMS2];
+            // complete DP + traceback of the extensions that gain, in batches that bound the direction scratch
+            const int rows_per_ext = maxm;
+            const int64_t per_ext = (int64_t)rows_per_ext * DIR_ROW_WORDS;
+            int64_t batch = std::max<int64_t>(1, (int64_t)(2ll << 30) / (per_ext * 4));       // 2 GB of directions at most
+            if (const char *e = getenv("MCX_GAP_BATCH")) batch = std::max(1, atoi(e));
+            batch = std::min(batch, std::max<int64_t>(n_gain, 1));
+            if (n_gain > 0 && (rc = ensure(ctx, &ctx->d_dirs, &ctx->cap_dirs, batch * per_ext)) != MCX_OK) return rc;
+            for (int64_t g0 = 0; g0 < n_gain; g0 += batch) {
+                const int64_t ng = std::min(batch, n_gain - g0);
+                CK(cudaMemsetAsync(ctx->d_cnt + C_WORK1, 0, sizeof(unsigned long long), st));
+                k_gap_dp<FNT><<<resident(k_gap_dp<FNT>, FNT, (unsigned)((ng + FNT - 1) / FNT)), FNT, 0, st>>>(
+                    G, gainers, g0, ng, ctx->d_dirs, rows_per_ext, wide, ctx->d_cnt + C_NWIDE, reinterpret_cast<unsigned int *>(ctx->d_cnt + C_WORK1));
+                k_gap_trace<<<(unsigned)((ng + 127) / 128), 128, 0, st>>>(G, gainers, g0, ng, ctx->d_dirs, rows_per_ext);
+                ctx->launches += 2;
+            }
+            {   // fallback for extensions whose window outgrew the ring: score pass + statistics pass with rows in local memory
+                unsigned long long *wide2 = ctx->d_gitems + G.n_surv;
+                unsigned int *work2 = reinterpret_cast<unsigned int *>(ctx->d_cnt + C_WORK2), *work3 = reinterpret_cast<unsigned int *>(ctx->d_cnt + C_NWIDE + 2);
+                constexpr int GW = MAX_FRAME + GAP_SLACK + 2;
+                k_gap_dir<GAP_NT, GW, false><<<resident(k_gap_dir<GAP_NT, GW, false>, GAP_NT, 64), GAP_NT, 0, st>>>(G, wide, ctx->d_cnt + C_NWIDE, wide2, ctx->d_cnt + C_NWIDE + 1, work2);
+                k_gap_dir<GAP_NT, GW, true><<<resident(k_gap_dir<GAP_NT, GW, true>, GAP_NT, 64), GAP_NT, 0, st>>>(G, wide2, ctx->d_cnt + C_NWIDE + 1, nullptr, nullptr, work3);
+            }
+            ctx->launches += 8;
             k_gap_finish<<<(unsigned)((G.n_surv + 255) / 256), 256, 0, st>>>(G);
             ctx->launches += 3;
         }
@@ -2773,10 +3200,10 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
     R.too_short = (int64_t)hc[C_QC0 + 1]; R.low_qual = (int64_t)hc[C_QC0 + 2]; R.dups = (int64_t)hc[C_QC0 + 3];
     R.reads_with_hits = (int64_t)acc[0]; R.reads_classified = (int64_t)acc[1]; R.n_hsp = (int64_t)acc[2];
-    R.n_gapped = (int64_t)n_gapped_total; R.gapped_cells = (int64_t)hc[C_CELLS];
+    R.n_gapped = (int64_t)hc[C_NGAPTOT]; R.gapped_cells = (int64_t)hc[C_CELLS];
     R.n_capped_reads = (int64_t)hc[C_NCAP];
     if (getenv("MCX_DEBUG")) fprintf(stderr, "[mcx] candidates %llu, accepted seeds %llu, ungapped HSPs %llu; gapped extensions %llu, with gain > 0: %llu, cells %llu; host syncs %lld\n",
-                                     n_cand_total, n_seeds_total, n_surv, n_gapped_total, hc[C_GAPPED], hc[C_CELLS], (long long)ctx->host_syncs);
+                                     n_cand_total, n_seeds_total, n_surv, hc[C_NGAPTOT], hc[C_GAPPED], hc[C_CELLS], (long long)ctx->host_syncs);
     for (int f = 0; f < MCX_N_FAM; ++f) { R.fam_hits[f] = (int64_t)acc[3 + f]; R.fam_aln[f] = (int64_t)acc[3 + MCX_N_FAM + f]; }
     for (size_t k = 0; k < abl.size(); ++k) R.aln_by_len[k] = (int64_t)abl[k];
     ctx->ms[1] = ms_qc; ctx->ms[2] = ms_probe; ctx->ms[7] = ms_ext; ctx->ms[3] = ms_gap; ctx->ms[8] = ms_frames; ctx->ms[9] = ms_seg;

@@ -514,8 +514,12 @@ static int ungapped_walk(const uint8_t *q, const uint8_t *t, int step, int nq, i
  * Output: gain (<= 0: nothing appended), rows/cols consumed, identities, gap columns, gap runs. */
 typedef struct { int gain, eq, et, ident, gapcols, gapopens, aln; } gext_t;
 
+/* diagnostics for the tests of the CUDA path's fixed-size column window: per extension, the widest span of columns
+ * [cs - 1, last column written] any row needed (index = that width, capped at 255), split by gain / no gain */
+long oc_gap_width_hist[2][256];
 static void gapped_xdrop(const uint8_t *q, const uint8_t *t, int step, int nQ, int nD, gext_t *g) {
     memset(g, 0, sizeof *g);
+    int widest = 0;
     const int GI = GAP_OPEN, GE = GAP_EXT;
     int limit = (int)((GAP_XDROP - (double)GI) / (double)GE);
     if (nQ <= 0 || limit <= 1) return;
@@ -560,8 +564,11 @@ static void gapped_xdrop(const uint8_t *q, const uint8_t *t, int step, int nQ, i
                 if (j > nD || j > ce) break;
             }
         }
+        { int lastw = j < nD ? j : nD; if (lastw - (cs - 1) + 1 > widest) widest = lastw - (cs - 1) + 1; }
         if (!skip_tail) {
+            int cs_row = cs;
             for (int jj = ce + 1; jj <= nD; ++jj) {           /* 0x40ac45: run on by horizontal gaps */
+                if (jj - (cs_row - 1) + 1 > widest) widest = jj - (cs_row - 1) + 1;
                 int a = hl - (GI + GE), b = E - GE; char fl;
                 if (a > b) { E = a; fl = 'E'; } else { E = b; fl = 'e'; }
                 AT(M, i, jj) = AT(EM, i, jj) = fl;
@@ -577,6 +584,7 @@ static void gapped_xdrop(const uint8_t *q, const uint8_t *t, int step, int nQ, i
         }
         if (!(cs < ce)) break;
     }
+    __atomic_fetch_add(&oc_gap_width_hist[best > 0][widest > 255 ? 255 : widest], 1, __ATOMIC_RELAXED);
     if (best > 0) {
         if (AT(M, brow, bcol) != 's') { fprintf(stderr, "oracle: gapped traceback does not end on a match\n"); abort(); }
         int i = brow, j = bcol; char c = 's', prev = 0;

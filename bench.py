@@ -406,17 +406,39 @@ def main():
     per_gpu_reads = total_reads / world
     k_ms = stage_dev["probe"]
     achieved = per_gpu_reads * bytes_per_read / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_probe (6-frame translation + SEG + murphy10 seed-word lookup)",
+    # SURVEY 8d names the random-access transaction rate, not bandwidth, as this kernel's bound: probes/s against the
+    # measured rate of independent random 4-byte loads over the same 32 MB filter (mcx_l2_peak)
+    l2_peak = eng.l2_peak()
+    probes_per_s = per_gpu_reads * probes / (k_ms * 1e-3)
+    roofline = {"bound": "hbm", "kernel": "k_probe (murphy10 seed-word lookup: presence filter in L2, hash slots and postings in HBM)",
                 "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_read": bytes_per_read, "kernel_ms": k_ms,
-                "kernel_timing": "CUDA events around the k_probe launch on the library's stream (mcx_timings[2])",
-                "kernel_share_of_step": k_ms / (t_dev * 1e3)}
-    prof = os.path.join(ROOT, "profiles", "r01_k_probe_traffic.json")
-    if os.path.exists(prof):
-        try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+                "kernel_timing": "CUDA events around the k_probe launches on the library's stream (mcx_timings[2])",
+                "kernel_share_of_step": k_ms / (t_dev * 1e3),
+                "lookups": {"probes_per_read": probes, "probes_per_s": probes_per_s, "bytes_per_lookup": 4,
+                            "l2_random_loads_per_s_measured": l2_peak * 1e9, "frac_of_l2_random_rate": probes_per_s / (l2_peak * 1e9),
+                            "note": "each probe is one 32-byte L2 sector; the microbenchmark issues nothing but such loads"}}
+    for prof in ("r02_k_probe_traffic.json", "r01_k_probe_traffic.json"):
+        prof = os.path.join(ROOT, "profiles", prof)
+        if os.path.exists(prof):
+            try:
+                pj = json.load(open(prof))
+                # the capture is of one launch over `reads` reads: scale to this step's reads per GPU
+                roofline["traffic"] = pj.get("dram_bytes_per_launch") * (per_gpu_reads / pj["reads"]) if pj.get("reads") else pj.get("dram_bytes_per_launch")
+                roofline["traffic_source"] = os.path.basename(prof)
+                break
+            except Exception:
+                pass
+    # K1 (the kernel SURVEY 8d calls HBM-bound): bytes per read of the survey's table -- 2-bit bases ceil(L/4) + mask
+    # ceil(L/8), + L quality bytes when -q/-m are active, one verdict byte written -- over the k_qc launches alone
+    k1_bytes = (L + 3) // 4 + (L + 7) // 8 + (L if wl["fastq"] else 0) + 1
+    k1_ms = stage_dev.get("k_qc") or 0.0
+    n_in = n                                   # reads pushed per GPU (k_qc sees all of them)
+    roofline_k1 = {"bound": "hbm", "kernel": "k_qc (trim to -l, unknown-base, mean / minimum quality filters on the packed reads)",
+                   "achieved": (n_in * k1_bytes / (k1_ms * 1e-3) / 1e9) if k1_ms else None, "peak": hbm, "unit": "GB/s",
+                   "frac": (n_in * k1_bytes / (k1_ms * 1e-3) / 1e9 / hbm) if k1_ms else None, "algorithmic_bytes_per_read": k1_bytes,
+                   "kernel_ms": k1_ms, "kernel_timing": "CUDA events around the k_qc launches (mcx_timings[10])",
+                   "moved_bytes_per_read": 12 * ((L + 31) // 32) + (L if wl["fastq"] else 0) + 4 + 8 + (8 if wl["fastq"] else 0) + 1}
     gcups = res.gapped_cells / world / (stage_dev["gapped"] * 1e-3) / 1e9 if stage_dev.get("gapped") else None
     # the DPX-bound cell rate = measured DPX issue rate / 3 DPX instructions per affine-gap cell
     dpx = eng.dpx_peak()
@@ -429,11 +451,12 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": wl["name"], "reads_per_gpu": n, "read_length": L, "parallelism": "reads sharded x%d, marker index replicated" % world,
                        "l2": "inputs (%d MB per GPU) larger than L2, no flush needed" % (h2d_bytes >> 20),
+                       "genome_pack": "%s (%d bp in %d contigs)" % (os.path.basename(synth.genome_pack_path()), len(synth.genome()[0]), len(synth.genome()[2])),
                        "input_layout": "2-bit bases + mask bit-planes (%d B/read), lengths, quality bytes; %d MB instead of %d MB of ASCII" % (
                            4 * 3 * ((L + 31) // 32), h2d_bytes >> 20, ascii_bytes >> 20), "rank0_numa_node": numa_node},
             "e2e": {"value": total_reads / t_e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": int(res.counts_vector().nbytes), "ms_per_step": t_e2e * 1e3},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_k1": roofline_k1,
             "stages_ms": stage_dev, "stages_ms_e2e": stage_e2e,
             "gapped_gcups": gcups, "gapped": gapped, "ags": ags, "ags_e2e": ags2,
             "counts": {"sampled_reads": res.sampled_reads, "reads_with_hits": res.reads_with_hits,

@@ -165,13 +165,20 @@ int  mcx_get_classified(mcx_ctx *ctx, int32_t *best_subject, int64_t n);
 
 /* device time (ms, CUDA events on the context's stream) of the stages of the last push/search:
  * [0] h2d copy, [1] k_qc + compaction, [2] k_probe, [3] gapped stage (k_gap_*), [4] sort, [5] classifier (k_cls_*),
- * [6] d2h, [7] k_seed + k_walk, [8] k_frames, [9] k_seg; and the number of kernel launches */
-int  mcx_timings(mcx_ctx *ctx, float ms[10], int64_t *launches);
+ * [6] d2h, [7] k_seed + k_walk, [8] k_frames, [9] k_seg, [10] k_qc alone (part of [1]), [11] -d: fingerprints + sort + marks
+ * (part of [1]); and the number of kernel launches.  [0] is the span of the copies on the copy stream: they overlap
+ * the other stages. */
+int  mcx_timings(mcx_ctx *ctx, float ms[12], int64_t *launches);
 
 /* Measurement aid: issue rate of the DPX instructions an affine-gap cell uses (viaddmax_s32 /
  * vimax3_s32_relu, independent chains on every SM), in 1e9 thread-instructions per second.  The DPX-bound cell rate
  * that the gapped stage's GCUPS is quoted against is this number / 3 (two viaddmax + one vimax3 per cell). */
 int  mcx_dpx_peak(mcx_ctx *ctx, double *gops_per_s);
+
+/* Measurement aid ("seeding: L2/HBM random-access transaction rate"): rate of independent 4-byte loads at
+ * random words of the 32 MB presence filter (one 32-byte L2 sector each), in 1e9 loads per second -- the access pattern
+ * of the seed-word probes with nothing else in the way.  k_probe's probes/s are quoted against it. */
+int  mcx_l2_peak(mcx_ctx *ctx, double *gsectors_per_s);
 
 const char *mcx_last_error(mcx_ctx *ctx);
 const char *mcx_version(void);

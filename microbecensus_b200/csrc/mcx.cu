@@ -2105,7 +2105,7 @@ struct mcx_ctx {
     int32_t *d_kept = nullptr;
     int64_t cap_code = 0, cap_kept = 0;
     int64_t qc_upto = 0;                       // reads [0, qc_upto) have their verdict
-    bool dedup_done = false, fp_done = false, counts_valid = false;
+    bool dedup_done = false, fp_done = false, counts_valid = false, kqc_pending = false;
     mcx_qc qc{};
     bool pushed = false, searched = false;
     // search buffers
@@ -2752,10 +2752,12 @@ static int wait_copies(mcx_ctx *ctx, int64_t words, int64_t qbytes) {
     return MCX_OK;
 }
 
+static void collect_kqc_time(mcx_ctx *ctx);
 static int sync_stream(mcx_ctx *ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
     ++ctx->host_syncs;
+    collect_kqc_time(ctx);
     return MCX_OK;
 }
 
@@ -2764,11 +2766,22 @@ static int qc_range(mcx_ctx *ctx, int64_t upto) {
     if (upto <= ctx->qc_upto) return MCX_OK;
     const mcx_params &P = ctx->par;
     const int64_t r0 = ctx->qc_upto, nr = upto - r0;
+    CK(cudaEventRecord(ctx->ev[16], ctx->stream));
     k_qc<<<(unsigned)((nr * 8 + 255) / 256), 256, 0, ctx->stream>>>(read_store(ctx), r0, upto, P.read_length, P.quality_offset,
                                                                   P.min_quality, P.mean_quality, P.max_unknown, ctx->d_code);
+    CK(cudaEventRecord(ctx->ev[17], ctx->stream));
+    ctx->kqc_pending = true;
     ++ctx->launches;
     ctx->qc_upto = upto;
     return MCX_OK;
+}
+
+// after a synchronisation: add the time of the last k_qc launch to ms[10]
+static void collect_kqc_time(mcx_ctx *ctx) {
+    if (!ctx->kqc_pending) return;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, ctx->ev[16], ctx->ev[17]) == cudaSuccess) ctx->ms[10] += t;
+    ctx->kqc_pending = false;
 }
 
 // everything decided over all pushed reads: verdicts and, with -d, the duplicates
@@ -2780,6 +2793,8 @@ static int qc_all(mcx_ctx *ctx) {
     CK(cudaEventRecord(ctx->ev[14], st));
     if ((rc = qc_range(ctx, n)) != MCX_OK) return rc;
     if (ctx->par.filter_dups && !ctx->dedup_done && n > 0) {
+        if ((rc = sync_stream(ctx)) != MCX_OK) return rc;          // (k_qc's events are read before they are reused)
+        CK(cudaEventRecord(ctx->ev[18], st));
         if ((rc = ensure(ctx, &ctx->d_fp, &ctx->cap_fp, n)) != MCX_OK) return rc;
         if ((rc = ensure(ctx, &ctx->d_fpa, &ctx->cap_fpa, n)) != MCX_OK) return rc;
         if ((rc = ensure(ctx, &ctx->d_fpa2, &ctx->cap_fpa2, n)) != MCX_OK) return rc;
@@ -2803,6 +2818,9 @@ static int qc_all(mcx_ctx *ctx) {
             k_mark_dups<<<(unsigned)((nk + 255) / 256), 256, 0, st>>>(ctx->d_fpa, ctx->d_fpi, ctx->d_fp, nk, ctx->d_code);
             ctx->launches += 12;
         }
+        CK(cudaEventRecord(ctx->ev[12], st));
+        if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
+        { float t = 0.f; if (cudaEventElapsedTime(&t, ctx->ev[18], ctx->ev[12]) == cudaSuccess) ctx->ms[11] += t; }
         ctx->dedup_done = true;
     }
     CK(cudaEventRecord(ctx->ev[15], st));
@@ -3302,9 +3320,49 @@ extern "C" int mcx_dpx_peak(mcx_ctx *ctx, double *gops_per_s) {
     return MCX_OK;
 }
 
-extern "C" int mcx_timings(mcx_ctx *ctx, float ms[10], int64_t *launches) {
+// ------------------------------------------------------------------------------------------------
+// L2 random-access microbenchmark (the seed-word lookup is bound by the random-access transaction rate, not
+// by bandwidth).  Every thread issues independent 4-byte loads at pseudo-random words of the context's own 32 MB
+// presence filter -- the access pattern of k_probe's filter probes, with nothing else in the way: one 32-byte sector per
+// load, eight loads in flight per thread, full occupancy.  The result is the rate k_probe's probes/s are quoted against.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_l2_bench(const uint32_t *__restrict__ words, uint32_t mask, int iters, uint32_t seed, uint32_t *out) {
+    uint32_t x = (blockIdx.x * 256u + threadIdx.x) * 2654435761u + seed, acc = 0;
+    for (int it = 0; it < iters; ++it) {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { x = x * 1664525u + 1013904223u; v[k] = __ldg(words + ((x >> 7) & mask)); }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc ^= v[k];
+    }
+    if (acc == 0x9e3779b9u) out[0] = acc;                 // keeps the loads alive
+}
+
+extern "C" int mcx_l2_peak(mcx_ctx *ctx, double *gsectors_per_s) {
+    if (!ctx || !gsectors_per_s) return fail(ctx, MCX_EINVAL, "mcx_l2_peak: null argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int blocks = ctx->n_sm * 8, iters = 512;
+    uint32_t *d_out = reinterpret_cast<uint32_t *>(ctx->d_cnt + C_N - 1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(ctx->ev[12], st));
+        k_l2_bench<<<blocks, 256, 0, st>>>(ctx->db.bloom, (1u << BLOOM_WORD_BITS) - 1u, iters, 777u + rep, d_out);
+        CK(cudaEventRecord(ctx->ev[13], st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[12], ctx->ev[13]));
+        const double loads = (double)blocks * 256.0 * (double)iters * 8.0;
+        if (rep > 0) best = std::max(best, loads / (ms * 1e-3) / 1e9);
+    }
+    *gsectors_per_s = best;
+    return MCX_OK;
+}
+
+extern "C" int mcx_timings(mcx_ctx *ctx, float ms[12], int64_t *launches) {
     if (!ctx || !ms) return fail(ctx, MCX_EINVAL, "mcx_timings: null argument");
-    memcpy(ms, ctx->ms, sizeof(float) * 10);
+    memcpy(ms, ctx->ms, sizeof(float) * 12);
     if (launches) *launches = ctx->launches;
     return MCX_OK;
 }

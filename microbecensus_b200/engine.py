@@ -329,11 +329,17 @@ class MarkerSearch:
         self._ck(self.lib.mcx_dpx_peak(self.ctx, C.byref(v)))
         return v.value
 
+    def l2_peak(self):
+        """1e9 random 4-byte loads (32-byte L2 sectors) per second over the 32 MB presence filter (microbenchmark)."""
+        v = C.c_double(0.0)
+        self._ck(self.lib.mcx_l2_peak(self.ctx, C.byref(v)))
+        return v.value
+
     def timings(self):
-        ms = (C.c_float * 10)()
+        ms = (C.c_float * 12)()
         launches = C.c_int64(0)
         self._ck(self.lib.mcx_timings(self.ctx, C.byref(ms), C.byref(launches)))
-        names = ("h2d", "qc", "probe", "gapped", "sort", "classify", "d2h", "extend", "frames", "seg")
+        names = ("h2d", "qc", "probe", "gapped", "sort", "classify", "d2h", "extend", "frames", "seg", "k_qc", "dedupe")
         return {k: float(ms[i]) for i, k in enumerate(names)}, int(launches.value)
 
 

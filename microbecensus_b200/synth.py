@@ -19,11 +19,21 @@ SEED = 20260101
 _genome = None
 
 
+def genome_pack_path():
+    """data/genomes30.pack (all 30 training genomes of the reference, 84.8 Mbp; written by
+    tools/build_genome_pack.py --all at build time where the reference tree is mounted) if present, else the committed
+    ten-genome data/genomes.pack; $MCX_GENOME_PACK overrides."""
+    if os.environ.get("MCX_GENOME_PACK"):
+        return os.environ["MCX_GENOME_PACK"]
+    full = os.path.join(_HERE, "data", "genomes30.pack")
+    return full if os.path.isfile(full) else os.path.join(_HERE, "data", "genomes.pack")
+
+
 def genome():
     """(bases as uint8 codes 0..3, contig start offsets, contig lengths)"""
     global _genome
     if _genome is None:
-        blob = open(os.path.join(_HERE, "data", "genomes.pack"), "rb").read()
+        blob = open(genome_pack_path(), "rb").read()
         assert blob[:8] == b"MCXGEN01"
         n = struct.unpack_from("<i", blob, 8)[0]
         lens = np.frombuffer(blob, np.int64, n, 12)

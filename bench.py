@@ -458,6 +458,7 @@ def main():
                     "d2h_bytes_per_step": int(res.counts_vector().nbytes), "ms_per_step": t_e2e * 1e3},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_k1": roofline_k1,
             "stages_ms": stage_dev, "stages_ms_e2e": stage_e2e,
+            "exchange_ms": getattr(eng, "exchange_ms", None) if (dups and world > 1) else None,
             "gapped_gcups": gcups, "gapped": gapped, "ags": ags, "ags_e2e": ags2,
             "counts": {"sampled_reads": res.sampled_reads, "reads_with_hits": res.reads_with_hits,
                        "reads_classified": res.reads_classified, "n_hsp": res.n_hsp, "n_seed_hits": res.n_seed_hits,

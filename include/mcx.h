@@ -155,6 +155,20 @@ int  mcx_qc_import(mcx_ctx *ctx, const uint8_t *code);
  * list.  Used by the cross-GPU duplicate exchange, which never brings fingerprints to the host. */
 int  mcx_qc_device(mcx_ctx *ctx, void **d_code, void **d_fingerprints, int64_t *n);
 int  mcx_qc_refresh(mcx_ctx *ctx);
+/* -d across GPUs (one context per GPU, reads sharded; mc.py:345 decided over all of them).  Three compute steps on the
+ * device with two all-to-all transfers by the caller in between (NCCL; microbecensus_b200/distributed.py):
+ *   mcx_dedup_begin   QC of all pushed reads, fingerprints, records {uint64 a, uint64 b, int64 global index << 1 |
+ *                     passed-QC} of the long-enough reads grouped by owner rank (a mod world); *d_send = the records
+ *                     (device memory of the context), send_counts[world] = records per owner (host);
+ *   mcx_dedup_owner   d_recv = the m records this rank owns (device memory of the caller); sorts them by (fingerprint,
+ *                     global index) and marks every record behind the first QC-passing read of its fingerprint;
+ *                     *d_marks = m bytes in the order of d_recv (device memory of the context);
+ *   mcx_dedup_finish  d_marks_back = the marks of this rank's own records in the order of *d_send; rewrites the
+ *                     verdicts (3 = duplicate) and recounts.
+ * first_index = global index of this rank's first read. */
+int  mcx_dedup_begin(mcx_ctx *ctx, int world, int64_t first_index, void **d_send, int64_t *send_counts);
+int  mcx_dedup_owner(mcx_ctx *ctx, const void *d_recv, int64_t m, void **d_marks);
+int  mcx_dedup_finish(mcx_ctx *ctx, const void *d_marks_back);
 /* search the first `quota` kept reads (quota < 0: all of them) */
 int  mcx_search(mcx_ctx *ctx, int64_t quota);
 int  mcx_result_get(mcx_ctx *ctx, mcx_result *out);

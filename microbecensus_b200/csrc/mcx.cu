@@ -428,43 +428,41 @@ __global__ void __launch_bounds__(128) k_fingerprint(ReadStore S, int64_t n, FpK
     k.idx = (uint32_t)r; k.pad = 0;
     keys[r] = k;
 }
-// sort input of the duplicate test: (a, read index) of the reads that are long enough; too-short reads are decided
-// before the duplicate test and stay out
-__global__ void k_fp_keys(const FpKey *__restrict__ fp, const uint8_t *__restrict__ code, int64_t n,
-                          unsigned long long *__restrict__ ka, uint32_t *__restrict__ vi, unsigned long long *n_out) {
+// sort input of the duplicate test: (a, read index) of every read, in read order
+__global__ void k_fp_keys(const FpKey *__restrict__ fp, int64_t n, unsigned long long *__restrict__ ka, uint32_t *__restrict__ vi) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool take = r < n && code[r] != 1;
-    const uint32_t bm = __ballot_sync(0xffffffffu, take);
-    if (!bm) return;
-    const int lane = threadIdx.x & 31;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(n_out, (unsigned long long)__popc(bm));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (take) { const unsigned long long o = base + __popc(bm & ((1u << lane) - 1)); ka[o] = fp[r].a; vi[o] = (uint32_t)r; }
+    if (r < n) { ka[r] = fp[r].a; vi[r] = (uint32_t)r; }
 }
-// One thread per run of equal `a` in the sorted (a, index) list (the sort is stable, so indices ascend inside a run).
-// Runs are fingerprint groups except when two fingerprints share `a` (never expected; handled all the same: the
-// thread walks the run once per distinct `b` it meets).
+// One thread per run of equal sort key (the upper FP_SORT_BITS of `a`) in the sorted list.  Inside a run the reads are
+// grouped by their full fingerprint (runs of more than one fingerprint are a once-in-a-billion event, handled all the
+// same): the first QC-passing read of a group -- smallest index -- stays, every other long-enough read of the group
+// behind it is a duplicate.  Too-short reads are decided before the duplicate test (mc.py:342) and skipped.
+constexpr int FP_SORT_BITS = 48;
 __global__ void k_mark_dups(const unsigned long long *__restrict__ ka, const uint32_t *__restrict__ vi,
                             const FpKey *__restrict__ fp, int64_t n, uint8_t *__restrict__ code) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    const unsigned long long a = ka[p];
-    if (p > 0 && ka[p - 1] == a) return;                      // not the first of its run
+    const unsigned long long key = ka[p] >> (64 - FP_SORT_BITS);
+    if (p > 0 && (ka[p - 1] >> (64 - FP_SORT_BITS)) == key) return;      // not the first of its run
     int64_t e = p + 1;
-    while (e < n && ka[e] == a) ++e;
+    while (e < n && (ka[e] >> (64 - FP_SORT_BITS)) == key) ++e;
     if (e == p + 1) return;
     for (int64_t s = p; s < e; ++s) {
-        const unsigned long long b = fp[vi[s]].b;
-        bool first_of_b = true;
-        for (int64_t q = p; q < s; ++q) if (fp[vi[q]].b == b) { first_of_b = false; break; }
-        if (!first_of_b) continue;
-        bool seen_kept = false;
+        const FpKey ks = fp[vi[s]];
+        bool first = true;
+        for (int64_t q = p; q < s; ++q) { const FpKey kq = fp[vi[q]]; if (kq.a == ks.a && kq.b == ks.b) { first = false; break; } }
+        if (!first) continue;
+        uint32_t keeper = 0xffffffffu;                        // smallest index among the group's reads that pass QC
         for (int64_t q = s; q < e; ++q) {
             const uint32_t i = vi[q];
-            if (q > s && fp[i].b != b) continue;
-            if (seen_kept) code[i] = 3;
-            else if (code[i] == 0) seen_kept = true;
+            if (q > s) { const FpKey kq = fp[i]; if (kq.a != ks.a || kq.b != ks.b) continue; }
+            if (code[i] == 0 && i < keeper) keeper = i;
+        }
+        if (keeper == 0xffffffffu) continue;
+        for (int64_t q = s; q < e; ++q) {
+            const uint32_t i = vi[q];
+            if (q > s) { const FpKey kq = fp[i]; if (kq.a != ks.a || kq.b != ks.b) continue; }
+            if (i > keeper && code[i] != 1) code[i] = 3;
         }
     }
 }
@@ -2104,6 +2102,12 @@ struct mcx_ctx {
     int64_t cap_fp = 0, cap_fpa = 0, cap_fpa2 = 0, cap_fpi = 0, cap_fpi2 = 0;
     int32_t *d_kept = nullptr;
     int64_t cap_code = 0, cap_kept = 0;
+    // cross-GPU -d exchange
+    long long *d_xsend = nullptr;
+    uint8_t *d_xmarks = nullptr;
+    unsigned long long *d_xkg = nullptr;
+    uint32_t *d_xvi = nullptr;
+    int64_t cap_xsend = 0, cap_xmarks = 0, cap_xkg = 0, cap_xvi = 0, x_nsend = 0;
     int64_t qc_upto = 0;                       // reads [0, qc_upto) have their verdict
     bool dedup_done = false, fp_done = false, counts_valid = false, kqc_pending = false;
     mcx_qc qc{};
@@ -2146,7 +2150,8 @@ struct mcx_ctx {
 // slots of d_cnt
 enum Cnt { C_QC0 = 0 /* ..3: verdict counts of the search */, C_QCALL = 4 /* ..7: verdict counts over all pushed reads */,
            C_SURV = 8, C_SEEDQ = 9, C_GAPPED = 10, C_CELLS = 11, C_SEGQ = 12, C_WORK = 13, C_ITEMS2 = 14, C_NCAP = 15,
-           C_WORK1 = 16, C_WORK2 = 17, C_ITEMS = 18, C_NKEPT = 20, C_NWIDE = 24 /* ..26 */, C_NGAPTOT = 27, C_NFP = 21, C_TOTW = 22, C_TOTQ = 23, C_N = 64 };
+           C_WORK1 = 16, C_WORK2 = 17, C_ITEMS = 18, C_NKEPT = 20, C_NWIDE = 24 /* ..26 */, C_NGAPTOT = 27, C_NFP = 21, C_TOTW = 22, C_TOTQ = 23,
+           C_XCNT = 64 /* ..191: owner counts and cursors of the -d exchange */, C_N = 192 };
 
 static thread_local std::string g_err;
 
@@ -2509,7 +2514,7 @@ extern "C" void mcx_destroy(mcx_ctx *ctx) {
     if (!ctx->ext_len) cudaFree(ctx->d_len);
     if (!ctx->ext_quals) cudaFree(ctx->d_quals);
     void *bufs[] = {ctx->d_woff, ctx->d_qoff, ctx->d_ascii, ctx->d_aoffs, ctx->d_code, ctx->d_fp, ctx->d_fpa, ctx->d_fpa2, ctx->d_fpi, ctx->d_fpi2,
-                    ctx->d_kept, ctx->d_surv, ctx->d_hsp, ctx->d_hits_out, ctx->d_keys, ctx->d_idx, ctx->d_best, ctx->d_hflag,
+                    ctx->d_kept, ctx->d_xsend, ctx->d_xmarks, ctx->d_xkg, ctx->d_xvi, ctx->d_surv, ctx->d_hsp, ctx->d_hits_out, ctx->d_keys, ctx->d_idx, ctx->d_best, ctx->d_hflag,
                     ctx->d_hpos, ctx->d_keep, ctx->d_cnt, ctx->d_acc, ctx->d_abl, ctx->d_temp, ctx->d_frames, ctx->d_cand,
                     ctx->d_segq, ctx->d_qcnt, ctx->d_gitems, ctx->d_gext, ctx->d_dirs, ctx->d_nrep, ctx->d_bestkey, ctx->d_seen, ctx->d_seedq};
     for (void *p : bufs) if (p) cudaFree(p);
@@ -2801,22 +2806,16 @@ static int qc_all(mcx_ctx *ctx) {
         if ((rc = ensure(ctx, &ctx->d_fpi, &ctx->cap_fpi, n)) != MCX_OK) return rc;
         if ((rc = ensure(ctx, &ctx->d_fpi2, &ctx->cap_fpi2, n)) != MCX_OK) return rc;
         if (!ctx->fp_done) { k_fingerprint<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(read_store(ctx), n, ctx->d_fp); ++ctx->launches; ctx->fp_done = true; }
-        CK(cudaMemsetAsync(ctx->d_cnt + C_NFP, 0, sizeof(unsigned long long), st));
-        k_fp_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_fp, ctx->d_code, n, ctx->d_fpa, ctx->d_fpi, ctx->d_cnt + C_NFP);
-        CK(cudaMemcpyAsync(ctx->h_cnt + C_NFP, ctx->d_cnt + C_NFP, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
-        const int64_t nk = (int64_t)ctx->h_cnt[C_NFP];
-        if (nk > 1) {
-            // k_fp_keys appends warp by warp in no fixed order; the radix sort is stable, so the indices are sorted first
-            // (low 27 bits are enough) and then the fingerprints: equal fingerprints end up in index order
-            size_t tb = 0, tb2 = 0;
-            cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_fpi, ctx->d_fpi2, ctx->d_fpa, ctx->d_fpa2, (int)nk, 0, 27, st);
-            cub::DeviceRadixSort::SortPairs(nullptr, tb2, ctx->d_fpa2, ctx->d_fpa, ctx->d_fpi2, ctx->d_fpi, (int)nk, 0, 64, st);
-            if ((rc = ensure_temp(ctx, std::max(tb, tb2))) != MCX_OK) return rc;
-            cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_fpi, ctx->d_fpi2, ctx->d_fpa, ctx->d_fpa2, (int)nk, 0, 27, st);
-            cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb2, ctx->d_fpa2, ctx->d_fpa, ctx->d_fpi2, ctx->d_fpi, (int)nk, 0, 64, st);
-            k_mark_dups<<<(unsigned)((nk + 255) / 256), 256, 0, st>>>(ctx->d_fpa, ctx->d_fpi, ctx->d_fp, nk, ctx->d_code);
-            ctx->launches += 12;
+        if (n > 1) {
+            // one radix sort on the upper 48 bits of the fingerprint brings equal fingerprints together; which read of a
+            // group stays is decided by index inside k_mark_dups, so neither a stable sort nor a second key is needed
+            k_fp_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_fp, n, ctx->d_fpa, ctx->d_fpi);
+            size_t tb = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_fpi, ctx->d_fpi2, (int)n, 64 - FP_SORT_BITS, 64, st);
+            if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
+            cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_fpi, ctx->d_fpi2, (int)n, 64 - FP_SORT_BITS, 64, st);
+            k_mark_dups<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_fpa2, ctx->d_fpi2, ctx->d_fp, n, ctx->d_code);
+            ctx->launches += 9;
         }
         CK(cudaEventRecord(ctx->ev[12], st));
         if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
@@ -2915,6 +2914,156 @@ extern "C" int mcx_qc_counts(mcx_ctx *ctx, mcx_qc *out) {
     if ((rc = qc_counts_all(ctx)) != MCX_OK) return rc;
     *out = ctx->qc;
     return MCX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// -d across GPUs (the path's one real exchange step).  Every long-enough read sends (fingerprint a, b,
+// global index << 1 | passed QC) to the rank that owns its fingerprint; the owner sorts what it received and marks every
+// record behind the first QC-passing read of its fingerprint; the marks travel back.  The library does the three
+// compute steps on the context's stream -- mcx_dedup_begin (partition by owner), mcx_dedup_owner (sort + mark),
+// mcx_dedup_finish (apply) -- and the caller moves the two buffers between ranks (NCCL all-to-all through
+// torch.distributed, microbecensus_b200/distributed.py).  (Round 1 did these steps with eager torch ops: three argsorts,
+// bincount, scatter_reduce -- 17 ms of a 200 ms step, untimed.)
+// ------------------------------------------------------------------------------------------------
+struct XRec { unsigned long long a, b; long long gp; };     // gp = global read index << 1 | passed QC
+__device__ __forceinline__ int owner_of(unsigned long long a, int world) { return (int)((a & 0x7fffffffffffffffull) % (unsigned long long)world); }
+
+__global__ void k_x_count(const FpKey *__restrict__ fp, const uint8_t *__restrict__ code, int64_t n, int world, unsigned long long *cnt) {
+    __shared__ unsigned int s[64];
+    if (threadIdx.x < 64) s[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        if (code[r] != 1) atomicAdd(&s[owner_of(fp[r].a, world)], 1u);
+    __syncthreads();
+    if (threadIdx.x < world && s[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], (unsigned long long)s[threadIdx.x]);
+}
+// cursor[o] starts at the first slot of owner o in the send buffer
+__global__ void k_x_scatter(const FpKey *__restrict__ fp, const uint8_t *__restrict__ code, int64_t n, int world, long long first_index,
+                            unsigned long long *cursor, XRec *__restrict__ send, uint32_t *__restrict__ send_read) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n || code[r] == 1) return;
+    const FpKey k = fp[r];
+    const unsigned long long at = atomicAdd(&cursor[owner_of(k.a, world)], 1ull);
+    XRec x; x.a = k.a; x.b = k.b; x.gp = ((first_index + r) << 1) | (long long)(code[r] == 0);
+    send[at] = x;
+    send_read[at] = (uint32_t)r;
+}
+__global__ void k_x_keys(const XRec *__restrict__ recv, int64_t m, unsigned long long *__restrict__ kg, unsigned long long *__restrict__ ka, uint32_t *__restrict__ vi) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < m) { kg[p] = (unsigned long long)recv[p].gp; ka[p] = recv[p].a; vi[p] = (uint32_t)p; }
+}
+// one thread per run of equal sort key in the list sorted by the upper bits of `a`: marks[record] = 1 for every record
+// of a fingerprint group behind (by global index) the group's first QC-passing read
+__global__ void k_x_mark(const unsigned long long *__restrict__ ka, const uint32_t *__restrict__ vi, const XRec *__restrict__ recv,
+                         int64_t m, uint8_t *__restrict__ marks) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= m) return;
+    const unsigned long long key = ka[p] >> (64 - FP_SORT_BITS);
+    if (p > 0 && (ka[p - 1] >> (64 - FP_SORT_BITS)) == key) return;
+    int64_t e = p + 1;
+    while (e < m && (ka[e] >> (64 - FP_SORT_BITS)) == key) ++e;
+    if (e == p + 1) return;
+    for (int64_t s = p; s < e; ++s) {
+        const XRec xs = recv[vi[s]];
+        bool first = true;
+        for (int64_t q = p; q < s; ++q) { const XRec xq = recv[vi[q]]; if (xq.a == xs.a && xq.b == xs.b) { first = false; break; } }
+        if (!first) continue;
+        long long keeper = LLONG_MAX;
+        for (int64_t q = s; q < e; ++q) {
+            const XRec xq = recv[vi[q]];
+            if (xq.a != xs.a || xq.b != xs.b) continue;
+            if ((xq.gp & 1) && (xq.gp >> 1) < keeper) keeper = xq.gp >> 1;
+        }
+        if (keeper == LLONG_MAX) continue;
+        for (int64_t q = s; q < e; ++q) {
+            const XRec xq = recv[vi[q]];
+            if (xq.a != xs.a || xq.b != xs.b) continue;
+            if ((xq.gp >> 1) > keeper) marks[vi[q]] = 1;
+        }
+    }
+}
+__global__ void k_x_apply(const uint8_t *__restrict__ marks, const uint32_t *__restrict__ send_read, int64_t ns, uint8_t *__restrict__ code) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < ns && marks[p]) code[send_read[p]] = 3;
+}
+
+extern "C" int mcx_dedup_begin(mcx_ctx *ctx, int world, int64_t first_index, void **d_send, int64_t *send_counts) {
+    if (!ctx || !d_send || !send_counts || world < 1 || world > 64) return fail(ctx, MCX_EINVAL, "mcx_dedup_begin: bad argument (1 <= world <= 64)");
+    if (!ctx->pushed) return fail(ctx, MCX_ESTATE, "mcx_dedup_begin: no reads pushed");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t n = ctx->n_reads;
+    int rc;
+    if ((rc = qc_all(ctx)) != MCX_OK) return rc;
+    if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
+    CK(cudaEventRecord(ctx->ev[18], st));
+    if ((rc = ensure(ctx, &ctx->d_fp, &ctx->cap_fp, std::max<int64_t>(n, 1))) != MCX_OK) return rc;
+    if (n > 0 && !ctx->fp_done) { k_fingerprint<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(read_store(ctx), n, ctx->d_fp); ++ctx->launches; ctx->fp_done = true; }
+    if ((rc = ensure(ctx, &ctx->d_xsend, &ctx->cap_xsend, std::max<int64_t>(n, 1) * 3)) != MCX_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_fpi, &ctx->cap_fpi, std::max<int64_t>(n, 1))) != MCX_OK) return rc;
+    unsigned long long *cnt = ctx->d_cnt + C_XCNT, *cur = ctx->d_cnt + C_XCNT + 64 + 0;   // counts, then cursors (exclusive prefix)
+    CK(cudaMemsetAsync(cnt, 0, 128 * sizeof(unsigned long long), st));
+    if (n > 0) k_x_count<<<592, 256, 0, st>>>(ctx->d_fp, ctx->d_code, n, world, cnt);
+    CK(cudaMemcpyAsync(ctx->h_cnt, cnt, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
+    unsigned long long pre[64], acc = 0;
+    for (int o = 0; o < 64; ++o) { pre[o] = acc; if (o < world) { send_counts[o] = (int64_t)ctx->h_cnt[o]; acc += ctx->h_cnt[o]; } }
+    ctx->x_nsend = (int64_t)acc;
+    CK(cudaMemcpyAsync(cur, pre, 64 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    if (n > 0) k_x_scatter<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_fp, ctx->d_code, n, world, (long long)first_index, cur,
+                                                                       reinterpret_cast<XRec *>(ctx->d_xsend), ctx->d_fpi);
+    ctx->launches += 2;
+    CK(cudaEventRecord(ctx->ev[12], st));
+    if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
+    { float t = 0.f; if (cudaEventElapsedTime(&t, ctx->ev[18], ctx->ev[12]) == cudaSuccess) ctx->ms[11] += t; }
+    *d_send = ctx->d_xsend;
+    return MCX_OK;
+}
+
+extern "C" int mcx_dedup_owner(mcx_ctx *ctx, const void *d_recv, int64_t m, void **d_marks) {
+    if (!ctx || !d_marks || m < 0 || (m > 0 && !d_recv)) return fail(ctx, MCX_EINVAL, "mcx_dedup_owner: bad argument");
+    if (m >= (1ll << 31)) return fail(ctx, MCX_EINVAL, "mcx_dedup_owner: at most 2^31 records per rank");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int rc;
+    const int64_t mm = std::max<int64_t>(m, 1);
+    if ((rc = ensure(ctx, &ctx->d_xmarks, &ctx->cap_xmarks, mm)) != MCX_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_fpa, &ctx->cap_fpa, mm)) != MCX_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_fpa2, &ctx->cap_fpa2, mm)) != MCX_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_xkg, &ctx->cap_xkg, mm)) != MCX_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_xvi, &ctx->cap_xvi, mm)) != MCX_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_fpi2, &ctx->cap_fpi2, mm)) != MCX_OK) return rc;
+    CK(cudaEventRecord(ctx->ev[18], st));
+    CK(cudaMemsetAsync(ctx->d_xmarks, 0, (size_t)mm, st));
+    if (m > 1) {
+        const XRec *recv = reinterpret_cast<const XRec *>(d_recv);
+        const unsigned gb = (unsigned)((m + 255) / 256);
+        k_x_keys<<<gb, 256, 0, st>>>(recv, m, ctx->d_xkg, ctx->d_fpa, ctx->d_xvi);
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_xvi, ctx->d_fpi2, (int)m, 64 - FP_SORT_BITS, 64, st);
+        if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
+        cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_xvi, ctx->d_fpi2, (int)m, 64 - FP_SORT_BITS, 64, st);
+        k_x_mark<<<gb, 256, 0, st>>>(ctx->d_fpa2, ctx->d_fpi2, recv, m, ctx->d_xmarks);
+        ctx->launches += 9;
+    }
+    CK(cudaEventRecord(ctx->ev[12], st));
+    if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
+    { float t = 0.f; if (cudaEventElapsedTime(&t, ctx->ev[18], ctx->ev[12]) == cudaSuccess) ctx->ms[11] += t; }
+    *d_marks = ctx->d_xmarks;
+    return MCX_OK;
+}
+
+extern "C" int mcx_dedup_finish(mcx_ctx *ctx, const void *d_marks_back) {
+    if (!ctx || (ctx->x_nsend > 0 && !d_marks_back)) return fail(ctx, MCX_EINVAL, "mcx_dedup_finish: bad argument");
+    if (!ctx->pushed) return fail(ctx, MCX_ESTATE, "mcx_dedup_finish: no reads pushed");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->x_nsend > 0) {
+        k_x_apply<<<(unsigned)((ctx->x_nsend + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint8_t *>(d_marks_back), ctx->d_fpi, ctx->x_nsend, ctx->d_code);
+        ++ctx->launches;
+    }
+    ctx->dedup_done = true;
+    ctx->counts_valid = false; ctx->searched = false;
+    return qc_counts_all(ctx);
 }
 
 struct IsKept {

@@ -128,28 +128,44 @@ class _CudaView:
 
 
 def exchange_duplicates_device(engine, first_index, group=None, device=None):
-    """The same on the verdicts and fingerprints as they sit in the engine's device memory (mcx_qc_device): nothing but
-    the two all-to-alls leaves the GPU.  Rewrites the verdicts in place and returns the refreshed QC counters."""
+    """The same with the reads where they are, in the engine's device memory: libmcx partitions the fingerprint records
+    by owner (mcx_dedup_begin), sorts and marks what this rank owns (mcx_dedup_owner) and applies the marks that come
+    back (mcx_dedup_finish); this function only moves the two buffers between ranks (NCCL all-to-all).  Returns the
+    refreshed QC counters; `engine.exchange_ms` = device time of the whole exchange."""
     import torch
+    import torch.distributed as dist
     dev_idx = (device.index if device is not None and device.index is not None else torch.cuda.current_device())
     if getattr(engine, "device", dev_idx) != dev_idx:
         raise RuntimeError("exchange_duplicates_device: the engine lives on GPU %d but the exchange tensors on GPU %d "
                            "(one process per GPU: create the engine on the rank's own device)" % (engine.device, dev_idx))
-    dc, df, n = engine.qc_device(True)
-    if n == 0:
-        dev = device or torch.device("cuda", torch.cuda.current_device())
-        z = torch.zeros(0, dtype=torch.int64, device=dev)
-        _exchange_marks(z, z, z, group)
-        return engine.qc_refresh()
-    dev = device or torch.device("cuda", torch.cuda.current_device())
-    codes = torch.as_tensor(_CudaView(dc, (n,), "|u1"), device=dev)
-    fp = torch.as_tensor(_CudaView(df, (n, 3), "<i8"), device=dev)
-    sel = torch.nonzero(codes != 1).squeeze(1)
-    gp = ((first_index + sel) << 1) | (codes[sel] == 0).to(torch.int64)
-    dup = _exchange_marks(fp[sel, 0].contiguous(), fp[sel, 1].contiguous(), gp, group)
-    codes[sel[dup == 1]] = 3
-    torch.cuda.current_stream(dev).synchronize()
-    return engine.qc_refresh()
+    dev = device or torch.device("cuda", dev_idx)
+    world = dist.get_world_size(group)
+    stream = torch.cuda.current_stream(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream.synchronize()
+    e0.record(stream)
+    d_send, counts = engine.dedup_begin(world, first_index)
+    n_send = sum(counts)
+    send = (torch.as_tensor(_CudaView(d_send, (n_send, 3), "<i8"), device=dev) if n_send
+            else torch.zeros((0, 3), dtype=torch.int64, device=dev))
+    cnt = torch.tensor(counts, dtype=torch.int64, device=dev)
+    rcnt = torch.empty_like(cnt)
+    dist.all_to_all_single(rcnt, cnt, group=group)
+    out_split = [int(x) for x in rcnt.tolist()]
+    m = sum(out_split)
+    recv = torch.empty((m, 3), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv, send, output_split_sizes=out_split, input_split_sizes=counts, group=group)
+    stream.synchronize()
+    d_marks = engine.dedup_owner(recv.data_ptr() if m else 0, m)
+    marks = (torch.as_tensor(_CudaView(d_marks, (m,), "|u1"), device=dev) if m else torch.zeros(0, dtype=torch.uint8, device=dev))
+    back = torch.empty(n_send, dtype=torch.uint8, device=dev)
+    dist.all_to_all_single(back, marks, output_split_sizes=counts, input_split_sizes=out_split, group=group)
+    stream.synchronize()
+    qc = engine.dedup_finish(back.data_ptr() if n_send else 0)
+    e1.record(stream)
+    stream.synchronize()
+    engine.exchange_ms = e0.elapsed_time(e1)
+    return qc
 
 
 def sharded_search(engine, batch, first_index, nreads=None, filter_dups=False, group=None, device=None, push=None):

@@ -300,6 +300,24 @@ class MarkerSearch:
         self._ck(self.lib.mcx_qc_refresh(self.ctx))
         return self.qc()
 
+    def dedup_begin(self, world, first_index):
+        """-d across ranks, step 1 (mcx_dedup_begin): (device pointer to the records grouped by owner rank, records per owner)"""
+        d_send = C.c_void_p(0)
+        counts = (C.c_int64 * int(world))()
+        self._ck(self.lib.mcx_dedup_begin(self.ctx, int(world), int(first_index), C.byref(d_send), counts))
+        return d_send.value or 0, [int(c) for c in counts]
+
+    def dedup_owner(self, d_recv_ptr, m):
+        """step 2 (mcx_dedup_owner): device pointer to the m mark bytes of the records this rank owns"""
+        d_marks = C.c_void_p(0)
+        self._ck(self.lib.mcx_dedup_owner(self.ctx, C.c_void_p(d_recv_ptr or 0), int(m), C.byref(d_marks)))
+        return d_marks.value or 0
+
+    def dedup_finish(self, d_marks_back_ptr):
+        """step 3 (mcx_dedup_finish): verdicts rewritten, counters of all pushed reads"""
+        self._ck(self.lib.mcx_dedup_finish(self.ctx, C.c_void_p(d_marks_back_ptr or 0)))
+        return self.qc()
+
     def qc_import(self, code):
         code = np.ascontiguousarray(code, np.uint8)
         self._ck(self.lib.mcx_qc_import(self.ctx, _ptr(code)))

@@ -332,12 +332,16 @@ def main():
                                       d_quals.data_ptr() if d_quals is not None else 0, host_batch.n_bases, n)
 
     def step_device():
+        if dups:
+            eng.dedup_reset()                  # every step is a run of its own: the duplicate filter starts empty
         if dups and world > 1:                 # -d needs the cross-rank exchange of fingerprints
             return finish_reduced(sharded_search(eng, None, lo, nreads=None, filter_dups=True, push=push_dev))
         push_dev()
         return finish(eng.search(-1))
 
     def step_e2e():
+        if dups:
+            eng.dedup_reset()
         if dups and world > 1:
             return finish_reduced(sharded_search(eng, host_batch, lo, nreads=None, filter_dups=True))
         eng.push(host_batch)

@@ -155,6 +155,10 @@ int  mcx_qc_import(mcx_ctx *ctx, const uint8_t *code);
  * list.  Used by the cross-GPU duplicate exchange, which never brings fingerprints to the host. */
 int  mcx_qc_device(mcx_ctx *ctx, void **d_code, void **d_fingerprints, int64_t *n);
 int  mcx_qc_refresh(mcx_ctx *ctx);
+/* -d over several pushes (batches of one run): the context remembers the fingerprints of the reads it has kept -- after
+ * every mcx_search with filter_dups set, and on the owner side of mcx_dedup_owner -- and later pushes are tested against
+ * them as well (mc.py:345 keeps one set for the whole run).  mcx_set_params and mcx_dedup_reset forget them (start of a run). */
+int  mcx_dedup_reset(mcx_ctx *ctx);
 /* -d across GPUs (one context per GPU, reads sharded; mc.py:345 decided over all of them).  Three compute steps on the
  * device with two all-to-all transfers by the caller in between (NCCL; microbecensus_b200/distributed.py):
  *   mcx_dedup_begin   QC of all pushed reads, fingerprints, records {uint64 a, uint64 b, int64 global index << 1 |

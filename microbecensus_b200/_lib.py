@@ -54,7 +54,7 @@ class Hit(C.Structure):
 
 EXPORTS = ("mcx_create", "mcx_destroy", "mcx_set_params", "mcx_set_stream", "mcx_push_reads", "mcx_push_reads_dev",
            "mcx_push_reads_packed", "mcx_push_reads_packed_dev", "mcx_host_alloc", "mcx_host_free",
-           "mcx_qc_counts", "mcx_qc_export", "mcx_qc_import", "mcx_qc_device", "mcx_qc_refresh", "mcx_dedup_begin", "mcx_dedup_owner", "mcx_dedup_finish", "mcx_search", "mcx_result_get", "mcx_get_hits", "mcx_get_classified",
+           "mcx_qc_counts", "mcx_qc_export", "mcx_qc_import", "mcx_qc_device", "mcx_qc_refresh", "mcx_dedup_reset", "mcx_dedup_begin", "mcx_dedup_owner", "mcx_dedup_finish", "mcx_search", "mcx_result_get", "mcx_get_hits", "mcx_get_classified",
            "mcx_timings", "mcx_dpx_peak", "mcx_l2_peak", "mcx_last_error", "mcx_version")
 
 _lib = None
@@ -87,6 +87,7 @@ def load():
     lib.mcx_qc_import.argtypes = [vp, vp]
     lib.mcx_qc_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
     lib.mcx_qc_refresh.argtypes = [vp]
+    lib.mcx_dedup_reset.argtypes = [vp]
     lib.mcx_dedup_begin.argtypes = [vp, C.c_int, i64, C.POINTER(vp), C.POINTER(i64)]
     lib.mcx_dedup_owner.argtypes = [vp, vp, i64, C.POINTER(vp)]
     lib.mcx_dedup_finish.argtypes = [vp, vp]

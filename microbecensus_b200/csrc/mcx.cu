@@ -428,18 +428,31 @@ __global__ void __launch_bounds__(128) k_fingerprint(ReadStore S, int64_t n, FpK
     k.idx = (uint32_t)r; k.pad = 0;
     keys[r] = k;
 }
-// sort input of the duplicate test: (a, read index) of every read, in read order
-__global__ void k_fp_keys(const FpKey *__restrict__ fp, int64_t n, unsigned long long *__restrict__ ka, uint32_t *__restrict__ vi) {
+// Streamed -d: reads arrive in several pushes (batches of a large file), and a read is a duplicate of any KEPT read of an
+// earlier push as well (mc.py:345 keeps one set for the whole run).  The context therefore keeps the fingerprints of the
+// reads it has kept so far (`store`, 16 bytes per read); they enter the sort next to the reads of the push -- entries with
+// bit 31 of the index set -- and a fingerprint group that holds one has its keeper already: every read of the push in it
+// is a duplicate.  mcx_dedup_reset empties the store (start of a run).
+struct FpStore { const unsigned long long *a, *b; };
+constexpr uint32_t FP_STORED = 0x80000000u;
+__device__ __forceinline__ void fp_of_entry(uint32_t v, const FpKey *__restrict__ fp, const FpStore &S, unsigned long long &a, unsigned long long &b) {
+    if (v & FP_STORED) { a = S.a[v & ~FP_STORED]; b = S.b[v & ~FP_STORED]; }
+    else { a = fp[v].a; b = fp[v].b; }
+}
+// sort input of the duplicate test: (a, read index) of every read, in read order, then the stored fingerprints
+__global__ void k_fp_keys(const FpKey *__restrict__ fp, int64_t n, FpStore S, int64_t n_store, unsigned long long *__restrict__ ka, uint32_t *__restrict__ vi) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r < n) { ka[r] = fp[r].a; vi[r] = (uint32_t)r; }
+    else if (r < n + n_store) { ka[r] = S.a[r - n]; vi[r] = FP_STORED | (uint32_t)(r - n); }
 }
 // One thread per run of equal sort key (the upper FP_SORT_BITS of `a`) in the sorted list.  Inside a run the reads are
 // grouped by their full fingerprint (runs of more than one fingerprint are a once-in-a-billion event, handled all the
 // same): the first QC-passing read of a group -- smallest index -- stays, every other long-enough read of the group
-// behind it is a duplicate.  Too-short reads are decided before the duplicate test (mc.py:342) and skipped.
+// behind it is a duplicate; if the group holds a stored fingerprint, every long-enough read of it is.  Too-short reads
+// are decided before the duplicate test (mc.py:342) and skipped.
 constexpr int FP_SORT_BITS = 48;
 __global__ void k_mark_dups(const unsigned long long *__restrict__ ka, const uint32_t *__restrict__ vi,
-                            const FpKey *__restrict__ fp, int64_t n, uint8_t *__restrict__ code) {
+                            const FpKey *__restrict__ fp, FpStore S, int64_t n, uint8_t *__restrict__ code) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const unsigned long long key = ka[p] >> (64 - FP_SORT_BITS);
@@ -448,23 +461,40 @@ __global__ void k_mark_dups(const unsigned long long *__restrict__ ka, const uin
     while (e < n && (ka[e] >> (64 - FP_SORT_BITS)) == key) ++e;
     if (e == p + 1) return;
     for (int64_t s = p; s < e; ++s) {
-        const FpKey ks = fp[vi[s]];
+        unsigned long long sa, sb, qa, qb;
+        fp_of_entry(vi[s], fp, S, sa, sb);
         bool first = true;
-        for (int64_t q = p; q < s; ++q) { const FpKey kq = fp[vi[q]]; if (kq.a == ks.a && kq.b == ks.b) { first = false; break; } }
+        for (int64_t q = p; q < s; ++q) { fp_of_entry(vi[q], fp, S, qa, qb); if (qa == sa && qb == sb) { first = false; break; } }
         if (!first) continue;
+        bool stored = false;
         uint32_t keeper = 0xffffffffu;                        // smallest index among the group's reads that pass QC
         for (int64_t q = s; q < e; ++q) {
             const uint32_t i = vi[q];
-            if (q > s) { const FpKey kq = fp[i]; if (kq.a != ks.a || kq.b != ks.b) continue; }
-            if (code[i] == 0 && i < keeper) keeper = i;
+            if (q > s) { fp_of_entry(i, fp, S, qa, qb); if (qa != sa || qb != sb) continue; }
+            if (i & FP_STORED) stored = true;
+            else if (code[i] == 0 && i < keeper) keeper = i;
         }
-        if (keeper == 0xffffffffu) continue;
+        if (!stored && keeper == 0xffffffffu) continue;
         for (int64_t q = s; q < e; ++q) {
             const uint32_t i = vi[q];
-            if (q > s) { const FpKey kq = fp[i]; if (kq.a != ks.a || kq.b != ks.b) continue; }
-            if (i > keeper && code[i] != 1) code[i] = 3;
+            if (i & FP_STORED) continue;
+            if (q > s) { fp_of_entry(i, fp, S, qa, qb); if (qa != sa || qb != sb) continue; }
+            if ((stored || i > keeper) && code[i] != 1) code[i] = 3;
         }
     }
+}
+// the kept reads of a push join the store (reads [0, upto): the reads examined by the search)
+__global__ void k_store_append(const FpKey *__restrict__ fp, const uint8_t *__restrict__ code, int64_t upto,
+                               unsigned long long *__restrict__ sa, unsigned long long *__restrict__ sb, unsigned long long *n_store) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool take = r < upto && code[r] == 0;
+    const uint32_t bm = __ballot_sync(0xffffffffu, take);
+    if (!bm) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(n_store, (unsigned long long)__popc(bm));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (take) { const unsigned long long o = base + __popc(bm & ((1u << lane) - 1)); sa[o] = fp[r].a; sb[o] = fp[r].b; }
 }
 
 // counts of codes 0..3 among reads [0, upto)
@@ -2102,6 +2132,9 @@ struct mcx_ctx {
     int64_t cap_fp = 0, cap_fpa = 0, cap_fpa2 = 0, cap_fpi = 0, cap_fpi2 = 0;
     int32_t *d_kept = nullptr;
     int64_t cap_code = 0, cap_kept = 0;
+    // fingerprints of the reads kept by earlier pushes of the run (streamed -d)
+    unsigned long long *d_store_a = nullptr, *d_store_b = nullptr;
+    int64_t cap_store = 0, n_store = 0;
     // cross-GPU -d exchange
     long long *d_xsend = nullptr;
     uint8_t *d_xmarks = nullptr;
@@ -2151,7 +2184,7 @@ struct mcx_ctx {
 enum Cnt { C_QC0 = 0 /* ..3: verdict counts of the search */, C_QCALL = 4 /* ..7: verdict counts over all pushed reads */,
            C_SURV = 8, C_SEEDQ = 9, C_GAPPED = 10, C_CELLS = 11, C_SEGQ = 12, C_WORK = 13, C_ITEMS2 = 14, C_NCAP = 15,
            C_WORK1 = 16, C_WORK2 = 17, C_ITEMS = 18, C_NKEPT = 20, C_NWIDE = 24 /* ..26 */, C_NGAPTOT = 27, C_NFP = 21, C_TOTW = 22, C_TOTQ = 23,
-           C_XCNT = 64 /* ..191: owner counts and cursors of the -d exchange */, C_N = 192 };
+           C_NSTORE = 28, C_XCNT = 64 /* ..191: owner counts and cursors of the -d exchange */, C_N = 192 };
 
 static thread_local std::string g_err;
 
@@ -2514,7 +2547,7 @@ extern "C" void mcx_destroy(mcx_ctx *ctx) {
     if (!ctx->ext_len) cudaFree(ctx->d_len);
     if (!ctx->ext_quals) cudaFree(ctx->d_quals);
     void *bufs[] = {ctx->d_woff, ctx->d_qoff, ctx->d_ascii, ctx->d_aoffs, ctx->d_code, ctx->d_fp, ctx->d_fpa, ctx->d_fpa2, ctx->d_fpi, ctx->d_fpi2,
-                    ctx->d_kept, ctx->d_xsend, ctx->d_xmarks, ctx->d_xkg, ctx->d_xvi, ctx->d_surv, ctx->d_hsp, ctx->d_hits_out, ctx->d_keys, ctx->d_idx, ctx->d_best, ctx->d_hflag,
+                    ctx->d_kept, ctx->d_store_a, ctx->d_store_b, ctx->d_xsend, ctx->d_xmarks, ctx->d_xkg, ctx->d_xvi, ctx->d_surv, ctx->d_hsp, ctx->d_hits_out, ctx->d_keys, ctx->d_idx, ctx->d_best, ctx->d_hflag,
                     ctx->d_hpos, ctx->d_keep, ctx->d_cnt, ctx->d_acc, ctx->d_abl, ctx->d_temp, ctx->d_frames, ctx->d_cand,
                     ctx->d_segq, ctx->d_qcnt, ctx->d_gitems, ctx->d_gext, ctx->d_dirs, ctx->d_nrep, ctx->d_bestkey, ctx->d_seen, ctx->d_seedq};
     for (void *p : bufs) if (p) cudaFree(p);
@@ -2546,6 +2579,7 @@ extern "C" int mcx_set_params(mcx_ctx *ctx, const mcx_params *p) {
     CK(cudaSetDevice(ctx->device));
     ctx->par = *p;
     ctx->have_par = true;
+    ctx->n_store = 0;            // a new run: the duplicate filter starts empty
     CK(cudaMemcpyToSymbol(c_cut, p->cut, sizeof(mcx_cutoff) * MCX_N_FAM));
     return MCX_OK;
 }
@@ -2801,20 +2835,23 @@ static int qc_all(mcx_ctx *ctx) {
         if ((rc = sync_stream(ctx)) != MCX_OK) return rc;          // (k_qc's events are read before they are reused)
         CK(cudaEventRecord(ctx->ev[18], st));
         if ((rc = ensure(ctx, &ctx->d_fp, &ctx->cap_fp, n)) != MCX_OK) return rc;
-        if ((rc = ensure(ctx, &ctx->d_fpa, &ctx->cap_fpa, n)) != MCX_OK) return rc;
-        if ((rc = ensure(ctx, &ctx->d_fpa2, &ctx->cap_fpa2, n)) != MCX_OK) return rc;
-        if ((rc = ensure(ctx, &ctx->d_fpi, &ctx->cap_fpi, n)) != MCX_OK) return rc;
-        if ((rc = ensure(ctx, &ctx->d_fpi2, &ctx->cap_fpi2, n)) != MCX_OK) return rc;
+        const int64_t nt = n + ctx->n_store;               // reads of this push + fingerprints kept by earlier pushes
+        if (nt >= (1ll << 31)) return fail(ctx, MCX_EINVAL, "mcx: more than 2^31 fingerprints in the duplicate filter");
+        if ((rc = ensure(ctx, &ctx->d_fpa, &ctx->cap_fpa, nt)) != MCX_OK) return rc;
+        if ((rc = ensure(ctx, &ctx->d_fpa2, &ctx->cap_fpa2, nt)) != MCX_OK) return rc;
+        if ((rc = ensure(ctx, &ctx->d_fpi, &ctx->cap_fpi, nt)) != MCX_OK) return rc;
+        if ((rc = ensure(ctx, &ctx->d_fpi2, &ctx->cap_fpi2, nt)) != MCX_OK) return rc;
         if (!ctx->fp_done) { k_fingerprint<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(read_store(ctx), n, ctx->d_fp); ++ctx->launches; ctx->fp_done = true; }
-        if (n > 1) {
+        if (nt > 1) {
             // one radix sort on the upper 48 bits of the fingerprint brings equal fingerprints together; which read of a
             // group stays is decided by index inside k_mark_dups, so neither a stable sort nor a second key is needed
-            k_fp_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_fp, n, ctx->d_fpa, ctx->d_fpi);
+            const FpStore S{ctx->d_store_a, ctx->d_store_b};
+            k_fp_keys<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(ctx->d_fp, n, S, ctx->n_store, ctx->d_fpa, ctx->d_fpi);
             size_t tb = 0;
-            cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_fpi, ctx->d_fpi2, (int)n, 64 - FP_SORT_BITS, 64, st);
+            cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_fpi, ctx->d_fpi2, (int)nt, 64 - FP_SORT_BITS, 64, st);
             if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
-            cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_fpi, ctx->d_fpi2, (int)n, 64 - FP_SORT_BITS, 64, st);
-            k_mark_dups<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_fpa2, ctx->d_fpi2, ctx->d_fp, n, ctx->d_code);
+            cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_fpi, ctx->d_fpi2, (int)nt, 64 - FP_SORT_BITS, 64, st);
+            k_mark_dups<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(ctx->d_fpa2, ctx->d_fpi2, ctx->d_fp, S, nt, ctx->d_code);
             ctx->launches += 9;
         }
         CK(cudaEventRecord(ctx->ev[12], st));
@@ -2925,7 +2962,22 @@ extern "C" int mcx_qc_counts(mcx_ctx *ctx, mcx_qc *out) {
 // torch.distributed, microbecensus_b200/distributed.py).  (Round 1 did these steps with eager torch ops: three argsorts,
 // bincount, scatter_reduce -- 17 ms of a 200 ms step, untimed.)
 // ------------------------------------------------------------------------------------------------
-struct XRec { unsigned long long a, b; long long gp; };     // gp = global read index << 1 | passed QC
+struct XRec { unsigned long long a, b; long long gp; };
+// room for `need` stored fingerprints, keeping the ones there are
+static int reserve_store(mcx_ctx *ctx, int64_t need) {
+    if (need <= ctx->cap_store) return MCX_OK;
+    const int64_t cap = need + need / 2 + 1024;
+    int rc;
+    if ((rc = grow_keep(ctx, &ctx->d_store_a, ctx->n_store, cap)) != MCX_OK) return rc;
+    if ((rc = grow_keep(ctx, &ctx->d_store_b, ctx->n_store, cap)) != MCX_OK) return rc;
+    ctx->cap_store = cap;
+    return MCX_OK;
+}
+extern "C" int mcx_dedup_reset(mcx_ctx *ctx) {
+    if (!ctx) return fail(ctx, MCX_EINVAL, "mcx_dedup_reset: null context");
+    ctx->n_store = 0;
+    return MCX_OK;
+}     // gp = global read index << 1 | passed QC
 __device__ __forceinline__ int owner_of(unsigned long long a, int world) { return (int)((a & 0x7fffffffffffffffull) % (unsigned long long)world); }
 
 __global__ void k_x_count(const FpKey *__restrict__ fp, const uint8_t *__restrict__ code, int64_t n, int world, unsigned long long *cnt) {
@@ -2953,32 +3005,47 @@ __global__ void k_x_keys(const XRec *__restrict__ recv, int64_t m, unsigned long
     if (p < m) { kg[p] = (unsigned long long)recv[p].gp; ka[p] = recv[p].a; vi[p] = (uint32_t)p; }
 }
 // one thread per run of equal sort key in the list sorted by the upper bits of `a`: marks[record] = 1 for every record
-// of a fingerprint group behind (by global index) the group's first QC-passing read
-__global__ void k_x_mark(const unsigned long long *__restrict__ ka, const uint32_t *__restrict__ vi, const XRec *__restrict__ recv,
-                         int64_t m, uint8_t *__restrict__ marks) {
+// of a fingerprint group behind (by global index) the group's first QC-passing read -- or for every record of the group
+// if its fingerprint is already in the owner's store (kept in an earlier round of a streamed run); the fingerprint of a
+// group that gets its keeper now joins the store
+__device__ __forceinline__ void x_of_entry(uint32_t v, const XRec *__restrict__ recv, const FpStore &S, unsigned long long &a, unsigned long long &b) {
+    if (v & FP_STORED) { a = S.a[v & ~FP_STORED]; b = S.b[v & ~FP_STORED]; }
+    else { a = recv[v].a; b = recv[v].b; }
+}
+__global__ void k_x_keys_store(FpStore S, int64_t m, int64_t n_store, unsigned long long *__restrict__ ka, uint32_t *__restrict__ vi) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n_store) { ka[m + p] = S.a[p]; vi[m + p] = FP_STORED | (uint32_t)p; }
+}
+__global__ void k_x_mark(const unsigned long long *__restrict__ ka, const uint32_t *__restrict__ vi, const XRec *__restrict__ recv, FpStore S,
+                         int64_t m, uint8_t *__restrict__ marks, unsigned long long *__restrict__ new_a, unsigned long long *__restrict__ new_b,
+                         unsigned long long *n_store) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= m) return;
     const unsigned long long key = ka[p] >> (64 - FP_SORT_BITS);
     if (p > 0 && (ka[p - 1] >> (64 - FP_SORT_BITS)) == key) return;
     int64_t e = p + 1;
     while (e < m && (ka[e] >> (64 - FP_SORT_BITS)) == key) ++e;
-    if (e == p + 1) return;
     for (int64_t s = p; s < e; ++s) {
-        const XRec xs = recv[vi[s]];
+        unsigned long long sa, sb, qa, qb;
+        x_of_entry(vi[s], recv, S, sa, sb);
         bool first = true;
-        for (int64_t q = p; q < s; ++q) { const XRec xq = recv[vi[q]]; if (xq.a == xs.a && xq.b == xs.b) { first = false; break; } }
+        for (int64_t q = p; q < s; ++q) { x_of_entry(vi[q], recv, S, qa, qb); if (qa == sa && qb == sb) { first = false; break; } }
         if (!first) continue;
+        bool stored = false;
         long long keeper = LLONG_MAX;
         for (int64_t q = s; q < e; ++q) {
-            const XRec xq = recv[vi[q]];
-            if (xq.a != xs.a || xq.b != xs.b) continue;
-            if ((xq.gp & 1) && (xq.gp >> 1) < keeper) keeper = xq.gp >> 1;
+            const uint32_t v = vi[q];
+            if (q > s) { x_of_entry(v, recv, S, qa, qb); if (qa != sa || qb != sb) continue; }
+            if (v & FP_STORED) stored = true;
+            else { const long long gp = recv[v].gp; if ((gp & 1) && (gp >> 1) < keeper) keeper = gp >> 1; }
         }
-        if (keeper == LLONG_MAX) continue;
+        if (!stored && keeper == LLONG_MAX) continue;
+        if (!stored) { const unsigned long long o = atomicAdd(n_store, 1ull); new_a[o] = sa; new_b[o] = sb; }
         for (int64_t q = s; q < e; ++q) {
-            const XRec xq = recv[vi[q]];
-            if (xq.a != xs.a || xq.b != xs.b) continue;
-            if ((xq.gp >> 1) > keeper) marks[vi[q]] = 1;
+            const uint32_t v = vi[q];
+            if (v & FP_STORED) continue;
+            if (q > s) { x_of_entry(v, recv, S, qa, qb); if (qa != sa || qb != sb) continue; }
+            if (stored || (recv[v].gp >> 1) > keeper) marks[v] = 1;
         }
     }
 }
@@ -3035,19 +3102,31 @@ extern "C" int mcx_dedup_owner(mcx_ctx *ctx, const void *d_recv, int64_t m, void
     if ((rc = ensure(ctx, &ctx->d_fpi2, &ctx->cap_fpi2, mm)) != MCX_OK) return rc;
     CK(cudaEventRecord(ctx->ev[18], st));
     CK(cudaMemsetAsync(ctx->d_xmarks, 0, (size_t)mm, st));
-    if (m > 1) {
+    const int64_t mt = m + ctx->n_store;                 // the records of this round + the fingerprints this rank has kept before
+    if (mt >= (1ll << 31)) return fail(ctx, MCX_EINVAL, "mcx_dedup_owner: more than 2^31 fingerprints on one rank");
+    if (m > 0) {
+        if ((rc = ensure(ctx, &ctx->d_fpa, &ctx->cap_fpa, mt)) != MCX_OK) return rc;
+        if ((rc = ensure(ctx, &ctx->d_fpa2, &ctx->cap_fpa2, mt)) != MCX_OK) return rc;
+        if ((rc = ensure(ctx, &ctx->d_xvi, &ctx->cap_xvi, mt)) != MCX_OK) return rc;
+        if ((rc = ensure(ctx, &ctx->d_fpi2, &ctx->cap_fpi2, mt)) != MCX_OK) return rc;
+        if ((rc = reserve_store(ctx, ctx->n_store + m)) != MCX_OK) return rc;
         const XRec *recv = reinterpret_cast<const XRec *>(d_recv);
-        const unsigned gb = (unsigned)((m + 255) / 256);
-        k_x_keys<<<gb, 256, 0, st>>>(recv, m, ctx->d_xkg, ctx->d_fpa, ctx->d_xvi);
+        const FpStore S{ctx->d_store_a, ctx->d_store_b};
+        k_x_keys<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(recv, m, ctx->d_xkg, ctx->d_fpa, ctx->d_xvi);
+        if (ctx->n_store > 0) k_x_keys_store<<<(unsigned)((ctx->n_store + 255) / 256), 256, 0, st>>>(S, m, ctx->n_store, ctx->d_fpa, ctx->d_xvi);
         size_t tb = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_xvi, ctx->d_fpi2, (int)m, 64 - FP_SORT_BITS, 64, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_xvi, ctx->d_fpi2, (int)mt, 64 - FP_SORT_BITS, 64, st);
         if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
-        cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_xvi, ctx->d_fpi2, (int)m, 64 - FP_SORT_BITS, 64, st);
-        k_x_mark<<<gb, 256, 0, st>>>(ctx->d_fpa2, ctx->d_fpi2, recv, m, ctx->d_xmarks);
-        ctx->launches += 9;
+        cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_xvi, ctx->d_fpi2, (int)mt, 64 - FP_SORT_BITS, 64, st);
+        ctx->h_cnt[C_NSTORE] = (unsigned long long)ctx->n_store;
+        CK(cudaMemcpyAsync(ctx->d_cnt + C_NSTORE, ctx->h_cnt + C_NSTORE, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+        k_x_mark<<<(unsigned)((mt + 255) / 256), 256, 0, st>>>(ctx->d_fpa2, ctx->d_fpi2, recv, S, mt, ctx->d_xmarks, ctx->d_store_a, ctx->d_store_b, ctx->d_cnt + C_NSTORE);
+        CK(cudaMemcpyAsync(ctx->h_cnt + C_NSTORE, ctx->d_cnt + C_NSTORE, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        ctx->launches += 10;
     }
     CK(cudaEventRecord(ctx->ev[12], st));
     if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
+    if (m > 0) ctx->n_store = (int64_t)ctx->h_cnt[C_NSTORE];
     { float t = 0.f; if (cudaEventElapsedTime(&t, ctx->ev[18], ctx->ev[12]) == cudaSuccess) ctx->ms[11] += t; }
     *d_marks = ctx->d_xmarks;
     return MCX_OK;
@@ -3144,7 +3223,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
 
     float ms_frames = 0, ms_seg = 0, ms_probe = 0, ms_ext = 0, ms_gap = 0;
     unsigned long long n_surv = 0, n_cand_total = 0, n_seeds_total = 0;
-    int64_t remaining = quota, sampled = 0;
+    int64_t remaining = quota, sampled = 0, examined = 0;
     for (int c = 0; c < nb && (quota < 0 || remaining > 0); ++c) {
         const int64_t r0 = bounds[(size_t)c], r1 = bounds[(size_t)c + 1], nr_in = r1 - r0;
         // ---- K1 on this chunk: verdicts, list of kept reads
@@ -3176,6 +3255,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             remaining -= nr;
         }
         if (upto > r0) { k_count_codes<<<592, 256, 0, st>>>(ctx->d_code + r0, upto - r0, ctx->d_cnt + C_QC0); ++ctx->launches; }
+        examined = upto;
         if (nr == 0) continue;
         const int64_t nr_max = nr < 0 ? nr_in : nr;        // launch bound; the kernels read the count on the device
         CK(cudaMemsetAsync(ctx->d_cnt + C_SEGQ, 0, 2 * sizeof(unsigned long long), st));   // SEG queue length, k_seg's work counter
@@ -3331,6 +3411,14 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[8]); ms_ext += t;
         cudaEventElapsedTime(&t, ctx->ev[8], ctx->ev[9]); ms_gap += t;
     }
+    if (P.filter_dups && ctx->fp_done && examined > 0) {
+        // streamed -d: the reads kept by this push are what later pushes of the run must not repeat (mc.py:355)
+        if ((rc = reserve_store(ctx, ctx->n_store + examined)) != MCX_OK) return rc;
+        hc[C_NSTORE] = (unsigned long long)ctx->n_store;
+        CK(cudaMemcpyAsync(ctx->d_cnt + C_NSTORE, hc + C_NSTORE, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+        k_store_append<<<(unsigned)((examined + 255) / 256), 256, 0, st>>>(ctx->d_fp, ctx->d_code, examined, ctx->d_store_a, ctx->d_store_b, ctx->d_cnt + C_NSTORE);
+        ++ctx->launches;
+    }
     R.sampled_reads = sampled;
     R.n_seed_hits = (int64_t)n_surv;
     ctx->n_cand_last = (int64_t)n_cand_total;
@@ -3366,6 +3454,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     CK(cudaEventRecord(ctx->ev[7], st));
     if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
     R.too_short = (int64_t)hc[C_QC0 + 1]; R.low_qual = (int64_t)hc[C_QC0 + 2]; R.dups = (int64_t)hc[C_QC0 + 3];
+    if (P.filter_dups && ctx->fp_done && examined > 0) ctx->n_store = (int64_t)hc[C_NSTORE];
     R.reads_with_hits = (int64_t)acc[0]; R.reads_classified = (int64_t)acc[1]; R.n_hsp = (int64_t)acc[2];
     R.n_gapped = (int64_t)hc[C_NGAPTOT]; R.gapped_cells = (int64_t)hc[C_CELLS];
     R.n_capped_reads = (int64_t)hc[C_NCAP];

@@ -168,6 +168,47 @@ def exchange_duplicates_device(engine, first_index, group=None, device=None):
     return qc
 
 
+def sharded_round(engine, batch, first_index, remaining, filter_dups=False, group=None, device=None):
+    """One round of a streamed sharded run: every rank pushes ITS batch of the round (global index of its first read =
+    first_index; an empty batch when the input has run out for it), duplicates are settled across ranks (and against the
+    reads kept in earlier rounds: the owners remember them), the -n quota still open (`remaining`, None = no limit) is
+    shared out by an all-gather of the kept counts, and the rank searches its part.  Returns (local SearchResult -- NOT
+    reduced --, reads sampled by all ranks in this round)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    engine.push(batch)
+    dev = device or (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu"))
+    qc = None
+    if filter_dups:
+        if dev.type == "cuda":
+            qc = exchange_duplicates_device(engine, first_index, group=group, device=dev)
+        else:
+            codes, fps = engine.qc_export(True)
+            qc = engine.qc_import(exchange_duplicates(codes, fps, first_index, group=group, device=dev))
+    if qc is None:
+        qc = engine.qc()
+    kept = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(kept, torch.tensor([qc["kept"]], dtype=torch.int64, device=dev), group=group)
+    kept = [int(k) for k in kept]
+    quota = shard_quota(kept, remaining, rank)
+    res = engine.search(quota)
+    total = sum(kept)
+    return res, (total if remaining is None or remaining < 0 else min(total, remaining))
+
+
+def allreduce_result(res, group=None, device=None):
+    """sum the additive results over the ranks, in place"""
+    import torch
+    import torch.distributed as dist
+    dev = device or (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu"))
+    v = torch.from_numpy(res.counts_vector()).to(dev)
+    dist.all_reduce(v, group=group)
+    res.load_counts_vector(v.cpu().numpy())
+    return res
+
+
 def sharded_search(engine, batch, first_index, nreads=None, filter_dups=False, group=None, device=None, push=None):
     """Search this rank's block of reads (already `set_params`-ed engine) and return the all-reduced SearchResult.
 

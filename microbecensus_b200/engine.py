@@ -212,6 +212,11 @@ class MarkerSearch:
         rc = self.lib.mcx_create(C.byref(self.ctx), C.byref(self._db), int(device))
         if rc != 0:
             _lib.check(self.lib, None, rc)
+        try:                                     # batches of the file reader now come in page-locked memory
+            from . import seqio
+            seqio.use_pinned_buffers(self.lib)
+        except OSError:
+            pass
         self.read_length = None
         self._batch = None
 
@@ -299,6 +304,10 @@ class MarkerSearch:
         """rebuild the kept list after the verdicts were rewritten in device memory"""
         self._ck(self.lib.mcx_qc_refresh(self.ctx))
         return self.qc()
+
+    def dedup_reset(self):
+        """forget the fingerprints kept by earlier pushes (start of a run with -d)"""
+        self._ck(self.lib.mcx_dedup_reset(self.ctx))
 
     def dedup_begin(self, world, first_index):
         """-d across ranks, step 1 (mcx_dedup_begin): (device pointer to the records grouped by owner rank, records per owner)"""

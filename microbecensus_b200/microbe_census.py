@@ -297,24 +297,92 @@ def _dump_m8(eng, fh, read_length, first_id):
 
 
 # ------------------------------------------------------------------------------------------------ the GPU seam
+class _Prefetch:
+    """Batches of one input file, parsed and packed ahead of the search by a thread of their own (libmcxio does the work
+    with the GIL released, on `threads` threads: the -t option).  Paired files get one of these each, so the second file is
+    inflating / being parsed while the first is searched.  Under a sharded run every rank walks the whole file but only
+    keeps every world-th batch (the others are skipped without being stored)."""
+
+    def __init__(self, path, per_batch, threads, first_batch_no, world, rank, want_total):
+        import queue
+        import threading
+        self.path, self.q = path, queue.Queue(maxsize=2)
+        self.halt = threading.Event()
+        self.error = None
+        self.n_batches = None                        # batches this file was cut into, known once the thread is done
+        self.bases_total = None
+        self.records_seen = 0                        # records in the batches handed out (or skipped) so far
+        self._args = (per_batch, threads, first_batch_no, world, rank, want_total)
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        per_batch, threads, batch_no, world, rank, want_total = self._args
+        try:
+            with SeqFile(self.path) as rd:
+                first_record = 0
+                while not rd.eof and not self.halt.is_set():
+                    if batch_no % world == rank:
+                        pb = rd.next_packed(per_batch, threads)
+                        n = pb.n
+                        item = (batch_no, first_record, pb, getattr(rd, "last_without_quality", False))
+                    else:
+                        n = rd.skip_packed(per_batch, threads)
+                        item = (batch_no, first_record, None, False)
+                    if n == 0 and rd.eof:
+                        break
+                    self.q.put(item)
+                    first_record += n
+                    self.records_seen = first_record
+                    batch_no += 1
+                if not rd.eof and want_total:
+                    rd.skip_rest()
+                if rd.eof:
+                    self.bases_total = rd.bases_total
+                self.n_batches = batch_no
+        except BaseException as exc:              # handed to the consumer
+            self.error = exc
+        self.q.put(None)
+
+    def __iter__(self):
+        while True:
+            item = self.q.get()
+            if item is None:
+                if self.error is not None:
+                    raise self.error
+                return
+            yield item
+
+    def stop(self):
+        self.halt.set()
+        while self.thread.is_alive():           # let a producer blocked on the full queue see the flag
+            try:
+                self.q.get(timeout=0.05)
+            except Exception:
+                pass
+        self.thread.join()
+
+
+# ------------------------------------------------------------------------------------------------ the GPU seam
 def sample_and_search(args, engine=None):
     """process_seqfile + search_seqs + classify_reads + aggregate_hits (mc.py:611-620) on the GPU.
 
-    Files are taken in order and concatenated (mc.py:337: paired files are processed one after the other);
-    the device applies the filter chain too-short -> low-quality per read and the `-n` cut as "first nreads
-    kept reads"; counters are those of the reference loop up to the read that filled the quota."""
+    Files are taken in order (mc.py:337: paired files are processed one after the other) and streamed: libmcxio parses
+    and packs batches of records on args['threads'] threads into page-locked buffers, each batch is pushed (an
+    asynchronous copy) and searched while the next one is being parsed; reading stops with the batch in which the
+    `-n`-th read was kept (mc.py:356).  The device applies the filter chain too-short -> duplicate -> low-quality per read
+    (the duplicate filter remembers the reads kept by earlier batches) and the `-n` cut as "first nreads kept reads";
+    the counters are those of the reference loop up to the read that filled the quota.  Under torchrun (one process per
+    GPU) the ranks walk the files together, rank r keeps every world-th batch, and -n / -d / the sums are made global by
+    microbecensus_b200.distributed -- no rank ever holds more than its batches."""
     eng = engine or get_engine()
     if args["verbose"]:
         print("====Estimating Average Genome Size====")
         print("Sampling & trimming reads...")
     L = args["read_length"]
     fastq = args["file_type"] == "fastq"
-    eng.set_params(L, quality_offset=args.get("quality_offset") if fastq else None,
-                   min_quality=args["min_quality"], mean_quality=args["mean_quality"],
-                   max_unknown=args["max_unknown"], filter_dups=bool(args.get("filter_dups")))
     nreads = args["nreads"]
-    # under torchrun every rank parses the input and searches its contiguous block of the read stream; -n, -d and
-    # the sums are made global by microbecensus_b200.distributed (one all-reduce + two small all-gathers)
+    threads = max(1, int(args.get("threads") or 1))
     world, rank = 1, 0
     if "torch" in sys.modules or int(os.environ.get("WORLD_SIZE", "1")) > 1:
         # (a plain single-GPU run never imports torch: the import alone costs more than searching a million reads)
@@ -324,11 +392,11 @@ def sample_and_search(args, engine=None):
                 world, rank = dist.get_world_size(), dist.get_rank()
         except ImportError:
             pass
-
-    def checked(batch):
-        if fastq and batch.quals is None and batch.n:
-            raise ValueError("FASTQ input without qualities")
-        return batch if fastq else ReadBatch(batch.bases, batch.offsets, None)
+    dups = bool(args.get("filter_dups"))
+    # in a sharded run the duplicates are settled between the ranks (the engine's own filter only sees its batches)
+    eng.set_params(L, quality_offset=args.get("quality_offset") if fastq else None,
+                   min_quality=args["min_quality"], mean_quality=args["mean_quality"],
+                   max_unknown=args["max_unknown"], filter_dups=dups and world == 1)
 
     want_total = args.get("no_equivs") is False      # the CLI will ask count_bases() next: finish the files in this pass
     # optional m8-compatible dump of the reported HSPs (args["m8_out"] or $MCX_M8_OUT; single-GPU runs)
@@ -336,50 +404,75 @@ def sample_and_search(args, engine=None):
     m8 = open(m8_path, "w") if m8_path and world == 1 else None
     if m8:
         m8.write("# Fields: Query\tSubject\tidentity\taln-len\tmismatch\tgap-openings\tq.start\tq.end\ts.start\ts.end\tlog(e-value)\tbit-score\n")
-    if world > 1 or args.get("filter_dups"):
-        # -d and the sharded run need the whole read stream at once (duplicates are decided over all reads)
-        batch = checked(concat_batches([load_reads(f) for f in args["seqfiles"]]))
-        if world > 1:
-            from .distributed import sharded_search
-            eng.set_params(L, quality_offset=args.get("quality_offset") if fastq else None, min_quality=args["min_quality"],
-                           mean_quality=args["mean_quality"], max_unknown=args["max_unknown"], filter_dups=False)
-            lo, hi = rank * batch.n // world, (rank + 1) * batch.n // world
-            res = sharded_search(eng, batch.slice(lo, hi), lo, nreads=nreads, filter_dups=bool(args.get("filter_dups")))
-        else:
-            eng.push(batch)
-            res = eng.search(-1 if nreads is None else nreads)
-            if m8:
-                _dump_m8(eng, m8, L, 0)
-    else:
-        # stream: batches of records go to the GPU as they are parsed; reading stops with the read that fills -n
-        # (mc.py:356) and the additive results of the batches are summed
-        per_batch = int(os.environ.get("MCX_BATCH_READS", "8000000"))
-        res, remaining = None, nreads
-        for path in args["seqfiles"]:
+    per_batch = int(os.environ.get("MCX_BATCH_READS", "4000000"))
+    empty = ReadBatch(np.zeros(0, np.uint8), np.zeros(1, np.int64), None if not fastq else np.zeros(0, np.uint8))
+
+    def checked(pb, cut_short):
+        if fastq and pb.n and pb.quals is None:
+            raise ValueError("FASTQ input without qualities")
+        if fastq and cut_short and pb.n and int(pb.lengths[-1]) >= L:
+            # the file ends inside a FASTQ record: the reference yields it without qualities (mc.py:323) and fails in
+            # quality_filter (mc.py:272, rec.phred() of None) -- the same error text, caught by run_pipeline the same way
+            raise TypeError("'NoneType' object is not iterable")
+        if not fastq and pb.quals is not None:
+            pb.quals = None
+        return pb
+
+    res, remaining = None, nreads
+    records_before = 0            # records of the files already finished (global read index = this + index in the file)
+    batch_no = 0
+    if world > 1:
+        from .distributed import sharded_round, allreduce_result
+    readers = [_Prefetch(path, per_batch, threads, 0, world, rank, want_total) for path in args["seqfiles"][:1]]
+    try:
+        for fi, path in enumerate(args["seqfiles"]):
             if remaining is not None and remaining <= 0:
                 break
-            with SeqFile(path) as rd:
-                while not rd.eof and (remaining is None or remaining > 0):
-                    batch = checked(rd.next_batch(per_batch, copy=False))
-                    if batch.n == 0:
-                        break
-                    eng.push(batch)
+            rd = readers[fi]
+            if fi + 1 < len(args["seqfiles"]) and len(readers) == fi + 1:
+                # the next file starts being read now (its batch numbers continue where this file will end only matter for
+                # the round-robin of a sharded run, which therefore reads the files one after the other)
+                if world == 1:
+                    readers.append(_Prefetch(args["seqfiles"][fi + 1], per_batch, threads, 0, 1, 0, want_total))
+            pending = []                      # sharded: the batches of the current round
+            for bno, first_record, pb, cut_short in rd:
+                if world == 1:
+                    eng.push(checked(pb, cut_short))
                     part = eng.search(-1 if remaining is None else remaining)
                     if m8:
                         _dump_m8(eng, m8, L, 0 if res is None else res.sampled_reads)
                     if remaining is not None:
                         remaining -= part.sampled_reads
-                    if res is None:
-                        res = part
-                    else:
-                        res.load_counts_vector(res.counts_vector() + part.counts_vector())
-                if want_total and not rd.eof:
-                    rd.skip_rest()
-                if rd.eof:
-                    _base_counts[_file_key(path)] = rd.bases_total
-        if res is None:
-            eng.push(ReadBatch(np.zeros(0, np.uint8), np.zeros(1, np.int64), None if not fastq else np.zeros(0, np.uint8)))
-            res = eng.search(-1)
+                    res = part if res is None else _add_results(res, part)
+                    if remaining is not None and remaining <= 0:
+                        break
+                else:
+                    pending.append((bno, first_record, pb, cut_short))
+                    if len(pending) == world:
+                        res, remaining = _sharded_round(eng, pending, rank, records_before, remaining, dups, res, checked, empty, sharded_round)
+                        pending = []
+                        if remaining is not None and remaining <= 0:
+                            break
+            if world > 1 and pending and not (remaining is not None and remaining <= 0):
+                res, remaining = _sharded_round(eng, pending, rank, records_before, remaining, dups, res, checked, empty, sharded_round)
+            if remaining is not None and remaining <= 0:
+                rd.stop()
+            else:
+                rd.thread.join()
+            if world > 1 and fi + 1 < len(args["seqfiles"]) and not (remaining is not None and remaining <= 0):
+                readers.append(_Prefetch(args["seqfiles"][fi + 1], per_batch, threads, 0, world, rank, want_total))
+            if rd.bases_total is not None:
+                _base_counts[_file_key(path)] = rd.bases_total
+            records_before += rd.records_seen
+    finally:
+        for r in readers:
+            if r.thread.is_alive():
+                r.stop()
+    if res is None:
+        eng.push(empty)
+        res = eng.search(-1)
+    if world > 1:
+        res = allreduce_result(res)
     if m8:
         m8.close()
     if res.sampled_reads == 0:
@@ -398,6 +491,27 @@ def sample_and_search(args, engine=None):
     if args["verbose"]:
         print("\t%s reads assigned to a marker protein" % res.reads_classified)
     return res.agg_hits(), res
+
+
+def _add_results(res, part):
+    res.load_counts_vector(res.counts_vector() + part.counts_vector())
+    return res
+
+
+def _sharded_round(eng, pending, rank, records_before, remaining, dups, res, checked, empty, sharded_round):
+    """one round of a sharded streamed run: `pending` = the (up to world) consecutive batches of the round, of which this
+    rank owns at most one (the one with a payload)"""
+    mine = [p for p in pending if p[2] is not None]
+    if mine:
+        bno, first_record, pb, cut_short = mine[0]
+        batch, first_index = checked(pb, cut_short), records_before + first_record
+    else:
+        batch, first_index = empty, records_before
+    part, sampled = sharded_round(eng, batch, first_index, remaining, filter_dups=dups)
+    res = part if res is None else _add_results(res, part)
+    if remaining is not None:
+        remaining -= sampled
+    return res, remaining
 
 
 def estimate_average_genome_size(args, paths, agg_hits):

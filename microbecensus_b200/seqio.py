@@ -6,15 +6,43 @@ import os
 
 import numpy as np
 
-from .engine import ReadBatch
+from .engine import ReadBatch, PackedBatch
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmcxio.so")
-EXPORTS = ("mcxio_open", "mcxio_open_mem", "mcxio_next_batch", "mcxio_skip_rest", "mcxio_close", "mcxio_last_error")
+EXPORTS = ("mcxio_open", "mcxio_open_mem", "mcxio_next_batch", "mcxio_next_packed", "mcxio_skip_packed", "mcxio_state", "mcxio_free_packed", "mcxio_set_allocator",
+           "mcxio_skip_rest", "mcxio_close", "mcxio_last_error")
 
 
 class Batch(C.Structure):
     _fields_ = [("bases", C.c_void_p), ("quals", C.c_void_p), ("offsets", C.c_void_p), ("n", C.c_int64),
                 ("records_total", C.c_int64), ("bases_total", C.c_int64), ("eof", C.c_int32)]
+
+
+class Packed(C.Structure):
+    _fields_ = [("packed", C.c_void_p), ("lengths", C.c_void_p), ("quals", C.c_void_p), ("n", C.c_int64), ("n_words", C.c_int64),
+                ("n_bases", C.c_int64), ("records_total", C.c_int64), ("bases_total", C.c_int64), ("eof", C.c_int32),
+                ("last_without_quality", C.c_int32), ("reparsed", C.c_int64)]
+
+
+class _PackedOwner:
+    """keeps the reader's output buffers alive for the numpy views and releases them through the reader's allocator"""
+    def __init__(self, lib, rec):
+        self.lib, self.rec = lib, rec
+
+    def __del__(self):
+        try:
+            if self.rec is not None:
+                self.lib.mcxio_free_packed(C.byref(self.rec))
+                self.rec = None
+        except Exception:
+            pass
+
+
+def use_pinned_buffers(libmcx):
+    """Packed batches from now on come in page-locked memory from libmcx (mcx_host_alloc): the push to the GPU is then an
+    asynchronous DMA that overlaps the search (called by MarkerSearch once a GPU context exists)."""
+    lib = load()
+    lib.mcxio_set_allocator(C.cast(libmcx.mcx_host_alloc, C.c_void_p), C.cast(libmcx.mcx_host_free, C.c_void_p))
 
 
 class SeqIOError(IOError):
@@ -35,6 +63,12 @@ def load():
     lib.mcxio_open.argtypes = [C.POINTER(vp), C.c_char_p]
     lib.mcxio_open_mem.argtypes = [C.POINTER(vp), vp, i64]
     lib.mcxio_next_batch.argtypes = [vp, i64, C.POINTER(Batch)]
+    lib.mcxio_next_packed.argtypes = [vp, i64, C.c_int, C.POINTER(Packed)]
+    lib.mcxio_skip_packed.argtypes = [vp, i64, C.c_int, C.POINTER(i64)]
+    lib.mcxio_state.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_int32)]
+    lib.mcxio_free_packed.argtypes = [C.POINTER(Packed)]
+    lib.mcxio_free_packed.restype = None
+    lib.mcxio_set_allocator.argtypes = [vp, vp]
     lib.mcxio_skip_rest.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     lib.mcxio_close.argtypes = [vp]
     lib.mcxio_close.restype = None
@@ -103,6 +137,36 @@ class SeqFile:
             offs, bases, quals = offs.copy(), bases.copy(), None if quals is None else quals.copy()
         self.records_total, self.bases_total, self.eof = b.records_total, b.bases_total, bool(b.eof)
         return ReadBatch(bases, offs, quals)
+
+    def next_packed(self, target_records=None, threads=1):
+        """About target_records further records (None: the rest of the file) as a PackedBatch -- the layout of the reads
+        in HBM -- parsed and packed by `threads` threads (include/mcxio.h).  The batch owns its buffers."""
+        rec = Packed()
+        rc = self._lib.mcxio_next_packed(self._h, -1 if target_records is None else int(target_records), int(threads), C.byref(rec))
+        if rc != 0:
+            raise SeqIOError(self._lib.mcxio_last_error(self._h).decode())
+        owner = _PackedOwner(self._lib, rec)
+        pb = PackedBatch.__new__(PackedBatch)
+        pb.packed = _view(rec.packed, rec.n_words, np.uint32)
+        pb.lengths = _view(rec.lengths, rec.n, np.uint32)
+        pb.quals = _view(rec.quals, rec.n_bases, np.uint8) if rec.quals else None
+        pb.n, pb.n_bases = int(rec.n), int(rec.n_bases)
+        pb._owners = [owner]
+        self.records_total, self.bases_total, self.eof = rec.records_total, rec.bases_total, bool(rec.eof)
+        self.last_without_quality = bool(rec.last_without_quality)
+        self.reparsed = int(rec.reparsed)
+        return pb
+
+    def skip_packed(self, target_records=None, threads=1):
+        """Advance by the records the same next_packed call would return, without storing them; returns how many."""
+        n = C.c_int64(0)
+        rc = self._lib.mcxio_skip_packed(self._h, -1 if target_records is None else int(target_records), int(threads), C.byref(n))
+        if rc != 0:
+            raise SeqIOError(self._lib.mcxio_last_error(self._h).decode())
+        rt, bt, eof = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+        self._lib.mcxio_state(self._h, C.byref(rt), C.byref(bt), C.byref(eof))
+        self.records_total, self.bases_total, self.eof = rt.value, bt.value, bool(eof.value)
+        return int(n.value)
 
     def skip_rest(self):
         """Parse to the end of the file without storing records; returns (records, bases) of the whole file."""

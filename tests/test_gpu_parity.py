@@ -361,6 +361,40 @@ def test_streamed_batches_equal_one_push(eng, markers, tmp_path, monkeypatch):
     assert mcb.estimate_average_genome_size({"read_length": 100, "sampled_reads": 411, "verbose": False}, None, res.agg_hits()) == results[2][1]
 
 
+def test_streamed_duplicate_filter_and_threads(eng, oracle, markers, tmp_path, monkeypatch):
+    """-d over a file that arrives in many batches (the context remembers the reads kept by earlier batches), parsed by
+    several threads (-t): counters and AGS are those of the oracle's sequential set / of one push of everything."""
+    n = 20000
+    base = synth.reads(9, 0, n, 100, with_quals=True)
+    rng = np.random.default_rng(4)
+    b, q = base.bases.reshape(n, 100).copy(), base.quals.reshape(n, 100).copy()
+    comp = np.zeros(256, np.uint8); comp[[65, 67, 71, 84, 78]] = [84, 71, 67, 65, 78]
+    for i in np.flatnonzero(rng.random(n) < 0.08):
+        if i >= 10:
+            j = int(rng.integers(0, i))
+            b[i] = b[j] if rng.random() < 0.8 else comp[b[j][::-1]]
+    seqs = [bytes(r).decode() for r in b]
+    quals = [bytes(r).decode() for r in q]
+    p = tmp_path / "d.fq"
+    p.write_text("".join("@r%d\n%s\n+\n%s\n" % (i, s, q) for i, (s, q) in enumerate(zip(seqs, quals))))
+    batch = ReadBatch.from_strings(seqs, quals)
+    for nreads in (None, 9000):
+        sampled, code, cnt = oracle.process_reads(batch, 100, 32, -5, 29, 100, nreads, filter_dups=True)
+        assert cnt["dups"] > 500 and cnt["low_qual"] > 50
+        eng.set_params(100, quality_offset=32, mean_quality=29, filter_dups=True)
+        eng.push(batch)
+        one = eng.search(-1 if nreads is None else nreads)
+        want = mcb.estimate_average_genome_size({"read_length": 100, "sampled_reads": one.sampled_reads, "verbose": False}, None, one.agg_hits())
+        for per_batch, threads in (("1500", 1), ("1500", 4), ("100000", 8)):
+            monkeypatch.setenv("MCX_BATCH_READS", per_batch)
+            monkeypatch.setenv("MCXIO_WINDOW_BYTES", "300000")
+            args = {"seqfiles": [str(p)], "verbose": False, "nreads": nreads, "read_length": 100, "mean_quality": 29, "filter_dups": True, "threads": threads}
+            est, out = mcb.run_pipeline(args)
+            assert out["sampled_reads"] == sampled == one.sampled_reads, (nreads, per_batch, threads)
+            assert est == want, (nreads, per_batch, threads)
+    monkeypatch.delenv("MCXIO_WINDOW_BYTES")
+
+
 @pytest.mark.gpu
 def test_m8_dump_matches_rapsearch_lines(eng, markers, tmp_path):
     """args['m8_out']: the m8-compatible dump.  On the reference's own reads >= 99 % of RAPsearch2's

@@ -20,7 +20,7 @@ REF = "/root/reference"
 def test_abi_library_exports_every_declared_symbol():
     """libmcx.so loads without a GPU and exports exactly the functions include/mcx.h declares."""
     header = open(os.path.join(ROOT, "include", "mcx.h")).read()
-    declared = set(re.findall(r"\b(mcx_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(mcx_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     lib = _lib.load()
     for name in declared:

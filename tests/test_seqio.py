@@ -57,7 +57,7 @@ def check(batch, recs, label):
 
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "mcxio.h")).read()
-    declared = set(re.findall(r"\b(mcxio_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(mcxio_[a-z0-9_]+)\s*\(", header))
     assert declared == set(seqio.EXPORTS), declared ^ set(seqio.EXPORTS)
     lib = seqio.load()
     for name in declared:
@@ -78,6 +78,98 @@ def test_known_shapes(label, tmp_path):
             fh.write(text.encode())
         with seqio.SeqFile(str(p)) as f:
             check(f.next_batch(), recs, label + ext)
+
+
+def check_packed(parts, recs, label):
+    """batches of SeqFile.next_packed against the readfq records: bit-planes decoded back to letters"""
+    from test_host import _unpack
+    seqs = [s for p in parts for s in _unpack(p)]
+    assert seqs == ["".join(c if c in "ACGTN" else "x" for c in s) for s, _ in recs], label
+    any_q = any(q is not None for _, q in recs)
+    if any_q and seqs:
+        quals = b"".join(p.quals.tobytes() for p in parts if p.quals is not None).decode()
+        want = "".join((q[:len(s)] if q is not None else "~" * len(s)) for s, q in recs)
+        if all(p.quals is not None for p in parts if p.n):
+            assert quals == want, label
+
+
+@pytest.mark.parametrize("label", sorted(CASES))
+def test_packed_reader_known_shapes(label, tmp_path, monkeypatch):
+    """mcxio_next_packed (parallel pieces of a plain file, each checked against the sequential state machine's position;
+    packed output) on the same shapes, with pieces of a few bytes so that every guess / re-parse path runs."""
+    text = CASES[label]
+    recs = records(text)
+    p = tmp_path / "x.txt"
+    p.write_bytes(text.encode())
+    for env in ({}, {"MCXIO_PIECE_BYTES": "7", "MCXIO_MARGIN_BYTES": "5", "MCXIO_WINDOW_BYTES": "23"},
+                {"MCXIO_PIECE_BYTES": "3", "MCXIO_MARGIN_BYTES": "64"}):
+        for k in ("MCXIO_PIECE_BYTES", "MCXIO_MARGIN_BYTES", "MCXIO_WINDOW_BYTES"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for threads in (1, 3, 8):
+            with seqio.SeqFile(str(p)) as f:
+                parts = []
+                for _ in range(10000):
+                    if f.eof:
+                        break
+                    parts.append(f.next_packed(2, threads))
+                assert f.eof and f.records_total == len(recs) and f.bases_total == sum(len(s) for s, _ in recs), (label, env, threads)
+            check_packed(parts, recs, (label, env, threads))
+    with gzip.open(tmp_path / "x.gz", "wb") as fh:
+        fh.write(text.encode())
+    with seqio.SeqFile(str(tmp_path / "x.gz")) as f:
+        parts = [f.next_packed(None, 4)]
+    check_packed(parts, recs, label + ".gz")
+
+
+def test_packed_reader_large_random_files(tmp_path, monkeypatch):
+    """FASTQ with '@' / '+' / '>' quality lines, multi-line FASTA, ragged lengths: the threaded reader returns the records
+    of the sequential one whatever the piece size, and skip_packed / skip_rest walk the same batches."""
+    from microbecensus_b200.engine import PackedBatch
+    rng = random.Random(11)
+    fq = "".join("@r%d d\n%s\n+\n%s\n" % (i, "".join(rng.choice("ACGTN") for _ in range(n)), "".join(rng.choice("@+>I#5") for _ in range(n)))
+                 for i, n in enumerate(rng.randrange(1, 160) for _ in range(6000)))
+    fa = "".join(">s%d\n%s\n" % (i, "\n".join("".join(rng.choice("ACGTacgtN") for _ in range(rng.randrange(1, 70))) for _ in range(rng.randrange(1, 4))))
+                 for i in range(5000))
+    for name, text in (("a.fq", fq), ("a.fa", fa)):
+        p = tmp_path / name
+        p.write_bytes(text.encode())
+        with seqio.SeqFile(str(p)) as f:
+            ref = PackedBatch.from_batch(f.next_batch(None))
+        for env in ({}, {"MCXIO_PIECE_BYTES": "4000", "MCXIO_MARGIN_BYTES": "1500", "MCXIO_WINDOW_BYTES": "50000"},
+                    {"MCXIO_PIECE_BYTES": "200", "MCXIO_MARGIN_BYTES": "100", "MCXIO_WINDOW_BYTES": "3000"}):
+            for k in ("MCXIO_PIECE_BYTES", "MCXIO_MARGIN_BYTES", "MCXIO_WINDOW_BYTES"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            for threads in (2, 8):
+                with seqio.SeqFile(str(p)) as f:
+                    parts, skipped = [], 0
+                    turn = 0
+                    while not f.eof:
+                        if turn % 3 == 2:
+                            skipped += f.skip_packed(700, threads)       # a batch another rank would own
+                            parts.append(None)
+                        else:
+                            parts.append(f.next_packed(700, threads))
+                        turn += 1
+                    assert f.records_total == ref.n and f.bases_total == ref.n_bases
+                # replay: the kept batches are contiguous runs of the reference, the skipped ones fill the holes
+                pos, woff = 0, np.concatenate([[0], np.cumsum(3 * ((ref.lengths.astype(np.int64) + 31) // 32))])
+                with seqio.SeqFile(str(p)) as f2:
+                    k = 0
+                    while not f2.eof:
+                        b = f2.next_packed(700, threads)
+                        if parts[k] is not None:
+                            assert np.array_equal(parts[k].lengths, b.lengths) and np.array_equal(parts[k].packed, b.packed)
+                        assert np.array_equal(b.lengths, ref.lengths[pos:pos + b.n])
+                        assert np.array_equal(b.packed, ref.packed[woff[pos]:woff[pos + b.n]])
+                        if ref.quals is not None:
+                            assert b.quals is not None
+                        pos += b.n
+                        k += 1
+                    assert pos == ref.n and k == len(parts)
 
 
 def test_batches_and_skip_rest(tmp_path):

@@ -39,6 +39,31 @@ for nreads, dups in ((None, False), (250000, False), (None, True), (300000, True
               "classified", res.reads_classified, "EQUAL" if same else "DIFFERENT", flush=True)
         ok &= same
     dist.barrier()
+# ---- run_pipeline under torchrun: the ranks walk the files together in batches, every rank keeps its own; -n, -d (with the
+# owners remembering the reads kept in earlier rounds) and the sums must give what one GPU reading everything gives
+import tempfile
+from microbecensus_b200 import microbe_census as mcb
+tmp = os.environ.get("TMPDIR", "/tmp")
+half = n // 2
+paths = [os.path.join(tmp, "shard_check_%d.fq" % k) for k in (1, 2)]
+if rank == 0:
+    synth.write_fastq(ReadBatch(b[:half].reshape(-1), base.offsets[:half + 1], q[:half].reshape(-1)), paths[0])
+    synth.write_fastq(ReadBatch(b[half:].reshape(-1), base.offsets[:n - half + 1], q[half:].reshape(-1)), paths[1])
+dist.barrier()
+os.environ["MCX_BATCH_READS"] = "30000"
+for nreads, dups in ((None, False), (300000, True), (None, True)):
+    args = {"seqfiles": list(paths), "verbose": False, "nreads": nreads, "read_length": L, "threads": 4, "filter_dups": dups,
+            "min_quality": 5, "mean_quality": 20, "max_unknown": 5}
+    est, out = mcb.run_pipeline(args)
+    if rank == 0:
+        eng.set_params(L, quality_offset=out["quality_offset"], min_quality=5, mean_quality=20, max_unknown=5, filter_dups=dups)
+        eng.push(whole)
+        ref = eng.search(-1 if nreads is None else nreads)
+        want = mcb.estimate_average_genome_size({"read_length": L, "sampled_reads": ref.sampled_reads, "verbose": False}, None, ref.agg_hits())
+        same = est == want and out["sampled_reads"] == ref.sampled_reads
+        print("run_pipeline nreads", nreads, "dups", dups, "sampled", out["sampled_reads"], "AGS", est, "EQUAL" if same else "DIFFERENT (want %s, %s)" % (ref.sampled_reads, want), flush=True)
+        ok &= same
+    dist.barrier()
 if rank == 0:
     print("SHARDED OK" if ok else "SHARDED MISMATCH")
 dist.destroy_process_group()

@@ -2143,6 +2143,7 @@ struct mcx_ctx {
     int64_t cap_xsend = 0, cap_xmarks = 0, cap_xkg = 0, cap_xvi = 0, x_nsend = 0;
     int64_t qc_upto = 0;                       // reads [0, qc_upto) have their verdict
     bool dedup_done = false, fp_done = false, counts_valid = false, kqc_pending = false;
+    bool h2d_timed = false;                    // the last push recorded its copy events (host pushes only)
     mcx_qc qc{};
     bool pushed = false, searched = false;
     // search buffers
@@ -2187,6 +2188,15 @@ enum Cnt { C_QC0 = 0 /* ..3: verdict counts of the search */, C_QCALL = 4 /* ..7
            C_NSTORE = 28, C_XCNT = 64 /* ..191: owner counts and cursors of the -d exchange */, C_N = 192 };
 
 static thread_local std::string g_err;
+
+// elapsed time between two events, 0 when either was never recorded; never leaves an error behind (CUB aborts its next
+// dispatch when cudaPeekAtLastError() still holds the "invalid resource handle" of such a call: a scan that silently did
+// not run once left stale record offsets for the next push)
+static float elapsed_ms(cudaEvent_t a, cudaEvent_t b) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, a, b) != cudaSuccess) { (void)cudaGetLastError(); return 0.f; }
+    return t;
+}
 
 static int fail(mcx_ctx *ctx, int code, const std::string &msg) {
     if (ctx) ctx->err = msg;
@@ -2611,12 +2621,12 @@ static int scan_offsets(mcx_ctx *ctx, bool with_quals) {
     auto gw = thrust::make_transform_iterator(static_cast<const uint32_t *>(ctx->d_len), GroupsOf());
     auto gl = thrust::make_transform_iterator(static_cast<const uint32_t *>(ctx->d_len), LenOf());
     size_t tb = 0, tb2 = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, gw, ctx->d_woff, (int)(n + 1), st);
-    cub::DeviceScan::ExclusiveSum(nullptr, tb2, gl, ctx->d_qoff, (int)(n + 1), st);
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, gw, ctx->d_woff, (int)(n + 1), st));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb2, gl, ctx->d_qoff, (int)(n + 1), st));
     if ((rc = ensure_temp(ctx, std::max(tb, tb2))) != MCX_OK) return rc;
-    cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, gw, ctx->d_woff, (int)(n + 1), st);
+    CK(cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, gw, ctx->d_woff, (int)(n + 1), st));
     ctx->launches += 2;
-    if (with_quals) { cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb2, gl, ctx->d_qoff, (int)(n + 1), st); ctx->launches += 2; }
+    if (with_quals) { CK(cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb2, gl, ctx->d_qoff, (int)(n + 1), st)); ctx->launches += 2; }
     return MCX_OK;
 }
 
@@ -2628,7 +2638,8 @@ static int begin_push(mcx_ctx *ctx, const char *who, int64_t n, bool quals_given
     release_external(ctx);
     ctx->launches = 0; ctx->host_syncs = 0;
     memset(ctx->ms, 0, sizeof ctx->ms);
-    ctx->n_steps = 0; ctx->steps_waited = 0;
+    (void)cudaGetLastError();                  // nothing an earlier call left behind may stop CUB's dispatches
+    ctx->n_steps = 0; ctx->steps_waited = 0; ctx->h2d_timed = false;
     ctx->qc_upto = 0; ctx->dedup_done = false; ctx->fp_done = false; ctx->counts_valid = false;
     ctx->pushed = false; ctx->searched = false;
     return MCX_OK;
@@ -2680,7 +2691,7 @@ extern "C" int mcx_push_reads_packed(mcx_ctx *ctx, const uint32_t *packed, int64
         CK(cudaEventRecord(ctx->ev_copy[k], cs));
     }
     CK(cudaEventRecord(ctx->ev[19], cs));
-    ctx->n_steps = K;
+    ctx->n_steps = K; ctx->h2d_timed = true;
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_len, 0));
     if ((rc = scan_offsets(ctx, quals != nullptr)) != MCX_OK) return rc;
     return end_push(ctx);
@@ -2718,6 +2729,12 @@ static int pack_ascii(mcx_ctx *ctx, const uint8_t *d_bases, const int64_t *d_off
     if ((rc = ensure(ctx, &ctx->d_pk, &ctx->cap_pk, bound)) != MCX_OK) return rc;
     if (n > 0) k_pack_ascii<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(d_bases, d_offsets, n, ctx->d_woff, ctx->d_pk);
     ctx->launches += 2;
+    if (getenv("MCX_DEBUG_PACK")) {
+        long long w[3] = {0, 0, 0}; uint32_t l0 = 0, p0[4] = {0, 0, 0, 0};
+        cudaMemcpy(&w[0], ctx->d_woff + 1, 8, cudaMemcpyDeviceToHost); cudaMemcpy(&w[1], ctx->d_woff + n, 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&l0, ctx->d_len, 4, cudaMemcpyDeviceToHost); cudaMemcpy(p0, ctx->d_pk + w[0], 16, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[mcx] pack_ascii: n %lld len0 %u woff[1] %lld woff[n] %lld bound %lld cap_pk %lld rec1 %08x %08x %08x %08x\n", (long long)n, l0, w[0], w[1], (long long)bound, (long long)ctx->cap_pk, p0[0], p0[1], p0[2], p0[3]);
+    }
     ctx->n_words = -1;            // not known on the host (and not needed: nothing waits on copy steps)
     (void)with_quals;
     return MCX_OK;
@@ -2739,6 +2756,7 @@ extern "C" int mcx_push_reads(mcx_ctx *ctx, const uint8_t *bases, const uint8_t 
     if (quals && total > 0) CK(cudaMemcpyAsync(ctx->d_quals, quals, (size_t)total, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_aoffs, offsets, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(ctx->ev[19], st));
+    ctx->h2d_timed = true;
     if ((rc = pack_ascii(ctx, ctx->d_ascii, ctx->d_aoffs, n, total, quals != nullptr)) != MCX_OK) return rc;
     // the qualities keep the caller's offsets (one byte per base, same offsets as the bases)
     if (quals) {
@@ -2818,8 +2836,7 @@ static int qc_range(mcx_ctx *ctx, int64_t upto) {
 // after a synchronisation: add the time of the last k_qc launch to ms[10]
 static void collect_kqc_time(mcx_ctx *ctx) {
     if (!ctx->kqc_pending) return;
-    float t = 0.f;
-    if (cudaEventElapsedTime(&t, ctx->ev[16], ctx->ev[17]) == cudaSuccess) ctx->ms[10] += t;
+    ctx->ms[10] += elapsed_ms(ctx->ev[16], ctx->ev[17]);
     ctx->kqc_pending = false;
 }
 
@@ -2848,15 +2865,15 @@ static int qc_all(mcx_ctx *ctx) {
             const FpStore S{ctx->d_store_a, ctx->d_store_b};
             k_fp_keys<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(ctx->d_fp, n, S, ctx->n_store, ctx->d_fpa, ctx->d_fpi);
             size_t tb = 0;
-            cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_fpi, ctx->d_fpi2, (int)nt, 64 - FP_SORT_BITS, 64, st);
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_fpi, ctx->d_fpi2, (int)nt, 64 - FP_SORT_BITS, 64, st));
             if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
-            cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_fpi, ctx->d_fpi2, (int)nt, 64 - FP_SORT_BITS, 64, st);
+            CK(cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_fpi, ctx->d_fpi2, (int)nt, 64 - FP_SORT_BITS, 64, st));
             k_mark_dups<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(ctx->d_fpa2, ctx->d_fpi2, ctx->d_fp, S, nt, ctx->d_code);
             ctx->launches += 9;
         }
         CK(cudaEventRecord(ctx->ev[12], st));
         if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
-        { float t = 0.f; if (cudaEventElapsedTime(&t, ctx->ev[18], ctx->ev[12]) == cudaSuccess) ctx->ms[11] += t; }
+        ctx->ms[11] += elapsed_ms(ctx->ev[18], ctx->ev[12]);
         ctx->dedup_done = true;
     }
     CK(cudaEventRecord(ctx->ev[15], st));
@@ -3082,7 +3099,7 @@ extern "C" int mcx_dedup_begin(mcx_ctx *ctx, int world, int64_t first_index, voi
     ctx->launches += 2;
     CK(cudaEventRecord(ctx->ev[12], st));
     if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
-    { float t = 0.f; if (cudaEventElapsedTime(&t, ctx->ev[18], ctx->ev[12]) == cudaSuccess) ctx->ms[11] += t; }
+    ctx->ms[11] += elapsed_ms(ctx->ev[18], ctx->ev[12]);
     *d_send = ctx->d_xsend;
     return MCX_OK;
 }
@@ -3115,9 +3132,9 @@ extern "C" int mcx_dedup_owner(mcx_ctx *ctx, const void *d_recv, int64_t m, void
         k_x_keys<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(recv, m, ctx->d_xkg, ctx->d_fpa, ctx->d_xvi);
         if (ctx->n_store > 0) k_x_keys_store<<<(unsigned)((ctx->n_store + 255) / 256), 256, 0, st>>>(S, m, ctx->n_store, ctx->d_fpa, ctx->d_xvi);
         size_t tb = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_xvi, ctx->d_fpi2, (int)mt, 64 - FP_SORT_BITS, 64, st);
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_xvi, ctx->d_fpi2, (int)mt, 64 - FP_SORT_BITS, 64, st));
         if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
-        cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_xvi, ctx->d_fpi2, (int)mt, 64 - FP_SORT_BITS, 64, st);
+        CK(cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_fpa, ctx->d_fpa2, ctx->d_xvi, ctx->d_fpi2, (int)mt, 64 - FP_SORT_BITS, 64, st));
         ctx->h_cnt[C_NSTORE] = (unsigned long long)ctx->n_store;
         CK(cudaMemcpyAsync(ctx->d_cnt + C_NSTORE, ctx->h_cnt + C_NSTORE, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
         k_x_mark<<<(unsigned)((mt + 255) / 256), 256, 0, st>>>(ctx->d_fpa2, ctx->d_fpi2, recv, S, mt, ctx->d_xmarks, ctx->d_store_a, ctx->d_store_b, ctx->d_cnt + C_NSTORE);
@@ -3127,7 +3144,7 @@ extern "C" int mcx_dedup_owner(mcx_ctx *ctx, const void *d_recv, int64_t m, void
     CK(cudaEventRecord(ctx->ev[12], st));
     if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
     if (m > 0) ctx->n_store = (int64_t)ctx->h_cnt[C_NSTORE];
-    { float t = 0.f; if (cudaEventElapsedTime(&t, ctx->ev[18], ctx->ev[12]) == cudaSuccess) ctx->ms[11] += t; }
+    ctx->ms[11] += elapsed_ms(ctx->ev[18], ctx->ev[12]);
     *d_marks = ctx->d_xmarks;
     return MCX_OK;
 }
@@ -3218,7 +3235,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     if (P.filter_dups || ctx->counts_valid) {     // -d is decided over all reads before anything is searched
         if ((rc = qc_all(ctx)) != MCX_OK) return rc;
         if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
-        float t = 0; cudaEventElapsedTime(&t, ctx->ev[14], ctx->ev[15]); ms_qc += t;
+        ms_qc += elapsed_ms(ctx->ev[14], ctx->ev[15]);
     }
 
     float ms_frames = 0, ms_seg = 0, ms_probe = 0, ms_ext = 0, ms_gap = 0;
@@ -3233,9 +3250,9 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         {
             size_t tb = 0;
             thrust::counting_iterator<int32_t> it((int32_t)r0);
-            cub::DeviceSelect::If(nullptr, tb, it, ctx->d_kept, ctx->d_cnt + C_NKEPT, (int)nr_in, IsKept{ctx->d_code}, st);
+            CK(cub::DeviceSelect::If(nullptr, tb, it, ctx->d_kept, ctx->d_cnt + C_NKEPT, (int)nr_in, IsKept{ctx->d_code}, st));
             if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
-            cub::DeviceSelect::If(ctx->d_temp, tb, it, ctx->d_kept, ctx->d_cnt + C_NKEPT, (int)nr_in, IsKept{ctx->d_code}, st);
+            CK(cub::DeviceSelect::If(ctx->d_temp, tb, it, ctx->d_kept, ctx->d_cnt + C_NKEPT, (int)nr_in, IsKept{ctx->d_code}, st));
             ctx->launches += 2;
         }
         int64_t upto = r1;                      // verdicts counted up to here (mc.py:356 leaves the loop at the read that fills -n)
@@ -3357,9 +3374,9 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             k_gap_list<<<(unsigned)((G.n_surv + 255) / 256), 256, 0, st>>>(G);
             {
                 size_t tb = 0;
-                cub::DeviceRadixSort::SortKeys(nullptr, tb, G.items, list1, (int)(2 * G.n_surv), 32, 40, st);
+                CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, G.items, list1, (int)(2 * G.n_surv), 32, 40, st));
                 if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
-                cub::DeviceRadixSort::SortKeys(ctx->d_temp, tb, G.items, list1, (int)(2 * G.n_surv), 32, 40, st);
+                CK(cub::DeviceRadixSort::SortKeys(ctx->d_temp, tb, G.items, list1, (int)(2 * G.n_surv), 32, 40, st));
             }
             CK(cudaMemsetAsync(ctx->d_cnt + C_ITEMS2, 0, sizeof(unsigned long long), st));
             CK(cudaMemsetAsync(ctx->d_cnt + C_WORK1, 0, 2 * sizeof(unsigned long long), st));
@@ -3403,13 +3420,12 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         }
         CK(cudaEventRecord(ctx->ev[9], st));
         if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
-        float t;
-        cudaEventElapsedTime(&t, ctx->ev[14], ctx->ev[2]); ms_qc += t;
-        cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[10]); ms_frames += t;
-        cudaEventElapsedTime(&t, ctx->ev[10], ctx->ev[11]); ms_seg += t;
-        cudaEventElapsedTime(&t, ctx->ev[11], ctx->ev[3]); ms_probe += t;
-        cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[8]); ms_ext += t;
-        cudaEventElapsedTime(&t, ctx->ev[8], ctx->ev[9]); ms_gap += t;
+        ms_qc += elapsed_ms(ctx->ev[14], ctx->ev[2]);
+        ms_frames += elapsed_ms(ctx->ev[2], ctx->ev[10]);
+        ms_seg += elapsed_ms(ctx->ev[10], ctx->ev[11]);
+        ms_probe += elapsed_ms(ctx->ev[11], ctx->ev[3]);
+        ms_ext += elapsed_ms(ctx->ev[3], ctx->ev[8]);
+        ms_gap += elapsed_ms(ctx->ev[8], ctx->ev[9]);
     }
     if (P.filter_dups && ctx->fp_done && examined > 0) {
         // streamed -d: the reads kept by this push are what later pushes of the run must not repeat (mc.py:355)
@@ -3426,9 +3442,9 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     CK(cudaEventRecord(ctx->ev[4], st));
     if (ns > 0) {
         size_t tb = 0;
-        cub::DeviceMergeSort::SortPairs(nullptr, tb, ctx->d_keys, ctx->d_idx, ns, SortKeyLess(), st);
+        CK(cub::DeviceMergeSort::SortPairs(nullptr, tb, ctx->d_keys, ctx->d_idx, ns, SortKeyLess(), st));
         if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
-        cub::DeviceMergeSort::SortPairs(ctx->d_temp, tb, ctx->d_keys, ctx->d_idx, ns, SortKeyLess(), st);
+        CK(cub::DeviceMergeSort::SortPairs(ctx->d_temp, tb, ctx->d_keys, ctx->d_idx, ns, SortKeyLess(), st));
         ctx->launches += 3;
     }
     CK(cudaEventRecord(ctx->ev[5], st));
@@ -3463,10 +3479,11 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     for (int f = 0; f < MCX_N_FAM; ++f) { R.fam_hits[f] = (int64_t)acc[3 + f]; R.fam_aln[f] = (int64_t)acc[3 + MCX_N_FAM + f]; }
     for (size_t k = 0; k < abl.size(); ++k) R.aln_by_len[k] = (int64_t)abl[k];
     ctx->ms[1] = ms_qc; ctx->ms[2] = ms_probe; ctx->ms[7] = ms_ext; ctx->ms[3] = ms_gap; ctx->ms[8] = ms_frames; ctx->ms[9] = ms_seg;
-    cudaEventElapsedTime(&ctx->ms[4], ctx->ev[4], ctx->ev[5]);
-    cudaEventElapsedTime(&ctx->ms[5], ctx->ev[5], ctx->ev[6]);
-    cudaEventElapsedTime(&ctx->ms[6], ctx->ev[6], ctx->ev[7]);
-    if (cudaEventQuery(ctx->ev[19]) == cudaSuccess && cudaEventQuery(ctx->ev_h2d0) == cudaSuccess) cudaEventElapsedTime(&ctx->ms[0], ctx->ev_h2d0, ctx->ev[19]);
+    ctx->ms[4] = elapsed_ms(ctx->ev[4], ctx->ev[5]);
+    ctx->ms[5] = elapsed_ms(ctx->ev[5], ctx->ev[6]);
+    ctx->ms[6] = elapsed_ms(ctx->ev[6], ctx->ev[7]);
+    if (ctx->h2d_timed && cudaEventQuery(ctx->ev[19]) == cudaSuccess) ctx->ms[0] = elapsed_ms(ctx->ev_h2d0, ctx->ev[19]);
+    (void)cudaGetLastError();
     ctx->n_hsp_sorted = ns;
     ctx->searched = true;
     return MCX_OK;
@@ -3491,9 +3508,9 @@ extern "C" int mcx_get_hits(mcx_ctx *ctx, mcx_hit *out, int64_t cap, int64_t *n)
     k_keep_sorted<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(ctx->d_keep, ns, ctx->d_hflag);
     CK(cudaMemsetAsync(ctx->d_hflag + ns, 0, sizeof(int32_t), st));
     size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->d_hflag, ctx->d_hpos, (int)(ns + 1), st);
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->d_hflag, ctx->d_hpos, (int)(ns + 1), st));
     if ((rc = ensure_temp(ctx, tb)) != MCX_OK) return rc;
-    cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, ctx->d_hflag, ctx->d_hpos, (int)(ns + 1), st);
+    CK(cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, ctx->d_hflag, ctx->d_hpos, (int)(ns + 1), st));
     k_gather_hits<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(ctx->d_hsp, ctx->d_idx, ctx->d_keep, ctx->d_hpos, ns, ctx->d_hits_out);
     const int64_t take = std::min<int64_t>(cap, ctx->res.n_hsp);
     CK(cudaMemcpyAsync(out, ctx->d_hits_out, (size_t)take * sizeof(mcx_hit), cudaMemcpyDeviceToHost, st));

@@ -198,6 +198,39 @@ def test_full_size_invariants(eng, markers):
     assert 1.0e6 < ags < 4.0e6
 
 
+def test_consecutive_device_pushes_of_growing_reads(eng, markers):
+    """Device-resident pushes one after the other with a growing read length (the read-length sweep): every push must
+    rebuild the record offsets.  (Regression: an error code left behind by cudaEventElapsedTime on a never-recorded event
+    made CUB skip the offset scan of the NEXT push without a word; with equal lengths nobody noticed.)"""
+    import torch
+    n = 30000
+    pool = synth.reads(5, 0, n, 120).bases.reshape(n, 120)
+    d_pool = torch.from_numpy(pool).cuda()
+    for L in (60, 70, 100, 50):
+        eng.set_params(L)
+        eng.push(ReadBatch(np.ascontiguousarray(pool[:, :L]).reshape(-1), np.arange(n + 1, dtype=np.int64) * L))
+        want = eng.search(-1).counts_vector()
+        d_b = d_pool[:, :L].contiguous()
+        d_o = torch.arange(n + 1, dtype=torch.int64, device="cuda") * L
+        torch.cuda.synchronize()
+        for _ in range(2):
+            eng.push_device(d_b.data_ptr(), 0, d_o.data_ptr(), n, n * L)
+            assert np.array_equal(eng.search(-1).counts_vector(), want), L
+    # and the same in the packed device layout
+    from microbecensus_b200.engine import PackedBatch
+    for L in (60, 70, 100):
+        eng.set_params(L)
+        hb = ReadBatch(np.ascontiguousarray(pool[:, :L]).reshape(-1), np.arange(n + 1, dtype=np.int64) * L)
+        eng.push(hb)
+        want = eng.search(-1).counts_vector()
+        pb = PackedBatch.from_batch(hb)
+        d_p = torch.from_numpy(pb.packed.view(np.int32)).cuda(); d_l = torch.from_numpy(pb.lengths.view(np.int32)).cuda()
+        torch.cuda.synchronize()
+        for _ in range(2):
+            eng.push_packed_device(d_p.data_ptr(), int(d_p.numel()), d_l.data_ptr(), 0, pb.n_bases, n)
+            assert np.array_equal(eng.search(-1).counts_vector(), want), L
+
+
 FULL = os.path.join(golden_io.GOLD, "full")
 
 

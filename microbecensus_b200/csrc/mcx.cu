@@ -76,19 +76,48 @@ struct DevDB {
     const uint2 *htab;             // N_PAT open-addressing tables of 2^hbits slots, one after the other: x = word code
     int hbits;                     // (0xffffffff = empty), y = 25-bit posting start | 7-bit (count - 1)
     const uint32_t *post;          // (subject << 11 | position), bit 31 = last posting of the word
-    const uint32_t *bloom;         // 2^28-bit presence filter over (pattern, word): absorbs ~97 % of the probes in L2
+    const uint4 *filt_a;           // presence filter (below): 2^FILT_BITS blocks for the exact word and the wildcards at 3 / 4,
+    const uint2 *filt_b;           // and as many for the wildcards at 5 / 6; absorbs ~96 % of the probes in L2
 };
 
-// presence filter: 2^23 words of 32 bits; a key sets two bits of ONE word (same L2 sector traffic as a one-bit filter,
-// false-positive rate ~1.3 % instead of 5.6 % at this load, so fewer than half as many table lookups follow)
-#define BLOOM_WORD_BITS 23
-__host__ __device__ __forceinline__ uint32_t bloom_hash(int p, uint32_t code) {
-    return (code ^ ((uint32_t)p * 0x3243F6A9u)) * 2246822519u;
+// presence filter, blocked by what the five words of a window have in common.  All five patterns fix the letters
+// 0,1,2,7,8; the exact word and the wildcards at 3 / 4 also share 5,6 (group A, 7 letters), the wildcards at 5 / 6 share
+// 3,4,9 (group B, 8 letters).  The block address is a hash of the group's shared letters, so ONE 16-byte load answers
+// the three group-A words of a window and ONE 8-byte load the two group-B words: two L1 / L2 requests per lane and
+// window instead of five (the loop was bound by the rate of scattered requests, not by bytes; profiles/).  Inside a
+// block every pattern owns its word(s) -- exact: one bit in word 0 and one in word 3; wildcard 3 / 4: two bits of word
+// 1 / 2; wildcard 5 / 6: two bits of word 0 / 1 of the B block -- so no lane selects a register by a computed index.
+// Bit positions come from the letters outside the shared set, the pattern and the address hash.  Measured on the
+// marker set with translated synthetic reads (6.0 M distinct words): 1.4 % false positives at 2^21 blocks (the
+// one-word-per-key filter before: 1.3 %), 2.1 % at 2^20.  The filter only ever says "maybe": results cannot change.
+#ifndef MCX_FILT_BITS
+#define MCX_FILT_BITS 21
+#endif
+constexpr int FILT_BITS = MCX_FILT_BITS;       // log2(blocks) of each of the two arrays: 2^21 x (16 + 8) bytes = 48 MB
+// `lo` = reduced letters 0..7 of the window as nibbles, `hi` = letters 8, 9
+__host__ __device__ __forceinline__ uint32_t filt_hash_a(uint32_t lo, uint32_t hi) {
+    uint32_t h = (lo & 0xFFF00FFFu) * 0x9E3779B1u; h ^= h >> 15;
+    h = (h + (hi & 0xFu) * 0x85EBCA77u) * 0xC2B2AE3Du; h ^= h >> 13;
+    return h;
 }
-__host__ __device__ __forceinline__ uint32_t bloom_word(uint32_t h) { return h >> (32 - BLOOM_WORD_BITS); }
-__host__ __device__ __forceinline__ uint32_t bloom_mask(uint32_t h) {
-    const uint32_t h2 = h * 0x85EBCA6Bu;
-    return (1u << (h2 >> 27)) | (1u << ((h2 >> 22) & 31u));
+__host__ __device__ __forceinline__ uint32_t filt_hash_b(uint32_t lo, uint32_t hi) {
+    uint32_t h = (lo & 0xF00FFFFFu) * 0x9E3779B1u; h ^= h >> 15;
+    h = (h + (hi & 0xFFu) * 0x85EBCA77u + 0x68E31DA4u) * 0xC2B2AE3Du; h ^= h >> 13;
+    return h;
+}
+__host__ __device__ __forceinline__ uint32_t filt_block(uint32_t h) { return h >> (32 - FILT_BITS); }
+// the letters of pattern p that are not in its group's shared set
+__host__ __device__ __forceinline__ uint32_t filt_free(int p, uint32_t lo, uint32_t hi) {
+    return p == 0 ? (lo >> 12) & 0xFFu                          // letters 3, 4
+         : p == 1 ? ((lo >> 16) & 0xFu) | (hi & 0xF0u)            // 4, 9
+         : p == 2 ? ((lo >> 12) & 0xFu) | (hi & 0xF0u)            // 3, 9
+         : p == 3 ? (lo >> 24) & 0xFu                             // 6
+                  : (lo >> 20) & 0xFu;                            // 5
+}
+__host__ __device__ __forceinline__ void filt_bits(int p, uint32_t lo, uint32_t hi, uint32_t h, uint32_t &b1, uint32_t &b2) {
+    uint32_t x = ((filt_free(p, lo, hi) | ((uint32_t)(p + 1) << 8)) ^ (h << 11)) * 0x2C1B3C6Du; x ^= x >> 16;
+    x *= 0x297A2D39u;
+    b1 = 1u << (x >> 27); b2 = 1u << ((x >> 22) & 31u);
 }
 
 struct Surv {                      // ungapped HSP that reached the report floor
@@ -523,6 +552,8 @@ struct FrameArgs {
     uint8_t *frames;               // rows of fstride bytes, one per (read, frame)
     uint32_t *segq;                // frames that need the full SEG
     unsigned long long *n_segq;
+    uint32_t *segm;                // per queued frame: nwr words "window start k is at or below locut", then nwr words for hicut
+    int nwr;                       // words per mask = ceil(number of 12-windows of the longest frame / 32), <= 6
 };
 
 // Translation goes through a 2 x 125-entry table in shared memory indexed by three base codes (T C A G = 0..3,
@@ -540,7 +571,8 @@ __global__ void __launch_bounds__(NT) k_frames(FrameArgs A, int fstride) {
     uint8_t *s_aa = s_lut + 256;                                 // NT rows of fstride bytes
     uint8_t *s_code = s_aa + NT * fstride;                       // RPB reads of L base codes
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int L = A.L;
+    const int L = A.L, nwr = A.nwr;
+    uint32_t *wm = reinterpret_cast<uint32_t *>(s_code + ((RPB * L + 3) & ~3)) + tid;   // [2 * nwr][NT] window masks, this thread's column
     for (int k = tid; k < (int)(sizeof(SegTab) / 4); k += NT) reinterpret_cast<uint32_t *>(s_tab)[k] = reinterpret_cast<const uint32_t *>(&g_segtab)[k];
     for (int k = tid; k < 64; k += NT) reinterpret_cast<uint32_t *>(s_lut)[k] = reinterpret_cast<const uint32_t *>(g_codon_lut)[k];
     for (int k = tid; k < NT * fstride / 4; k += NT) reinterpret_cast<uint32_t *>(s_aa)[k] = 0x14141414u;  // AA_STOP
@@ -570,14 +602,21 @@ __global__ void __launch_bounds__(NT) k_frames(FrameArgs A, int fstride) {
         const uint8_t *cd = s_code + r * L + (rev ? L - 1 - o : o);
         const uint8_t *lut = s_lut + (rev ? 125 : 0);
         for (int k = 0; k < m; ++k, cd += 3 * step) fr[k] = lut[25 * cd[0] + 5 * cd[step] + cd[2 * step]];
-        // does any 12-window have entropy <= locut?  (Seg::segseq only acts on frames that have one)
+        // does any 12-window have entropy <= locut?  (Seg::segseq only acts on frames that have one.)  The window
+        // slides here at one letter out, one in per position, so the verdicts of every window against both cut-offs are
+        // kept as bit masks and handed to k_seg with the queue entry (k_seg used to rebuild each window from scratch:
+        // 28 % of its instructions)
         if (m >= SEG_WINDOW) {
             const SegTab &T = *s_tab;
+            for (int k = 0; k < 2 * nwr; ++k) wm[k * NT] = 0;
             WinG w; w.clear();
             for (int k = 0; k < SEG_WINDOW; ++k) w.add(fr[k], T);
+            uint32_t clo = 0, chi = 0;
             for (int st = 0;; ++st) {
-                trig |= w.low(T);
-                if (st + SEG_WINDOW >= m) break;
+                clo |= (uint32_t)w.low(T) << (st & 31); chi |= (uint32_t)w.high(T) << (st & 31);
+                const bool last = st + SEG_WINDOW >= m;
+                if ((st & 31) == 31 || last) { wm[(st >> 5) * NT] = clo; wm[(nwr + (st >> 5)) * NT] = chi; trig |= clo != 0; clo = chi = 0; }
+                if (last) break;
                 w.sub(fr[st], T); w.add(fr[st + SEG_WINDOW], T);
             }
         }
@@ -587,7 +626,12 @@ __global__ void __launch_bounds__(NT) k_frames(FrameArgs A, int fstride) {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(A.n_segq, (unsigned long long)__popc(tm));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (trig) A.segq[base + __popc(tm & ((1u << lane) - 1))] = (uint32_t)g;
+        if (trig) {
+            const unsigned long long at = base + __popc(tm & ((1u << lane) - 1));
+            A.segq[at] = (uint32_t)g;
+            uint32_t *dm = A.segm + at * (unsigned long long)(2 * nwr);
+            for (int k = 0; k < 2 * nwr; ++k) dm[k] = wm[k * NT];
+        }
     }
     __syncwarp();
     const int64_t row0 = (int64_t)blockIdx.x * NT + (tid - lane);
@@ -710,6 +754,7 @@ __device__ void coop_trim(const uint8_t *fr, int off, int tl, uint8_t *P, uint8_
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_seg(uint8_t *frames, int fstride, int L, const uint32_t *__restrict__ segq,
+                                                    const uint32_t *__restrict__ segm, int nwr,
                                                     const unsigned long long *n_queued, int maxm, unsigned int *work) {
     const int64_t n = (int64_t)*n_queued;      // device-side count: no host round trip between k_frames and this launch
     if ((int64_t)blockIdx.x * WARPS >= n) return;
@@ -737,13 +782,18 @@ __global__ void __launch_bounds__(WARPS * 32) k_seg(uint8_t *frames, int fstride
     // registers while the current one is processed (up to two words per lane)
     const int64_t gfirst = (int64_t)gridDim.x * WARPS;        // entries below it are the warps' first frames
     const int fw = fstride / 4;
-    uint32_t nrow = 0, nw0 = 0, nw1 = 0;
+    uint32_t nrow = 0, nw0 = 0, nw1 = 0, nmw = 0;
+    // lanes 0..5 / 6..11 carry the locut / hicut mask words of the frame (k_frames computed them), lanes 12..17 clear the result
+    const int mword = lane < 6 ? lane : lane - 6;
+    const bool mlane = lane < 12 && mword < nwr;
+    const int msrc = lane < 6 ? mword : nwr + mword;
     int64_t g = (int64_t)blockIdx.x * WARPS + warp;
     if (g < n) {
         nrow = segq[g];
         const uint32_t *src = reinterpret_cast<const uint32_t *>(frames + (int64_t)nrow * fstride);
         if (lane < fw) nw0 = src[lane];
         if (lane + 32 < fw) nw1 = src[lane + 32];
+        if (mlane) nmw = segm[g * (2 * nwr) + msrc];
     }
     for (int64_t gn; g < n; g = gn) {
         const uint32_t row = nrow;
@@ -752,6 +802,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_seg(uint8_t *frames, int fstride
         __syncwarp();
         if (lane < fw) reinterpret_cast<uint32_t *>(fr)[lane] = nw0;
         if (lane + 32 < fw) reinterpret_cast<uint32_t *>(fr)[lane + 32] = nw1;
+        if (lane < 18) s_m[lane] = nmw;
         {
             unsigned int t = 0;
             if (lane == 0) t = atomicAdd(work, 1u);
@@ -762,22 +813,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_seg(uint8_t *frames, int fstride
             const uint32_t *src = reinterpret_cast<const uint32_t *>(frames + (int64_t)nrow * fstride);
             if (lane < fw) nw0 = src[lane];
             if (lane + 32 < fw) nw1 = src[lane + 32];
-        }
-        __syncwarp();
-        // entropy of every 12-window against the two cut-offs, one window per lane
-        for (int r = 0; r < 6; ++r) {
-            uint32_t bl = 0, bh = 0;
-            if (r * 32 + SEG_WINDOW <= m) {
-                const int w = r * 32 + lane;
-                bool lo = false, hi = false;
-                if (w + SEG_WINDOW <= m) {
-                    WinG c; c.clear();
-                    for (int k = 0; k < SEG_WINDOW; ++k) c.add(fr[w + k], *s_tab);
-                    lo = c.low(*s_tab); hi = c.high(*s_tab);
-                }
-                bl = __ballot_sync(0xffffffffu, lo); bh = __ballot_sync(0xffffffffu, hi);
-            }
-            if (lane == 0) { s_m[r] = bl; s_m[6 + r] = bh; s_m[12 + r] = 0; }
+            if (mlane) nmw = segm[gn * (2 * nwr) + msrc];
         }
         __syncwarp();
         // Seg::segseq (downset 0, upset 1); the recursion of seg.c only adds segments, so the left parts are queued.
@@ -839,6 +875,9 @@ struct ProbeArgs {
     int L;
     DevDB db;
     const uint8_t *frames;
+    Cand *passq;                   // NQ sub-queues of cap_pass entries: words that passed the filter (gframe, letters 0..7, ip | letters 8, 9 << 16)
+    unsigned long long *n_pass;    // NQ counters
+    unsigned long long cap_pass;   // per sub-queue
     Cand *cand;                    // NQ sub-queues of cap_cand entries each (spreads the append atomics)
     unsigned long long *n_cand;    // NQ counters
     unsigned long long cap_cand;   // per sub-queue
@@ -851,30 +890,17 @@ __device__ __forceinline__ int warp_scan_add(int v, int lane) {
     return v;
 }
 
-// Lanes slide their own windows in lock step.  Words that pass the filter (a few per warp and position) are
-// compacted into a per-warp list and resolved by as many lanes in parallel: table slot, posting list, then ONE
-// reservation for the warp and a cooperative, coalesced copy of all postings into the candidate queue.  (First
-// version resolved hits inside the per-lane loop: ~1.3 lanes active on four dependent memory round trips per hit.)
-// (Tried and measured slower, 5.9 -> 8.8 ms: letting the filter passes wait in a per-warp ring until 32 of them can do
-// their table lookups together.  The kernel as it stands issues at 66 % of peak; the ring version executes 27 % fewer
-// instructions but stalls on the MIO pipe (shuffles, shared-memory traffic of the ring) and issues at 24 %.)
-// word codes (base 10) of the 10-window d0..d9 held as nibbles in `win`: the exact word d0..d8 and, for a wildcard at
-// offset w = 3..6, the nine letters around it = (d0..d[w-1]) * 10^(9-w) + (d[w+1]..d9); prefixes and suffixes shared
-__device__ __forceinline__ void window_codes(unsigned long long win, uint32_t *code, bool &ok9, bool &ok10) {
-    uint32_t d[10];
+// word code (base 10, the key of the slot tables) of pattern p in the window (lo = letters 0..7 as nibbles, hi = 8, 9):
+// the nine letters that are not the wildcard, first letter most significant.  Only words that passed the filter get here.
+__device__ __forceinline__ uint32_t word_code(uint32_t lo, uint32_t hi, int p) {
+    const int skip = p == 0 ? 9 : p + 2;
+    uint32_t c = 0;
 #pragma unroll
-    for (int k = 0; k < 10; ++k) d[k] = (uint32_t)(win >> (4 * k)) & 15;
-    int bad9 = 0;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) bad9 |= (d[k] >= 10);
-    ok9 = !bad9; ok10 = !(bad9 | (d[9] >= 10));
-    const uint32_t h3 = (d[0] * 10 + d[1]) * 10 + d[2], h4 = h3 * 10 + d[3], h5 = h4 * 10 + d[4], h6 = h5 * 10 + d[5];
-    const uint32_t t6 = (d[7] * 10 + d[8]) * 10 + d[9], t5 = d[6] * 1000 + t6, t4 = d[5] * 10000 + t5, t3 = d[4] * 100000 + t4;
-    code[0] = h6 * 1000 + (d[6] * 10 + d[7]) * 10 + d[8];
-    code[1] = h3 * 1000000 + t3;
-    code[2] = h4 * 100000 + t4;
-    code[3] = h5 * 10000 + t5;
-    code[4] = h6 * 1000 + t6;
+    for (int k = 0; k < 10; ++k) {
+        const uint32_t d = k < 8 ? (lo >> (4 * k)) & 15u : (hi >> (4 * (k - 8))) & 15u;
+        if (k != skip) c = c * 10u + d;
+    }
+    return c;
 }
 
 #ifndef MCX_PROBE_POS
@@ -883,20 +909,26 @@ __device__ __forceinline__ void window_codes(unsigned long long win, uint32_t *c
 #ifndef MCX_PROBE_NT
 #define MCX_PROBE_NT 64               /* threads per block of k_probe: small blocks retire early (measured 64 / 96 / 128 / 160 / 192 / 256: 5.17 / 5.19 / 5.30 / 5.41 / 5.71 / 6.18 ms at 100 bp) */
 #endif
-constexpr int PROBE_POS = MCX_PROBE_POS;   // window positions per loop iteration (2: one compaction round for 10 filter probes)
-constexpr int PROBE_Q = 32 * N_PAT * PROBE_POS;
+#ifndef MCX_RESOLVE_NT
+#define MCX_RESOLVE_NT 128
+#endif
+constexpr int PROBE_POS = MCX_PROBE_POS;   // window positions per loop iteration (2: four filter blocks in flight, one queue reservation)
 
+// K2b, filter half: one thread per frame of the store slides the 10-letter murphy10 window and tests its five words
+// against the presence filter (two block loads per window).  Nothing else happens here: the ~4 % of the words that pass
+// are appended to a queue (one reservation per warp and iteration, positions from ballots) and resolved by k_resolve,
+// one LANE per word.  (Before: the warp resolved its own passes inside this loop -- table slot, posting list, copy --
+// with 3 of 32 lanes in the slot lookup and every lane of the warp waiting on two dependent DRAM round trips per
+// iteration; 43 % of the stall samples of the kernel sat on those lines.  An earlier attempt to batch the passes in a
+// per-warp shared-memory ring inside this kernel lost to MIO stalls; a global queue and a second kernel does not touch
+// the MIO pipe here at all.)
 template <int NT>
 __global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
     extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int NW = NT / 32;
     const int64_t n_frames = 6 * (int64_t)*A.n_reads;
     if ((int64_t)blockIdx.x * NT >= n_frames) return;
-    uint32_t *s_qcode = reinterpret_cast<uint32_t *>(smem);            // [NW][PROBE_Q] words that passed the filter
-    uint32_t *s_x = s_qcode + NW * PROBE_Q;                            // [NW][4][32] incl. prefix, posting start, gframe, ip
-    uint16_t *s_qmeta = reinterpret_cast<uint16_t *>(s_x + NW * 128);  // [NW][PROBE_Q] lane | pattern << 5 | position offset << 8
-    uint8_t *s_aa = reinterpret_cast<uint8_t *>(s_qmeta + NW * PROBE_Q);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t *s_aa = smem;
+    const int tid = threadIdx.x, lane = tid & 31;
     {   // each warp stages its 32 rows
         const int64_t row0 = (int64_t)blockIdx.x * NT + (tid - lane);
         const uint32_t *src = reinterpret_cast<const uint32_t *>(A.frames + row0 * fstride);
@@ -904,90 +936,120 @@ __global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
         for (int k = lane; k < 32 * fstride / 4; k += 32) dst[k] = src[k];
     }
     __syncwarp();
-    uint32_t *qcode = s_qcode + warp * PROBE_Q, *xs = s_x + warp * 128;
-    uint16_t *qmeta = s_qmeta + warp * PROBE_Q;
     const int64_t g = (int64_t)blockIdx.x * NT + tid;
     const uint8_t *fr = s_aa + tid * fstride;
     const int m = g < n_frames ? (A.L - (int)(g % 6) % 3) / 3 : 0;
     const int sq = blockIdx.x & (NQ - 1);
+    const uint32_t lt = (1u << lane) - 1u;
     // reduced letters of the 10-window [i, i+10) as nibbles (letter k at bits 4k); 15 past the end
     unsigned long long win = 0;
     for (int k = 0; k < 10; ++k) win |= (unsigned long long)(k < m ? red_of(fr[k]) : 15) << (4 * k);
     const int mmax = A.L / 3;
     for (int i = 0; i + 9 <= mmax; i += PROBE_POS) {
-        uint32_t code[N_PAT * PROBE_POS];
+        uint32_t lo[PROBE_POS], hi[PROBE_POS];
         bool ok9[PROBE_POS], ok10[PROBE_POS];
 #pragma unroll
         for (int h = 0; h < PROBE_POS; ++h) {
-            window_codes(win, code + N_PAT * h, ok9[h], ok10[h]);
+            lo[h] = (uint32_t)win; hi[h] = (uint32_t)(win >> 32);
+            // letters >= 10 (stop, masked, past the end) as one bit per nibble: bit 3 and (bit 2 or bit 1)
+            const uint32_t blo = (lo[h] >> 3) & ((lo[h] >> 2) | (lo[h] >> 1)) & 0x11111111u;
+            const uint32_t bhi = (hi[h] >> 3) & ((hi[h] >> 2) | (hi[h] >> 1)) & 0x11u;
+            ok9[h] = (blo | (bhi & 1u)) == 0u; ok10[h] = (blo | bhi) == 0u;
             if (i + h + 9 > mmax) { ok9[h] = false; ok10[h] = false; }      // past the last window of the longest frame
             const int nx = i + h + 10;
             win = (win >> 4) | ((unsigned long long)(nx < m ? red_of(fr[nx]) : 15) << 36);
         }
-        // all filter words of the iteration in flight together
-        uint32_t bw[N_PAT * PROBE_POS], bh[N_PAT * PROBE_POS];
+        // the two filter blocks of every window of the iteration in flight together
+        uint32_t ha[PROBE_POS], hb[PROBE_POS];
+        uint4 fa[PROBE_POS];
+        uint2 fb[PROBE_POS];
 #pragma unroll
-        for (int q = 0; q < N_PAT * PROBE_POS; ++q) {
-            const int p = q % N_PAT, h = q / N_PAT;
-            bh[q] = bloom_hash(p, code[q]);
-            bw[q] = (p == 0 ? ok9[h] : ok10[h]) ? __ldg(A.db.bloom + bloom_word(bh[q])) : 0u;
+        for (int h = 0; h < PROBE_POS; ++h) {
+            ha[h] = filt_hash_a(lo[h], hi[h]); hb[h] = filt_hash_b(lo[h], hi[h]);
+            fa[h] = ok9[h] ? __ldg(A.db.filt_a + filt_block(ha[h])) : make_uint4(0u, 0u, 0u, 0u);
+            fb[h] = ok10[h] ? __ldg(A.db.filt_b + filt_block(hb[h])) : make_uint2(0u, 0u);
         }
         bool pass[N_PAT * PROBE_POS];
-        int npass = 0;
+        uint32_t bal[N_PAT * PROBE_POS];
+        int total = 0;
 #pragma unroll
-        for (int q = 0; q < N_PAT * PROBE_POS; ++q) { const uint32_t mk = bloom_mask(bh[q]); pass[q] = (bw[q] & mk) == mk; npass += pass[q]; }
-        const int incl = warp_scan_add(npass, lane);
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total > 0) {
-            int o = incl - npass;
+        for (int h = 0; h < PROBE_POS; ++h) {
+            uint32_t b1, b2;
+            filt_bits(0, lo[h], hi[h], ha[h], b1, b2); pass[N_PAT * h + 0] = (fa[h].x & b1) && (fa[h].w & b2);
+            filt_bits(1, lo[h], hi[h], ha[h], b1, b2); pass[N_PAT * h + 1] = ok10[h] && (fa[h].y & (b1 | b2)) == (b1 | b2);
+            filt_bits(2, lo[h], hi[h], ha[h], b1, b2); pass[N_PAT * h + 2] = ok10[h] && (fa[h].z & (b1 | b2)) == (b1 | b2);
+            filt_bits(3, lo[h], hi[h], hb[h], b1, b2); pass[N_PAT * h + 3] = (fb[h].x & (b1 | b2)) == (b1 | b2);
+            filt_bits(4, lo[h], hi[h], hb[h], b1, b2); pass[N_PAT * h + 4] = (fb[h].y & (b1 | b2)) == (b1 | b2);
 #pragma unroll
-            for (int q = 0; q < N_PAT * PROBE_POS; ++q)
-                if (pass[q]) { qcode[o] = code[q]; qmeta[o] = (uint16_t)(lane | ((q % N_PAT) << 5) | ((q / N_PAT) << 8)); ++o; }
-            __syncwarp();
-            for (int base = 0; base < total; base += 32) {
-                const int t = base + lane;
-                uint32_t cnt = 0, pi = 0, meta = 0;
-                if (t < total) {
-                    const uint32_t c = qcode[t];
-                    meta = qmeta[t];
-                    const int p = (meta >> 5) & 7;
-                    // key and value share an 8-byte slot: one load per probe, no second round trip for the value
-                    const uint2 *__restrict__ tb = A.db.htab + ((size_t)p << A.db.hbits);
-                    const uint32_t hmask = (1u << A.db.hbits) - 1u;
-                    uint32_t sl = (c * 2654435761u) >> (32 - A.db.hbits);
-                    uint2 kv = __ldg(tb + sl);
-                    while (kv.x != 0xffffffffu && kv.x != c) { sl = (sl + 1) & hmask; kv = __ldg(tb + sl); }
-                    if (kv.x == c) {
-                        const uint32_t v = kv.y;
-                        pi = v & 0x1ffffffu;                              // 25-bit start, 7-bit (count - 1)
-                        cnt = (v >> 25) + 1;
-                        if ((v >> 25) == 127) { cnt = __ldg(A.db.post + pi); ++pi; }   // longer lists start with their length
-                    }
-                }
-                const int inc2 = warp_scan_add((int)cnt, lane);
-                const int tot2 = __shfl_sync(0xffffffffu, inc2, 31);
-                if (tot2 == 0) continue;
-                unsigned long long basepos = 0;
-                if (lane == 0) basepos = atomicAdd(A.n_cand + sq, (unsigned long long)tot2);
-                basepos = __shfl_sync(0xffffffffu, basepos, 0);
-                xs[lane] = (uint32_t)inc2; xs[32 + lane] = pi;
-                xs[64 + lane] = (uint32_t)(g - lane + (meta & 31)); xs[96 + lane] = ((uint32_t)(i + (int)(meta >> 8)) << 8) | ((meta >> 5) & 7);
-                __syncwarp();
-                if (basepos + (unsigned long long)tot2 <= A.cap_cand) {
-                    Cand *dst = A.cand + (unsigned long long)sq * A.cap_cand + basepos;
-                    for (int e = lane; e < tot2; e += 32) {
-                        int lo = 0;                                       // first owner whose inclusive prefix exceeds e
-#pragma unroll
-                        for (int step = 16; step; step >>= 1) if (xs[lo + step - 1] <= (uint32_t)e) lo += step;
-                        const uint32_t q = (uint32_t)e - (lo ? xs[lo - 1] : 0u);
-                        Cand c; c.gframe = xs[64 + lo]; c.sj = __ldg(A.db.post + xs[32 + lo] + q) & 0x7fffffffu; c.ip = xs[96 + lo];
-                        dst[e] = c;
-                    }
-                }
-                __syncwarp();
-            }
-            __syncwarp();
+            for (int p = 0; p < N_PAT; ++p) { bal[N_PAT * h + p] = __ballot_sync(0xffffffffu, pass[N_PAT * h + p]); total += __popc(bal[N_PAT * h + p]); }
         }
+        if (total > 0) {
+            unsigned long long basepos = 0;
+            if (lane == 0) basepos = atomicAdd(A.n_pass + sq, (unsigned long long)total);
+            basepos = __shfl_sync(0xffffffffu, basepos, 0);
+            if (basepos + (unsigned long long)total <= A.cap_pass) {
+                Cand *dst = A.passq + (unsigned long long)sq * A.cap_pass + basepos;
+                int o = 0;
+#pragma unroll
+                for (int q = 0; q < N_PAT * PROBE_POS; ++q) {
+                    if (pass[q]) {
+                        Cand r; r.gframe = (uint32_t)g; r.sj = lo[q / N_PAT];
+                        r.ip = ((uint32_t)(i + q / N_PAT) << 8) | (uint32_t)(q % N_PAT) | (hi[q / N_PAT] << 16);
+                        dst[o + __popc(bal[q] & lt)] = r;
+                    }
+                    o += __popc(bal[q]);
+                }
+            }
+        }
+    }
+}
+
+// K2b, table half: one lane per word that passed the filter: slot of its pattern's table (key and value share 8
+// bytes: one load), then ONE reservation per warp and a cooperative, coalesced copy of all postings of the warp's 32
+// words into the candidate queue (gframe, subject, subject position, query position, pattern).
+template <int NT>
+__global__ void __launch_bounds__(NT) k_resolve(ProbeArgs A) {
+    __shared__ uint32_t s_x[NT / 32][128];          // per warp: inclusive prefix of posting counts, posting start, gframe, ip
+    const int sq = blockIdx.y, lane = threadIdx.x & 31;
+    const unsigned long long fill = min(A.n_pass[sq], A.cap_pass);
+    const unsigned long long k = (unsigned long long)blockIdx.x * NT + threadIdx.x;
+    if (k - lane >= fill) return;
+    uint32_t *xs = s_x[threadIdx.x >> 5];
+    uint32_t cnt = 0, pi = 0, gframe = 0, ip = 0;
+    if (k < fill) {
+        const Cand r = A.passq[(unsigned long long)sq * A.cap_pass + k];
+        const int p = (int)(r.ip & 0xffu);
+        const uint32_t c = word_code(r.sj, r.ip >> 16, p);
+        gframe = r.gframe; ip = r.ip & 0xffffu;
+        const uint2 *__restrict__ tb = A.db.htab + ((size_t)p << A.db.hbits);
+        const uint32_t hmask = (1u << A.db.hbits) - 1u;
+        uint32_t sl = (c * 2654435761u) >> (32 - A.db.hbits);
+        uint2 kv = __ldg(tb + sl);
+        while (kv.x != 0xffffffffu && kv.x != c) { sl = (sl + 1) & hmask; kv = __ldg(tb + sl); }
+        if (kv.x == c) {
+            const uint32_t v = kv.y;
+            pi = v & 0x1ffffffu;                              // 25-bit start, 7-bit (count - 1)
+            cnt = (v >> 25) + 1;
+            if ((v >> 25) == 127) { cnt = __ldg(A.db.post + pi); ++pi; }   // longer lists start with their length
+        }
+    }
+    const int inc2 = warp_scan_add((int)cnt, lane);
+    const int tot2 = __shfl_sync(0xffffffffu, inc2, 31);
+    if (tot2 == 0) return;
+    unsigned long long basepos = 0;
+    if (lane == 0) basepos = atomicAdd(A.n_cand + sq, (unsigned long long)tot2);
+    basepos = __shfl_sync(0xffffffffu, basepos, 0);
+    xs[lane] = (uint32_t)inc2; xs[32 + lane] = pi; xs[64 + lane] = gframe; xs[96 + lane] = ip;
+    __syncwarp();
+    if (basepos + (unsigned long long)tot2 > A.cap_cand) return;
+    Cand *dst = A.cand + (unsigned long long)sq * A.cap_cand + basepos;
+    for (int e = lane; e < tot2; e += 32) {
+        int lo = 0;                                       // first owner whose inclusive prefix exceeds e
+#pragma unroll
+        for (int step = 16; step; step >>= 1) if (xs[lo + step - 1] <= (uint32_t)e) lo += step;
+        const uint32_t q = (uint32_t)e - (lo ? xs[lo - 1] : 0u);
+        Cand c; c.gframe = xs[64 + lo]; c.sj = __ldg(A.db.post + xs[32 + lo] + q) & 0x7fffffffu; c.ip = xs[96 + lo];
+        dst[e] = c;
     }
 }
 
@@ -2149,7 +2211,7 @@ struct mcx_ctx {
     // search buffers
     uint4 *d_surv = nullptr;
     uint8_t *d_frames = nullptr;
-    uint32_t *d_segq = nullptr;
+    uint32_t *d_segq = nullptr, *d_segm = nullptr;
     unsigned long long *d_seen = nullptr;     // k_walk's duplicate filter
     uint4 *d_seedq = nullptr;                 // accepted seeds between k_seed and k_walk
     int64_t cap_seen = 0, cap_seedq = 0;
@@ -2157,9 +2219,9 @@ struct mcx_ctx {
     GExtRec *d_gext = nullptr;
     uint32_t *d_dirs = nullptr;               // direction nibbles of k_gap_dp for k_gap_trace
     int64_t cap_gitems = 0, cap_gext = 0, cap_dirs = 0;
-    int64_t cap_segq = 0;
-    Cand *d_cand = nullptr;
-    int64_t cap_frames = 0, cap_cand = 0, n_cand_last = 0;
+    int64_t cap_segq = 0, cap_segm = 0;
+    Cand *d_cand = nullptr, *d_passq = nullptr;
+    int64_t cap_frames = 0, cap_cand = 0, cap_passq = 0, n_cand_last = 0;
     mcx_hit *d_hsp = nullptr, *d_hits_out = nullptr;
     SortKey *d_keys = nullptr;
     int32_t *d_idx = nullptr, *d_best = nullptr, *d_hflag = nullptr, *d_hpos = nullptr;
@@ -2169,7 +2231,7 @@ struct mcx_ctx {
     int64_t cap_surv = 0, cap_best = 0, cap_nrep = 0, cap_bestkey = 0;
     unsigned long long *d_cnt = nullptr;     // 64 scalar counters (layout: enum Cnt)
     int n_sm = 148;                          // multiprocessors of the device (sizes the resident grids)
-    unsigned long long *d_qcnt = nullptr;    // NQ candidate sub-queue fills
+    unsigned long long *d_qcnt = nullptr;    // NQ candidate sub-queue fills, then NQ filter-pass sub-queue fills
     unsigned long long *d_acc = nullptr;     // 3 + 60
     unsigned long long *d_abl = nullptr;     // 30 * 1280
     unsigned long long *h_cnt = nullptr;     // pinned mirror for counter read-backs (64 + NQ)
@@ -2271,7 +2333,7 @@ static int build_index(mcx_ctx *ctx, const mcx_db *db) {
     for (int s = 0; s < ns; ++s)
         if (db->off[s + 1] - db->off[s] >= 2048) return fail(ctx, MCX_EINVAL, "subject longer than 2047 residues");
     // the five patterns are independent: one host thread each (entries + sort, then table fill into its own region)
-    std::vector<uint32_t> bloom((size_t)1 << BLOOM_WORD_BITS, 0u);
+    std::vector<uint32_t> filt_a((size_t)4 << FILT_BITS, 0u), filt_b((size_t)2 << FILT_BITS, 0u);
     std::vector<unsigned long long> ent[N_PAT];
     size_t distinct[N_PAT] = {0}, long_lists[N_PAT] = {0};
     auto collect = [&](int p) {
@@ -2325,8 +2387,23 @@ static int build_index(mcx_ctx *ctx, const mcx_db *db) {
             size_t e = k;
             while (e + 1 < en.size() && (en[e + 1] >> 32) == code) ++e;
             const uint32_t cnt = (uint32_t)(e - k + 1);
-            const uint32_t h = bloom_hash(p, code);
-            __atomic_fetch_or(&bloom[bloom_word(h)], bloom_mask(h), __ATOMIC_RELAXED);
+            {   // the word as a nibble window (wildcard letter 0: no pattern looks at its own wildcard) -> its filter bits
+                uint32_t d[10] = {0}, cc = code;
+                for (int k = PAT_LEN[p] - 1; k >= 0; --k) if (k != PAT_WILD[p]) { d[k] = cc % 10u; cc /= 10u; }
+                uint32_t lo = 0, hi = d[8] | (d[9] << 4), b1, b2;
+                for (int k = 0; k < 8; ++k) lo |= d[k] << (4 * k);
+                if (p <= 2) {
+                    const uint32_t h = filt_hash_a(lo, hi);
+                    uint32_t *blk = filt_a.data() + (size_t)4 * filt_block(h);
+                    filt_bits(p, lo, hi, h, b1, b2);
+                    if (p == 0) { __atomic_fetch_or(&blk[0], b1, __ATOMIC_RELAXED); __atomic_fetch_or(&blk[3], b2, __ATOMIC_RELAXED); }
+                    else __atomic_fetch_or(&blk[p], b1 | b2, __ATOMIC_RELAXED);
+                } else {
+                    const uint32_t h = filt_hash_b(lo, hi);
+                    filt_bits(p, lo, hi, h, b1, b2);
+                    __atomic_fetch_or(&filt_b[(size_t)2 * filt_block(h) + (size_t)(p - 3)], b1 | b2, __ATOMIC_RELAXED);
+                }
+            }
             uint32_t slot = (code * 2654435761u) >> (32 - bits);
             while (ht[slot].x != 0xffffffffu) slot = (slot + 1) & (size - 1);
             ht[slot] = make_uint2(code, (uint32_t)w | ((cnt > 127 ? 127u : cnt - 1) << 25));
@@ -2351,10 +2428,12 @@ static int build_index(mcx_ctx *ctx, const mcx_db *db) {
     CK(dev_alloc(&dp, post_all.size())); ctx->db_allocs.push_back(dp);
     CK(cudaMemcpy(dp, post_all.data(), post_all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     ctx->db.post = dp;
-    uint32_t *db_ = nullptr;
-    CK(dev_alloc(&db_, bloom.size())); ctx->db_allocs.push_back(db_);
-    CK(cudaMemcpy(db_, bloom.data(), bloom.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    ctx->db.bloom = db_;
+    uint32_t *dfa = nullptr, *dfb = nullptr;
+    CK(dev_alloc(&dfa, filt_a.size())); ctx->db_allocs.push_back(dfa);
+    CK(cudaMemcpy(dfa, filt_a.data(), filt_a.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CK(dev_alloc(&dfb, filt_b.size())); ctx->db_allocs.push_back(dfb);
+    CK(cudaMemcpy(dfb, filt_b.data(), filt_b.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    ctx->db.filt_a = reinterpret_cast<const uint4 *>(dfa); ctx->db.filt_b = reinterpret_cast<const uint2 *>(dfb);
     return MCX_OK;
 }
 
@@ -2520,7 +2599,7 @@ extern "C" int mcx_create(mcx_ctx **out, const mcx_db *db, int device) {
         for (auto &ev : ctx->ev_copy) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ev_len, cudaEventDisableTiming));
         CK(cudaEventCreate(&ctx->ev_h2d0));
-        CK(cudaHostAlloc((void **)&ctx->h_cnt, (C_N + NQ) * sizeof(unsigned long long), cudaHostAllocDefault));
+        CK(cudaHostAlloc((void **)&ctx->h_cnt, (C_N + 2 * NQ) * sizeof(unsigned long long), cudaHostAllocDefault));
         const int ns = db->n_subj;
         const int64_t nres = db->off[ns];
         int32_t *doff = nullptr; uint8_t *dres = nullptr, *dfam = nullptr;
@@ -2537,7 +2616,7 @@ extern "C" int mcx_create(mcx_ctx **out, const mcx_db *db, int device) {
         int r = upload_tables(ctx); if (r) return r;
         r = build_index(ctx, db); if (r) return r;
         CK(dev_alloc(&ctx->d_cnt, C_N));
-        CK(dev_alloc(&ctx->d_qcnt, NQ));
+        CK(dev_alloc(&ctx->d_qcnt, 2 * NQ));
         CK(dev_alloc(&ctx->d_acc, 3 + 2 * MCX_N_FAM));
         CK(dev_alloc(&ctx->d_abl, (size_t)MCX_N_FAM * MCX_LEN_BINS));
         return MCX_OK;
@@ -2559,7 +2638,7 @@ extern "C" void mcx_destroy(mcx_ctx *ctx) {
     void *bufs[] = {ctx->d_woff, ctx->d_qoff, ctx->d_ascii, ctx->d_aoffs, ctx->d_code, ctx->d_fp, ctx->d_fpa, ctx->d_fpa2, ctx->d_fpi, ctx->d_fpi2,
                     ctx->d_kept, ctx->d_store_a, ctx->d_store_b, ctx->d_xsend, ctx->d_xmarks, ctx->d_xkg, ctx->d_xvi, ctx->d_surv, ctx->d_hsp, ctx->d_hits_out, ctx->d_keys, ctx->d_idx, ctx->d_best, ctx->d_hflag,
                     ctx->d_hpos, ctx->d_keep, ctx->d_cnt, ctx->d_acc, ctx->d_abl, ctx->d_temp, ctx->d_frames, ctx->d_cand,
-                    ctx->d_segq, ctx->d_qcnt, ctx->d_gitems, ctx->d_gext, ctx->d_dirs, ctx->d_nrep, ctx->d_bestkey, ctx->d_seen, ctx->d_seedq};
+                    ctx->d_segq, ctx->d_segm, ctx->d_passq, ctx->d_qcnt, ctx->d_gitems, ctx->d_gext, ctx->d_dirs, ctx->d_nrep, ctx->d_bestkey, ctx->d_seen, ctx->d_seedq};
     for (void *p : bufs) if (p) cudaFree(p);
     if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -3191,17 +3270,22 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     const int thr = std::max(1, std::min(P.min_report_raw, 49));
     // the stages run per chunk of pushed reads so that the frame store and the queues stay bounded
     const int fstride = frame_stride(maxm);
+    const int nwr = std::max(1, (maxm - SEG_WINDOW + 1 + 31) / 32);     // words of a 12-window mask
     int64_t chunk = 2000000, cand_per_read = 96;
     chunk = std::min<int64_t>(chunk, std::max<int64_t>(250000, 300000000 / P.read_length));   // queues scale with bases, not reads
     if (const char *e = getenv("MCX_CHUNK_READS")) chunk = std::min(2700000, std::max(1, atoi(e)));   // frame rows < 2^24
     if (const char *e = getenv("MCX_CAND_PER_READ")) cand_per_read = std::max(1, atoi(e));
+    int64_t pass_per_read = std::max<int64_t>(32, (int64_t)(0.4 * P.read_length));    // ~0.23 L words per read pass the filter
+    if (const char *e = getenv("MCX_PASS_PER_READ")) pass_per_read = std::max(1, atoi(e));
     chunk = std::min<int64_t>(chunk, std::max<int64_t>(n, 1));
     {
         const int64_t need_fr = (chunk * 6 + 512) * fstride + 128, need_cand = std::max<int64_t>(chunk * cand_per_read, 1 << 16);
         if ((rc = ensure(ctx, &ctx->d_frames, &ctx->cap_frames, need_fr)) != MCX_OK) return rc;
         if ((rc = ensure(ctx, &ctx->d_cand, &ctx->cap_cand, need_cand)) != MCX_OK) return rc;
+        if ((rc = ensure(ctx, &ctx->d_passq, &ctx->cap_passq, std::max<int64_t>(chunk * pass_per_read, 1 << 16))) != MCX_OK) return rc;
         if ((rc = ensure(ctx, &ctx->d_seedq, &ctx->cap_seedq, std::max<int64_t>(ctx->cap_cand / 2, 1 << 16))) != MCX_OK) return rc;
         if ((rc = ensure(ctx, &ctx->d_segq, &ctx->cap_segq, chunk * 6 + 512)) != MCX_OK) return rc;
+        if ((rc = ensure(ctx, &ctx->d_segm, &ctx->cap_segm, (chunk * 6 + 512) * 2 * nwr)) != MCX_OK) return rc;
         if ((rc = ensure(ctx, &ctx->d_kept, &ctx->cap_kept, chunk + 1)) != MCX_OK) return rc;
     }
     uint8_t *const frames = ctx->d_frames + 64;      // rows are also read as aligned words around a position (load_residues)
@@ -3239,7 +3323,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     }
 
     float ms_frames = 0, ms_seg = 0, ms_probe = 0, ms_ext = 0, ms_gap = 0;
-    unsigned long long n_surv = 0, n_cand_total = 0, n_seeds_total = 0;
+    unsigned long long n_surv = 0, n_cand_total = 0, n_seeds_total = 0, n_pass_total = 0;
     int64_t remaining = quota, sampled = 0, examined = 0;
     for (int c = 0; c < nb && (quota < 0 || remaining > 0); ++c) {
         const int64_t r0 = bounds[(size_t)c], r1 = bounds[(size_t)c + 1], nr_in = r1 - r0;
@@ -3282,7 +3366,8 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             FrameArgs F;
             F.S = read_store(ctx); F.kept = ctx->d_kept; F.first = 0; F.n_search = ctx->d_cnt + C_NKEPT;
             F.L = P.read_length; F.frames = frames; F.segq = ctx->d_segq; F.n_segq = ctx->d_cnt + C_SEGQ;
-            const size_t smem = sizeof(SegTab) + 256 + (size_t)fstride * NTF + (size_t)(NTF / 6) * P.read_length;
+            F.segm = ctx->d_segm; F.nwr = nwr;
+            const size_t smem = sizeof(SegTab) + 256 + (size_t)fstride * NTF + (size_t)((NTF / 6 * P.read_length + 3) & ~3) + (size_t)2 * nwr * NTF * 4;
             CK(cudaFuncSetAttribute(k_frames<NTF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_frames<NTF><<<(unsigned)((nr_max * 6 + NTF - 1) / NTF), NTF, smem, st>>>(F, fstride);
             ++ctx->launches;
@@ -3296,23 +3381,26 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seg<SW>, SW * 32, smem));
             const unsigned long long resident = (unsigned long long)std::max(per_sm, 1) * (unsigned long long)ctx->n_sm;
             k_seg<SW><<<(unsigned)std::min<unsigned long long>((nr_max * 6 + SW - 1) / SW, resident), SW * 32, smem, st>>>(
-                frames, fstride, P.read_length, ctx->d_segq, ctx->d_cnt + C_SEGQ, maxm, reinterpret_cast<unsigned int *>(ctx->d_cnt + C_WORK));
+                frames, fstride, P.read_length, ctx->d_segq, ctx->d_segm, nwr, ctx->d_cnt + C_SEGQ, maxm, reinterpret_cast<unsigned int *>(ctx->d_cnt + C_WORK));
             ++ctx->launches;
         }
         CK(cudaEventRecord(ctx->ev[11], st));
         const unsigned long long surv_before = n_surv;
-        unsigned long long n_cand = 0, n_seeds = 0;
+        unsigned long long n_cand = 0, n_seeds = 0, n_pass = 0;
         for (int attempt = 0;; ++attempt) {
             // ---- K2: probe -> seed -> walk, queue lengths read on the device; one read-back behind the three
-            CK(cudaMemsetAsync(ctx->d_qcnt, 0, NQ * sizeof(unsigned long long), st));
+            CK(cudaMemsetAsync(ctx->d_qcnt, 0, 2 * NQ * sizeof(unsigned long long), st));
             CK(cudaMemsetAsync(ctx->d_cnt + C_SEEDQ, 0, sizeof(unsigned long long), st));
             ProbeArgs A;
             A.n_reads = ctx->d_cnt + C_NKEPT; A.L = P.read_length; A.db = ctx->db; A.frames = frames; A.cand = ctx->d_cand;
             A.n_cand = ctx->d_qcnt; A.cap_cand = (unsigned long long)(ctx->cap_cand / NQ);
-            constexpr int NTP = MCX_PROBE_NT;
-            const size_t smem = (size_t)(NTP / 32) * (PROBE_Q * 4 + 128 * 4 + PROBE_Q * 2) + (size_t)fstride * NTP;
+            A.passq = ctx->d_passq; A.n_pass = ctx->d_qcnt + NQ; A.cap_pass = (unsigned long long)(ctx->cap_passq / NQ);
+            constexpr int NTP = MCX_PROBE_NT, NTR = MCX_RESOLVE_NT;
+            const size_t smem = (size_t)fstride * NTP;
             CK(cudaFuncSetAttribute(k_probe<NTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_probe<NTP><<<(unsigned)((nr_max * 6 + NTP - 1) / NTP), NTP, smem, st>>>(A, fstride);
+            k_resolve<NTR><<<dim3((unsigned)((A.cap_pass + NTR - 1) / NTR), NQ), NTR, 0, st>>>(A);
+            ++ctx->launches;
             if (attempt == 0) CK(cudaEventRecord(ctx->ev[3], st));
             ExtArgs E;
             E.kept = ctx->d_kept; E.first = 0; E.L = P.read_length; E.fstride = fstride; E.thr_report = thr; E.db = ctx->db;
@@ -3336,25 +3424,29 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             }
             ctx->launches += 3;
             CK(cudaEventRecord(ctx->ev[8], st));
-            CK(cudaMemcpyAsync(hc + C_N, ctx->d_qcnt, NQ * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(hc + C_N, ctx->d_qcnt, 2 * NQ * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(hc, ctx->d_cnt, C_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             if ((rc = sync_stream(ctx)) != MCX_OK) return rc;
-            unsigned long long worst = 0;
+            unsigned long long worst = 0, worst_pass = 0;
             n_cand = 0;
-            for (int q = 0; q < NQ; ++q) { n_cand += hc[C_N + q]; worst = std::max(worst, hc[C_N + q]); }
+            for (int q = 0; q < NQ; ++q) { n_cand += hc[C_N + q]; worst = std::max(worst, hc[C_N + q]); worst_pass = std::max(worst_pass, hc[C_N + NQ + q]); n_pass += hc[C_N + NQ + q]; }
             n_seeds = hc[C_SEEDQ];
+            const bool over_pass = (int64_t)worst_pass > ctx->cap_passq / NQ;
             const bool over_cand = (int64_t)worst > ctx->cap_cand / NQ, over_seed = (int64_t)n_seeds > ctx->cap_seedq,
                        over_surv = (int64_t)hc[C_SURV] > ctx->cap_surv;
-            if (!over_cand && !over_seed && !over_surv) { n_surv = hc[C_SURV]; break; }
-            if (attempt >= 3) return fail(ctx, MCX_ENOMEM, "mcx_search: a queue (candidates / seeds / survivors) overflowed after regrowth");
-            // the fills are exact: size the queue that overflowed for what was seen and run the chunk's seed stage again
+            if (!over_pass && !over_cand && !over_seed && !over_surv) { n_surv = hc[C_SURV]; break; }
+            if (attempt >= 4) return fail(ctx, MCX_ENOMEM, "mcx_search: a queue (filter passes / candidates / seeds / survivors) overflowed after regrowth");
+            // the fills are exact (of what the earlier queues let through): size the queue that overflowed for what was
+            // seen and run the chunk's seed stage again
+            n_pass = 0;
+            if (over_pass && (rc = ensure(ctx, &ctx->d_passq, &ctx->cap_passq, (int64_t)(worst_pass + worst_pass / 16 + 1024) * NQ)) != MCX_OK) return rc;
             if (over_cand && (rc = ensure(ctx, &ctx->d_cand, &ctx->cap_cand, (int64_t)(worst + worst / 16 + 1024) * NQ)) != MCX_OK) return rc;
             if ((over_cand || over_seed) && (rc = ensure(ctx, &ctx->d_seedq, &ctx->cap_seedq, std::max<int64_t>((int64_t)(n_seeds + n_seeds / 8), ctx->cap_cand / 2))) != MCX_OK) return rc;
             if (over_surv && (rc = grow_survivors(ctx, (int64_t)surv_before, (int64_t)hc[C_SURV] + (int64_t)hc[C_SURV] / 4)) != MCX_OK) return rc;
             hc[C_SURV] = surv_before;
             CK(cudaMemcpyAsync(ctx->d_cnt + C_SURV, hc + C_SURV, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
         }
-        n_cand_total += n_cand; n_seeds_total += n_seeds;
+        n_cand_total += n_cand; n_seeds_total += n_seeds; n_pass_total += n_pass;
         sampled += nr < 0 ? (int64_t)hc[C_NKEPT] : nr;
         if (n_surv > surv_before) {
             GapArgs G;
@@ -3474,8 +3566,8 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     R.reads_with_hits = (int64_t)acc[0]; R.reads_classified = (int64_t)acc[1]; R.n_hsp = (int64_t)acc[2];
     R.n_gapped = (int64_t)hc[C_NGAPTOT]; R.gapped_cells = (int64_t)hc[C_CELLS];
     R.n_capped_reads = (int64_t)hc[C_NCAP];
-    if (getenv("MCX_DEBUG")) fprintf(stderr, "[mcx] candidates %llu, accepted seeds %llu, ungapped HSPs %llu; gapped extensions %llu, with gain > 0: %llu, cells %llu; host syncs %lld\n",
-                                     n_cand_total, n_seeds_total, n_surv, hc[C_NGAPTOT], hc[C_GAPPED], hc[C_CELLS], (long long)ctx->host_syncs);
+    if (getenv("MCX_DEBUG")) fprintf(stderr, "[mcx] filter passes %llu, candidates %llu, accepted seeds %llu, ungapped HSPs %llu; gapped extensions %llu, with gain > 0: %llu, cells %llu; host syncs %lld\n",
+                                     n_pass_total, n_cand_total, n_seeds_total, n_surv, hc[C_NGAPTOT], hc[C_GAPPED], hc[C_CELLS], (long long)ctx->host_syncs);
     for (int f = 0; f < MCX_N_FAM; ++f) { R.fam_hits[f] = (int64_t)acc[3 + f]; R.fam_aln[f] = (int64_t)acc[3 + MCX_N_FAM + f]; }
     for (size_t k = 0; k < abl.size(); ++k) R.aln_by_len[k] = (int64_t)abl[k];
     ctx->ms[1] = ms_qc; ctx->ms[2] = ms_probe; ctx->ms[7] = ms_ext; ctx->ms[3] = ms_gap; ctx->ms[8] = ms_frames; ctx->ms[9] = ms_seg;
@@ -3602,7 +3694,7 @@ extern "C" int mcx_l2_peak(mcx_ctx *ctx, double *gsectors_per_s) {
     double best = 0.0;
     for (int rep = 0; rep < 4; ++rep) {
         CK(cudaEventRecord(ctx->ev[12], st));
-        k_l2_bench<<<blocks, 256, 0, st>>>(ctx->db.bloom, (1u << BLOOM_WORD_BITS) - 1u, iters, 777u + rep, d_out);
+        k_l2_bench<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint32_t *>(ctx->db.filt_a), (4u << FILT_BITS) - 1u, iters, 777u + rep, d_out);
         CK(cudaEventRecord(ctx->ev[13], st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());

@@ -75,7 +75,7 @@ struct DevDB {
     const uint8_t *fam;
     const uint2 *htab;             // N_PAT open-addressing tables of 2^hbits slots, one after the other: x = word code
     int hbits;                     // (0xffffffff = empty), y = 25-bit posting start | 7-bit (count - 1)
-    const uint32_t *post;          // (subject << 11 | position), bit 31 = last posting of the word
+    const uint32_t *post;          // (subject << 11 | position), bits 26..29 = a murphy10 letter of the subject (build_index), bit 31 = last posting of the word
     const uint4 *filt_a;           // presence filter (below): 2^FILT_BITS blocks for the exact word and the wildcards at 3 / 4,
     const uint2 *filt_b;           // and as many for the wildcards at 5 / 6; absorbs ~96 % of the probes in L2
 };
@@ -88,7 +88,7 @@ struct DevDB {
 // block every pattern owns its word(s) -- exact: one bit in word 0 and one in word 3; wildcard 3 / 4: two bits of word
 // 1 / 2; wildcard 5 / 6: two bits of word 0 / 1 of the B block -- so no lane selects a register by a computed index.
 // Bit positions come from the letters outside the shared set, the pattern and the address hash.  Measured on the
-// marker set with translated synthetic reads (6.0 M distinct words): 1.4 % false positives at 2^21 blocks (the
+// marker set with translated synthetic reads (6.0 M distinct words): 1.2 % false positives at 2^21 blocks (the
 // one-word-per-key filter before: 1.3 %), 2.1 % at 2^20.  The filter only ever says "maybe": results cannot change.
 #ifndef MCX_FILT_BITS
 #define MCX_FILT_BITS 21
@@ -115,8 +115,7 @@ __host__ __device__ __forceinline__ uint32_t filt_free(int p, uint32_t lo, uint3
                   : (lo >> 20) & 0xFu;                            // 5
 }
 __host__ __device__ __forceinline__ void filt_bits(int p, uint32_t lo, uint32_t hi, uint32_t h, uint32_t &b1, uint32_t &b2) {
-    uint32_t x = ((filt_free(p, lo, hi) | ((uint32_t)(p + 1) << 8)) ^ (h << 11)) * 0x2C1B3C6Du; x ^= x >> 16;
-    x *= 0x297A2D39u;
+    const uint32_t x = ((filt_free(p, lo, hi) | ((uint32_t)(p + 1) << 8)) ^ (h << 11)) * 0x2C1B3C6Du;   // one round is enough: 1.2 % false positives, as with two
     b1 = 1u << (x >> 27); b2 = 1u << ((x >> 22) & 31u);
 }
 
@@ -687,8 +686,9 @@ __host__ __device__ inline int seg_warp_bytes(int fstride, int maxm) {   // shar
     return 18 * 4 + fstride + (((maxm + 1) * 20 + 3) & ~3) + (maxm + 2) * 32;
 }
 
+constexpr int SEG_TRI = 1328;       // window numbers whose row is tabulated (segments of up to 51 residues: every frame of a 150 bp read)
 __device__ void coop_trim(const uint8_t *fr, int off, int tl, uint8_t *P, uint8_t *nc, int lane, const double *lnfac,
-                          const double *ln20, const uint32_t *zt, int &leftend, int &rightend) {
+                          const double *ln20, const uint32_t *zt, const uint8_t *tri, int &leftend, int &rightend) {
     __syncwarp();
     if (lane < 20) {                       // P[k][a] = occurrences of letter a among the first k residues
         int acc = 0;
@@ -707,9 +707,13 @@ __device__ void coop_trim(const uint8_t *fr, int off, int tl, uint8_t *P, uint8_
         double prob = 1.0e300;
         int st = 0, len = tl;
         if (w < NW) {
-            int d = (int)((sqrtf(8.0f * (float)w + 1.0f) - 1.0f) * 0.5f);
-            while (d * (d + 1) / 2 > w) --d;
-            while ((d + 1) * (d + 2) / 2 <= w) ++d;
+            int d;
+            if (w < SEG_TRI) d = tri[w];
+            else {
+                d = (int)((sqrtf(8.0f * (float)w + 1.0f) - 1.0f) * 0.5f);
+                while (d * (d + 1) / 2 > w) --d;
+                while ((d + 1) * (d + 2) / 2 <= w) ++d;
+            }
             len = tl - d; st = w - d * (d + 1) / 2;
             // composition of the window = difference of two rows of the prefix table, four letters per word
             const uint32_t *w0 = reinterpret_cast<const uint32_t *>(P + st * 20), *w1 = reinterpret_cast<const uint32_t *>(P + (st + len) * 20);
@@ -763,9 +767,12 @@ __global__ void __launch_bounds__(WARPS * 32) k_seg(uint8_t *frames, int fstride
     double *s_ln20 = s_lnfac + SEG_TAB;                         // [SEG_TAB] i ln 20
     SegTab *s_tab = reinterpret_cast<SegTab *>(s_ln20 + SEG_TAB);
     uint32_t *s_z = reinterpret_cast<uint32_t *>(s_tab + 1);   // [32] signature words
+    uint8_t *s_tri = reinterpret_cast<uint8_t *>(s_z + 32);    // [SEG_TRI] row of window number w in the triangular scan order of Seg::trim
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t *wbase = smem + 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + 128 + (size_t)warp * seg_warp_bytes(fstride, maxm);
+    uint8_t *wbase = smem + 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + 128 + SEG_TRI + (size_t)warp * seg_warp_bytes(fstride, maxm);
     if (threadIdx.x < 32) s_z[threadIdx.x] = g_segz[threadIdx.x];
+    for (int d = threadIdx.x; d * (d + 1) / 2 < SEG_TRI; d += WARPS * 32)
+        for (int w = d * (d + 1) / 2; w < (d + 1) * (d + 2) / 2 && w < SEG_TRI; ++w) s_tri[w] = (uint8_t)d;
     uint32_t *s_m = reinterpret_cast<uint32_t *>(wbase);       // [0..5] lo, [6..11] hi, [12..17] result mask
     uint8_t *fr = wbase + 18 * 4;
     uint8_t *P = fr + fstride;                                 // [maxm + 1][20] prefix counts of the segment being trimmed
@@ -844,7 +851,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_seg(uint8_t *frames, int fstride
                     if (k >= 0) hii = k - off - 1;
                 }
                 int leftend = loi, rightend = hii;
-                coop_trim(fr, off + leftend, rightend - leftend + 1, P, nc, lane, s_lnfac, s_ln20, s_z, leftend, rightend);
+                coop_trim(fr, off + leftend, rightend - leftend + 1, P, nc, lane, s_lnfac, s_ln20, s_z, s_tri, leftend, rightend);
                 if (i < leftend && nwl < 12) { wl_off[nwl] = off + loi; wl_len[nwl] = leftend - loi; ++nwl; }
                 if (lane < 6) {                    // mask[off + leftend .. off + rightend], one word per lane
                     const int b0 = max(off + leftend, lane * 32), b1 = min(off + rightend, lane * 32 + 31);
@@ -870,12 +877,37 @@ struct Cand {                      // 12 bytes
     uint32_t ip;                   // query position << 8 | pattern
 };
 
+// Queue space is taken in runs: a warp keeps [cur, end) of a queue and only goes to the queue's counter (an atomic
+// whose round trip to L2 the whole warp waits for, serialised per address) when the run is used up.  A batch of `total`
+// records that does not fit fills the rest of the run and continues in a new one: record e of the batch goes to
+// run_pos().  Only what a warp has left when it finishes is wasted; it is marked empty by the caller.
+struct QueueRun {
+    uint32_t cur = 0, end = 0;     // warp-uniform
+    uint32_t room = 0, base = 0, next = 0;   // of the last batch: the first `room` records start at base, record e of the rest is at next + e
+};
+__device__ __forceinline__ void run_take(QueueRun &r, uint32_t total, unsigned long long *counter, uint32_t chunk, int lane) {
+    r.room = r.end - r.cur;
+    if (total > r.room) {
+        const uint32_t want = max(total - r.room, chunk);
+        uint32_t nb = 0;
+        if (lane == 0) nb = (uint32_t)min(atomicAdd(counter, (unsigned long long)want), 0xf0000000ull);   // fills stay far below 2^32
+        nb = __shfl_sync(0xffffffffu, nb, 0);
+        r.next = nb - r.room;                       // record e >= room goes to nb + (e - room)
+        r.base = r.cur;
+        r.cur = nb + (total - r.room); r.end = nb + want;
+    } else {
+        r.room = total; r.base = r.cur; r.next = 0;
+        r.cur += total;
+    }
+}
+__device__ __forceinline__ uint32_t run_pos(const QueueRun &r, uint32_t e) { return e < r.room ? r.base + e : r.next + e; }
+
 struct ProbeArgs {
     const unsigned long long *n_reads;   // reads of this chunk (device counter); frames = 6 per read
     int L;
     DevDB db;
     const uint8_t *frames;
-    Cand *passq;                   // NQ sub-queues of cap_pass entries: words that passed the filter (gframe, letters 0..7, ip | letters 8, 9 << 16)
+    Cand *passq;                   // NQ sub-queues of cap_pass entries: words that passed the filter (gframe, letters 0..7, ip | letters 8, 9 << 16 | letter before the window << 24)
     unsigned long long *n_pass;    // NQ counters
     unsigned long long cap_pass;   // per sub-queue
     Cand *cand;                    // NQ sub-queues of cap_cand entries each (spreads the append atomics)
@@ -912,7 +944,12 @@ __device__ __forceinline__ uint32_t word_code(uint32_t lo, uint32_t hi, int p) {
 #ifndef MCX_RESOLVE_NT
 #define MCX_RESOLVE_NT 128
 #endif
-constexpr int PROBE_POS = MCX_PROBE_POS;   // window positions per loop iteration (2: four filter blocks in flight, one queue reservation)
+constexpr int PROBE_POS = MCX_PROBE_POS;   // window positions per loop iteration (2: four filter blocks in flight)
+#ifndef MCX_PASS_CHUNK
+#define MCX_PASS_CHUNK 256
+#endif
+constexpr int PASS_CHUNK = MCX_PASS_CHUNK;  // records a warp of k_probe reserves at a time (a warp queues ~170 at 150 bp)
+constexpr uint32_t PASS_EMPTY = 0xffffffffu; // ip of a reserved record that was not used
 
 // K2b, filter half: one thread per frame of the store slides the 10-letter murphy10 window and tests its five words
 // against the presence filter (two block loads per window).  Nothing else happens here: the ~4 % of the words that pass
@@ -922,42 +959,54 @@ constexpr int PROBE_POS = MCX_PROBE_POS;   // window positions per loop iteratio
 // iteration; 43 % of the stall samples of the kernel sat on those lines.  An earlier attempt to batch the passes in a
 // per-warp shared-memory ring inside this kernel lost to MIO stalls; a global queue and a second kernel does not touch
 // the MIO pipe here at all.)
+#ifndef MCX_PROBE_MINB
+#define MCX_PROBE_MINB 16             /* caps k_probe at 64 registers (46 used): 3.54 ms against 3.67 ms uncapped (72 registers) for probe + resolve at 1M x 150 bp */
+#endif
 template <int NT>
-__global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
+__global__ void __launch_bounds__(NT, MCX_PROBE_MINB) k_probe(ProbeArgs A, int fstride) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int64_t n_frames = 6 * (int64_t)*A.n_reads;
-    if ((int64_t)blockIdx.x * NT >= n_frames) return;
     uint8_t *s_aa = smem;
+    __shared__ uint8_t s_red[32];                  // residue -> murphy10 letter (one LDS instead of a 64-bit shift-and-mask per residue)
     const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 32) s_red[tid] = (uint8_t)(tid < 21 ? red_of(tid) : 15);
+    __syncthreads();
+    const int sq = blockIdx.x & (NQ - 1);
+    const uint32_t lt = (1u << lane) - 1u;
+    QueueRun run;                                  // this warp's space in the pass queue
+    Cand *const qbase = A.passq + (unsigned long long)sq * A.cap_pass;
+    // resident blocks stride over the frame rows, 32 per warp and step
+    for (int64_t blk = blockIdx.x; blk * NT < n_frames; blk += gridDim.x) {
+    __syncwarp();
     {   // each warp stages its 32 rows
-        const int64_t row0 = (int64_t)blockIdx.x * NT + (tid - lane);
+        const int64_t row0 = blk * NT + (tid - lane);
         const uint32_t *src = reinterpret_cast<const uint32_t *>(A.frames + row0 * fstride);
         uint32_t *dst = reinterpret_cast<uint32_t *>(s_aa + (tid - lane) * fstride);
         for (int k = lane; k < 32 * fstride / 4; k += 32) dst[k] = src[k];
     }
     __syncwarp();
-    const int64_t g = (int64_t)blockIdx.x * NT + tid;
+    const int64_t g = blk * NT + tid;
     const uint8_t *fr = s_aa + tid * fstride;
     const int m = g < n_frames ? (A.L - (int)(g % 6) % 3) / 3 : 0;
-    const int sq = blockIdx.x & (NQ - 1);
-    const uint32_t lt = (1u << lane) - 1u;
     // reduced letters of the 10-window [i, i+10) as nibbles (letter k at bits 4k); 15 past the end
     unsigned long long win = 0;
-    for (int k = 0; k < 10; ++k) win |= (unsigned long long)(k < m ? red_of(fr[k]) : 15) << (4 * k);
+    for (int k = 0; k < 10; ++k) win |= (unsigned long long)(k < m ? s_red[fr[k]] : 15) << (4 * k);
     const int mmax = A.L / 3;
+    uint32_t before = 15;                          // reduced letter left of the window (15: none)
     for (int i = 0; i + 9 <= mmax; i += PROBE_POS) {
-        uint32_t lo[PROBE_POS], hi[PROBE_POS];
+        uint32_t lo[PROBE_POS], hi[PROBE_POS], left[PROBE_POS];
         bool ok9[PROBE_POS], ok10[PROBE_POS];
 #pragma unroll
         for (int h = 0; h < PROBE_POS; ++h) {
             lo[h] = (uint32_t)win; hi[h] = (uint32_t)(win >> 32);
+            left[h] = before; before = lo[h] & 15u;
             // letters >= 10 (stop, masked, past the end) as one bit per nibble: bit 3 and (bit 2 or bit 1)
             const uint32_t blo = (lo[h] >> 3) & ((lo[h] >> 2) | (lo[h] >> 1)) & 0x11111111u;
             const uint32_t bhi = (hi[h] >> 3) & ((hi[h] >> 2) | (hi[h] >> 1)) & 0x11u;
             ok9[h] = (blo | (bhi & 1u)) == 0u; ok10[h] = (blo | bhi) == 0u;
             if (i + h + 9 > mmax) { ok9[h] = false; ok10[h] = false; }      // past the last window of the longest frame
             const int nx = i + h + 10;
-            win = (win >> 4) | ((unsigned long long)(nx < m ? red_of(fr[nx]) : 15) << 36);
+            win = (win >> 4) | ((unsigned long long)(nx < m ? s_red[fr[nx]] : 15) << 36);
         }
         // the two filter blocks of every window of the iteration in flight together
         uint32_t ha[PROBE_POS], hb[PROBE_POS];
@@ -984,73 +1033,95 @@ __global__ void __launch_bounds__(NT) k_probe(ProbeArgs A, int fstride) {
             for (int p = 0; p < N_PAT; ++p) { bal[N_PAT * h + p] = __ballot_sync(0xffffffffu, pass[N_PAT * h + p]); total += __popc(bal[N_PAT * h + p]); }
         }
         if (total > 0) {
-            unsigned long long basepos = 0;
-            if (lane == 0) basepos = atomicAdd(A.n_pass + sq, (unsigned long long)total);
-            basepos = __shfl_sync(0xffffffffu, basepos, 0);
-            if (basepos + (unsigned long long)total <= A.cap_pass) {
-                Cand *dst = A.passq + (unsigned long long)sq * A.cap_pass + basepos;
+            run_take(run, (uint32_t)total, A.n_pass + sq, PASS_CHUNK, lane);
+            if ((unsigned long long)run.end <= A.cap_pass) {
                 int o = 0;
 #pragma unroll
                 for (int q = 0; q < N_PAT * PROBE_POS; ++q) {
                     if (pass[q]) {
                         Cand r; r.gframe = (uint32_t)g; r.sj = lo[q / N_PAT];
-                        r.ip = ((uint32_t)(i + q / N_PAT) << 8) | (uint32_t)(q % N_PAT) | (hi[q / N_PAT] << 16);
-                        dst[o + __popc(bal[q] & lt)] = r;
+                        r.ip = ((uint32_t)(i + q / N_PAT) << 8) | (uint32_t)(q % N_PAT) | (hi[q / N_PAT] << 16) | (left[q / N_PAT] << 24);
+                        qbase[run_pos(run, (uint32_t)(o + __popc(bal[q] & lt)))] = r;
                     }
                     o += __popc(bal[q]);
                 }
             }
         }
     }
+    }
+    for (uint32_t e = run.cur + lane; e < run.end; e += 32) if (e < A.cap_pass) qbase[e].ip = PASS_EMPTY;
 }
 
 // K2b, table half: one lane per word that passed the filter: slot of its pattern's table (key and value share 8
-// bytes: one load), then ONE reservation per warp and a cooperative, coalesced copy of all postings of the warp's 32
-// words into the candidate queue (gframe, subject, subject position, query position, pattern).
+// bytes: one load), then a cooperative, coalesced copy of all postings of the warp's 32 words into the candidate queue
+// (gframe, subject, subject position, query position, pattern).  Resident warps walk their sub-queue in steps of 32
+// words and take queue space CAND_CHUNK candidates at a time (unused records are marked empty), so the reservation --
+// a round trip to L2 on which the whole warp waited, a third of the stall samples -- is paid once per several steps.
+#ifndef MCX_CAND_CHUNK
+#define MCX_CAND_CHUNK 512
+#endif
+constexpr int CAND_CHUNK = MCX_CAND_CHUNK;
+constexpr uint32_t CAND_EMPTY = 0xffffffffu;    // ip of a reserved candidate record that was not used
 template <int NT>
 __global__ void __launch_bounds__(NT) k_resolve(ProbeArgs A) {
     __shared__ uint32_t s_x[NT / 32][128];          // per warp: inclusive prefix of posting counts, posting start, gframe, ip
     const int sq = blockIdx.y, lane = threadIdx.x & 31;
     const unsigned long long fill = min(A.n_pass[sq], A.cap_pass);
-    const unsigned long long k = (unsigned long long)blockIdx.x * NT + threadIdx.x;
-    if (k - lane >= fill) return;
     uint32_t *xs = s_x[threadIdx.x >> 5];
-    uint32_t cnt = 0, pi = 0, gframe = 0, ip = 0;
-    if (k < fill) {
-        const Cand r = A.passq[(unsigned long long)sq * A.cap_pass + k];
-        const int p = (int)(r.ip & 0xffu);
-        const uint32_t c = word_code(r.sj, r.ip >> 16, p);
-        gframe = r.gframe; ip = r.ip & 0xffffu;
-        const uint2 *__restrict__ tb = A.db.htab + ((size_t)p << A.db.hbits);
-        const uint32_t hmask = (1u << A.db.hbits) - 1u;
-        uint32_t sl = (c * 2654435761u) >> (32 - A.db.hbits);
-        uint2 kv = __ldg(tb + sl);
-        while (kv.x != 0xffffffffu && kv.x != c) { sl = (sl + 1) & hmask; kv = __ldg(tb + sl); }
-        if (kv.x == c) {
-            const uint32_t v = kv.y;
-            pi = v & 0x1ffffffu;                              // 25-bit start, 7-bit (count - 1)
-            cnt = (v >> 25) + 1;
-            if ((v >> 25) == 127) { cnt = __ldg(A.db.post + pi); ++pi; }   // longer lists start with their length
+    Cand *const qbase = A.cand + (unsigned long long)sq * A.cap_cand;
+    QueueRun run;                                   // this warp's space in the candidate queue
+    for (unsigned long long k = (unsigned long long)blockIdx.x * NT + threadIdx.x; k - lane < fill; k += (unsigned long long)gridDim.x * NT) {
+        uint32_t cnt = 0, pi = 0, gframe = 0, ip = 0;
+        Cand r; r.ip = PASS_EMPTY;
+        if (k < fill) r = A.passq[(unsigned long long)sq * A.cap_pass + k];
+        if (r.ip != PASS_EMPTY) {
+            const int p = (int)(r.ip & 0xffu);
+            const uint32_t c = word_code(r.sj, (r.ip >> 16) & 0xffu, p);
+            // the query letter of the first rejection test (ExtendSeq2Set 0x4140c0-0x414113): the letter left of an exact
+            // word (a word whose left neighbours also agree is found again one position to the left: left-maximal only), the
+            // letter under the wildcard of a one-substitution word (if it agrees, the exact word finds the stretch)
+            const uint32_t ql = p == 0 ? (r.ip >> 24) & 15u : (r.sj >> (4 * (p + 2))) & 15u;
+            gframe = r.gframe; ip = (r.ip & 0xffffu) | (ql << 16);
+            const uint2 *__restrict__ tb = A.db.htab + ((size_t)p << A.db.hbits);
+            const uint32_t hmask = (1u << A.db.hbits) - 1u;
+            uint32_t sl = (c * 2654435761u) >> (32 - A.db.hbits);
+            uint2 kv = __ldg(tb + sl);
+            while (kv.x != 0xffffffffu && kv.x != c) { sl = (sl + 1) & hmask; kv = __ldg(tb + sl); }
+            if (kv.x == c) {
+                const uint32_t v = kv.y;
+                pi = v & 0x1ffffffu;                              // 25-bit start, 7-bit (count - 1)
+                cnt = (v >> 25) + 1;
+                if ((v >> 25) == 127) { cnt = __ldg(A.db.post + pi); ++pi; }   // longer lists start with their length
+            }
+        }
+        const int inc2 = warp_scan_add((int)cnt, lane);
+        const int tot2 = __shfl_sync(0xffffffffu, inc2, 31);
+        if (tot2 == 0) continue;
+        __syncwarp();
+        xs[lane] = (uint32_t)inc2; xs[32 + lane] = pi; xs[64 + lane] = gframe; xs[96 + lane] = ip;
+        __syncwarp();
+        for (int e0 = 0; e0 < tot2; e0 += 32) {
+            const int e = e0 + lane;
+            bool keep = false;
+            Cand c; c.gframe = c.sj = c.ip = 0;
+            if (e < tot2) {
+                int lo = 0;                                   // first owner whose inclusive prefix exceeds e
+#pragma unroll
+                for (int step = 16; step; step >>= 1) if (xs[lo + step - 1] <= (uint32_t)e) lo += step;
+                const uint32_t q = (uint32_t)e - (lo ? xs[lo - 1] : 0u);
+                const uint32_t post = __ldg(A.db.post + xs[32 + lo] + q), meta = xs[96 + lo];
+                const uint32_t ql = meta >> 16, tl = (post >> 26) & 15u;
+                keep = !(ql == tl && ql < 10u);               // equal valid letters: rejected (three candidates in five)
+                c.gframe = xs[64 + lo]; c.sj = post & 0x3ffffffu; c.ip = meta & 0xffffu;
+            }
+            const uint32_t km = __ballot_sync(0xffffffffu, keep);
+            if (km == 0u) continue;
+            run_take(run, (uint32_t)__popc(km), A.n_cand + sq, CAND_CHUNK, lane);
+            if ((unsigned long long)run.end > A.cap_cand) continue;
+            if (keep) qbase[run_pos(run, (uint32_t)__popc(km & ((1u << lane) - 1u)))] = c;
         }
     }
-    const int inc2 = warp_scan_add((int)cnt, lane);
-    const int tot2 = __shfl_sync(0xffffffffu, inc2, 31);
-    if (tot2 == 0) return;
-    unsigned long long basepos = 0;
-    if (lane == 0) basepos = atomicAdd(A.n_cand + sq, (unsigned long long)tot2);
-    basepos = __shfl_sync(0xffffffffu, basepos, 0);
-    xs[lane] = (uint32_t)inc2; xs[32 + lane] = pi; xs[64 + lane] = gframe; xs[96 + lane] = ip;
-    __syncwarp();
-    if (basepos + (unsigned long long)tot2 > A.cap_cand) return;
-    Cand *dst = A.cand + (unsigned long long)sq * A.cap_cand + basepos;
-    for (int e = lane; e < tot2; e += 32) {
-        int lo = 0;                                       // first owner whose inclusive prefix exceeds e
-#pragma unroll
-        for (int step = 16; step; step >>= 1) if (xs[lo + step - 1] <= (uint32_t)e) lo += step;
-        const uint32_t q = (uint32_t)e - (lo ? xs[lo - 1] : 0u);
-        Cand c; c.gframe = xs[64 + lo]; c.sj = __ldg(A.db.post + xs[32 + lo] + q) & 0x7fffffffu; c.ip = xs[96 + lo];
-        dst[e] = c;
-    }
+    for (uint32_t e = run.cur + lane; e < run.end; e += 32) if (e < A.cap_cand) qbase[e].ip = CAND_EMPTY;
 }
 
 // K2b: one thread per candidate: grow the word to the maximal murphy10-identical stretch, apply the seed
@@ -1109,6 +1180,12 @@ constexpr int SEED_NT = MCX_SEED_NT;   // threads per block of k_seed
 constexpr int WALK_NT = MCX_WALK_NT;   // threads per block of k_walk
 constexpr int GAP_NT = MCX_GAP_NT;     // threads per block of k_gap_dir
 #define SAME(a, b) ((s_same[(a)] >> (b)) & 1u)   /* red_eq() from the shared-memory masks */
+__device__ uint32_t g_same[32];                  // bit b of g_same[a]: residues a and b share a murphy10 letter (upload_tables)
+#ifndef MCX_SEED_CHUNK
+#define MCX_SEED_CHUNK 256
+#endif
+constexpr int SEED_CHUNK = MCX_SEED_CHUNK;
+constexpr uint32_t SEED_EMPTY = 0xffffffffu;     // x (frame row) of a reserved seed record that was not used
 // K2c: one thread per candidate: the cheap rejections, growth of the word to the maximal murphy10-identical stretch
 // and the seed acceptance test (ExtendSeq2Set 0x413fc4-0x414073); accepted seeds are queued for k_walk.
 template <int NT>
@@ -1116,18 +1193,20 @@ __global__ void __launch_bounds__(NT) k_seed(ExtArgs A) {
     __shared__ __align__(4) int8_t s_bl[21 * 32];
     __shared__ uint32_t s_same[32];                 // bit b of s_same[a]: residues a and b share a murphy10 letter
     for (int k = threadIdx.x; k < 21 * 32 / 4; k += NT) reinterpret_cast<uint32_t *>(s_bl)[k] = reinterpret_cast<const uint32_t *>(g_blosum)[k];
-    if (threadIdx.x < 32) {
-        uint32_t mk = 0;
-        const int a = threadIdx.x;
-        if (a < 20) for (int b = 0; b < 20; ++b) mk |= (uint32_t)(red_of(a) == red_of(b)) << b;
-        s_same[a] = mk;
-    }
+    if (threadIdx.x < 32) s_same[threadIdx.x] = g_same[threadIdx.x];
     __syncthreads();
-    // grid.y = candidate sub-queue, grid.x covers a full one; the fills are read on the device
-    const int sq = blockIdx.y;
-    const unsigned long long k = (unsigned long long)blockIdx.x * NT + threadIdx.x;
-    if (k >= min(A.qfill[sq], A.cap_cand)) return;
+    // grid.y = candidate sub-queue, whose fill is read on the device; the blocks of a row are resident and stride over
+    // it (the tables above are staged once per block, not once per 128 candidates), and every warp takes space in the
+    // seed queue SEED_CHUNK records at a time, unused records marked empty: one counter, ~3 M additions per million
+    // reads when every warp added for itself, which the L2 serialises
+    const int sq = blockIdx.y, lane = threadIdx.x & 31;
+    const unsigned long long fill = min(A.qfill[sq], A.cap_cand);
+    QueueRun run;                                   // this warp's space in the seed queue
+    for (unsigned long long k = (unsigned long long)blockIdx.x * NT + threadIdx.x; k - lane < fill; k += (unsigned long long)gridDim.x * NT) {
+    uint4 rec;
+    const bool accepted = k < fill && [&]() -> bool {
     const Cand c = A.cand[(unsigned long long)sq * A.cap_cand + k];
+    if (c.ip == CAND_EMPTY) return false;
     const int frame = (int)(c.gframe % 6u);
     const int m = (A.L - frame % 3) / 3;
     const uint8_t *__restrict__ fr = A.frames + (int64_t)c.gframe * A.fstride;
@@ -1135,38 +1214,83 @@ __global__ void __launch_bounds__(NT) k_seed(ExtArgs A) {
     const int32_t o = __ldg(A.db.off + s);
     const int n = __ldg(A.db.off + s + 1) - o;
     const uint8_t *__restrict__ t = A.db.res + o;
-    if (p == 0) {                  // exact words: left-maximal only (ExtendSeq2Set 0x4140c0-0x414113)
-        if (i > 0 && j > 0 && SAME(fr[i - 1], t[j - 1])) return;
-    } else {                       // one-substitution words: the replaced letter differs by construction;
-        const int w = p + 2;       // keep one window per substituted position (all windows give the same seed)
-        if (red_of(fr[i + w]) == red_of(t[j + w])) return;
-        if (w >= 4 && i + 10 < m && j + 10 < n && SAME(fr[i + 10], t[j + 10])) return;
+    // The sixteen residues around the word on both sequences (positions i-3 .. i+12 and j-3 .. j+12) are fetched as
+    // five aligned words each, all in flight together, and every test below reads them from registers.  (Before: each
+    // test waited for its own pair of byte loads -- up to a dozen dependent round trips per candidate.)  Only a stretch
+    // that grows past the fetched window on either side takes the byte-wise path.
+    uint32_t Q[4], T[4];
+    {
+        const uint8_t *pq = fr + i - 3, *pt = t + j - 3;         // the frame store and the residues are padded on both sides
+        const uint32_t *aq = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(pq) & ~(uintptr_t)3);
+        const uint32_t *at = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(pt) & ~(uintptr_t)3);
+        const int shq = 8 * (int)(reinterpret_cast<uintptr_t>(pq) & 3), sht = 8 * (int)(reinterpret_cast<uintptr_t>(pt) & 3);
+        uint32_t wq[5], wt[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { wq[k] = __ldg(aq + k); wt[k] = __ldg(at + k); }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { Q[k] = __funnelshift_r(wq[k], wq[k + 1], shq); T[k] = __funnelshift_r(wt[k], wt[k + 1], sht); }
     }
-    int qb = i, sb = j, len = p == 0 ? 9 : 10;
-    while (qb + len < m && sb + len < n && SAME(fr[qb + len], t[sb + len])) ++len;
-    while (qb > 0 && sb > 0 && SAME(fr[qb - 1], t[sb - 1])) { --qb; --sb; ++len; }
-    int score0 = 0, id0 = 0;
-    for (int k = 0; k < len; ++k) {
-        const int a = fr[qb + k], b = t[sb + k];
-        score0 += s_bl[a * 32 + b];
-        id0 += (a == b && a < 20);
+#define QB(d) ((int)((Q[((d) + 3) >> 2] >> (8 * (((d) + 3) & 3))) & 0xffu))
+#define TB(d) ((int)((T[((d) + 3) >> 2] >> (8 * (((d) + 3) & 3))) & 0xffu))
+    // (exact words whose left neighbours agree and one-substitution words whose replaced letter agrees never get here:
+    // k_resolve drops them from the letter it finds in the posting)
+    // one-substitution words: keep one window per substituted position (all windows give the same seed)
+    if (p >= 2 && i + 10 < m && j + 10 < n && SAME(QB(10), TB(10))) return false;
+    int qb, sb, len, score0 = 0, id0 = 0;
+    {
+        int r = p == 0 ? 9 : 10, l = 0;             // the stretch is [i - l, i + r)
+        // (bitwise &, selects and unconditional table reads on purpose: with && / if the compiler turns these unrolled
+        // steps into per-lane branches and the warp runs them at 9 of 32 lanes)
+#pragma unroll
+        for (int d = 9; d <= 12; ++d) r += (int)((uint32_t)(d == r) & (uint32_t)(i + d < m) & (uint32_t)(j + d < n) & SAME(QB(d), TB(d)));
+#pragma unroll
+        for (int d = 1; d <= 3; ++d) l += (int)((uint32_t)(d == l + 1) & (uint32_t)(i - d >= 0) & (uint32_t)(j - d >= 0) & SAME(QB(-d), TB(-d)));
+        const bool beyond = (r == 13 && i + 13 < m && j + 13 < n) || (l == 3 && i - 4 >= 0 && j - 4 >= 0);
+        if (!beyond) {
+            qb = i - l; sb = j - l; len = r + l;
+#pragma unroll
+            for (int d = -3; d <= 12; ++d) {
+                const int a = QB(d), b = TB(d);                      // residues or padding: always 0..20
+                const int in = (int)((uint32_t)(d >= -l) & (uint32_t)(d < r));
+                score0 += in * (int)s_bl[a * 32 + b];
+                id0 += in & (int)((uint32_t)(a == b) & (uint32_t)(a < 20));
+            }
+        } else {
+            qb = i; sb = j; len = p == 0 ? 9 : 10;
+            while (qb + len < m && sb + len < n && SAME(fr[qb + len], t[sb + len])) ++len;
+            while (qb > 0 && sb > 0 && SAME(fr[qb - 1], t[sb - 1])) { --qb; --sb; ++len; }
+            for (int k = 0; k < len; ++k) {
+                const int a = fr[qb + k], b = t[sb + k];
+                score0 += s_bl[a * 32 + b];
+                id0 += (a == b && a < 20);
+            }
+        }
     }
-    if (score0 < SEED_MIN_SCORE || id0 < SEED_MIN_IDENT) return;
-    const uint32_t mask = __activemask();
-    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
-    unsigned long long base = 0;
-    if (lane == leader) base = atomicAdd(A.n_seedq, (unsigned long long)__popc(mask));
-    base = __shfl_sync(mask, base, leader);
-    const unsigned long long at = base + __popc(mask & ((1u << lane) - 1));
-    if (at < A.cap_seedq) A.seedq[at] = seed_pack(c.gframe, s, sb, qb, len, score0, id0);
+#undef QB
+#undef TB
+    if (score0 < SEED_MIN_SCORE || id0 < SEED_MIN_IDENT) return false;
+    rec = seed_pack(c.gframe, s, sb, qb, len, score0, id0);
+    return true;
+    }();
+    const uint32_t am = __ballot_sync(0xffffffffu, accepted);
+    if (am == 0u) continue;
+    run_take(run, (uint32_t)__popc(am), A.n_seedq, SEED_CHUNK, lane);
+    const uint32_t at = run_pos(run, (uint32_t)__popc(am & ((1u << lane) - 1u)));
+    if (accepted && at < A.cap_seedq) A.seedq[at] = rec;
+    }
+    for (uint32_t e = run.cur + lane; e < run.end; e += 32) if (e < A.cap_seedq) A.seedq[e].x = SEED_EMPTY;
 }
 
 #undef SAME
 // K2d: one thread per accepted seed: the ungapped X-drop walks both ways (AlignFwd / AlignBwd); HSPs reaching the
 // report floor are appended to the survivor list.
+// (Tried and measured slower, 1.61 -> 2.15 ms at 1M x 150 bp: loading the residues of four steps together, the next four
+// while the current four are scored.  The walks are short -- most stop after a few residues -- so the batches mostly
+// fetch what is never used, and the kernel went from 36 to 80 registers, 69 % to 35 % occupancy.)
 __device__ __forceinline__ void walk_one(const ExtArgs &A, const int8_t *s_bl, int64_t g) {
     const uint4 sd = A.seedq[g];
     const uint32_t gframe = sd.x;
+    if (gframe == SEED_EMPTY) return;
     const int s = (int)(sd.y & 0x7fffu), sb = (int)(sd.y >> 15), qb = (int)(sd.z & 0xffu), len = (int)((sd.z >> 8) & 0xffu);
     const int score0 = (int)(sd.z >> 16), id0 = (int)sd.w;
     const int frame = (int)(gframe % 6u);
@@ -2408,7 +2532,15 @@ static int build_index(mcx_ctx *ctx, const mcx_db *db) {
             while (ht[slot].x != 0xffffffffu) slot = (slot + 1) & (size - 1);
             ht[slot] = make_uint2(code, (uint32_t)w | ((cnt > 127 ? 127u : cnt - 1) << 25));
             if (cnt > 127) post_all[w++] = cnt;              // lists too long for the 7-bit field start with their length
-            for (size_t q = k; q <= e; ++q) post_all[w++] = (uint32_t)(en[q] & 0x7fffffffu) | (q == e ? 0x80000000u : 0u);
+            for (size_t q = k; q <= e; ++q) {
+                // bits 26..29: the murphy10 letter of the subject that decides the first rejection test of a candidate --
+                // the residue under the wildcard (one-substitution words), the residue left of the word (exact words;
+                // 15 at the start of the subject) -- so that k_resolve applies the test without touching the residues
+                const uint32_t sj = (uint32_t)(en[q] & 0x3ffffffu), subj = sj >> 11, jj = sj & 0x7ffu;
+                const uint8_t *r = red.data() + db->off[subj];
+                const uint32_t letter = p == 0 ? (jj > 0 ? r[jj - 1] : 15u) : r[jj + (uint32_t)PAT_WILD[p]];
+                post_all[w++] = sj | (letter << 26) | (q == e ? 0x80000000u : 0u);
+            }
             k = e + 1;
         }
         std::vector<unsigned long long>().swap(ent[p]);
@@ -2573,6 +2705,11 @@ static int upload_tables(mcx_ctx *ctx) {
         CK(cudaMemcpyToSymbol(g_fptab, &T, sizeof T));
     }
     CK(cudaMemcpyToSymbol(g_blosum, bl, sizeof bl));
+    {
+        uint32_t same[32] = {0};
+        for (int a = 0; a < 20; ++a) for (int b = 0; b < 20; ++b) same[a] |= (uint32_t)(MURPHY10[a] == MURPHY10[b]) << b;
+        CK(cudaMemcpyToSymbol(g_same, same, sizeof same));
+    }
     CK(cudaMemcpyToSymbol(g_lnfac, lnfac, sizeof lnfac));
     CK(cudaMemcpyToSymbol(g_ln20, ln20, sizeof ln20));
     return MCX_OK;
@@ -3271,7 +3408,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     // the stages run per chunk of pushed reads so that the frame store and the queues stay bounded
     const int fstride = frame_stride(maxm);
     const int nwr = std::max(1, (maxm - SEG_WINDOW + 1 + 31) / 32);     // words of a 12-window mask
-    int64_t chunk = 2000000, cand_per_read = 96;
+    int64_t chunk = 2000000, cand_per_read = std::max<int64_t>(96, (int64_t)(0.8 * P.read_length));   // ~0.69 L word-hit postings per read on the marker set
     chunk = std::min<int64_t>(chunk, std::max<int64_t>(250000, 300000000 / P.read_length));   // queues scale with bases, not reads
     if (const char *e = getenv("MCX_CHUNK_READS")) chunk = std::min(2700000, std::max(1, atoi(e)));   // frame rows < 2^24
     if (const char *e = getenv("MCX_CAND_PER_READ")) cand_per_read = std::max(1, atoi(e));
@@ -3280,7 +3417,10 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     chunk = std::min<int64_t>(chunk, std::max<int64_t>(n, 1));
     {
         const int64_t need_fr = (chunk * 6 + 512) * fstride + 128, need_cand = std::max<int64_t>(chunk * cand_per_read, 1 << 16);
+        const int64_t cap_fr_before = ctx->cap_frames;
         if ((rc = ensure(ctx, &ctx->d_frames, &ctx->cap_frames, need_fr)) != MCX_OK) return rc;
+        // k_seed reads 16-byte windows around a word without looking at the row ends: whatever lies there must be a residue code
+        if (ctx->cap_frames != cap_fr_before) CK(cudaMemsetAsync(ctx->d_frames, AA_STOP, (size_t)ctx->cap_frames, ctx->stream));
         if ((rc = ensure(ctx, &ctx->d_cand, &ctx->cap_cand, need_cand)) != MCX_OK) return rc;
         if ((rc = ensure(ctx, &ctx->d_passq, &ctx->cap_passq, std::max<int64_t>(chunk * pass_per_read, 1 << 16))) != MCX_OK) return rc;
         if ((rc = ensure(ctx, &ctx->d_seedq, &ctx->cap_seedq, std::max<int64_t>(ctx->cap_cand / 2, 1 << 16))) != MCX_OK) return rc;
@@ -3375,7 +3515,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         CK(cudaEventRecord(ctx->ev[10], st));
         {   // full SEG of the queued frames: resident blocks, queue length read on the device
             constexpr int SW = MCX_SEG_W;
-            const size_t smem = 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + 128 + (size_t)SW * seg_warp_bytes(fstride, maxm);
+            const size_t smem = 2 * SEG_TAB * sizeof(double) + sizeof(SegTab) + 128 + SEG_TRI + (size_t)SW * seg_warp_bytes(fstride, maxm);
             CK(cudaFuncSetAttribute(k_seg<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int per_sm = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seg<SW>, SW * 32, smem));
@@ -3398,8 +3538,19 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             constexpr int NTP = MCX_PROBE_NT, NTR = MCX_RESOLVE_NT;
             const size_t smem = (size_t)fstride * NTP;
             CK(cudaFuncSetAttribute(k_probe<NTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_probe<NTP><<<(unsigned)((nr_max * 6 + NTP - 1) / NTP), NTP, smem, st>>>(A, fstride);
-            k_resolve<NTR><<<dim3((unsigned)((A.cap_pass + NTR - 1) / NTR), NQ), NTR, 0, st>>>(A);
+            {
+                int per_sm = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_probe<NTP>, NTP, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+                const unsigned long long resident = (unsigned long long)per_sm * ctx->n_sm;
+                k_probe<NTP><<<(unsigned)std::min<unsigned long long>((nr_max * 6 + NTP - 1) / NTP, resident), NTP, smem, st>>>(A, fstride);
+            }
+            auto row_blocks = [&](auto kernel, int nt, unsigned long long cap) -> unsigned {   // resident blocks per sub-queue row
+                int per_sm = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+                const unsigned long long want = ((unsigned long long)per_sm * ctx->n_sm * 2 + NQ - 1) / NQ;
+                return (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(want, (cap + nt - 1) / nt));
+            };
+            k_resolve<NTR><<<dim3(row_blocks(k_resolve<NTR>, NTR, A.cap_pass), NQ), NTR, 0, st>>>(A);
             ++ctx->launches;
             if (attempt == 0) CK(cudaEventRecord(ctx->ev[3], st));
             ExtArgs E;
@@ -3416,7 +3567,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
                 CK(cudaMemsetAsync(ctx->d_seen, 0xff, (size_t)(1ll << bits) * sizeof(unsigned long long), st));
                 E.seen = ctx->d_seen; E.seen_mask = (1ull << bits) - 1; E.seen_shift = 64 - bits;
             }
-            k_seed<SEED_NT><<<dim3((unsigned)((E.cap_cand + SEED_NT - 1) / SEED_NT), NQ), SEED_NT, 0, st>>>(E);
+            k_seed<SEED_NT><<<dim3(row_blocks(k_seed<SEED_NT>, SEED_NT, E.cap_cand), NQ), SEED_NT, 0, st>>>(E);
             {
                 int per_sm = 0;
                 if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk<WALK_NT>, WALK_NT, 0) != cudaSuccess || per_sm < 1) per_sm = 1;

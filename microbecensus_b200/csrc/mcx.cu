@@ -960,7 +960,7 @@ constexpr uint32_t PASS_EMPTY = 0xffffffffu; // ip of a reserved record that was
 // per-warp shared-memory ring inside this kernel lost to MIO stalls; a global queue and a second kernel does not touch
 // the MIO pipe here at all.)
 #ifndef MCX_PROBE_MINB
-#define MCX_PROBE_MINB 16             /* caps k_probe at 64 registers (46 used): 3.54 ms against 3.67 ms uncapped (72 registers) for probe + resolve at 1M x 150 bp */
+#define MCX_PROBE_MINB 16             /* caps k_probe at 64 registers (56 used): probe + resolve 3.54 ms at 1M x 150 bp against 3.67 ms uncapped (72 registers) and 3.69 ms at 46 registers */
 #endif
 template <int NT>
 __global__ void __launch_bounds__(NT, MCX_PROBE_MINB) k_probe(ProbeArgs A, int fstride) {

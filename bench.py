@@ -402,37 +402,66 @@ def main():
     hbm = peaks.get("hbm_gbs")
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if hbm else "fallback 6650 GB/s (B200_PROFILING.md)"
     hbm = hbm or 6650.0
-    # algorithmic bytes of k_probe per searched read: the six frame rows it reads from the frame
-    # store and one 4-byte filter/hash word per seed-word probe (5 words per window position)
-    m = [(L - o) // 3 for o in (0, 1, 2)]
-    probes = 2 * sum(max(0, x - 8) + 4 * max(0, x - 9) for x in m)
-    bytes_per_read = 4 * probes + sum(m) * 2
+    # ---- roofline of every kernel of the step (DESIGN.md section 5 states the formulas): ALGORITHMIC bytes per launch =
+    # per-unit bytes x the units the launch worked on (reads, frames and the queue lengths the library counted), over
+    # the kernel's own CUDA-event time inside the timed region.  `roofline` is the entry of the kernel with the
+    # largest share of the step.
     per_gpu_reads = total_reads / world
-    k_ms = stage_dev["probe"]
-    achieved = per_gpu_reads * bytes_per_read / (k_ms * 1e-3) / 1e9
-    # SURVEY 8d names the random-access transaction rate, not bandwidth, as this kernel's bound: probes/s against the
-    # measured rate of independent random 4-byte loads over the same 32 MB filter (mcx_l2_peak)
+    work = eng.search_counters()                                  # rank 0's last search
+    m = [(L - o) // 3 for o in (0, 1, 2)]
+    sum_m = 2 * sum(m)                                            # residues of the six frames of a read
+    w9, w10 = 2 * sum(max(0, x - 8) for x in m), 2 * sum(max(0, x - 9) for x in m)    # 9- and 10-letter windows per read
+    G = (L + 31) // 32
+    nwr = max(1, ((L + 2) // 3 - 12 + 1 + 31) // 32)
+    R = per_gpu_reads
+    algo = {
+        "k_frames": R * (12 * G + 12 + sum_m),                                        # packed record, length, offset in; six rows out
+        "k_seg": work["seg_frames"] * (2 * sum_m / 6.0 + 8 * nwr + 4),               # row in and out, its two window masks, queue entry
+        "k_probe": R * (sum_m + 16 * w9 + 8 * w10) + 12 * work["filter_passes"],      # rows in, one 16 B and one 8 B filter block per window, pass records out
+        "k_resolve": work["filter_passes"] * (12 + 8) + work["candidates"] * (4 + 12),  # pass record + table slot in; posting in, candidate out
+        "k_seed": work["candidates"] * (12 + 2 * 16 + 8) + work["seeds"] * 16,        # candidate, two 16-residue windows, subject offsets in; seed out
+        "k_walk": work["seeds"] * 16 + work["ungapped_hsps"] * 16,                     # seed in, HSP out (the residues walked are L1 / L2 hits)
+    }
+    k_times = {"k_frames": stage_dev["frames"], "k_seg": stage_dev["seg"], "k_probe": stage_dev["k_probe"],
+               "k_resolve": stage_dev["k_resolve"], "k_seed": stage_dev["k_seed"], "k_walk": stage_dev["k_walk"]}
+    traffic = {}
+    try:
+        pj = json.load(open(os.path.join(ROOT, "profiles", "r02_kernel_traffic.json")))
+        traffic = {k: v * (per_gpu_reads / pj["reads"]) for k, v in pj["dram_bytes_per_launch"].items()}
+        issue = pj.get("issue_active_pct", {})
+    except Exception:
+        pj, issue = None, {}
+    what = {"k_frames": "translation of the six frames, SEG window verdicts",
+            "k_seg": "SEG (Wootton-Federhen) of the frames with a low-entropy window, one warp per frame",
+            "k_probe": "murphy10 seed-word presence filter: two filter blocks (L2) per window",
+            "k_resolve": "word tables and posting lists of the words that passed the filter (HBM), first rejection test",
+            "k_seed": "seed growth and acceptance from 16-residue windows",
+            "k_walk": "ungapped X-drop walks"}
+    kernels = []
+    for k, ms_k in k_times.items():
+        ach = algo[k] / (ms_k * 1e-3) / 1e9 if ms_k else None
+        kernels.append({"kernel": k, "ms": ms_k, "share_of_step": ms_k / (t_dev * 1e3), "algorithmic_bytes": algo[k],
+                        "achieved_gbs": ach, "frac_of_hbm": ach / hbm if ach else None, "dram_traffic_bytes": traffic.get(k),
+                        "issue_active_pct_ncu": issue.get(k)})
+    top = max(kernels, key=lambda r: r["ms"])
     l2_peak = eng.l2_peak()
-    probes_per_s = per_gpu_reads * probes / (k_ms * 1e-3)
-    roofline = {"bound": "hbm", "kernel": "k_probe (murphy10 seed-word lookup: presence filter in L2, hash slots and postings in HBM)",
-                "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
-                "peak_source": peak_src, "algorithmic_bytes_per_read": bytes_per_read, "kernel_ms": k_ms,
-                "kernel_timing": "CUDA events around the k_probe launches on the library's stream (mcx_timings[2])",
-                "kernel_share_of_step": k_ms / (t_dev * 1e3),
-                "lookups": {"probes_per_read": probes, "probes_per_s": probes_per_s, "bytes_per_lookup": 4,
-                            "l2_random_loads_per_s_measured": l2_peak * 1e9, "frac_of_l2_random_rate": probes_per_s / (l2_peak * 1e9),
-                            "note": "each probe is one 32-byte L2 sector; the microbenchmark issues nothing but such loads"}}
-    for prof in ("r02_k_probe_traffic.json", "r01_k_probe_traffic.json"):
-        prof = os.path.join(ROOT, "profiles", prof)
-        if os.path.exists(prof):
-            try:
-                pj = json.load(open(prof))
-                # the capture is of one launch over `reads` reads: scale to this step's reads per GPU
-                roofline["traffic"] = pj.get("dram_bytes_per_launch") * (per_gpu_reads / pj["reads"]) if pj.get("reads") else pj.get("dram_bytes_per_launch")
-                roofline["traffic_source"] = os.path.basename(prof)
-                break
-            except Exception:
-                pass
+    block_loads = R * (w9 + w10)
+    roofline = {"bound": "hbm", "kernel": "%s (%s)" % (top["kernel"], what[top["kernel"]]),
+                "achieved": top["achieved_gbs"], "peak": hbm, "unit": "GB/s", "frac": top["frac_of_hbm"], "traffic": top["dram_traffic_bytes"],
+                "peak_source": peak_src, "algorithmic_bytes_per_read": top["algorithmic_bytes"] / R, "kernel_ms": top["ms"],
+                "kernel_timing": "CUDA events around the kernel's launches on the library's stream (mcx_timings / mcx_timings_detail)",
+                "kernel_share_of_step": top["share_of_step"],
+                "issue_active_pct_ncu": top["issue_active_pct_ncu"],
+                "note": "integer work bound by issue slots, not by bytes: the HBM fraction is small by construction; "
+                        "issue_active_pct_ncu is the share of issue slots used under ncu (profiles/r02_ncu_summary.md)",
+                "traffic_source": "profiles/r02_kernel_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch at %d reads, scaled to this step)" % pj["reads"] if pj else None,
+                "lookups": {"kernel": "k_probe", "filter_block_loads_per_read": w9 + w10, "block_loads_per_s": block_loads / (stage_dev["k_probe"] * 1e-3),
+                            "bytes_per_lookup": "16 (exact word and wildcards 3 / 4) or 8 (wildcards 5 / 6): one 32-byte L2 sector either way",
+                            "l2_random_loads_per_s_measured": l2_peak * 1e9,
+                            "frac_of_l2_random_rate": block_loads / (stage_dev["k_probe"] * 1e-3) / (l2_peak * 1e9),
+                            "note": "upper bound on the loads issued (windows with a stop codon or masked residue are skipped); the "
+                                    "microbenchmark issues nothing but scattered 4-byte loads over the same filter"},
+                "kernels": kernels}
     # K1 (the kernel SURVEY 8d calls HBM-bound): bytes per read of the survey's table -- 2-bit bases ceil(L/4) + mask
     # ceil(L/8), + L quality bytes when -q/-m are active, one verdict byte written -- over the k_qc launches alone
     k1_bytes = (L + 3) // 4 + (L + 7) // 8 + (L if wl["fastq"] else 0) + 1

@@ -182,11 +182,19 @@ int  mcx_get_hits(mcx_ctx *ctx, mcx_hit *out, int64_t cap, int64_t *n);
 int  mcx_get_classified(mcx_ctx *ctx, int32_t *best_subject, int64_t n);
 
 /* device time (ms, CUDA events on the context's stream) of the stages of the last push/search:
- * [0] h2d copy, [1] k_qc + compaction, [2] k_probe, [3] gapped stage (k_gap_*), [4] sort, [5] classifier (k_cls_*),
+ * [0] h2d copy, [1] k_qc + compaction, [2] k_probe + k_resolve, [3] gapped stage (k_gap_*), [4] sort, [5] classifier (k_cls_*),
  * [6] d2h, [7] k_seed + k_walk, [8] k_frames, [9] k_seg, [10] k_qc alone (part of [1]), [11] -d: fingerprints + sort + marks
  * (part of [1]); and the number of kernel launches.  [0] is the span of the copies on the copy stream: they overlap
  * the other stages. */
 int  mcx_timings(mcx_ctx *ctx, float ms[12], int64_t *launches);
+/* the seed stage kernel by kernel: [0] k_probe (filter), [1] k_resolve (tables + postings), [2] k_seed, [3] k_walk;
+ * [0] + [1] = mcx_timings [2], [2] + [3] = mcx_timings [7] */
+int  mcx_timings_detail(mcx_ctx *ctx, float ms[4]);
+/* queue lengths of the last search (what the kernels between the stages worked on; the roofline figures of bench.py are
+ * formed from them): [0] frames with a low-entropy window (k_seg), [1] records of the filter-pass queue, [2] of the
+ * candidate queue, [3] of the seed queue ([1]-[3] include the few records a warp reserved and left empty), [4] ungapped
+ * HSPs at or above the report floor; [5]-[7] reserved (0) */
+int  mcx_search_counters(mcx_ctx *ctx, int64_t out[8]);
 
 /* Measurement aid: issue rate of the DPX instructions an affine-gap cell uses (viaddmax_s32 /
  * vimax3_s32_relu, independent chains on every SM), in 1e9 thread-instructions per second.  The DPX-bound cell rate

@@ -55,7 +55,7 @@ class Hit(C.Structure):
 EXPORTS = ("mcx_create", "mcx_destroy", "mcx_set_params", "mcx_set_stream", "mcx_push_reads", "mcx_push_reads_dev",
            "mcx_push_reads_packed", "mcx_push_reads_packed_dev", "mcx_host_alloc", "mcx_host_free",
            "mcx_qc_counts", "mcx_qc_export", "mcx_qc_import", "mcx_qc_device", "mcx_qc_refresh", "mcx_dedup_reset", "mcx_dedup_begin", "mcx_dedup_owner", "mcx_dedup_finish", "mcx_search", "mcx_result_get", "mcx_get_hits", "mcx_get_classified",
-           "mcx_timings", "mcx_dpx_peak", "mcx_l2_peak", "mcx_last_error", "mcx_version")
+           "mcx_timings", "mcx_timings_detail", "mcx_search_counters", "mcx_dpx_peak", "mcx_l2_peak", "mcx_last_error", "mcx_version")
 
 _lib = None
 
@@ -96,6 +96,8 @@ def load():
     lib.mcx_get_hits.argtypes = [vp, vp, i64, C.POINTER(i64)]
     lib.mcx_get_classified.argtypes = [vp, vp, i64]
     lib.mcx_timings.argtypes = [vp, C.POINTER(C.c_float * 12), C.POINTER(i64)]
+    lib.mcx_timings_detail.argtypes = [vp, C.POINTER(C.c_float * 4)]
+    lib.mcx_search_counters.argtypes = [vp, C.POINTER(C.c_int64 * 8)]
     lib.mcx_dpx_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.mcx_l2_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.mcx_last_error.argtypes = [vp]

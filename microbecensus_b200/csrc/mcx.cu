@@ -3,18 +3,22 @@
 // One context = one GPU.  The hot path is a chain of hand-written kernels with compaction between every two stages
 // whose per-item work varies (no CPU fallback anywhere):
 //
-//   k_qc          read QC                    mc.py:265-279, 342-356     one warp per read, HBM-bound
-//   k_frames      6-frame translation (RAPsearch2 BuildQHash) + "does any 12-window reach SEG's low cut?"
-//                 one thread per (read, frame); frames go to a global frame store
-//   k_seg         full SEG (Seg::segseq / Seg::trim) for the ~19 % of frames with such a window, one warp per frame,
+//   k_qc          read QC on the 2-bit packed reads   mc.py:265-279, 342-356     one warp per read, HBM-bound
+//   k_fingerprint / k_fp_keys / k_mark_dups   -d: 128-bit strand-canonical fingerprints, radix sort, marks (mc.py:333-355);
+//                 mcx_dedup_begin / _owner / _finish are the same steps split around the cross-GPU exchange
+//   k_frames      6-frame translation (RAPsearch2 BuildQHash) + the verdict of every 12-window against both SEG cut-offs
+//                 one thread per (read, frame); frames go to a global frame store, frames with a low window to the SEG queue
+//   k_seg         full SEG (Seg::segseq / Seg::trim) for the frames with such a window (34 % at 150 bp), one warp per frame,
 //                 frames drawn from the queue by resident blocks
-//   k_probe       murphy10 seed-word lookup (Searching / FindSeeds): Bloom filter + hash tables, every posting of a
-//                 word hit queued as a candidate
-//   k_seed        seed growth and acceptance (ExtendSeq2Set), one thread per candidate
+//   k_probe       murphy10 seed words against the presence filter (Searching / FindSeeds): two filter blocks per window,
+//                 passing words queued
+//   k_resolve     word tables + posting lists of the queued words, one lane per word; every posting that survives the
+//                 first rejection test is queued as a candidate
+//   k_seed        seed growth and acceptance (ExtendSeq2Set), one thread per candidate, residues from register windows
 //   k_walk        ungapped X-drop walks (AlignFwd / AlignBwd), one thread per accepted seed; duplicate HSPs dropped
-//   k_gap_list / k_gap_dir x2 / k_gap_finish   gapped X-drop extension (AlignSeqs / AlignGapped / CalRes): work list
-//                 sorted by size, score pass, statistics pass for the extensions that gained (one lane per extension,
-//                 refilled from the work list as extensions end), HSP records + sort keys
+//   k_gap_list / k_gap_screen / k_gap_dp / k_gap_trace / k_gap_finish   gapped X-drop extension (AlignSeqs / AlignGapped /
+//                 CalRes): work list sorted by size, screening pass (DPX) for all extensions, complete DP + traceback
+//                 for those that gain, HSP records + sort keys; k_gap_dir: fallback for windows wider than the ring
 //   k_cls_groups / _cap / _cap_apply / _filter / _sum   HSP de-duplication per (read, subject), the 500-line cap, the
 //                 three cutoffs, best hit per read and the per-family integer sums    mc.py:400-472
 // plus CUB scans/sorts for compaction and ordering.  mc.py = /root/reference/microbe_census/
@@ -2364,8 +2368,10 @@ struct mcx_ctx {
     int64_t n_hsp_sorted = 0;
     mcx_result res{};
     float ms[12] = {0};
+    float ms_detail[4] = {0};                  // k_probe, k_resolve, k_seed, k_walk of the last search
+    int64_t work[8] = {0};                     // mcx_search_counters of the last search
     int64_t launches = 0, host_syncs = 0;
-    cudaEvent_t ev[20] = {nullptr};
+    cudaEvent_t ev[22] = {nullptr};
 };
 // slots of d_cnt
 enum Cnt { C_QC0 = 0 /* ..3: verdict counts of the search */, C_QCALL = 4 /* ..7: verdict counts over all pushed reads */,
@@ -3432,9 +3438,16 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     // chunk boundaries; while host -> device copies are in flight the first chunks are small, so that the search starts
     // as soon as a few tens of megabytes have arrived
     std::vector<int64_t> bounds(1, 0);
+    // While host -> device copies are in flight the reads are cut into pieces of a sixteenth of a chunk, and every
+    // round of the loop below searches the pieces that have ARRIVED by then (at least two, at most a chunk): with one
+    // GPU on the link that is a small first round and then full chunks; with eight GPUs sharing the host's memory system
+    // (copies 2.3x slower) the rounds stay as large as the link allows and the search never waits for more than it
+    // needs.  (Before: rounds of 1/8, 1/4, 1/2, 1 chunk whatever the link did -- at 8 GPUs the search idled 11 ms of an
+    // 80 ms step waiting for rounds twice as large as what it had just finished.)
+    const bool streaming = ctx->steps_waited < ctx->n_steps && ctx->n_steps > 1 && !P.filter_dups;
     {
-        int64_t c = ctx->n_steps > 1 ? std::max<int64_t>(chunk / 8, 65536) : chunk;
-        while (bounds.back() < n) { bounds.push_back(std::min(n, bounds.back() + c)); c = std::min(chunk, c * 2); }
+        const int64_t c = streaming ? std::max<int64_t>(chunk / 16, 65536) : chunk;
+        while (bounds.back() < n) bounds.push_back(std::min(n, bounds.back() + c));
     }
     const int nb = (int)bounds.size() - 1;
     std::vector<long long> bw((size_t)nb + 1, -1), bq((size_t)nb + 1, -1);
@@ -3462,13 +3475,28 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         ms_qc += elapsed_ms(ctx->ev[14], ctx->ev[15]);
     }
 
-    float ms_frames = 0, ms_seg = 0, ms_probe = 0, ms_ext = 0, ms_gap = 0;
-    unsigned long long n_surv = 0, n_cand_total = 0, n_seeds_total = 0, n_pass_total = 0;
+    float ms_frames = 0, ms_seg = 0, ms_probe = 0, ms_ext = 0, ms_gap = 0, ms_kprobe = 0, ms_kseed = 0;
+    unsigned long long n_surv = 0, n_cand_total = 0, n_seeds_total = 0, n_pass_total = 0, n_segq_total = 0;
     int64_t remaining = quota, sampled = 0, examined = 0;
-    for (int c = 0; c < nb && (quota < 0 || remaining > 0); ++c) {
-        const int64_t r0 = bounds[(size_t)c], r1 = bounds[(size_t)c + 1], nr_in = r1 - r0;
+    auto arrived = [&](long long words, long long qbytes) -> bool {     // have the copy steps holding [0, words) / [0, qbytes) finished?
+        int need = 0;
+        if (words > 0 && ctx->step_words > 0) need = (int)std::min<int64_t>(ctx->n_steps, (words + ctx->step_words - 1) / ctx->step_words);
+        if (ctx->have_quals && qbytes > 0 && ctx->step_qbytes > 0)
+            need = std::max(need, (int)std::min<int64_t>(ctx->n_steps, (qbytes + 15 + ctx->step_qbytes - 1) / ctx->step_qbytes));
+        if (need <= ctx->steps_waited) return true;
+        const cudaError_t q = cudaEventQuery(ctx->ev_copy[need - 1]);   // the steps complete in order
+        if (q != cudaSuccess) (void)cudaGetLastError();                  // cudaErrorNotReady is not an error
+        return q == cudaSuccess;
+    };
+    for (int c = 0, c1 = 0; c < nb && (quota < 0 || remaining > 0); c = c1) {
+        c1 = c + 1;
+        if (streaming) {
+            c1 = std::min(nb, c + 2);
+            while (c1 < nb && bounds[(size_t)c1 + 1] - bounds[(size_t)c] <= chunk && arrived(bw[(size_t)c1 + 1], bq[(size_t)c1 + 1])) ++c1;
+        }
+        const int64_t r0 = bounds[(size_t)c], r1 = bounds[(size_t)c1], nr_in = r1 - r0;
         // ---- K1 on this chunk: verdicts, list of kept reads
-        if ((rc = wait_copies(ctx, bw[(size_t)c + 1], bq[(size_t)c + 1])) != MCX_OK) return rc;
+        if ((rc = wait_copies(ctx, bw[(size_t)c1], bq[(size_t)c1])) != MCX_OK) return rc;
         CK(cudaEventRecord(ctx->ev[14], st));
         if ((rc = qc_range(ctx, r1)) != MCX_OK) return rc;
         {
@@ -3544,6 +3572,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
                 const unsigned long long resident = (unsigned long long)per_sm * ctx->n_sm;
                 k_probe<NTP><<<(unsigned)std::min<unsigned long long>((nr_max * 6 + NTP - 1) / NTP, resident), NTP, smem, st>>>(A, fstride);
             }
+            if (attempt == 0) CK(cudaEventRecord(ctx->ev[20], st));
             auto row_blocks = [&](auto kernel, int nt, unsigned long long cap) -> unsigned {   // resident blocks per sub-queue row
                 int per_sm = 0;
                 if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
@@ -3568,6 +3597,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
                 E.seen = ctx->d_seen; E.seen_mask = (1ull << bits) - 1; E.seen_shift = 64 - bits;
             }
             k_seed<SEED_NT><<<dim3(row_blocks(k_seed<SEED_NT>, SEED_NT, E.cap_cand), NQ), SEED_NT, 0, st>>>(E);
+            if (attempt == 0) CK(cudaEventRecord(ctx->ev[21], st));
             {
                 int per_sm = 0;
                 if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk<WALK_NT>, WALK_NT, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
@@ -3597,7 +3627,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
             hc[C_SURV] = surv_before;
             CK(cudaMemcpyAsync(ctx->d_cnt + C_SURV, hc + C_SURV, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
         }
-        n_cand_total += n_cand; n_seeds_total += n_seeds; n_pass_total += n_pass;
+        n_cand_total += n_cand; n_seeds_total += n_seeds; n_pass_total += n_pass; n_segq_total += hc[C_SEGQ];
         sampled += nr < 0 ? (int64_t)hc[C_NKEPT] : nr;
         if (n_surv > surv_before) {
             GapArgs G;
@@ -3667,6 +3697,8 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
         ms_frames += elapsed_ms(ctx->ev[2], ctx->ev[10]);
         ms_seg += elapsed_ms(ctx->ev[10], ctx->ev[11]);
         ms_probe += elapsed_ms(ctx->ev[11], ctx->ev[3]);
+        ms_kprobe += elapsed_ms(ctx->ev[11], ctx->ev[20]);
+        ms_kseed += elapsed_ms(ctx->ev[3], ctx->ev[21]);
         ms_ext += elapsed_ms(ctx->ev[3], ctx->ev[8]);
         ms_gap += elapsed_ms(ctx->ev[8], ctx->ev[9]);
     }
@@ -3681,6 +3713,8 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     R.sampled_reads = sampled;
     R.n_seed_hits = (int64_t)n_surv;
     ctx->n_cand_last = (int64_t)n_cand_total;
+    ctx->work[0] = (int64_t)n_segq_total; ctx->work[1] = (int64_t)n_pass_total; ctx->work[2] = (int64_t)n_cand_total;
+    ctx->work[3] = (int64_t)n_seeds_total; ctx->work[4] = (int64_t)n_surv;
     const int64_t ns = (int64_t)n_surv;
     CK(cudaEventRecord(ctx->ev[4], st));
     if (ns > 0) {
@@ -3721,6 +3755,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
                                      n_pass_total, n_cand_total, n_seeds_total, n_surv, hc[C_NGAPTOT], hc[C_GAPPED], hc[C_CELLS], (long long)ctx->host_syncs);
     for (int f = 0; f < MCX_N_FAM; ++f) { R.fam_hits[f] = (int64_t)acc[3 + f]; R.fam_aln[f] = (int64_t)acc[3 + MCX_N_FAM + f]; }
     for (size_t k = 0; k < abl.size(); ++k) R.aln_by_len[k] = (int64_t)abl[k];
+    ctx->ms_detail[0] = ms_kprobe; ctx->ms_detail[1] = ms_probe - ms_kprobe; ctx->ms_detail[2] = ms_kseed; ctx->ms_detail[3] = ms_ext - ms_kseed;
     ctx->ms[1] = ms_qc; ctx->ms[2] = ms_probe; ctx->ms[7] = ms_ext; ctx->ms[3] = ms_gap; ctx->ms[8] = ms_frames; ctx->ms[9] = ms_seg;
     ctx->ms[4] = elapsed_ms(ctx->ev[4], ctx->ev[5]);
     ctx->ms[5] = elapsed_ms(ctx->ev[5], ctx->ev[6]);
@@ -3855,6 +3890,18 @@ extern "C" int mcx_l2_peak(mcx_ctx *ctx, double *gsectors_per_s) {
         if (rep > 0) best = std::max(best, loads / (ms * 1e-3) / 1e9);
     }
     *gsectors_per_s = best;
+    return MCX_OK;
+}
+
+extern "C" int mcx_search_counters(mcx_ctx *ctx, int64_t out[8]) {
+    if (!ctx || !out) return fail(ctx, MCX_EINVAL, "mcx_search_counters: null argument");
+    memcpy(out, ctx->work, sizeof(int64_t) * 8);
+    return MCX_OK;
+}
+
+extern "C" int mcx_timings_detail(mcx_ctx *ctx, float ms[4]) {
+    if (!ctx || !ms) return fail(ctx, MCX_EINVAL, "mcx_timings_detail: null argument");
+    memcpy(ms, ctx->ms_detail, sizeof(float) * 4);
     return MCX_OK;
 }
 

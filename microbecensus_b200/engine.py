@@ -362,12 +362,22 @@ class MarkerSearch:
         self._ck(self.lib.mcx_l2_peak(self.ctx, C.byref(v)))
         return v.value
 
+    def search_counters(self):
+        """queue lengths of the last search (include/mcx.h mcx_search_counters)"""
+        out = (C.c_int64 * 8)()
+        self._ck(self.lib.mcx_search_counters(self.ctx, C.byref(out)))
+        return dict(zip(("seg_frames", "filter_passes", "candidates", "seeds", "ungapped_hsps"), (int(x) for x in out[:5])))
+
     def timings(self):
         ms = (C.c_float * 12)()
         launches = C.c_int64(0)
         self._ck(self.lib.mcx_timings(self.ctx, C.byref(ms), C.byref(launches)))
         names = ("h2d", "qc", "probe", "gapped", "sort", "classify", "d2h", "extend", "frames", "seg", "k_qc", "dedupe")
-        return {k: float(ms[i]) for i, k in enumerate(names)}, int(launches.value)
+        out = {k: float(ms[i]) for i, k in enumerate(names)}
+        det = (C.c_float * 4)()
+        self._ck(self.lib.mcx_timings_detail(self.ctx, C.byref(det)))
+        out.update({k: float(det[i]) for i, k in enumerate(("k_probe", "k_resolve", "k_seed", "k_walk"))})
+        return out, int(launches.value)
 
 
 HIT_FIELDS = ("read", "subject", "frame", "score", "aln", "ident", "mism", "gapo", "q0", "q1", "t0", "t1")

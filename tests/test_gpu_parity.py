@@ -51,6 +51,37 @@ def test_seeded_synthetic_reads_bit_exact(eng, oracle, markers, L, n):
     assert res.reads_classified > 0
 
 
+def test_large_sample_bit_exact_at_the_metric_length(eng, oracle, markers):
+    """200,000 reads of the bench workload's stream at 150 bp (ten times the largest sample above): every HSP, the
+    classification of every read and the per-family sums against the oracle, which runs on all host cores (slices of the
+    batch on threads; the C calls release the GIL and only read the index)."""
+    import concurrent.futures as cf
+    n, L = 200_000, 150
+    batch = synth.reads(3, 0, n, L)
+    eng.set_params(L)
+    eng.push(batch)
+    res = eng.search(-1)
+    hits = eng.hits()
+    oracle.search(batch.slice(0, 8), L, eng.min_report_raw)            # one-time table set-up before the threads start
+    workers = max(1, min(32, os.cpu_count() or 1))
+    cuts = np.linspace(0, n, 4 * workers + 1).astype(np.int64)
+
+    def part(k):
+        lo, hi = int(cuts[k]), int(cuts[k + 1])
+        oh, _ = oracle.search(batch.slice(lo, hi), L, eng.min_report_raw, cap=400_000)
+        oh[:, 0] += lo                                                 # read index within the whole batch
+        return oh
+    with cf.ThreadPoolExecutor(workers) as ex:
+        oh = np.concatenate(list(ex.map(part, range(len(cuts) - 1))))
+    assert hits.shape == oh[:, MCX_ORDER].shape
+    assert np.array_equal(hits, oh[:, MCX_ORDER])
+    oc = oracle.classify(oh, L, markers, n)
+    assert res.reads_classified == oc["classified"] > 1000
+    assert np.array_equal(res.fam_hits, oc["fam_hits"]) and np.array_equal(res.fam_aln, oc["fam_aln"])
+    assert np.array_equal(res.aln_by_len, oc["aln_by_len"])
+    assert np.array_equal(eng.classified(n), oc["best_subject"])
+
+
 @pytest.mark.parametrize("n", [1, 2, 7, 33])
 def test_small_batches_bit_exact(eng, oracle, markers, n):
     """Fewer gapped extensions than lanes of a warp: the work-list refill of k_gap_dir / k_seg with lanes that never get work."""

@@ -337,3 +337,20 @@ dist.destroy_process_group()
     for nproc, port in ((2, "29518"), (3, "29519")):
         subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nproc, "--master-addr", "127.0.0.1",
                                "--master-port", port, str(script)], stdout=subprocess.DEVNULL, timeout=600)
+
+
+def test_marker_blob_equals_reference_maps():
+    """find_opt_pars / read_dic (mc.py:61-88): every cut-off, coefficient and weight per (read length, family) and the
+    family and length of every subject in the packed blob equal the reference's own *.map files -- line by line where the
+    reference tree is mounted, by the committed digest of those lines (tools/marker_digest.py) elsewhere."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import marker_digest as md
+    from microbecensus_b200.markers import Markers
+    m = Markers()
+    ours = md.lines_from_blob(m)
+    want, n = open(os.path.join(ROOT, "tests", "golden", "marker_maps.sha256")).read().split()
+    assert len(ours) == int(n) == 3 * 600 + m.n_subj
+    assert md.digest(ours) == want
+    if os.path.isdir("/root/reference/microbe_census/data"):
+        theirs = md.lines_from_reference("/root/reference", set(m.names))
+        assert theirs == ours

@@ -1372,9 +1372,10 @@ __device__ __forceinline__ void walk_one(const ExtArgs &A, const int8_t *s_bl, i
 template <int NT>
 __global__ void __launch_bounds__(NT) k_walk(ExtArgs A) {
     __shared__ __align__(4) int8_t s_bl[21 * 32];
+    const int64_t n_seeds = (int64_t)min(*A.n_seedq, A.cap_seedq);
+    if ((int64_t)blockIdx.x * NT >= n_seeds) return;          // the grid is sized for a full chunk: small batches leave most blocks without work
     for (int k = threadIdx.x; k < 21 * 32 / 4; k += NT) reinterpret_cast<uint32_t *>(s_bl)[k] = reinterpret_cast<const uint32_t *>(g_blosum)[k];
     __syncthreads();
-    const int64_t n_seeds = (int64_t)min(*A.n_seedq, A.cap_seedq);
     for (int64_t g = (int64_t)blockIdx.x * NT + threadIdx.x; g < n_seeds; g += (int64_t)gridDim.x * NT) walk_one(A, s_bl, g);
 }
 
@@ -2454,6 +2455,9 @@ static int ensure_temp(mcx_ctx *ctx, size_t bytes) {
 extern "C" const char *mcx_version(void) { return "mcx 0.1 (sm_100a)"; }
 extern "C" const char *mcx_last_error(mcx_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
 
+#ifndef MCX_SLOT_ROOM_X10
+#define MCX_SLOT_ROOM_X10 20               /* slots per distinct word x 10, rounded up to a power of two: 2^22 slots for 1.21 M words */
+#endif
 // seed index: one open-addressing table per word pattern over the murphy10 letters of the database
 static int build_index(mcx_ctx *ctx, const mcx_db *db) {
     const int ns = db->n_subj;
@@ -2504,7 +2508,7 @@ static int build_index(mcx_ctx *ctx, const mcx_db *db) {
     if (post_base[N_PAT] >= (1u << 25)) return fail(ctx, MCX_EINVAL, "seed index too large for 25-bit posting offsets");
     // one table size for all patterns (load factor <= 0.5 for the fullest), slots of (key, value)
     uint32_t size = 1024; int bits = 10;
-    while (size < max_distinct * 2) { size <<= 1; ++bits; }
+    while ((double)size < (double)max_distinct * (MCX_SLOT_ROOM_X10 / 10.0)) { size <<= 1; ++bits; }
     std::vector<uint2> tab((size_t)N_PAT << bits);
     std::vector<uint32_t> post_all(post_base[N_PAT]);
     auto fill = [&](int p) {

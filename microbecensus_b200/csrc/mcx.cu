@@ -1290,7 +1290,10 @@ __global__ void __launch_bounds__(NT) k_seed(ExtArgs A) {
 // report floor are appended to the survivor list.
 // (Tried and measured slower, 1.61 -> 2.15 ms at 1M x 150 bp: loading the residues of four steps together, the next four
 // while the current four are scored.  The walks are short -- most stop after a few residues -- so the batches mostly
-// fetch what is never used, and the kernel went from 36 to 80 registers, 69 % to 35 % occupancy.)
+// fetch what is never used, and the kernel went from 36 to 80 registers, 69 % to 35 % occupancy.
+// Also slower, 1.69 -> 1.96 ms: one loop stepping the forward and the backward walk together, so that their byte loads
+// are in flight at the same time -- 48 registers, and every iteration carries the bookkeeping of both directions although
+// one of them has usually stopped.)
 __device__ __forceinline__ void walk_one(const ExtArgs &A, const int8_t *s_bl, int64_t g) {
     const uint4 sd = A.seedq[g];
     const uint32_t gframe = sd.x;

@@ -95,6 +95,9 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------- CPU reference arm
+LAST_M8 = None
+
+
 def reference_available():
     ref = os.path.join(ROOT, "baseline", "_ref", "microbe_census")
     return all(os.path.exists(os.path.join(ref, p)) for p in ("microbe_census.py", "bin/rapsearch_Linux_2.15", "data/rapdb_2.15"))
@@ -136,9 +139,16 @@ def run_reference_once(batches, wl, threads, tmpdir):
     mc.search_seqs(args, paths)
     best = mc.classify_reads(args, paths)
     agg = mc.aggregate_hits(args, paths, best)
+    dt_before_cleanup = time.perf_counter() - t0
+    global LAST_M8                      # the child's .m8 lines, kept for the parity block (read outside the timed span)
+    try:
+        LAST_M8 = [l.rstrip("\n") for l in open(paths["tempfile"] + ".m8") if l[0] != "#"]
+    except OSError:
+        LAST_M8 = None
+    t1 = time.perf_counter()
     mc.clean_up(paths)
     ags = mc.estimate_average_genome_size(args, paths, agg)
-    return time.perf_counter() - t0, ags, args["sampled_reads"], agg, best
+    return dt_before_cleanup + (time.perf_counter() - t1), ags, args["sampled_reads"], agg, best
 
 
 def run_oracle_port_once(batches, wl, threads, tmpdir):
@@ -229,6 +239,20 @@ def parity_block(eng, markers, wl, sample_reads, cb):
         out["reads_classified"] = {"gpu": len(ours), "reference": len(theirs), "common": len(set(ours) & set(theirs))}
         out["discrepant_reads"] = disc[:50]
         out["n_discrepant_reads"] = len(disc)
+    if LAST_M8 is not None:
+        # alignment level: the lines RAPsearch2 wrote for the sample against the GPU's HSPs in the same
+        # text layout -- all twelve fields (identity, lengths, coordinates, log E, bits) of every single-HSP line
+        from microbecensus_b200.engine import format_m8
+        hits = eng.hits()
+        codes, _ = eng.qc_export(False)
+        rank = np.cumsum(codes == 0) - 1
+        names = {int(r): str(int(rank[r])) for r in np.unique(hits[:, 0])} if len(hits) else {}
+        mine = set(format_m8(hits, markers, L, names))
+        single = [l for l in LAST_M8 if len(l.split("\t")[10].split(".")[-1]) <= 2]      # two-decimal E-values; sum-statistics lines carry six
+        found = sum(1 for l in single if l in mine)
+        out["m8_lines"] = {"reference": len(LAST_M8), "reference_single_hsp": len(single), "reproduced_character_for_character": found,
+                           "gpu": len(mine), "note": "reference lines not reproduced: pairs with several HSPs (sum-statistics E-values) and "
+                                                     "reads at RAPsearch2's 500-line cap (DESIGN.md section 2 (b), (c))"}
     return out
 
 
@@ -501,9 +525,14 @@ def main():
             cb = cpu_baseline(wl, a.ref_sample)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["cpu_baseline"]["ags_on_sample"] = cb["ags"]
-            line["parity"] = parity_block(eng, markers, wl, a.ref_sample, cb)
         except Exception as exc:      # the baseline is reporting only; never lose the GPU line over it
+            cb = None
             line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(exc)[:200]}
+        if cb is not None:
+            try:
+                line["parity"] = parity_block(eng, markers, wl, a.ref_sample, cb)
+            except Exception as exc:
+                line["parity"] = {"error": str(exc)[:200]}
     print(json.dumps(line, default=lambda o: o.item() if hasattr(o, "item") else str(o)))
     if world > 1:
         dist.destroy_process_group()

@@ -1053,7 +1053,8 @@ __global__ void __launch_bounds__(NT, MCX_PROBE_MINB) k_probe(ProbeArgs A, int f
         }
     }
     }
-    for (uint32_t e = run.cur + lane; e < run.end; e += 32) if (e < A.cap_pass) qbase[e].ip = PASS_EMPTY;
+    for (uint32_t e = run.cur + lane; e < run.end; e += 32)          // whole records: the readers load all three words
+        if (e < A.cap_pass) { Cand z; z.gframe = 0u; z.sj = 0u; z.ip = PASS_EMPTY; qbase[e] = z; }
 }
 
 // K2b, table half: one lane per word that passed the filter: slot of its pattern's table (key and value share 8
@@ -1125,7 +1126,8 @@ __global__ void __launch_bounds__(NT) k_resolve(ProbeArgs A) {
             if (keep) qbase[run_pos(run, (uint32_t)__popc(km & ((1u << lane) - 1u)))] = c;
         }
     }
-    for (uint32_t e = run.cur + lane; e < run.end; e += 32) if (e < A.cap_cand) qbase[e].ip = CAND_EMPTY;
+    for (uint32_t e = run.cur + lane; e < run.end; e += 32)
+        if (e < A.cap_cand) { Cand z; z.gframe = 0u; z.sj = 0u; z.ip = CAND_EMPTY; qbase[e] = z; }
 }
 
 // K2b: one thread per candidate: grow the word to the maximal murphy10-identical stretch, apply the seed
@@ -1282,7 +1284,7 @@ __global__ void __launch_bounds__(NT) k_seed(ExtArgs A) {
     const uint32_t at = run_pos(run, (uint32_t)__popc(am & ((1u << lane) - 1u)));
     if (accepted && at < A.cap_seedq) A.seedq[at] = rec;
     }
-    for (uint32_t e = run.cur + lane; e < run.end; e += 32) if (e < A.cap_seedq) A.seedq[e].x = SEED_EMPTY;
+    for (uint32_t e = run.cur + lane; e < run.end; e += 32) if (e < A.cap_seedq) A.seedq[e] = make_uint4(SEED_EMPTY, 0u, 0u, 0u);
 }
 
 #undef SAME

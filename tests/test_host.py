@@ -354,3 +354,20 @@ def test_marker_blob_equals_reference_maps():
     if os.path.isdir("/root/reference/microbe_census/data"):
         theirs = md.lines_from_reference("/root/reference", set(m.names))
         assert theirs == ours
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's CPU arm): one JSON line with the metric, unit and config of the GPU arm, the
+    reference's own functions and rapsearch child on a bounded sample, no GPU and none of this package's search code."""
+    import json
+    if not os.path.exists(os.path.join(ROOT, "baseline", "_ref", "microbe_census", "data", "rapdb_2.15")):
+        pytest.skip("reference install (baseline/_ref) not present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-sample", "400"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-400:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "reads/sec end-to-end AGS" and line["unit"] == "reads/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["config"]["read_length"] == 150 and "150 bp" in line["config"]["workload"]
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

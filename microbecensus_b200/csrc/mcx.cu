@@ -3455,7 +3455,7 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     // 80 ms step waiting for rounds twice as large as what it had just finished.)
     const bool streaming = ctx->steps_waited < ctx->n_steps && ctx->n_steps > 1 && !P.filter_dups;
     {
-        const int64_t c = streaming ? std::max<int64_t>(chunk / 16, 65536) : chunk;
+        const int64_t c = streaming ? std::min<int64_t>(chunk, std::max<int64_t>(chunk / 16, 65536)) : chunk;   // never more than the buffers hold
         while (bounds.back() < n) bounds.push_back(std::min(n, bounds.back() + c));
     }
     const int nb = (int)bounds.size() - 1;
@@ -3499,10 +3499,9 @@ extern "C" int mcx_search(mcx_ctx *ctx, int64_t quota) {
     };
     for (int c = 0, c1 = 0; c < nb && (quota < 0 || remaining > 0); c = c1) {
         c1 = c + 1;
-        if (streaming) {
-            c1 = std::min(nb, c + 2);
-            while (c1 < nb && bounds[(size_t)c1 + 1] - bounds[(size_t)c] <= chunk && arrived(bw[(size_t)c1 + 1], bq[(size_t)c1 + 1])) ++c1;
-        }
+        if (streaming)                           // a second piece whatever has arrived (if a chunk holds two), then what has arrived
+            while (c1 < nb && bounds[(size_t)c1 + 1] - bounds[(size_t)c] <= chunk &&
+                   (c1 - c < 2 || arrived(bw[(size_t)c1 + 1], bq[(size_t)c1 + 1]))) ++c1;
         const int64_t r0 = bounds[(size_t)c], r1 = bounds[(size_t)c1], nr_in = r1 - r0;
         // ---- K1 on this chunk: verdicts, list of kept reads
         if ((rc = wait_copies(ctx, bw[(size_t)c1], bq[(size_t)c1])) != MCX_OK) return rc;
